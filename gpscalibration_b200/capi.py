@@ -1,0 +1,300 @@
+"""ctypes binding of the C ABI in include/loamgpu.h (libloamgpu.so, built in-tree under csrc/).
+
+This is the boundary a maintainer of the reference binds to; nothing here computes anything.  If the shared library
+is missing the import of the package still works but every call raises (no CPU fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+LOAM_OK, LOAM_EINVAL, LOAM_ECUDA, LOAM_ENOSPC, LOAM_ESTATE = 0, -1, -2, -3, -4
+
+CLOUD = dict(full=0, sharp=1, less_sharp=2, flat=3, less_flat=4, corner_last=5, surf_last=6, full_res3=7, corner_stack=8,
+             surf_stack=9, corner_map=10, surf_map=11, surround=12, registered=13)
+DIAG = dict(curvature=(0, np.float32), picked_mask=(1, np.uint8), label=(2, np.int8), scan_start=(3, np.int32),
+            scan_end=(4, np.int32))
+
+
+class LoamError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: error {code} ({detail})")
+
+
+class Params(C.Structure):
+    _fields_ = [("n_scans", C.c_int), ("ring_mode", C.c_int), ("ring_ang_min", C.c_float), ("ring_ang_step", C.c_float),
+                ("skip_frame_num", C.c_int), ("max_points", C.c_int), ("max_map_points", C.c_int),
+                ("want_registered", C.c_int), ("want_surround", C.c_int)]
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_full", C.c_int), ("n_sharp", C.c_int), ("n_less_sharp", C.c_int), ("n_flat", C.c_int),
+                ("n_less_flat", C.c_int)]
+
+
+class OdomResult(C.Structure):
+    _fields_ = [("transform_sum", C.c_float * 6), ("transformation", C.c_float * 6), ("odom_published", C.c_int),
+                ("clouds_published", C.c_int), ("fullres_published", C.c_int), ("iterations", C.c_int),
+                ("n_corner_last", C.c_int), ("n_surf_last", C.c_int)]
+
+
+class MapResult(C.Structure):
+    _fields_ = [("transform_aft_mapped", C.c_float * 6), ("transform_bef_mapped", C.c_float * 6),
+                ("transform_tobe_mapped", C.c_float * 6), ("optimised", C.c_int), ("iterations", C.c_int),
+                ("surround_published", C.c_int), ("n_corner_stack", C.c_int), ("n_surf_stack", C.c_int),
+                ("n_corner_map", C.c_int), ("n_surf_map", C.c_int), ("n_surround", C.c_int), ("n_registered", C.c_int)]
+
+
+class SweepResult(C.Structure):
+    _fields_ = [("counts", Counts), ("odom", OdomResult), ("map", MapResult), ("mapping_ran", C.c_int)]
+
+
+# every symbol include/loamgpu.h declares (tests check the library exports all of them)
+SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
+           "loam_stream", "loam_launch_count", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_mapping_odometry", "loam_mapping_process", "loam_process_sweep", "loam_process_sweep_device",
+           "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
+           "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
+           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced"]
+
+
+def library_path():
+    return os.path.join(_HERE, "csrc", "libloamgpu.so")
+
+
+def load_library():
+    """Loads libloamgpu.so (fails loudly when it has not been built)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, ip, fp, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    lib.loam_strerror.restype = C.c_char_p
+    lib.loam_strerror.argtypes = [C.c_int]
+    lib.loam_last_cuda_error.restype = C.c_char_p
+    lib.loam_last_cuda_error.argtypes = [vp]
+    lib.loam_default_params.argtypes = [C.POINTER(Params)]
+    lib.loam_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
+    lib.loam_destroy.argtypes = [vp]
+    lib.loam_reset.argtypes = [vp]
+    lib.loam_stream.restype = vp
+    lib.loam_stream.argtypes = [vp]
+    lib.loam_launch_count.restype = C.c_longlong
+    lib.loam_launch_count.argtypes = [vp]
+    lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
+    lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
+    lib.loam_odometry_process.argtypes = [vp, C.POINTER(OdomResult)]
+    lib.loam_mapping_odometry.argtypes = [vp, vp]
+    lib.loam_mapping_process.argtypes = [vp, C.POINTER(MapResult)]
+    lib.loam_process_sweep.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
+    lib.loam_process_sweep_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
+    lib.loam_get_cloud.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    lib.loam_get_diag.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    lib.loam_voxel_grid.argtypes = [vp, vp, C.c_int, C.c_float, vp, C.c_int, ip]
+    lib.loam_odom_set_inputs.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.loam_odom_iter.argtypes = [vp, C.c_int, vp, vp, vp, ip]
+    lib.loam_odom_get_corr.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]
+    lib.loam_transform_to_end.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    lib.loam_map_set_inputs.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.loam_map_iter.argtypes = [vp, C.c_int, vp, vp, vp, ip]
+    lib.loam_map_get_corr.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    lib.loam_gn_solve.argtypes = [vp, vp, C.c_int, C.c_float, vp, vp]
+    lib.loam_map_iter_partial.argtypes = [vp, C.c_int, vp, vp]
+    lib.loam_map_finish_reduced.argtypes = [vp, vp, vp, ip]
+    _LIB = lib
+    return lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class LoamGpu:
+    """One handle = one GPU + one stream + the state of the three LOAM stages (thin wrapper, no logic)."""
+
+    def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
+                 want_registered=False, want_surround=False):
+        self.lib = load_library()
+        p = Params()
+        self.lib.loam_default_params(C.byref(p))
+        p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
+        p.skip_frame_num = skip_frame_num
+        p.want_registered, p.want_surround = int(want_registered), int(want_surround)
+        self.params = p
+        self._h = C.c_void_p()
+        self._check(self.lib.loam_create(C.byref(p), device, C.byref(self._h)), "loam_create")
+
+    def _check(self, rc, where):
+        if rc != 0:
+            detail = self.lib.loam_strerror(rc).decode()
+            if rc == LOAM_ECUDA:
+                detail += ": " + self.lib.loam_last_cuda_error(self._h).decode()
+            raise LoamError(rc, where, detail)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.loam_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- lifecycle
+    def reset(self):
+        self._check(self.lib.loam_reset(self._h), "loam_reset")
+
+    @property
+    def stream(self):
+        return self.lib.loam_stream(self._h)
+
+    @property
+    def launches(self):
+        return int(self.lib.loam_launch_count(self._h))
+
+    # ---- node level
+    def extract(self, xyz, stamp=0.0):
+        xyz = _f32(xyz)
+        c = Counts()
+        self._check(self.lib.loam_extract(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] if xyz.shape[0] > 1 else 12, stamp, None, C.byref(c)),
+                    "loam_extract")
+        return c
+
+    def extract_device(self, dev_ptr, n, stride_bytes=12, stamp=0.0):
+        c = Counts()
+        self._check(self.lib.loam_extract_device(self._h, dev_ptr, n, stride_bytes, stamp, None, C.byref(c)), "loam_extract_device")
+        return c
+
+    def odometry_process(self):
+        r = OdomResult()
+        self._check(self.lib.loam_odometry_process(self._h, C.byref(r)), "loam_odometry_process")
+        return r
+
+    def mapping_odometry(self, transform_sum):
+        t = _f32(transform_sum)
+        self._check(self.lib.loam_mapping_odometry(self._h, t.ctypes.data), "loam_mapping_odometry")
+
+    def mapping_process(self):
+        r = MapResult()
+        self._check(self.lib.loam_mapping_process(self._h, C.byref(r)), "loam_mapping_process")
+        return r
+
+    def process_sweep(self, xyz, stamp=0.0):
+        xyz = _f32(xyz)
+        r = SweepResult()
+        self._check(self.lib.loam_process_sweep(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] if xyz.shape[0] > 1 else 12, stamp, C.byref(r)),
+                    "loam_process_sweep")
+        return r
+
+    def process_sweep_device(self, dev_ptr, n, stride_bytes=12, stamp=0.0):
+        r = SweepResult()
+        self._check(self.lib.loam_process_sweep_device(self._h, dev_ptr, n, stride_bytes, stamp, C.byref(r)),
+                    "loam_process_sweep_device")
+        return r
+
+    # ---- data access
+    def cloud(self, which):
+        n = C.c_int()
+        w = CLOUD[which] if isinstance(which, str) else which
+        self._check(self.lib.loam_get_cloud(self._h, w, None, 0, C.byref(n)), "loam_get_cloud")
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            self._check(self.lib.loam_get_cloud(self._h, w, out.ctypes.data, n.value, C.byref(n)), "loam_get_cloud")
+        return out
+
+    def diag(self, which):
+        w, dt = DIAG[which]
+        n = C.c_int()
+        self._check(self.lib.loam_get_diag(self._h, w, None, 0, C.byref(n)), "loam_get_diag")
+        out = np.empty(n.value, dt)
+        if n.value:
+            self._check(self.lib.loam_get_diag(self._h, w, out.ctypes.data, out.nbytes, C.byref(n)), "loam_get_diag")
+        return out
+
+    # ---- stage level
+    def voxel_grid(self, pts4, leaf):
+        pts4 = _f32(pts4)
+        out = np.empty_like(pts4)
+        v = C.c_int()
+        self._check(self.lib.loam_voxel_grid(self._h, pts4.ctypes.data, pts4.shape[0], leaf, out.ctypes.data, out.shape[0], C.byref(v)),
+                    "loam_voxel_grid")
+        return out[:v.value].copy()
+
+    def odom_set_inputs(self, sharp, flat, corner_last, surf_last):
+        a, b, c, d = _f32(sharp), _f32(flat), _f32(corner_last), _f32(surf_last)
+        self._n_sharp, self._n_flat = a.shape[0], b.shape[0]
+        self._check(self.lib.loam_odom_set_inputs(self._h, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], c.ctypes.data,
+                                                  c.shape[0], d.ctypes.data, d.shape[0]), "loam_odom_set_inputs")
+
+    def odom_iter(self, it, T):
+        T = _f32(T)
+        AtA, AtB, n = np.zeros((6, 6), np.float32), np.zeros(6, np.float32), C.c_int()
+        self._check(self.lib.loam_odom_iter(self._h, it, T.ctypes.data, AtA.ctypes.data, AtB.ctypes.data, C.byref(n)), "loam_odom_iter")
+        return AtA, AtB, n.value
+
+    def odom_corr(self, n_sharp, n_flat):
+        c1, c2 = np.empty(n_sharp, np.int32), np.empty(n_sharp, np.int32)
+        s1, s2, s3 = np.empty(n_flat, np.int32), np.empty(n_flat, np.int32), np.empty(n_flat, np.int32)
+        self._check(self.lib.loam_odom_get_corr(self._h, c1.ctypes.data, c2.ctypes.data, n_sharp, s1.ctypes.data, s2.ctypes.data,
+                                                s3.ctypes.data, n_flat), "loam_odom_get_corr")
+        return c1, c2, s1, s2, s3
+
+    def transform_to_end(self, pts4, T, imu_trans=None):
+        pts4, T = _f32(pts4), _f32(T)
+        out = np.empty_like(pts4)
+        imu = _f32(imu_trans).ctypes.data if imu_trans is not None else None
+        self._check(self.lib.loam_transform_to_end(self._h, pts4.ctypes.data, pts4.shape[0], T.ctypes.data, imu, out.ctypes.data),
+                    "loam_transform_to_end")
+        return out
+
+    def map_set_inputs(self, corner_stack, surf_stack, corner_map, surf_map):
+        a, b, c, d = _f32(corner_stack), _f32(surf_stack), _f32(corner_map), _f32(surf_map)
+        self._n_cs, self._n_ss = a.shape[0], b.shape[0]
+        self._check(self.lib.loam_map_set_inputs(self._h, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], c.ctypes.data,
+                                                 c.shape[0], d.ctypes.data, d.shape[0]), "loam_map_set_inputs")
+
+    def map_iter(self, it, T):
+        T = _f32(T)
+        AtA, AtB, n = np.zeros((6, 6), np.float32), np.zeros(6, np.float32), C.c_int()
+        self._check(self.lib.loam_map_iter(self._h, it, T.ctypes.data, AtA.ctypes.data, AtB.ctypes.data, C.byref(n)), "loam_map_iter")
+        return AtA, AtB, n.value
+
+    def map_corr(self, n_cs, n_ss):
+        a, b = np.empty((n_cs, 5), np.int32), np.empty((n_ss, 5), np.int32)
+        self._check(self.lib.loam_map_get_corr(self._h, a.ctypes.data, n_cs, b.ctypes.data, n_ss), "loam_map_get_corr")
+        return a, b
+
+    def map_iter_partial(self, it, T, dev_ptr28):
+        T = _f32(T)
+        self._check(self.lib.loam_map_iter_partial(self._h, it, T.ctypes.data, dev_ptr28), "loam_map_iter_partial")
+
+
+def gn_solve(AtA, AtB, it, eig_threshold, state37):
+    """Host-side 6x6 solve + degeneracy projection (LO:975-1004 / LM:968-997); state37 is updated in place."""
+    lib = load_library()
+    AtA, AtB = _f32(AtA), _f32(AtB)
+    X = np.zeros(6, np.float32)
+    rc = lib.loam_gn_solve(AtA.ctypes.data, AtB.ctypes.data, it, eig_threshold, state37.ctypes.data, X.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_gn_solve")
+    return X
+
+
+def finish_reduced(reduced28):
+    lib = load_library()
+    r = np.ascontiguousarray(reduced28, np.float64)
+    AtA, AtB, n = np.zeros((6, 6), np.float32), np.zeros(6, np.float32), C.c_int()
+    rc = lib.loam_map_finish_reduced(r.ctypes.data, AtA.ctypes.data, AtB.ctypes.data, C.byref(n))
+    if rc:
+        raise LoamError(rc, "loam_map_finish_reduced")
+    return AtA, AtB, n.value

@@ -1,0 +1,1085 @@
+// libloamgpu C ABI (include/loamgpu.h): the handle, the node-level state machines that replace the bodies of the
+// reference's three LOAM nodes, and the stage-level entry points the parity tests call.
+// Host logic restated here (the reference keeps it on the CPU and so do we): the Gauss-Newton solve and degeneracy
+// projection LO:975-1004 / LM:968-997, convergence tests LO:1017-1028 / LM:1006-1017, pose accumulation LO:1035-1064,
+// transformAssociateToMap / transformUpdate LM:120-242, the rolling cube grid LM:489-715 (descriptor moves only) and
+// the reset protocol LO:411-415,519-563 / LM:316-319,434-461.
+// There is NO CPU fallback: every compute step below is a kernel launch; without a CUDA device loam_create fails.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#include "lg_extract.h"
+#include "lg_host.h"
+#include "lg_linalg.cuh"
+#include "lg_map.h"
+#include "lg_odom.h"
+#include "lg_reduce.cuh"
+#include "lg_voxel.h"
+
+static thread_local char g_cuda_err[512] = "";
+void lg_set_error(const char* msg, const char* file, int line) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s:%d)", msg, file, line); }
+
+namespace {
+
+struct Chunk {
+  int off, n;
+};
+constexpr int CW = 21, CH = 11, CD = 21, CNUM = CW * CH * CD;  // LM:72-75
+
+static SinCos3 host_sincos3(const float* T) {
+  SinCos3 s;
+  s.srx = sinf(T[0]); s.crx = cosf(T[0]);
+  s.sry = sinf(T[1]); s.cry = cosf(T[1]);
+  s.srz = sinf(T[2]); s.crz = cosf(T[2]);
+  return s;
+}
+
+}  // namespace
+
+struct loam_handle {
+  loam_params prm;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  long long launches = 0;
+  // pinned host staging
+  double* h_mail = nullptr;  // mapped: 28 doubles written by the reduction kernels
+  double* d_mail = nullptr;
+  int* h_ints = nullptr;     // pinned scratch for small device -> host reads
+  static constexpr int H_INTS = 8192;
+
+  // ---- scanRegistration
+  SrParams srp;
+  SrWs sr;
+  DevBuf xyz_in;
+  loam_counts counts = {0, 0, 0, 0, 0};
+  bool have_features = false;
+  float imu[12] = {0};
+  // current message set for odometry (device pointers; either sr.* or the explicit test buffers)
+  const float4 *cur_sharp = nullptr, *cur_less_sharp = nullptr, *cur_flat = nullptr, *cur_less_flat = nullptr, *cur_full = nullptr;
+  DevBuf t_sharp, t_flat;  // loam_odom_set_inputs
+
+  // ---- laserOdometry state (the reference's file-scope / main()-scope variables)
+  OdomWs od;
+  bool lo_inited = false;          // systemInited LO:53
+  int frameCount = 1;              // LO:495 (= skipFrameNum)
+  float T[6] = {0}, Tsum[6] = {0};  // transformation / transformationSum LO:111-112
+  LgGNState lo_gn;                 // matP / isDegenerate LO:489-492
+  DevBuf corner_last, surf_last, corner_new, surf_new, fullres3;
+  int n_corner_last = 0, n_surf_last = 0, n_fullres3 = 0;
+  int cornerLastNum = 0, surfLastNum = 0;  // LO:98-99 (gate values, lag one sweep behind after init)
+
+  // ---- laserMapping state
+  bool lm_inited = false;  // systemInited LM:49
+  int mapFrameCount = 4;   // LM:419
+  int cenW = 10, cenH = 5, cenD = 10;
+  float mTsum[6] = {0}, Tincre[6] = {0}, Ttobe[6] = {0}, Tbef[6] = {0}, Taft[6] = {0};
+  LgGNState lm_gn;
+  std::vector<std::vector<Chunk>> cubeC, cubeS;  // laserCloudCornerArray / laserCloudSurfArray LM:98-99 as arena chunks
+  DevBuf arena;
+  size_t bump = 0;  // in points
+  DevBuf stack2_c, stack2_s, stack_c, stack_s, map_c, map_s;
+  int n_stack_c = 0, n_stack_s = 0, n_map_c = 0, n_map_s = 0;
+  GridWs grid_c, grid_s;
+  bool grids_valid = false;
+  MapIterWs mi;
+  DevBuf d_ents, d_segs, d_ints, d_seg_off, d_seg_leaf, d_out_se;
+  VoxBigWs vb;
+  DevBuf ds_in, ins_sel, ins_sorted, d_runs;
+  DevBuf surround, registered, vg_in, vg_out;
+  int n_surround = 0, n_registered = 0;
+};
+
+namespace {
+
+int upload(loam_handle* h, DevBuf& dst, const void* src, size_t bytes) {
+  LG_CHECK(dst.ensure(bytes + 16, h->st));
+  if (bytes) LG_CHECK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->st));
+  return LOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ map storage
+size_t live_points(const loam_handle* h) {
+  size_t s = 0;
+  for (auto& v : h->cubeC)
+    for (auto& c : v) s += c.n;
+  for (auto& v : h->cubeS)
+    for (auto& c : v) s += c.n;
+  return s;
+}
+
+// Makes room for `need` more points at the bump pointer; compacts all live chunks into a larger arena when full.
+int arena_reserve(loam_handle* h, size_t need) {
+  size_t cap = h->arena.cap / 16;
+  if (h->bump + need <= cap) return LOAM_OK;
+  size_t live = live_points(h);
+  size_t ncap = std::max<size_t>(2 * (live + need), (size_t)1 << 20);
+  DevBuf fresh;
+  LG_CHECK(fresh.ensure(ncap * 16, h->st));
+  std::vector<CopyEnt> ents;
+  size_t off = 0;
+  int max_n = 0;
+  const float4* old = h->arena.as<float4>();
+  for (auto* arr : {&h->cubeC, &h->cubeS})
+    for (auto& v : *arr)
+      for (auto& c : v) {
+        if (c.n > 0) {
+          ents.push_back(CopyEnt{old + c.off, c.n, (int)off});
+          max_n = std::max(max_n, c.n);
+        }
+        c.off = (int)off;
+        off += c.n;
+      }
+  if (!ents.empty()) {
+    int rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+    if (rc) return rc;
+    rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, fresh.as<float4>(), h->st, &h->launches);
+    if (rc) return rc;
+  }
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  h->arena.release();
+  h->arena = fresh;
+  h->bump = off;
+  return LOAM_OK;
+}
+
+void map_reset(loam_handle* h) {  // LM:434-461
+  h->lm_gn = LgGNState();
+  for (auto& v : h->cubeC) v.clear();
+  for (auto& v : h->cubeS) v.clear();
+  h->bump = 0;
+  h->mapFrameCount = 4;
+  h->cenW = 10; h->cenH = 5; h->cenD = 10;
+  for (int i = 0; i < 6; i++) h->Tincre[i] = h->Ttobe[i] = h->Tbef[i] = h->Taft[i] = 0.f;
+  h->grids_valid = false;
+}
+
+// Move every cube one step along `axis` (+1: towards higher index, the last slab re-enters at 0 emptied), LM:497-657.
+void cube_shift(loam_handle* h, int axis, int dir) {
+  int dims[3] = {CW, CH, CD};
+  int n = dims[axis], a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+  for (auto* arr : {&h->cubeC, &h->cubeS})
+    for (int u = 0; u < dims[a1]; u++)
+      for (int v = 0; v < dims[a2]; v++) {
+        auto idx = [&](int t) {
+          int c[3];
+          c[axis] = t; c[a1] = u; c[a2] = v;
+          return c[0] + CW * c[1] + CW * CH * c[2];
+        };
+        if (dir > 0) {
+          for (int t = n - 1; t >= 1; t--) (*arr)[idx(t)].swap((*arr)[idx(t - 1)]);
+          (*arr)[idx(0)].clear();
+        } else {
+          for (int t = 0; t < n - 1; t++) (*arr)[idx(t)].swap((*arr)[idx(t + 1)]);
+          (*arr)[idx(n - 1)].clear();
+        }
+      }
+}
+
+// Gathers the chunks of the listed cubes (in list order) into dst; returns the point count through *n_out.
+int gather_cubes(loam_handle* h, const std::vector<int>& cubes, bool corner, bool surf, DevBuf& dst, int* n_out) {
+  std::vector<CopyEnt> ents;
+  const float4* ar = h->arena.as<float4>();
+  int off = 0, max_n = 0;
+  for (int ind : cubes) {
+    if (corner)
+      for (auto& c : h->cubeC[ind])
+        if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+    if (surf)
+      for (auto& c : h->cubeS[ind])
+        if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+  }
+  *n_out = off;
+  LG_CHECK(dst.ensure((size_t)(off + 16) * 16, h->st));
+  if (ents.empty()) return LOAM_OK;
+  int rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+  if (rc) return rc;
+  return lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, dst.as<float4>(), h->st, &h->launches);
+}
+
+// Voxel grid of a handful of device-resident clouds (segments); counts come back through pinned memory.
+// Small path when every segment fits the shared-memory sort, big path otherwise.
+int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vector<int>& counts) {
+  const int nseg = (int)segs_in.size();
+  counts.assign(nseg, 0);
+  int max_n = 0;
+  for (auto& s : segs_in) max_n = std::max(max_n, s.n);
+  if (max_n == 0) return LOAM_OK;
+  LG_CHECK(h->d_ints.ensure(4096, h->st));
+  int* d_counts = h->d_ints.as<int>();
+  if (max_n <= 16384) {
+    std::vector<VoxSegD> segs = segs_in;
+    for (int i = 0; i < nseg; i++) segs[i].out_count = d_counts + 1 + i;
+    int rc = upload(h, h->d_segs, segs.data(), nseg * sizeof(VoxSegD));
+    if (rc) return rc;
+    rc = lg_vox_small(h->d_segs.as<VoxSegD>(), nseg, max_n, d_counts, h->st, &h->launches);
+    if (rc) return rc;
+    LG_CHECK(cudaMemcpyAsync(h->h_ints, d_counts + 1, nseg * 4, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaStreamSynchronize(h->st));
+    for (int i = 0; i < nseg; i++) counts[i] = h->h_ints[i];
+    return LOAM_OK;
+  }
+  // big path: stage the segments contiguously
+  std::vector<CopyEnt> ents;
+  std::vector<int> seg_off(nseg + 1, 0);
+  std::vector<float> leaf(nseg);
+  for (int i = 0; i < nseg; i++) {
+    if (segs_in[i].valid) return LOAM_EINVAL;
+    if (segs_in[i].n > 0) ents.push_back(CopyEnt{segs_in[i].in, segs_in[i].n, seg_off[i]});
+    seg_off[i + 1] = seg_off[i] + segs_in[i].n;
+    leaf[i] = segs_in[i].leaf;
+  }
+  const int M = seg_off[nseg];
+  LG_CHECK(h->ds_in.ensure((size_t)(M + 16) * 16, h->st));
+  LG_CHECK(h->vg_out.ensure((size_t)(M + 16) * 16, h->st));
+  int rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+  if (rc) return rc;
+  rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+  if (rc) return rc;
+  rc = upload(h, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
+  if (rc) return rc;
+  rc = upload(h, h->d_seg_leaf, leaf.data(), nseg * 4);
+  if (rc) return rc;
+  LG_CHECK(h->d_out_se.ensure((size_t)nseg * 8 + 16, h->st));
+  int* d_start = h->d_out_se.as<int>();
+  int* d_end = d_start + nseg;
+  rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, M, h->vg_out.as<float4>(), d_start,
+                  d_end, h->st, &h->launches);
+  if (rc) return rc;
+  if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
+  LG_CHECK(cudaMemcpyAsync(h->h_ints, d_start, nseg * 8, cudaMemcpyDeviceToHost, h->st));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  for (int i = 0; i < nseg; i++) {
+    int s = h->h_ints[i], e = h->h_ints[nseg + i];
+    counts[i] = e - s;
+    if (counts[i] > 0)
+      LG_CHECK(cudaMemcpyAsync(segs_in[i].out, h->vg_out.as<float4>() + s, (size_t)counts[i] * 16, cudaMemcpyDeviceToDevice, h->st));
+  }
+  return LOAM_OK;
+}
+
+int read_sr_counts(loam_handle* h, loam_counts* out) {
+  LG_CHECK(cudaMemcpyAsync(h->h_ints, h->sr.meta.p, 8 * 4, cudaMemcpyDeviceToHost, h->st));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  if (h->h_ints[SRM_ERR]) return LOAM_ENOSPC;
+  if (h->h_ints[SRM_VOX_OVERFLOW]) return LOAM_ENOSPC;
+  h->counts.n_full = h->h_ints[SRM_N_FULL];
+  h->counts.n_sharp = h->h_ints[SRM_N_SHARP];
+  h->counts.n_less_sharp = h->h_ints[SRM_N_LESS_SHARP];
+  h->counts.n_flat = h->h_ints[SRM_N_FLAT];
+  h->counts.n_less_flat = h->h_ints[SRM_N_LESS_FLAT];
+  if (out) *out = h->counts;
+  return LOAM_OK;
+}
+
+int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out) {
+  if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return LOAM_EINVAL;
+  for (int i = 0; i < 12; i++) h->imu[i] = imu_trans ? imu_trans[i] : 0.f;
+  int rc = lg_extract_launch(h->sr, h->srp, d_xyz, n, stride_bytes, h->st, &h->launches);
+  if (rc) return rc;
+  rc = read_sr_counts(h, out);
+  if (rc) return rc;
+  h->cur_sharp = h->sr.sharp.as<float4>();
+  h->cur_less_sharp = h->sr.less_sharp.as<float4>();
+  h->cur_flat = h->sr.flat.as<float4>();
+  h->cur_less_flat = h->sr.less_flat.as<float4>();
+  h->cur_full = h->sr.full.as<float4>();
+  h->have_features = true;
+  return LOAM_OK;
+}
+
+// One odometry iteration: launch, wait for the 28-double mailbox, unpack.
+int odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel) {
+  OdomT ot;
+  for (int i = 0; i < 6; i++) ot.t[i] = T[i];
+  SinCos3 sc = host_sincos3(T);
+  int rc = lg_odom_iter_launch(h->od, ot, sc, iter, h->cur_sharp, h->counts.n_sharp, h->cur_flat, h->counts.n_flat,
+                               h->corner_last.as<float4>(), h->n_corner_last, h->surf_last.as<float4>(), h->n_surf_last, h->d_mail, h->st,
+                               &h->launches);
+  if (rc) return rc;
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  lg_unpack28(h->h_mail, AtA, AtB, n_sel);
+  return LOAM_OK;
+}
+
+int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, float* AtB, int* n_sel) {
+  MapT mt;
+  for (int i = 0; i < 6; i++) mt.t[i] = T[i];
+  mt.sc = host_sincos3(T);
+  int rc = lg_map_iter_launch(h->mi, mt, h->stack_c.as<float4>(), h->n_stack_c, h->stack_s.as<float4>(), h->n_stack_s, h->grid_c.d, h->grid_s.d,
+                              h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail, h->st, &h->launches);
+  if (rc) return rc;
+  if (out28_dev) return LOAM_OK;
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  lg_unpack28(h->h_mail, AtA, AtB, n_sel);
+  return LOAM_OK;
+}
+
+ImuSC imu_sc(const float* v) {
+  ImuSC s;
+  s.s_pitch_s = sinf(v[0]); s.c_pitch_s = cosf(v[0]);
+  s.s_yaw_s = sinf(v[1]); s.c_yaw_s = cosf(v[1]);
+  s.s_roll_s = sinf(v[2]); s.c_roll_s = cosf(v[2]);
+  s.s_pitch_l = sinf(v[3]); s.c_pitch_l = cosf(v[3]);
+  s.s_yaw_l = sinf(v[4]); s.c_yaw_l = cosf(v[4]);
+  s.s_roll_l = sinf(v[5]); s.c_roll_l = cosf(v[5]);
+  s.shift[0] = v[6]; s.shift[1] = v[7]; s.shift[2] = v[8];
+  return s;
+}
+
+}  // namespace
+
+// ===================================================================================================== lifecycle
+extern "C" {
+
+const char* loam_strerror(int code) {
+  switch (code) {
+    case LOAM_OK: return "ok";
+    case LOAM_EINVAL: return "invalid argument";
+    case LOAM_ECUDA: return "CUDA error";
+    case LOAM_ENOSPC: return "buffer or capacity too small";
+    case LOAM_ESTATE: return "call order violated";
+  }
+  return "unknown error";
+}
+const char* loam_last_cuda_error(const loam_handle*) { return g_cuda_err; }
+
+void loam_default_params(loam_params* p) {
+  p->n_scans = 16;
+  p->ring_mode = 0;
+  p->ring_ang_min = -15.f;
+  p->ring_ang_step = 2.f;
+  p->skip_frame_num = 1;
+  p->max_points = 60000;
+  p->max_map_points = 1 << 20;
+  p->want_registered = 0;
+  p->want_surround = 0;
+}
+
+int loam_create(const loam_params* p, int device, loam_handle** out) {
+  if (!out) return LOAM_EINVAL;
+  *out = nullptr;
+  loam_params prm;
+  if (p) prm = *p; else loam_default_params(&prm);
+  if (prm.n_scans < 1 || prm.n_scans > 64) return LOAM_EINVAL;
+  int ndev = 0;
+  LG_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(device));
+  loam_handle* h = new loam_handle;
+  h->prm = prm;
+  h->device = device;
+  h->srp.n_scans = prm.n_scans;
+  h->srp.ring_mode = prm.ring_mode;
+  h->srp.ring_ang_min = prm.ring_ang_min;
+  h->srp.ring_ang_step = prm.ring_ang_step;
+  h->srp.scan_period = 0.1;
+  h->frameCount = prm.skip_frame_num;
+  h->cubeC.resize(CNUM);
+  h->cubeS.resize(CNUM);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_mail, 64 * sizeof(double), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->d_mail, h->h_mail, 0);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_ints, loam_handle::H_INTS * sizeof(int), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+    delete h;
+    return LOAM_ECUDA;
+  }
+  *out = h;
+  return LOAM_OK;
+}
+
+int loam_destroy(loam_handle* h) {
+  if (!h) return LOAM_EINVAL;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  h->sr.release(); h->od.release(); h->grid_c.release(); h->grid_s.release(); h->mi.release(); h->vb.release();
+  DevBuf* all[] = {&h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
+                   &h->arena, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
+                   &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
+                   &h->surround, &h->registered, &h->vg_in, &h->vg_out};
+  for (DevBuf* b : all) b->release();
+  if (h->h_mail) cudaFreeHost(h->h_mail);
+  if (h->h_ints) cudaFreeHost(h->h_ints);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return LOAM_OK;
+}
+
+int loam_reset(loam_handle* h) {
+  if (!h) return LOAM_EINVAL;
+  h->lo_inited = false;  // LO:411-415; everything else follows on the next sweeps
+  return LOAM_OK;
+}
+void* loam_stream(loam_handle* h) { return h ? (void*)h->st : nullptr; }
+long long loam_launch_count(const loam_handle* h) { return h ? h->launches : 0; }
+
+// ============================================================================================ scanRegistration
+int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
+  if (!h || (!xyz_host && n > 0)) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = upload(h, h->xyz_in, xyz_host, (size_t)n * stride_bytes);
+  if (rc) return rc;
+  return extract_common(h, h->xyz_in.as<float>(), n, stride_bytes, imu_trans, out);
+}
+int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
+  if (!h || (!xyz_dev && n > 0)) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  return extract_common(h, xyz_dev, n, stride_bytes, imu_trans, out);
+}
+
+// ============================================================================================ laserOdometry
+int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
+  if (!h || !out) return LOAM_EINVAL;
+  if (!h->have_features) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  memset(out, 0, sizeof(*out));
+  const loam_counts& c = h->counts;
+  const float* imu = h->imu;
+  if (!h->lo_inited) {  // LO:519-563
+    h->cornerLastNum = 0;
+    h->surfLastNum = 0;
+    LG_CHECK(h->corner_last.ensure((size_t)(c.n_less_sharp + 16) * 16, h->st));
+    LG_CHECK(h->surf_last.ensure((size_t)(c.n_less_flat + 16) * 16, h->st));
+    if (c.n_less_sharp) LG_CHECK(cudaMemcpyAsync(h->corner_last.p, h->cur_less_sharp, (size_t)c.n_less_sharp * 16, cudaMemcpyDeviceToDevice, h->st));
+    if (c.n_less_flat) LG_CHECK(cudaMemcpyAsync(h->surf_last.p, h->cur_less_flat, (size_t)c.n_less_flat * 16, cudaMemcpyDeviceToDevice, h->st));
+    h->n_corner_last = c.n_less_sharp;
+    h->n_surf_last = c.n_less_flat;
+    for (int i = 0; i < 6; i++) h->T[i] = h->Tsum[i] = 0.f;
+    h->Tsum[0] += imu[0];  // imuPitchStart
+    h->Tsum[2] += imu[2];  // imuRollStart
+    h->lo_inited = true;
+    out->clouds_published = 1;
+    out->n_corner_last = h->n_corner_last;
+    out->n_surf_last = h->n_surf_last;
+    return LOAM_OK;
+  }
+  const float scanPeriod = 0.1f;  // LO:50
+  h->T[3] -= imu[9] * scanPeriod;
+  h->T[4] -= imu[10] * scanPeriod;
+  h->T[5] -= imu[11] * scanPeriod;
+  if (h->cornerLastNum > 10 && h->surfLastNum > 100) {  // LO:572
+    for (int iter = 0; iter < 25; iter++) {
+      out->iterations = iter + 1;
+      float AtA[36], AtB[6], X[6];
+      int n_sel = 0;
+      int rc = odom_iter(h, iter, h->T, AtA, AtB, &n_sel);
+      if (rc) return rc;
+      if (n_sel < 10) continue;  // LO:904-907
+      lg_gn_solve_step(AtA, AtB, iter, 10.f, h->lo_gn, X);
+      for (int i = 0; i < 6; i++) h->T[i] += X[i];
+      for (int i = 0; i < 6; i++)
+        if (isnan(h->T[i])) h->T[i] = 0;
+      float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
+      float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
+      if (deltaR < 0.1 && deltaT < 0.1) break;
+    }
+  }
+  // LO:1035-1064
+  float* T = h->T;
+  float* S = h->Tsum;
+  float rx, ry, rz, tx, ty, tz;
+  lgh::accumulate_rotation(S[0], S[1], S[2], -T[0], (float)(-T[1] * 1.05), -T[2], rx, ry, rz);
+  float x1 = cosf(rz) * (T[3] - imu[6]) - sinf(rz) * (T[4] - imu[7]);
+  float y1 = sinf(rz) * (T[3] - imu[6]) + cosf(rz) * (T[4] - imu[7]);
+  float z1 = (float)(T[5] * 1.05 - imu[8]);
+  float x2 = x1;
+  float y2 = cosf(rx) * y1 - sinf(rx) * z1;
+  float z2 = sinf(rx) * y1 + cosf(rx) * z1;
+  tx = S[3] - (cosf(ry) * x2 + sinf(ry) * z2);
+  ty = S[4] - y2;
+  tz = S[5] - (-sinf(ry) * x2 + cosf(ry) * z2);
+  lgh::plugin_imu_rotation(rx, ry, rz, imu[0], imu[1], imu[2], imu[3], imu[4], imu[5], rx, ry, rz);
+  S[0] = rx; S[1] = ry; S[2] = rz; S[3] = tx; S[4] = ty; S[5] = tz;
+  out->odom_published = 1;
+
+  // LO:1087-1121
+  h->frameCount++;
+  const bool pub = h->frameCount >= h->prm.skip_frame_num + 1;
+  LG_CHECK(h->corner_new.ensure((size_t)(c.n_less_sharp + 16) * 16, h->st));
+  LG_CHECK(h->surf_new.ensure((size_t)(c.n_less_flat + 16) * 16, h->st));
+  if (pub) LG_CHECK(h->fullres3.ensure((size_t)(c.n_full + 16) * 16, h->st));
+  OdomT ot;
+  for (int i = 0; i < 6; i++) ot.t[i] = T[i];
+  int rc = lg_odom_to_end_launch(ot, host_sincos3(T), imu_sc(imu), h->cur_less_sharp, h->corner_new.as<float4>(), c.n_less_sharp,
+                                 h->cur_less_flat, h->surf_new.as<float4>(), c.n_less_flat, h->cur_full, h->fullres3.as<float4>(),
+                                 pub ? c.n_full : 0, h->st, &h->launches);
+  if (rc) return rc;
+  std::swap(h->corner_last, h->corner_new);
+  std::swap(h->surf_last, h->surf_new);
+  h->n_corner_last = c.n_less_sharp;
+  h->n_surf_last = c.n_less_flat;
+  h->cornerLastNum = h->n_corner_last;
+  h->surfLastNum = h->n_surf_last;
+  if (pub) {
+    h->frameCount = 0;
+    h->n_fullres3 = c.n_full;
+    out->clouds_published = 1;
+    out->fullres_published = 1;
+  }
+  for (int i = 0; i < 6; i++) {
+    out->transform_sum[i] = S[i];
+    out->transformation[i] = T[i];
+  }
+  out->n_corner_last = h->n_corner_last;
+  out->n_surf_last = h->n_surf_last;
+  return LOAM_OK;
+}
+
+// ============================================================================================ laserMapping
+int loam_mapping_odometry(loam_handle* h, const float* Tsum) {
+  if (!h || !Tsum) return LOAM_EINVAL;
+  if (fabs((double)Tsum[3]) < 0.000001 && fabs((double)Tsum[4]) < 0.000001 && fabs((double)Tsum[5]) < 0.000001) h->lm_inited = false;  // LM:316-319
+  for (int i = 0; i < 6; i++) h->mTsum[i] = Tsum[i];
+  return LOAM_OK;
+}
+
+int loam_mapping_process(loam_handle* h, loam_map_result* out) {
+  if (!h || !out) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  memset(out, 0, sizeof(*out));
+  if (!h->lm_inited) {
+    h->lm_inited = true;
+    map_reset(h);
+  }
+  lgh::transform_associate_to_map(h->mTsum, h->Tbef, h->Taft, h->Tincre, h->Ttobe);  // LM:465
+  float* Tt = h->Ttobe;
+  MapT mt;
+  for (int i = 0; i < 6; i++) mt.t[i] = Tt[i];
+  mt.sc = host_sincos3(Tt);
+  const int ncl = h->n_corner_last, nsl = h->n_surf_last;
+  LG_CHECK(h->stack2_c.ensure((size_t)(ncl + 16) * 16, h->st));
+  LG_CHECK(h->stack2_s.ensure((size_t)(nsl + 16) * 16, h->st));
+  LG_CHECK(h->stack_c.ensure((size_t)(ncl + 16) * 16, h->st));
+  LG_CHECK(h->stack_s.ensure((size_t)(nsl + 16) * 16, h->st));
+  int rc = lg_map_stack_launch(mt, h->corner_last.as<float4>(), h->stack2_c.as<float4>(), ncl, h->surf_last.as<float4>(),
+                               h->stack2_s.as<float4>(), nsl, h->st, &h->launches);
+  if (rc) return rc;
+
+  float yax[3] = {0.f, 10.f, 0.f}, pOnY[3];
+  lgh::associate_to_map(Tt, yax, pOnY);  // LM:483-487
+  int cI = int((Tt[3] + 25.0) / 50.0) + h->cenW;
+  int cJ = int((Tt[4] + 25.0) / 50.0) + h->cenH;
+  int cK = int((Tt[5] + 25.0) / 50.0) + h->cenD;
+  if (Tt[3] + 25.0 < 0) cI--;
+  if (Tt[4] + 25.0 < 0) cJ--;
+  if (Tt[5] + 25.0 < 0) cK--;
+  while (cI < 3) { cube_shift(h, 0, +1); cI++; h->cenW++; }
+  while (cI >= CW - 3) { cube_shift(h, 0, -1); cI--; h->cenW--; }
+  while (cJ < 3) { cube_shift(h, 1, +1); cJ++; h->cenH++; }
+  while (cJ >= CH - 3) { cube_shift(h, 1, -1); cJ--; h->cenH--; }
+  while (cK < 3) { cube_shift(h, 2, +1); cK++; h->cenD++; }
+  while (cK >= CD - 3) { cube_shift(h, 2, -1); cK--; h->cenD--; }
+
+  std::vector<int> validInd, surroundInd;  // LM:659-715
+  for (int i = cI - 2; i <= cI + 2; i++)
+    for (int j = cJ - 2; j <= cJ + 2; j++)
+      for (int k = cK - 2; k <= cK + 2; k++) {
+        if (i >= 0 && i < CW && j >= 0 && j < CH && k >= 0 && k < CD) {
+          float centerX = (float)(50.0 * (i - h->cenW));
+          float centerY = (float)(50.0 * (j - h->cenH));
+          float centerZ = (float)(50.0 * (k - h->cenD));
+          bool inFOV = false;
+          for (int ii = -1; ii <= 1; ii += 2)
+            for (int jj = -1; jj <= 1; jj += 2)
+              for (int kk = -1; kk <= 1; kk += 2) {
+                float cornerX = (float)(centerX + 25.0 * ii);
+                float cornerY = (float)(centerY + 25.0 * jj);
+                float cornerZ = (float)(centerZ + 25.0 * kk);
+                float s1 = (Tt[3] - cornerX) * (Tt[3] - cornerX) + (Tt[4] - cornerY) * (Tt[4] - cornerY) + (Tt[5] - cornerZ) * (Tt[5] - cornerZ);
+                float s2 = (pOnY[0] - cornerX) * (pOnY[0] - cornerX) + (pOnY[1] - cornerY) * (pOnY[1] - cornerY) +
+                           (pOnY[2] - cornerZ) * (pOnY[2] - cornerZ);
+                float check1 = (float)(100.0 + s1 - s2 - 10.0 * sqrt(3.0) * sqrtf(s1));
+                float check2 = (float)(100.0 + s1 - s2 + 10.0 * sqrt(3.0) * sqrtf(s1));
+                if (check1 < 0 && check2 > 0) inFOV = true;
+              }
+          int ind = i + CW * j + CW * CH * k;
+          if (inFOV) validInd.push_back(ind);
+          surroundInd.push_back(ind);
+        }
+      }
+
+  // LM:717-724 gather the local map (reference order: valid cubes in loop order, points in cube order)
+  rc = gather_cubes(h, validInd, true, false, h->map_c, &h->n_map_c);
+  if (rc) return rc;
+  rc = gather_cubes(h, validInd, false, true, h->map_s, &h->n_map_s);
+  if (rc) return rc;
+  // LM:736-747 down-sample the stacks
+  {
+    std::vector<VoxSegD> segs(2);
+    segs[0] = VoxSegD{h->stack2_c.as<float4>(), nullptr, h->stack_c.as<float4>(), nullptr, ncl, 0.2f};
+    segs[1] = VoxSegD{h->stack2_s.as<float4>(), nullptr, h->stack_s.as<float4>(), nullptr, nsl, 0.4f};
+    std::vector<int> cnt;
+    rc = voxel_segments(h, segs, cnt);
+    if (rc) return rc;
+    h->n_stack_c = cnt[0];
+    h->n_stack_s = cnt[1];
+  }
+  out->n_corner_stack = h->n_stack_c;
+  out->n_surf_stack = h->n_stack_s;
+  out->n_corner_map = h->n_map_c;
+  out->n_surf_map = h->n_map_s;
+
+  if (h->n_map_c > 10 && h->n_map_s > 100) {  // LM:749
+    out->optimised = 1;
+    rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), h->n_map_c, h->st, &h->launches);
+    if (rc) return rc;
+    rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), h->n_map_s, h->st, &h->launches);
+    if (rc) return rc;
+    h->grids_valid = true;
+    for (int iter = 0; iter < 10; iter++) {
+      out->iterations = iter + 1;
+      float AtA[36], AtB[6], X[6];
+      int n_sel = 0;
+      rc = map_iter(h, Tt, nullptr, AtA, AtB, &n_sel);
+      if (rc) return rc;
+      if (n_sel < 50) continue;  // LM:929-932
+      lg_gn_solve_step(AtA, AtB, iter, 100.f, h->lm_gn, X);
+      for (int i = 0; i < 6; i++) Tt[i] += X[i];
+      float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
+      float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
+      if (deltaR < 0.05 && deltaT < 0.05) break;
+    }
+    for (int i = 0; i < 6; i++) {  // transformUpdate LM:238-241
+      h->Tbef[i] = h->mTsum[i];
+      h->Taft[i] = Tt[i];
+    }
+  }
+  for (int i = 0; i < 6; i++) mt.t[i] = Tt[i];
+  mt.sc = host_sincos3(Tt);
+
+  // LM:1023-1059 insert the stacks into their cubes
+  const int nins = h->n_stack_c + h->n_stack_s;
+  std::map<int, std::pair<int, int>> runC, runS;  // cube -> (start in ins_sorted, count)
+  if (nins > 0) {
+    rc = lg_radix_ensure(h->vb.rs, nins, h->st);
+    if (rc) return rc;
+    LG_CHECK(h->ins_sel.ensure((size_t)(nins + 16) * 16, h->st));
+    LG_CHECK(h->ins_sorted.ensure((size_t)(nins + 16) * 16, h->st));
+    const int cap_runs = 2048;
+    LG_CHECK(h->d_runs.ensure((size_t)cap_runs * 8 + 16, h->st));
+    CubeGeom cg{CW, CH, CD, h->cenW, h->cenH, h->cenD};
+    rc = lg_map_insert_launch(mt, cg, h->stack_c.as<float4>(), h->n_stack_c, h->stack_s.as<float4>(), h->n_stack_s, h->ins_sel.as<float4>(),
+                              h->vb.rs.keysA.as<unsigned long long>(), h->vb.rs.valsA.as<unsigned int>(), h->st, &h->launches);
+    if (rc) return rc;
+    int in_b = 0;
+    rc = lg_radix_sort(h->vb.rs, nins, 16, h->st, &h->launches, &in_b);
+    if (rc) return rc;
+    int* d_nruns = h->d_runs.as<int>();
+    int2* d_runs = (int2*)(d_nruns + 2);
+    rc = lg_map_runs_launch(in_b ? h->vb.rs.keysB.as<unsigned long long>() : h->vb.rs.keysA.as<unsigned long long>(),
+                            in_b ? h->vb.rs.valsB.as<unsigned int>() : h->vb.rs.valsA.as<unsigned int>(), h->ins_sel.as<float4>(), nins,
+                            h->ins_sorted.as<float4>(), d_nruns, d_runs, cap_runs, h->st, &h->launches);
+    if (rc) return rc;
+    LG_CHECK(cudaMemcpyAsync(h->h_ints, d_nruns, 8 + (size_t)cap_runs * 8, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaStreamSynchronize(h->st));
+    int nruns = h->h_ints[0];
+    if (nruns > cap_runs) return LOAM_ENOSPC;
+    std::vector<std::pair<int, int>> runs(nruns);  // (start, key)
+    for (int r = 0; r < nruns; r++) runs[r] = {h->h_ints[2 + 2 * r + 1], h->h_ints[2 + 2 * r]};
+    std::sort(runs.begin(), runs.end());
+    for (int r = 0; r < nruns; r++) {
+      int start = runs[r].first, key = runs[r].second;
+      int cnt = (r + 1 < nruns ? runs[r + 1].first : nins) - start;
+      int cube = key & 0x3fff;
+      if (cube == 0x3fff) continue;  // outside the 21 x 11 x 21 grid: dropped (LM:1034-1036)
+      if (key & (1 << 14)) runS[cube] = {start, cnt}; else runC[cube] = {start, cnt};
+    }
+  }
+  // LM:1061-1079 voxel-grid every valid cube (old points first, then the new ones: push_back order)
+  {
+    std::vector<CopyEnt> ents;
+    std::vector<int> seg_off(1, 0);
+    std::vector<float> leaf;
+    const float4* ins = h->ins_sorted.as<float4>();
+    int max_n = 0;
+    size_t extra = 0;  // raw appends to cubes outside the valid set
+    for (auto& kv : runC)
+      if (std::find(validInd.begin(), validInd.end(), kv.first) == validInd.end()) extra += kv.second.second;
+    for (auto& kv : runS)
+      if (std::find(validInd.begin(), validInd.end(), kv.first) == validInd.end()) extra += kv.second.second;
+    size_t M = 0;
+    for (int ind : validInd) {
+      for (auto& c : h->cubeC[ind]) M += c.n;
+      for (auto& c : h->cubeS[ind]) M += c.n;
+      auto a = runC.find(ind);
+      if (a != runC.end()) M += a->second.second;
+      auto b = runS.find(ind);
+      if (b != runS.end()) M += b->second.second;
+    }
+    rc = arena_reserve(h, M + extra);
+    if (rc) return rc;
+    const float4* ar = h->arena.as<float4>();
+    for (int ind : validInd)
+      for (int type = 0; type < 2; type++) {
+        auto& cube = type == 0 ? h->cubeC[ind] : h->cubeS[ind];
+        auto& runs = type == 0 ? runC : runS;
+        int off = seg_off.back();
+        for (auto& c : cube)
+          if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+        auto it = runs.find(ind);
+        if (it != runs.end()) {
+          ents.push_back(CopyEnt{ins + it->second.first, it->second.second, off});
+          off += it->second.second;
+          max_n = std::max(max_n, it->second.second);
+          runs.erase(it);
+        }
+        seg_off.push_back(off);
+        leaf.push_back(type == 0 ? 0.2f : 0.4f);
+      }
+    // runs left over belong to cubes that are not voxel-gridded this time: append raw (push_back semantics)
+    {
+      std::vector<CopyEnt> app;
+      int amax = 0;
+      for (int type = 0; type < 2; type++)
+        for (auto& kv : (type == 0 ? runC : runS)) {
+          auto& cube = type == 0 ? h->cubeC[kv.first] : h->cubeS[kv.first];
+          app.push_back(CopyEnt{ins + kv.second.first, kv.second.second, (int)h->bump});
+          cube.push_back(Chunk{(int)h->bump, kv.second.second});
+          h->bump += kv.second.second;
+          amax = std::max(amax, kv.second.second);
+        }
+      if (!app.empty()) {
+        rc = upload(h, h->d_ents, app.data(), app.size() * sizeof(CopyEnt));
+        if (rc) return rc;
+        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)app.size(), amax, h->arena.as<float4>(), h->st, &h->launches);
+        if (rc) return rc;
+      }
+    }
+    const int nseg = (int)leaf.size();
+    const int Mtot = seg_off.back();
+    if (nseg > 0 && Mtot > 0) {
+      LG_CHECK(h->ds_in.ensure((size_t)(Mtot + 16) * 16, h->st));
+      rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+      if (rc) return rc;
+      rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+      if (rc) return rc;
+      rc = upload(h, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
+      if (rc) return rc;
+      rc = upload(h, h->d_seg_leaf, leaf.data(), nseg * 4);
+      if (rc) return rc;
+      LG_CHECK(h->d_out_se.ensure((size_t)nseg * 8 + 16, h->st));
+      int* d_start = h->d_out_se.as<int>();
+      int* d_end = d_start + nseg;
+      float4* outp = h->arena.as<float4>() + h->bump;
+      rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, h->st,
+                      &h->launches);
+      if (rc) return rc;
+      if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
+      LG_CHECK(cudaMemcpyAsync(h->h_ints, d_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, h->st));
+      LG_CHECK(cudaStreamSynchronize(h->st));
+      int total = 0, s = 0;
+      for (int ind : validInd)
+        for (int type = 0; type < 2; type++) {
+          auto& cube = type == 0 ? h->cubeC[ind] : h->cubeS[ind];
+          int st0 = h->h_ints[s], en0 = h->h_ints[nseg + s];
+          cube.clear();
+          if (en0 > st0) cube.push_back(Chunk{(int)h->bump + st0, en0 - st0});
+          total = std::max(total, en0);
+          s++;
+        }
+      h->bump += total;
+    }
+  }
+  // LM:1081-1101
+  h->mapFrameCount++;
+  if (h->mapFrameCount >= 5) {
+    h->mapFrameCount = 0;
+    out->surround_published = 1;
+    if (h->prm.want_surround) {
+      DevBuf& tmp = h->vg_in;
+      int ns = 0;
+      rc = gather_cubes(h, surroundInd, true, true, tmp, &ns);
+      if (rc) return rc;
+      LG_CHECK(h->surround.ensure((size_t)(ns + 16) * 16, h->st));
+      std::vector<VoxSegD> segs(1);
+      segs[0] = VoxSegD{tmp.as<float4>(), nullptr, h->surround.as<float4>(), nullptr, ns, 0.2f};
+      std::vector<int> cnt;
+      rc = voxel_segments(h, segs, cnt);
+      if (rc) return rc;
+      h->n_surround = cnt[0];
+      out->n_surround = cnt[0];
+    }
+  }
+  // LM:1103-1106
+  if (h->prm.want_registered) {
+    LG_CHECK(h->registered.ensure((size_t)(h->n_fullres3 + 16) * 16, h->st));
+    rc = lg_map_register_launch(mt, h->fullres3.as<float4>(), h->registered.as<float4>(), h->n_fullres3, h->st, &h->launches);
+    if (rc) return rc;
+    h->n_registered = h->n_fullres3;
+    out->n_registered = h->n_registered;
+  }
+  for (int i = 0; i < 6; i++) {
+    out->transform_aft_mapped[i] = h->Taft[i];
+    out->transform_bef_mapped[i] = h->Tbef[i];
+    out->transform_tobe_mapped[i] = Tt[i];
+  }
+  return LOAM_OK;
+}
+
+// ============================================================================================ whole sweep
+static int process_common(loam_handle* h, loam_sweep_result* out) {
+  int rc = loam_odometry_process(h, &out->odom);
+  if (rc) return rc;
+  out->mapping_ran = 0;
+  if (out->odom.odom_published) {
+    rc = loam_mapping_odometry(h, out->odom.transform_sum);
+    if (rc) return rc;
+  }
+  if (out->odom.odom_published && out->odom.fullres_published) {
+    rc = loam_mapping_process(h, &out->map);
+    if (rc) return rc;
+    out->mapping_ran = 1;
+  }
+  return LOAM_OK;
+}
+int loam_process_sweep(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, loam_sweep_result* out) {
+  if (!h || !out) return LOAM_EINVAL;
+  memset(out, 0, sizeof(*out));
+  int rc = loam_extract(h, xyz_host, n, stride_bytes, stamp, nullptr, &out->counts);
+  if (rc) return rc;
+  return process_common(h, out);
+}
+int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, loam_sweep_result* out) {
+  if (!h || !out) return LOAM_EINVAL;
+  memset(out, 0, sizeof(*out));
+  int rc = loam_extract_device(h, xyz_dev, n, stride_bytes, stamp, nullptr, &out->counts);
+  if (rc) return rc;
+  return process_common(h, out);
+}
+
+// ============================================================================================ data access
+int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n) {
+  if (!h || !n) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  const void* src = nullptr;
+  int cnt = 0;
+  switch (which) {
+    case LOAM_CLOUD_FULL: src = h->cur_full; cnt = h->counts.n_full; break;
+    case LOAM_CLOUD_SHARP: src = h->cur_sharp; cnt = h->counts.n_sharp; break;
+    case LOAM_CLOUD_LESS_SHARP: src = h->cur_less_sharp; cnt = h->counts.n_less_sharp; break;
+    case LOAM_CLOUD_FLAT: src = h->cur_flat; cnt = h->counts.n_flat; break;
+    case LOAM_CLOUD_LESS_FLAT: src = h->cur_less_flat; cnt = h->counts.n_less_flat; break;
+    case LOAM_CLOUD_CORNER_LAST: src = h->corner_last.p; cnt = h->n_corner_last; break;
+    case LOAM_CLOUD_SURF_LAST: src = h->surf_last.p; cnt = h->n_surf_last; break;
+    case LOAM_CLOUD_FULL_RES3: src = h->fullres3.p; cnt = h->n_fullres3; break;
+    case LOAM_CLOUD_CORNER_STACK: src = h->stack_c.p; cnt = h->n_stack_c; break;
+    case LOAM_CLOUD_SURF_STACK: src = h->stack_s.p; cnt = h->n_stack_s; break;
+    case LOAM_CLOUD_CORNER_MAP: src = h->map_c.p; cnt = h->n_map_c; break;
+    case LOAM_CLOUD_SURF_MAP: src = h->map_s.p; cnt = h->n_map_s; break;
+    case LOAM_CLOUD_SURROUND: src = h->surround.p; cnt = h->n_surround; break;
+    case LOAM_CLOUD_REGISTERED: src = h->registered.p; cnt = h->n_registered; break;
+    default: return LOAM_EINVAL;
+  }
+  *n = cnt;
+  if (!host_buf) return LOAM_OK;
+  if (cap < cnt) return LOAM_ENOSPC;
+  if (cnt > 0) {
+    LG_CHECK(cudaMemcpyAsync(host_buf, src, (size_t)cnt * 16, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaStreamSynchronize(h->st));
+  }
+  return LOAM_OK;
+}
+
+int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int* n_items) {
+  if (!h || !n_items) return LOAM_EINVAL;
+  if (!h->sr.meta.p) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  const void* src = nullptr;
+  int cnt = 0, esz = 1;
+  switch (which) {
+    case LOAM_DIAG_CURVATURE: src = h->sr.curv.p; cnt = h->counts.n_full; esz = 4; break;
+    case LOAM_DIAG_PICKED_MASK: src = h->sr.mask_diag.p; cnt = h->counts.n_full; esz = 1; break;
+    case LOAM_DIAG_LABEL: src = h->sr.label.p; cnt = h->counts.n_full; esz = 1; break;
+    case LOAM_DIAG_SCAN_START: src = h->sr.meta.as<int>() + SRM_SCAN_START; cnt = h->prm.n_scans; esz = 4; break;
+    case LOAM_DIAG_SCAN_END: src = h->sr.meta.as<int>() + SRM_SCAN_END; cnt = h->prm.n_scans; esz = 4; break;
+    default: return LOAM_EINVAL;
+  }
+  *n_items = cnt;
+  if (!host_buf) return LOAM_OK;
+  if (cap_bytes < cnt * esz) return LOAM_ENOSPC;
+  if (cnt > 0) {
+    LG_CHECK(cudaMemcpyAsync(host_buf, src, (size_t)cnt * esz, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaStreamSynchronize(h->st));
+  }
+  return LOAM_OK;
+}
+
+// ============================================================================================ stage-level
+int loam_voxel_grid(loam_handle* h, const float* in4_host, int m, float leaf, float* out4_host, int cap, int* v) {
+  if (!h || !v || m < 0 || !(leaf > 0.f)) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  *v = 0;
+  if (m == 0) return LOAM_OK;
+  int rc = upload(h, h->vg_in, in4_host, (size_t)m * 16);
+  if (rc) return rc;
+  DevBuf outb;
+  LG_CHECK(outb.ensure((size_t)(m + 16) * 16, h->st));
+  std::vector<VoxSegD> segs(1);
+  segs[0] = VoxSegD{h->vg_in.as<float4>(), nullptr, outb.as<float4>(), nullptr, m, leaf};
+  std::vector<int> cnt;
+  rc = voxel_segments(h, segs, cnt);
+  if (rc == LOAM_OK) {
+    *v = cnt[0];
+    if (out4_host) {
+      if (cap < cnt[0]) rc = LOAM_ENOSPC;
+      else if (cnt[0] > 0) {
+        cudaError_t e = cudaMemcpyAsync(out4_host, outb.p, (size_t)cnt[0] * 16, cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+        if (e != cudaSuccess) { lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__); rc = LOAM_ECUDA; }
+      }
+    }
+  }
+  cudaStreamSynchronize(h->st);
+  outb.release();
+  return rc;
+}
+
+int loam_odom_set_inputs(loam_handle* h, const float* sharp, int n_sharp, const float* flat, int n_flat, const float* corner_last,
+                         int n_corner_last, const float* surf_last, int n_surf_last) {
+  if (!h || n_sharp < 0 || n_flat < 0 || n_corner_last < 0 || n_surf_last < 0) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = upload(h, h->t_sharp, sharp, (size_t)n_sharp * 16);
+  if (!rc) rc = upload(h, h->t_flat, flat, (size_t)n_flat * 16);
+  if (!rc) rc = upload(h, h->corner_last, corner_last, (size_t)n_corner_last * 16);
+  if (!rc) rc = upload(h, h->surf_last, surf_last, (size_t)n_surf_last * 16);
+  if (rc) return rc;
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  h->cur_sharp = h->t_sharp.as<float4>();
+  h->cur_flat = h->t_flat.as<float4>();
+  h->counts.n_sharp = n_sharp;
+  h->counts.n_flat = n_flat;
+  h->n_corner_last = n_corner_last;
+  h->n_surf_last = n_surf_last;
+  return LOAM_OK;
+}
+
+int loam_odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel) {
+  if (!h || !T || !AtA || !AtB || !n_sel || iter < 0) return LOAM_EINVAL;
+  if (!h->cur_sharp && h->counts.n_sharp > 0) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = odom_iter(h, iter, T, AtA, AtB, n_sel);
+  if (rc) return rc;
+  if (*n_sel < 10) {
+    memset(AtA, 0, 36 * sizeof(float));
+    memset(AtB, 0, 6 * sizeof(float));
+  }
+  return LOAM_OK;
+}
+
+int loam_odom_get_corr(loam_handle* h, int* c1, int* c2, int cap_c, int* s1, int* s2, int* s3, int cap_s) {
+  if (!h) return LOAM_EINVAL;
+  if (cap_c < h->counts.n_sharp || cap_s < h->counts.n_flat) return LOAM_ENOSPC;
+  LG_CHECK(cudaSetDevice(h->device));
+  size_t bc = (size_t)h->counts.n_sharp * 4, bs = (size_t)h->counts.n_flat * 4;
+  if (bc) {
+    LG_CHECK(cudaMemcpyAsync(c1, h->od.c1.p, bc, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaMemcpyAsync(c2, h->od.c2.p, bc, cudaMemcpyDeviceToHost, h->st));
+  }
+  if (bs) {
+    LG_CHECK(cudaMemcpyAsync(s1, h->od.s1.p, bs, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaMemcpyAsync(s2, h->od.s2.p, bs, cudaMemcpyDeviceToHost, h->st));
+    LG_CHECK(cudaMemcpyAsync(s3, h->od.s3.p, bs, cudaMemcpyDeviceToHost, h->st));
+  }
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  return LOAM_OK;
+}
+
+int loam_transform_to_end(loam_handle* h, const float* in4_host, int n, const float* T, const float* imu_trans, float* out4_host) {
+  if (!h || n < 0 || !T) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  if (n == 0) return LOAM_OK;
+  float imu[12] = {0};
+  if (imu_trans) memcpy(imu, imu_trans, sizeof(imu));
+  int rc = upload(h, h->vg_in, in4_host, (size_t)n * 16);
+  if (rc) return rc;
+  LG_CHECK(h->vg_out.ensure((size_t)(n + 16) * 16, h->st));
+  OdomT ot;
+  for (int i = 0; i < 6; i++) ot.t[i] = T[i];
+  rc = lg_odom_to_end_launch(ot, host_sincos3(T), imu_sc(imu), h->vg_in.as<float4>(), h->vg_out.as<float4>(), n, nullptr, nullptr, 0, nullptr,
+                             nullptr, 0, h->st, &h->launches);
+  if (rc) return rc;
+  LG_CHECK(cudaMemcpyAsync(out4_host, h->vg_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->st));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  return LOAM_OK;
+}
+
+int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, const float* surf_stack, int n_ss, const float* corner_map, int n_cm,
+                        const float* surf_map, int n_sm) {
+  if (!h || n_cs < 0 || n_ss < 0 || n_cm < 0 || n_sm < 0) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = upload(h, h->stack_c, corner_stack, (size_t)n_cs * 16);
+  if (!rc) rc = upload(h, h->stack_s, surf_stack, (size_t)n_ss * 16);
+  if (!rc) rc = upload(h, h->map_c, corner_map, (size_t)n_cm * 16);
+  if (!rc) rc = upload(h, h->map_s, surf_map, (size_t)n_sm * 16);
+  if (rc) return rc;
+  h->n_stack_c = n_cs; h->n_stack_s = n_ss; h->n_map_c = n_cm; h->n_map_s = n_sm;
+  rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), n_cm, h->st, &h->launches);
+  if (!rc) rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), n_sm, h->st, &h->launches);
+  if (rc) return rc;
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  h->grids_valid = true;
+  return LOAM_OK;
+}
+
+int loam_map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel) {
+  if (!h || !T || !AtA || !AtB || !n_sel || iter < 0) return LOAM_EINVAL;
+  if (!h->grids_valid) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = map_iter(h, T, nullptr, AtA, AtB, n_sel);
+  if (rc) return rc;
+  if (*n_sel < 50) {
+    memset(AtA, 0, 36 * sizeof(float));
+    memset(AtB, 0, 6 * sizeof(float));
+  }
+  return LOAM_OK;
+}
+
+int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int cap_s) {
+  if (!h) return LOAM_EINVAL;
+  if (cap_c < h->n_stack_c || cap_s < h->n_stack_s) return LOAM_ENOSPC;
+  if (!h->mi.nbr.p) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  if (h->n_stack_c) LG_CHECK(cudaMemcpyAsync(corner5, h->mi.nbr.p, (size_t)h->n_stack_c * 20, cudaMemcpyDeviceToHost, h->st));
+  if (h->n_stack_s)
+    LG_CHECK(cudaMemcpyAsync(surf5, h->mi.nbr.as<int>() + (size_t)h->n_stack_c * 5, (size_t)h->n_stack_s * 20, cudaMemcpyDeviceToHost, h->st));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  return LOAM_OK;
+}
+
+int loam_gn_solve(const float* AtA, const float* AtB, int iter, float eig_threshold, float* state37, float* X) {
+  if (!AtA || !AtB || !state37 || !X) return LOAM_EINVAL;
+  LgGNState st;
+  memcpy(st.matP, state37, sizeof(st.matP));
+  st.degenerate = state37[36] != 0.f;
+  lg_gn_solve_step(AtA, AtB, iter, eig_threshold, st, X);
+  memcpy(state37, st.matP, sizeof(st.matP));
+  state37[36] = st.degenerate ? 1.f : 0.f;
+  return LOAM_OK;
+}
+
+int loam_map_iter_partial(loam_handle* h, int iter, const float* T, double* partial_dev28) {
+  if (!h || !T || !partial_dev28 || iter < 0) return LOAM_EINVAL;
+  if (!h->grids_valid) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  int rc = map_iter(h, T, partial_dev28, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  return LOAM_OK;
+}
+
+int loam_map_finish_reduced(const double* reduced28_host, float* AtA, float* AtB, int* n_sel) {
+  if (!reduced28_host || !AtA || !AtB || !n_sel) return LOAM_EINVAL;
+  lg_unpack28(reduced28_host, AtA, AtB, n_sel);
+  if (*n_sel < 50) {
+    memset(AtA, 0, 36 * sizeof(float));
+    memset(AtB, 0, 6 * sizeof(float));
+  }
+  return LOAM_OK;
+}
+
+}  // extern "C"

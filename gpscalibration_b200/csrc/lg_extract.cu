@@ -1,0 +1,533 @@
+// K1-K4 — per-sweep feature extraction, the B200 replacement for the body of laserCloudHandler
+// (scanRegistration.cpp SR:238-752; IMU de-skew branch SR:364-434 dormant, SURVEY §8a note).
+//
+//   sr_ring_kernel     SR:260-362  NaN strip, axis remap, ring table, raw azimuth, halfPassed latch as a prefix-min,
+//                                  per-CTA ring histogram
+//   sr_scan_kernel     SR:444-447  exclusive scan of (ring, CTA) counts -> ring-major offsets (stable bucket by ring)
+//   sr_scatter_kernel  SR:340-362,436  relTime / intensity, stable scatter to the ring-major float4 cloud
+//   sr_curv_kernel     SR:454-549  11-tap curvature, ring bounds, occlusion / parallel-beam conditions, gap flags
+//   sr_select_kernel   SR:559-675  one CTA per ring: per-sector stable sort (shared-memory bitonic on (curvature,
+//                                  index) keys) + the sequential greedy pick with +-5 suppression
+//   sr_collect_kernel  SR:587-633  compacts the picks into the four feature clouds, sets up the per-ring voxel jobs
+//   (lg_vox_small)     SR:677-683  per-ring 0.2 m voxel grid of the less-flat points
+//   sr_concat_kernel   SR:683      concatenates the per-ring results
+// Every array is ring-major SoA/float4; algorithmic bytes per sweep 28 N + 16 F.
+#include "lg_extract.h"
+
+namespace {
+
+constexpr int SR_NT = 256, SR_ITEMS = 4, SR_TILE = SR_NT * SR_ITEMS;
+constexpr int MAXR = 64;
+
+// cond bits written by sr_curv_kernel
+constexpr unsigned char C_A = 1;    // SR:508-520 marks i-5..i
+constexpr unsigned char C_B = 2;    // SR:521-533 marks i+1..i+6
+constexpr unsigned char C_C = 4;    // SR:546-548 marks i
+constexpr unsigned char C_GAP = 8;  // gap^2(p_i, p_{i-1}) > 0.05 (SR:604,617,648,661)
+
+__device__ __forceinline__ bool finite3(const float* p) { return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]); }
+__device__ __forceinline__ const float* pt_at(const float* xyz, int stride_bytes, int i) {
+  return (const float*)((const char*)xyz + (size_t)i * stride_bytes);
+}
+
+// SR:297-320
+__device__ __forceinline__ int ring_of(const SrParams& prm, float angle) {
+  if (prm.ring_mode == 0) {
+    int r = int(angle + (angle < 0.0 ? -0.5 : +0.5));
+    switch (r) {
+      case -15: return 0;
+      case -13: return 1;
+      case -11: return 2;
+      case -9: return 3;
+      case -7: return 4;
+      case -5: return 5;
+      case -4: return 6;
+      case -3: return 7;
+      case -2: return 8;
+      case -1: return 9;
+      case 0: return 10;
+      case 1: return 11;
+      case 3: return 12;
+      case 5: return 13;
+      case 7: return 14;
+      case 9: return 15;
+      default: return -1;
+    }
+  }
+  float rel = (angle - prm.ring_ang_min) / prm.ring_ang_step;
+  int r = int(rel + 0.5);
+  if (rel + 0.5 < 0.0 || r >= prm.n_scans) return -1;
+  return r;
+}
+
+// atan / atan2 of fp32 arguments evaluated in fp64 and rounded once (see lg_sincosf_cr).
+__device__ __forceinline__ float atanf_cr(float a) { return (float)atan((double)a); }
+__device__ __forceinline__ float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+// SR:265-278: start / end azimuth from the first / last finite point.  Evaluated by one thread per CTA.
+__device__ void sweep_ori(const float* xyz, int n, int stride_bytes, float* startOri, float* endOri, int* ok) {
+  int f = 0;
+  while (f < n && !finite3(pt_at(xyz, stride_bytes, f))) f++;
+  if (f >= n) {
+    *ok = 0;
+    *startOri = 0.f;
+    *endOri = 0.f;
+    return;
+  }
+  int l = n - 1;
+  while (l > f && !finite3(pt_at(xyz, stride_bytes, l))) l--;
+  const float* pf = pt_at(xyz, stride_bytes, f);
+  const float* pl = pt_at(xyz, stride_bytes, l);
+  float so = -atan2f_cr(pf[1], pf[0]);
+  float eo = (float)(-atan2f_cr(pl[1], pl[0]) + 2 * M_PI);
+  if (eo - so > 3 * M_PI) {
+    eo = (float)(eo - 2 * M_PI);
+  } else if (eo - so < M_PI) {
+    eo = (float)(eo + 2 * M_PI);
+  }
+  *startOri = so;
+  *endOri = eo;
+  *ok = 1;
+}
+
+__global__ void __launch_bounds__(SR_NT) sr_ring_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+                                                         signed char* __restrict__ ring8, float* __restrict__ ori_raw,
+                                                         unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
+  __shared__ unsigned int h[MAXR];
+  __shared__ float s_ori[2];
+  __shared__ int s_ok;
+  __shared__ int s_jmin;
+  const int tid = threadIdx.x;
+  if (tid < MAXR) h[tid] = 0;
+  if (tid == 0) {
+    sweep_ori(xyz, n, stride_bytes, &s_ori[0], &s_ori[1], &s_ok);
+    s_jmin = 0x7fffffff;
+  }
+  __syncthreads();
+  const float startOri = s_ori[0];
+  int jmin = 0x7fffffff;
+  const int base = blockIdx.x * SR_TILE;
+#pragma unroll
+  for (int c = 0; c < SR_ITEMS; c++) {
+    int i = base + c * SR_NT + tid;
+    if (i >= n) break;
+    const float* p = pt_at(xyz, stride_bytes, i);
+    int ring = -1;
+    float ori = 0.f;
+    if (s_ok && finite3(p)) {
+      float px = p[1], py = p[2], pz = p[0];  // SR:293-295
+      float angle = (float)(atanf_cr(py / sqrtf(px * px + pz * pz)) * 180 / M_PI);
+      ring = ring_of(prm, angle);
+      if (ring >= 0) {
+        ori = -atan2f_cr(px, pz);
+        // SR:341-350 evaluated with the first-branch formula: the latch sets at the first kept point where it holds
+        float o1 = ori;
+        if (o1 < startOri - M_PI / 2) {
+          o1 = (float)(o1 + 2 * M_PI);
+        } else if (o1 > startOri + M_PI * 3 / 2) {
+          o1 = (float)(o1 - 2 * M_PI);
+        }
+        if (o1 - startOri > M_PI) jmin = min(jmin, i);
+        atomicAdd(&h[ring], 1u);
+      }
+    }
+    ring8[i] = (signed char)ring;
+    ori_raw[i] = ori;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+  if ((tid & 31) == 0 && jmin != 0x7fffffff) atomicMin(&s_jmin, jmin);
+  __syncthreads();
+  if (tid == 0 && s_jmin != 0x7fffffff) atomicMin(&meta[SRM_JSTAR], s_jmin);
+  if (tid < prm.n_scans) hist[tid * nblocks + blockIdx.x] = h[tid];
+}
+
+__global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
+  __shared__ int s_scan[34];
+  const int total = prm.n_scans * nblocks;
+  int per = (total + 1023) / 1024;
+  int b = min((int)threadIdx.x * per, total), e = min(b + per, total);
+  int local = 0;
+  for (int i = b; i < e; i++) local += (int)hist[i];
+  int tot;
+  int r = block_excl_scan<1024>(local, &tot, s_scan);
+  for (int i = b; i < e; i++) {
+    int v = (int)hist[i];
+    hist[i] = (unsigned int)r;
+    r += v;
+  }
+  __syncthreads();
+  if (threadIdx.x < prm.n_scans) {
+    meta[SRM_RING_START + threadIdx.x] = (int)hist[threadIdx.x * nblocks];
+    meta[SRM_SCAN_START + threadIdx.x] = 0;  // SR:251-253 std::vector<int>(N_SCANS, 0)
+    meta[SRM_SCAN_END + threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) {
+    meta[SRM_RING_START + prm.n_scans] = tot;
+    meta[SRM_N_FULL] = tot;
+    meta[SRM_VOX_OVERFLOW] = 0;
+    meta[SRM_ERR] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(SR_NT) sr_scatter_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+                                                            const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
+                                                            const unsigned int* __restrict__ hist, int nblocks, const int* __restrict__ meta,
+                                                            float4* __restrict__ full) {
+  __shared__ unsigned int s_base[MAXR];
+  __shared__ unsigned int s_wcnt[SR_NT / 32][MAXR];
+  __shared__ float s_ori[2];
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < MAXR) s_base[tid] = tid < prm.n_scans ? hist[tid * nblocks + blockIdx.x] : 0u;
+  if (tid == 0) sweep_ori(xyz, n, stride_bytes, &s_ori[0], &s_ori[1], &s_ok);
+  __syncthreads();
+  const float startOri = s_ori[0], endOri = s_ori[1];
+  const int jstar = meta[SRM_JSTAR];
+  const int base = blockIdx.x * SR_TILE;
+  for (int c = 0; c < SR_ITEMS; c++) {
+    if (tid < MAXR) {
+#pragma unroll
+      for (int k = 0; k < SR_NT / 32; k++) s_wcnt[k][tid] = 0;
+    }
+    __syncthreads();
+    int i = base + c * SR_NT + tid;
+    int ring = (i < n) ? (int)ring8[i] : -1;
+    bool valid = ring >= 0;
+    unsigned int m = __match_any_sync(0xffffffffu, valid ? (unsigned int)ring : (256u + lane));
+    unsigned int rank = __popc(m & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wcnt[w][ring] = __popc(m);
+    __syncthreads();
+    if (valid) {
+      unsigned int off = s_base[ring] + rank;
+      for (int k = 0; k < w; k++) off += s_wcnt[k][ring];
+      const float* p = pt_at(xyz, stride_bytes, i);
+      float ori = ori_raw[i];
+      if (i <= jstar) {  // halfPassed still false when this point is handled (SR:341-350)
+        if (ori < startOri - M_PI / 2) {
+          ori = (float)(ori + 2 * M_PI);
+        } else if (ori > startOri + M_PI * 3 / 2) {
+          ori = (float)(ori - 2 * M_PI);
+        }
+      } else {  // SR:351-359
+        ori = (float)(ori + 2 * M_PI);
+        if (ori < endOri - M_PI * 3 / 2) {
+          ori = (float)(ori + 2 * M_PI);
+        } else if (ori > endOri + M_PI / 2) {
+          ori = (float)(ori - 2 * M_PI);
+        }
+      }
+      float relTime = (ori - startOri) / (endOri - startOri);
+      float inten = (float)(ring + prm.scan_period * relTime);  // SR:362, scanPeriod is a double
+      full[off] = make_float4(p[1], p[2], p[0], inten);
+    }
+    __syncthreads();
+    if (tid < MAXR) {
+      unsigned int add = 0;
+#pragma unroll
+      for (int k = 0; k < SR_NT / 32; k++) add += s_wcnt[k][tid];
+      s_base[tid] += add;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float gap2(float4 a, float4 b) {
+  float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(256) sr_curv_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                       float* __restrict__ curv, unsigned char* __restrict__ cond, signed char* __restrict__ label) {
+  const int n = meta[SRM_N_FULL];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = c[i];
+  unsigned char cf = 0;
+  float cv = 0.f;
+  if (i >= 1 && gap2(p, c[i - 1]) > 0.05) cf |= C_GAP;
+  if (i >= 5 && i < n - 5) {  // SR:454-488
+    float4 m5 = c[i - 5], m4 = c[i - 4], m3 = c[i - 3], m2 = c[i - 2], m1 = c[i - 1];
+    float4 q1 = c[i + 1], q2 = c[i + 2], q3 = c[i + 3], q4 = c[i + 4], q5 = c[i + 5];
+    float dX = m5.x + m4.x + m3.x + m2.x + m1.x - 10 * p.x + q1.x + q2.x + q3.x + q4.x + q5.x;
+    float dY = m5.y + m4.y + m3.y + m2.y + m1.y - 10 * p.y + q1.y + q2.y + q3.y + q4.y + q5.y;
+    float dZ = m5.z + m4.z + m3.z + m2.z + m1.z - 10 * p.z + q1.z + q2.z + q3.z + q4.z + q5.z;
+    cv = dX * dX + dY * dY + dZ * dZ;
+    int sc = int(p.w);
+    int prev = (i == 5) ? -1 : int(m1.w);
+    if (sc != prev && sc > 0 && sc < prm.n_scans) {  // last writer wins in the reference == largest i
+      atomicMax(&meta[SRM_SCAN_START + sc], i + 5);
+      atomicMax(&meta[SRM_SCAN_END + sc - 1], i - 5);
+    }
+    if (i < n - 6) {  // SR:492-549
+      float diff = gap2(q1, p);
+      if (diff > 0.1) {
+        float depth1 = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+        float depth2 = sqrtf(q1.x * q1.x + q1.y * q1.y + q1.z * q1.z);
+        if (depth1 > depth2) {
+          float dx = q1.x - p.x * depth2 / depth1;
+          float dy = q1.y - p.y * depth2 / depth1;
+          float dz = q1.z - p.z * depth2 / depth1;
+          if (sqrtf(dx * dx + dy * dy + dz * dz) / depth2 < 0.1) cf |= C_A;
+        } else {
+          float dx = q1.x * depth1 / depth2 - p.x;
+          float dy = q1.y * depth1 / depth2 - p.y;
+          float dz = q1.z * depth1 / depth2 - p.z;
+          if (sqrtf(dx * dx + dy * dy + dz * dz) / depth1 < 0.1) cf |= C_B;
+        }
+      }
+      float diff2 = gap2(p, m1);
+      float dis = p.x * p.x + p.y * p.y + p.z * p.z;
+      if (diff > 0.0002 * dis && diff2 > 0.0002 * dis) cf |= C_C;
+    }
+  }
+  curv[i] = cv;
+  cond[i] = cf;
+  label[i] = 0;
+}
+
+// cloudNeighborPicked after SR:492-549 in gather form (the reference scatters; OR is order-independent).
+__device__ __forceinline__ unsigned char mask_at(const unsigned char* __restrict__ cond, int i, int n) {
+  unsigned char r = (cond[i] & C_C) ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j <= 5; j++)
+    if (i + j < n && (cond[i + j] & C_A)) r = 1;
+#pragma unroll
+  for (int j = 1; j <= 6; j++)
+    if (i - j >= 0 && (cond[i - j] & C_B)) r = 1;
+  return r;
+}
+
+constexpr int SEL_CAP = 4096;  // points per sector the shared-memory sort accepts (ring <= 6 * 4096 points)
+
+// SR:597-622 / 641-666 with FENCE (iv) (bounds) — see oracle/orc_sr.h suppress_neighbours
+__device__ __forceinline__ void suppress(unsigned char* picked, const unsigned char* __restrict__ cond, int ind, int n) {
+  for (int l = 1; l <= 5; l++) {
+    if (ind + l >= n || ind + l - 1 < 0) break;
+    if (cond[ind + l] & C_GAP) break;
+    picked[ind + l] = 1;
+  }
+  for (int l = -1; l >= -5; l--) {
+    if (ind + l < 0 || ind + l + 1 >= n) break;
+    if (cond[ind + l + 1] & C_GAP) break;
+    picked[ind + l] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                         const float* __restrict__ curv, const unsigned char* __restrict__ cond,
+                                                         unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
+                                                         signed char* __restrict__ label, int* __restrict__ picks) {
+  __shared__ unsigned long long skeys[SEL_CAP];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int n = meta[SRM_N_FULL];
+  const int R = prm.n_scans;
+  const int S = (r == 0) ? 5 : meta[SRM_SCAN_START + r];            // SR:489
+  const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];     // SR:490
+  int* my_picks = picks + r * SR_PICKS_PER_RING;
+  int* cnt = meta + SRM_PICK_CNT + r * 3;
+  // this ring's points: [S - 5, E + 5)
+  const int a = max(S - 5, 0), b = min(E + 5, n);
+  for (int i = a + tid; i < b; i += blockDim.x) {
+    unsigned char m = mask_at(cond, i, n);
+    picked[i] = m;
+    mask_diag[i] = m;
+  }
+  int nsharp = 0, nless = 0, nflat = 0;
+  bool too_big = false;
+  __syncthreads();
+  for (int j = 0; j < 6; j++) {
+    const int sp = (S * (6 - j) + E * j) / 6;
+    const int ep = (S * (5 - j) + E * (j + 1)) / 6 - 1;
+    const int m = ep - sp + 1;
+    if (m <= 0) continue;
+    if (m > SEL_CAP || sp < 0 || ep >= n) {
+      too_big = true;
+      continue;
+    }
+    int P = 2;
+    while (P < m) P <<= 1;
+    for (int t = tid; t < P; t += blockDim.x)
+      skeys[t] = t < m ? (((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned int)(sp + t)) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int t = tid; t < (P >> 1); t += blockDim.x) {
+          int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+          int l = i | jj;
+          unsigned long long x = skeys[i], y = skeys[l];
+          bool asc = (i & k) == 0;
+          if ((x > y) == asc) {
+            skeys[i] = y;
+            skeys[l] = x;
+          }
+        }
+        __syncthreads();
+      }
+    if (tid == 0) {
+      // SR:578-624, walking down from the largest curvature; everything below the first c <= 0.1 can never pass
+      int largest = 0;
+      for (int k = m - 1; k >= 0; k--) {
+        float cv = __uint_as_float((unsigned int)(skeys[k] >> 32));
+        if (!(cv > 0.1)) break;
+        int ind = (int)(unsigned int)(skeys[k] & 0xffffffffull);
+        if (picked[ind] == 0) {
+          largest++;
+          if (largest <= 16) {
+            label[ind] = 2;
+            my_picks[SR_PICK_SHARP + nsharp++] = ind;
+            my_picks[SR_PICK_LESS + nless++] = ind;
+          } else if (largest <= 20) {
+            label[ind] = 1;
+            my_picks[SR_PICK_LESS + nless++] = ind;
+          } else {
+            break;
+          }
+          picked[ind] = 1;
+          suppress(picked, cond, ind, n);
+        }
+      }
+      // SR:626-668, walking up from the smallest curvature
+      int smallest = 0;
+      for (int k = 0; k < m; k++) {
+        float cv = __uint_as_float((unsigned int)(skeys[k] >> 32));
+        if (!(cv < 0.1)) break;
+        int ind = (int)(unsigned int)(skeys[k] & 0xffffffffull);
+        if (picked[ind] == 0) {
+          label[ind] = -1;
+          my_picks[SR_PICK_FLAT + nflat++] = ind;
+          smallest++;
+          if (smallest >= 32) break;
+          picked[ind] = 1;
+          suppress(picked, cond, ind, n);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cnt[0] = nsharp;
+    cnt[1] = nless;
+    cnt[2] = nflat;
+    if (too_big) atomicExch(&meta[SRM_ERR], 1);
+  }
+}
+
+// Compacts picks to feature clouds, derives the less-flat mask (SR:670-674) and the per-ring voxel jobs (SR:677-683).
+__global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                          const signed char* __restrict__ label, const int* __restrict__ picks,
+                                                          float4* __restrict__ sharp, float4* __restrict__ less_sharp, float4* __restrict__ flat,
+                                                          unsigned char* __restrict__ lf_valid, float4* __restrict__ lf_tmp, VoxSegD* __restrict__ segs) {
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int n = meta[SRM_N_FULL];
+  const int R = prm.n_scans;
+  const int S = (r == 0) ? 5 : meta[SRM_SCAN_START + r];
+  const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];
+  int off[3] = {0, 0, 0}, tot[3] = {0, 0, 0};
+  for (int k = 0; k < R; k++)
+    for (int t = 0; t < 3; t++) {
+      int v = meta[SRM_PICK_CNT + k * 3 + t];
+      if (k < r) off[t] += v;
+      tot[t] += v;
+    }
+  const int* my = picks + r * SR_PICKS_PER_RING;
+  const int* cnt = meta + SRM_PICK_CNT + r * 3;
+  for (int i = tid; i < cnt[0]; i += blockDim.x) sharp[off[0] + i] = c[my[SR_PICK_SHARP + i]];
+  for (int i = tid; i < cnt[1]; i += blockDim.x) less_sharp[off[1] + i] = c[my[SR_PICK_LESS + i]];
+  for (int i = tid; i < cnt[2]; i += blockDim.x) flat[off[2] + i] = c[my[SR_PICK_FLAT + i]];
+  const int a = max(S - 5, 0), b = min(E + 5, n);
+  for (int i = a + tid; i < b; i += blockDim.x) lf_valid[i] = (i >= S && i < E && label[i] <= 0) ? 1 : 0;
+  if (tid == 0) {
+    VoxSegD sg;
+    sg.in = c + a;
+    sg.valid = lf_valid + a;
+    sg.out = lf_tmp + a;
+    sg.out_count = meta + SRM_LF_CNT + r;
+    sg.n = max(b - a, 0);
+    sg.leaf = 0.2f;
+    segs[r] = sg;
+    if (r == 0) {
+      meta[SRM_N_SHARP] = tot[0];
+      meta[SRM_N_LESS_SHARP] = tot[1];
+      meta[SRM_N_FLAT] = tot[2];
+    }
+    if (r == 0) meta[SRM_SCAN_START + 0] = 5;        // SR:489 (diagnostics see the final values)
+    if (r == R - 1) meta[SRM_SCAN_END + R - 1] = n - 5;  // SR:490
+  }
+}
+
+__global__ void __launch_bounds__(256) sr_concat_kernel(SrParams prm, int* __restrict__ meta, const VoxSegD* __restrict__ segs,
+                                                         float4* __restrict__ less_flat) {
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int R = prm.n_scans;
+  int off = 0, tot = 0;
+  for (int k = 0; k < R; k++) {
+    int v = max(meta[SRM_LF_CNT + k], 0);
+    if (k < r) off += v;
+    tot += v;
+  }
+  const int cnt = max(meta[SRM_LF_CNT + r], 0);
+  const float4* src = segs[r].out;
+  for (int i = tid; i < cnt; i += blockDim.x) less_flat[off + i] = src[i];
+  if (r == 0 && tid == 0) {
+    meta[SRM_N_LESS_FLAT] = tot;
+    meta[SRM_JSTAR] = 0x7fffffff;  // re-arm the prefix-min for the next sweep
+  }
+}
+
+}  // namespace
+
+int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches) {
+  const int R = prm.n_scans;
+  if (R > MAXR || R < 1) return LOAM_EINVAL;
+  const int nblocks = std::max(1, lg_div_up(n, SR_TILE));
+  LG_CHECK(ws.ring8.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.ori_raw.ensure((size_t)(n + 16) * 4, st));
+  LG_CHECK(ws.hist.ensure((size_t)R * nblocks * 4, st));
+  LG_CHECK(ws.full.ensure((size_t)(n + 16) * 16, st));
+  LG_CHECK(ws.curv.ensure((size_t)(n + 16) * 4, st));
+  LG_CHECK(ws.cond.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.picked.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.mask_diag.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.label.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.lf_valid.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.lf_tmp.ensure((size_t)(n + 16) * 16, st));
+  LG_CHECK(ws.less_flat.ensure((size_t)(n + 16) * 16, st));
+  LG_CHECK(ws.picks.ensure((size_t)R * SR_PICKS_PER_RING * 4, st));
+  LG_CHECK(ws.sharp.ensure((size_t)R * 96 * 16, st));
+  LG_CHECK(ws.less_sharp.ensure((size_t)R * 120 * 16, st));
+  LG_CHECK(ws.flat.ensure((size_t)R * 192 * 16, st));
+  LG_CHECK(ws.segs.ensure((size_t)R * sizeof(VoxSegD), st));
+  if (!ws.meta.p) {
+    LG_CHECK(ws.meta.ensure(SRM_SIZE * 4, st));
+    LG_CHECK(cudaMemsetAsync(ws.meta.p, 0, SRM_SIZE * 4, st));
+    int big = 0x7fffffff;
+    LG_CHECK(cudaMemcpyAsync(ws.meta.as<int>() + SRM_JSTAR, &big, 4, cudaMemcpyHostToDevice, st));
+    LG_CHECK(cudaStreamSynchronize(st));
+  }
+  int* meta = ws.meta.as<int>();
+  if (n <= 0) {
+    LG_CHECK(cudaMemsetAsync(meta + SRM_N_FULL, 0, 5 * 4, st));
+    return LOAM_OK;
+  }
+  sr_ring_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
+                                            ws.hist.as<unsigned int>(), nblocks, meta);
+  sr_scan_kernel<<<1, 1024, 0, st>>>(prm, ws.hist.as<unsigned int>(), nblocks, meta);
+  sr_scatter_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
+                                               ws.hist.as<unsigned int>(), nblocks, meta, ws.full.as<float4>());
+  sr_curv_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
+                                                    ws.label.as<signed char>());
+  sr_select_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
+                                      ws.picked.as<unsigned char>(), ws.mask_diag.as<unsigned char>(), ws.label.as<signed char>(),
+                                      ws.picks.as<int>());
+  sr_collect_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.label.as<signed char>(), ws.picks.as<int>(),
+                                       ws.sharp.as<float4>(), ws.less_sharp.as<float4>(), ws.flat.as<float4>(),
+                                       ws.lf_valid.as<unsigned char>(), ws.lf_tmp.as<float4>(), ws.segs.as<VoxSegD>());
+  (*launches) += 6;
+  int rc = lg_vox_small(ws.segs.as<VoxSegD>(), R, (n / R) * 2 + 64 <= 4096 ? 4096 : 16384, meta + SRM_VOX_OVERFLOW, st, launches);
+  if (rc) return rc;
+  sr_concat_kernel<<<R, 256, 0, st>>>(prm, meta, ws.segs.as<VoxSegD>(), ws.less_flat.as<float4>());
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}

@@ -1,0 +1,323 @@
+// K6 / K8 / K9 — scan-to-scan odometry kernels, the B200 replacement for the hot loops of laserOdometry.cpp:
+//   odom_knn_kernel     LO:603,758   exact nearest neighbour of every de-skewed feature in the previous sweep's
+//                                    corner / surf cloud (replaces KdTreeFLANN::nearestKSearch(k = 1)); brute force over
+//                                    shared-memory target tiles, (d2, index) packed into one 64-bit atomicMin key
+//   odom_iter_kernel    LO:595-971   TransformToStart, the +-1-ring scans for the 2nd / 3rd point on refresh
+//                                    iterations, point-to-line / point-to-plane coefficients, Jacobian row, and the
+//                                    21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
+//   odom_to_end_kernel  LO:1087-1106 TransformToEnd over less-sharp, less-flat and (every 2nd sweep) the full cloud
+// The 6x6 solve, degeneracy projection, convergence test and pose accumulation stay on the host (lg_api.cu).
+#include "lg_odom.h"
+#include "lg_reduce.cuh"
+
+namespace {
+
+// LO:123-150.  sin/cos of the per-point angles s*T[k] are evaluated in fp64 and rounded (lg_sincosf_cr).
+__device__ __forceinline__ float4 transform_to_start(const OdomT& T, float4 pi) {
+  float s = 10 * (pi.w - int(pi.w));
+  float rx = s * T.t[0], ry = s * T.t[1], rz = s * T.t[2];
+  float tx = s * T.t[3], ty = s * T.t[4], tz = s * T.t[5];
+  float srx, crx, sry, cry, srz, crz;
+  lg_sincosf_cr(rx, &srx, &crx);
+  lg_sincosf_cr(ry, &sry, &cry);
+  lg_sincosf_cr(rz, &srz, &crz);
+  float x1 = crz * (pi.x - tx) + srz * (pi.y - ty);
+  float y1 = -srz * (pi.x - tx) + crz * (pi.y - ty);
+  float z1 = (pi.z - tz);
+  float x2 = x1;
+  float y2 = crx * y1 + srx * z1;
+  float z2 = -srx * y1 + crx * z1;
+  float4 po;
+  po.x = cry * x2 - sry * z2;
+  po.y = y2;
+  po.z = sry * x2 + cry * z2;
+  po.w = pi.w;
+  return po;
+}
+
+constexpr int KNN_Q = 128, KNN_T = 512;
+
+__global__ void __launch_bounds__(KNN_Q) odom_knn_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
+                                                          int n_flat, const float4* __restrict__ corner_last, int n_cl,
+                                                          const float4* __restrict__ surf_last, int n_sl, int tiles_c,
+                                                          unsigned long long* __restrict__ best) {
+  __shared__ float4 s_t[KNN_T];
+  const bool is_c = (int)blockIdx.x < tiles_c;
+  const int tile = is_c ? blockIdx.x : blockIdx.x - tiles_c;
+  const float4* q = is_c ? sharp : flat;
+  const int nq = is_c ? n_sharp : n_flat;
+  const float4* tg = is_c ? corner_last : surf_last;
+  const int nt = is_c ? n_cl : n_sl;
+  const int t0 = blockIdx.y * KNN_T;
+  if (t0 >= nt) return;
+  const int cnt = min(KNN_T, nt - t0);
+  for (int i = threadIdx.x; i < cnt; i += KNN_Q) s_t[i] = tg[t0 + i];
+  __syncthreads();
+  const int qi = tile * KNN_Q + threadIdx.x;
+  if (qi >= nq) return;
+  const float4 sel = transform_to_start(T, q[qi]);
+  float bd = __int_as_float(0x7f800000);
+  int bi = -1;
+#pragma unroll 4
+  for (int j = 0; j < cnt; j++) {
+    float4 t = s_t[j];
+    float d = lg_sqdist(t.x, t.y, t.z, sel.x, sel.y, sel.z);
+    if (d < bd) {  // ascending j + strict '<' => smallest index wins ties
+      bd = d;
+      bi = t0 + j;
+    }
+  }
+  if (bi >= 0) atomicMin(&best[(is_c ? 0 : n_sharp) + qi], lg_pack_nbr(bd, bi));
+}
+
+__device__ __forceinline__ float sqd(float4 a, float4 sel) {
+  return (a.x - sel.x) * (a.x - sel.x) + (a.y - sel.y) * (a.y - sel.y) + (a.z - sel.z) * (a.z - sel.z);
+}
+
+// Point-to-line coefficients shared with mapping (LO:688-716 == LM:814-842).
+__device__ __forceinline__ void line_coeff(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2,
+                                           float& la, float& lb, float& lc, float& ld2) {
+  float cxy = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+  float cxz = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+  float cyz = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+  float a012 = sqrtf(cxy * cxy + cxz * cxz + cyz * cyz);
+  float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+  la = ((y1 - y2) * cxy + (z1 - z2) * cxz) / a012 / l12;
+  lb = -((x1 - x2) * cxy - (z1 - z2) * cyz) / a012 / l12;
+  lc = -((x1 - x2) * cxz + (y1 - y2) * cyz) / a012 / l12;
+  ld2 = a012 / l12;
+}
+
+constexpr int IT_NT = 128;
+
+__global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp,
+                                                           const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
+                                                           int n_cl, const float4* __restrict__ surf_last, int n_sl,
+                                                           const unsigned long long* __restrict__ best, int* __restrict__ c1, int* __restrict__ c2,
+                                                           int* __restrict__ s1, int* __restrict__ s2, int* __restrict__ s3,
+                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28) {
+  Acc28 acc;
+  acc.clear();
+  const int q = blockIdx.x * IT_NT + threadIdx.x;
+  const bool refresh = (iter % 5) == 0;
+  float4 ori, coef;
+  bool keep = false;
+  if (q < n_sharp) {
+    ori = sharp[q];
+    const float4 sel = transform_to_start(T, ori);
+    if (refresh) {  // LO:598-677
+      unsigned long long b = best[q];
+      int closest = -1, min2 = -1;
+      if (b != ~0ull && lg_nbr_d2(b) < 25) {
+        closest = lg_nbr_idx(b);
+        int scan = int(corner_last[closest].w);
+        float minD2 = 25;
+        // FENCE (i): the reference bounds this scan by cornerPointsSharpNum (LO:620); clamp to the cloud
+        int bound = min(n_sharp, n_cl);
+        for (int j = closest + 1; j < bound; j++) {
+          float4 t = corner_last[j];
+          if (int(t.w) > scan + 1.5) break;
+          float d = sqd(t, sel);
+          if (int(t.w) > scan && d < minD2) {
+            minD2 = d;
+            min2 = j;
+          }
+        }
+        for (int j = closest - 1; j >= 0; j--) {
+          float4 t = corner_last[j];
+          if (int(t.w) < scan - 1.5) break;
+          float d = sqd(t, sel);
+          if (int(t.w) < scan && d < minD2) {
+            minD2 = d;
+            min2 = j;
+          }
+        }
+      }
+      c1[q] = closest;
+      c2[q] = min2;
+    }
+    const int i2 = c2[q];
+    if (i2 >= 0) {  // LO:680-746
+      float4 t1 = corner_last[c1[q]], t2 = corner_last[i2];
+      float la, lb, lc, ld2;
+      line_coeff(sel.x, sel.y, sel.z, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, la, lb, lc, ld2);
+      float s = 1;
+      if (iter >= 5) s = (float)(1 - 1.8 * fabsf(ld2));
+      coef = make_float4(s * la, s * lb, s * lc, s * ld2);
+      keep = (s > 0.1 && ld2 != 0);
+    }
+  } else if (q < n_sharp + n_flat) {
+    const int f = q - n_sharp;
+    ori = flat[f];
+    const float4 sel = transform_to_start(T, ori);
+    if (refresh) {  // LO:756-844
+      unsigned long long b = best[q];
+      int closest = -1, min2 = -1, min3 = -1;
+      if (b != ~0ull && lg_nbr_d2(b) < 25) {
+        closest = lg_nbr_idx(b);
+        int scan = int(surf_last[closest].w);
+        float minD2 = 25, minD3 = 25;
+        int bound = min(n_flat, n_sl);  // FENCE (i), LO:776
+        for (int j = closest + 1; j < bound; j++) {
+          float4 t = surf_last[j];
+          if (int(t.w) > scan + 1.5) break;
+          float d = sqd(t, sel);
+          if (int(t.w) <= scan) {
+            if (d < minD2) { minD2 = d; min2 = j; }
+          } else {
+            if (d < minD3) { minD3 = d; min3 = j; }
+          }
+        }
+        for (int j = closest - 1; j >= 0; j--) {
+          float4 t = surf_last[j];
+          if (int(t.w) < scan - 1.5) break;
+          float d = sqd(t, sel);
+          if (int(t.w) >= scan) {
+            if (d < minD2) { minD2 = d; min2 = j; }
+          } else {
+            if (d < minD3) { minD3 = d; min3 = j; }
+          }
+        }
+      }
+      s1[f] = closest;
+      s2[f] = min2;
+      s3[f] = min3;
+    }
+    const int i2 = s2[f], i3 = s3[f];
+    if (i2 >= 0 && i3 >= 0) {  // LO:847-901
+      float4 t1 = surf_last[s1[f]], t2 = surf_last[i2], t3 = surf_last[i3];
+      float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+      float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+      float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+      float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+      float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+      pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+      float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+      float s = 1;
+      if (iter >= 5) s = (float)(1 - 1.8 * fabsf(pd2) / sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
+      coef = make_float4(s * pa, s * pb, s * pc, s * pd2);
+      keep = (s > 0.1 && pd2 != 0);
+    }
+  }
+  if (keep) {  // LO:915-971 with s = 1 folded away (x * 1.0f is exact)
+    const float srx = sc.srx, crx = sc.crx, sry = sc.sry, cry = sc.cry, srz = sc.srz, crz = sc.crz;
+    const float tx = T.t[3], ty = T.t[4], tz = T.t[5];
+    const float4 p = ori, c = coef;
+    float a[6];
+    a[0] = (-crx * sry * srz * p.x + crx * crz * sry * p.y + srx * sry * p.z + tx * crx * sry * srz - ty * crx * crz * sry - tz * srx * sry) * c.x +
+           (srx * srz * p.x - crz * srx * p.y + crx * p.z + ty * crz * srx - tz * crx - tx * srx * srz) * c.y +
+           (crx * cry * srz * p.x - crx * cry * crz * p.y - cry * srx * p.z + tz * cry * srx + ty * crx * cry * crz - tx * crx * cry * srz) * c.z;
+    a[1] = ((-crz * sry - cry * srx * srz) * p.x + (cry * crz * srx - sry * srz) * p.y - crx * cry * p.z + tx * (crz * sry + cry * srx * srz) +
+            ty * (sry * srz - cry * crz * srx) + tz * crx * cry) * c.x +
+           ((cry * crz - srx * sry * srz) * p.x + (cry * srz + crz * srx * sry) * p.y - crx * sry * p.z + tz * crx * sry -
+            ty * (cry * srz + crz * srx * sry) - tx * (cry * crz - srx * sry * srz)) * c.z;
+    a[2] = ((-cry * srz - crz * srx * sry) * p.x + (cry * crz - srx * sry * srz) * p.y + tx * (cry * srz + crz * srx * sry) -
+            ty * (cry * crz - srx * sry * srz)) * c.x +
+           (-crx * crz * p.x - crx * srz * p.y + ty * crx * srz + tx * crx * crz) * c.y +
+           ((cry * crz * srx - sry * srz) * p.x + (crz * sry + cry * srx * srz) * p.y + tx * (sry * srz - cry * crz * srx) -
+            ty * (crz * sry + cry * srx * srz)) * c.z;
+    a[3] = -(cry * crz - srx * sry * srz) * c.x + crx * srz * c.y - (crz * sry + cry * srx * srz) * c.z;
+    a[4] = -(cry * srz + crz * srx * sry) * c.x - crx * crz * c.y - (sry * srz - cry * crz * srx) * c.z;
+    a[5] = crx * sry * c.x - srx * c.y - crx * cry * c.z;
+    float b = (float)(-0.05 * c.w);
+    acc.add_row(a, b);
+  }
+  lg_reduce28<IT_NT>(acc, partials, ticket, out28);
+}
+
+// LO:156-227.  sT = sin/cos of the full transform, imu sin/cos evaluated on the host.
+__global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
+                                                           int n0, const float4* __restrict__ in1, float4* __restrict__ out1, int n1,
+                                                           const float4* __restrict__ in2, float4* __restrict__ out2, int n2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* in;
+  float4* out;
+  if (i < n0) {
+    in = in0; out = out0;
+  } else if (i < n0 + n1) {
+    in = in1; out = out1; i -= n0;
+  } else if (i < n0 + n1 + n2) {
+    in = in2; out = out2; i -= n0 + n1;
+  } else {
+    return;
+  }
+  const float4 pi = in[i];
+  const float4 a = transform_to_start(T, pi);
+  float x3 = a.x, y3 = a.y, z3 = a.z;
+  float x4 = sT.cry * x3 + sT.sry * z3;
+  float y4 = y3;
+  float z4 = -sT.sry * x3 + sT.cry * z3;
+  float x5 = x4;
+  float y5 = sT.crx * y4 - sT.srx * z4;
+  float z5 = sT.srx * y4 + sT.crx * z4;
+  float x6 = sT.crz * x5 - sT.srz * y5 + T.t[3];
+  float y6 = sT.srz * x5 + sT.crz * y5 + T.t[4];
+  float z6 = z5 + T.t[5];
+  float x7 = imu.c_roll_s * (x6 - imu.shift[0]) - imu.s_roll_s * (y6 - imu.shift[1]);
+  float y7 = imu.s_roll_s * (x6 - imu.shift[0]) + imu.c_roll_s * (y6 - imu.shift[1]);
+  float z7 = z6 - imu.shift[2];
+  float x8 = x7;
+  float y8 = imu.c_pitch_s * y7 - imu.s_pitch_s * z7;
+  float z8 = imu.s_pitch_s * y7 + imu.c_pitch_s * z7;
+  float x9 = imu.c_yaw_s * x8 + imu.s_yaw_s * z8;
+  float y9 = y8;
+  float z9 = -imu.s_yaw_s * x8 + imu.c_yaw_s * z8;
+  float x10 = imu.c_yaw_l * x9 - imu.s_yaw_l * z9;
+  float y10 = y9;
+  float z10 = imu.s_yaw_l * x9 + imu.c_yaw_l * z9;
+  float x11 = x10;
+  float y11 = imu.c_pitch_l * y10 + imu.s_pitch_l * z10;
+  float z11 = -imu.s_pitch_l * y10 + imu.c_pitch_l * z10;
+  float4 po;
+  po.x = imu.c_roll_l * x11 + imu.s_roll_l * y11;
+  po.y = -imu.s_roll_l * x11 + imu.c_roll_l * y11;
+  po.z = z11;
+  po.w = int(pi.w);
+  out[i] = po;
+}
+
+}  // namespace
+
+int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, cudaStream_t st, long long* launches) {
+  const int nq = n_sharp + n_flat;
+  const int nb = std::max(1, lg_div_up(nq, IT_NT));
+  LG_CHECK(ws.best.ensure((size_t)(nq + 1) * 8, st));
+  LG_CHECK(ws.c1.ensure((size_t)(n_sharp + 1) * 4, st, true));
+  LG_CHECK(ws.c2.ensure((size_t)(n_sharp + 1) * 4, st, true));
+  LG_CHECK(ws.s1.ensure((size_t)(n_flat + 1) * 4, st, true));
+  LG_CHECK(ws.s2.ensure((size_t)(n_flat + 1) * 4, st, true));
+  LG_CHECK(ws.s3.ensure((size_t)(n_flat + 1) * 4, st, true));
+  LG_CHECK(ws.partials.ensure((size_t)nb * 28 * 8, st));
+  if (!ws.ticket.p) {
+    LG_CHECK(ws.ticket.ensure(4, st));
+    LG_CHECK(cudaMemsetAsync(ws.ticket.p, 0, 4, st));
+  }
+  if (iter % 5 == 0 && nq > 0) {
+    LG_CHECK(cudaMemsetAsync(ws.best.p, 0xff, (size_t)nq * 8, st));
+    const int tiles_c = lg_div_up(n_sharp, KNN_Q), tiles_s = lg_div_up(n_flat, KNN_Q);
+    const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
+    if (tiles_c + tiles_s > 0) {
+      dim3 grid(tiles_c + tiles_s, chunks);
+      odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
+                                              ws.best.as<unsigned long long>());
+      (*launches)++;
+    }
+  }
+  odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
+                                         ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(),
+                                         ws.s3.as<int>(), ws.partials.as<double>(), ws.ticket.as<unsigned int>(), out28);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, const float4* in0, float4* out0, int n0, const float4* in1,
+                          float4* out1, int n1, const float4* in2, float4* out2, int n2, cudaStream_t st, long long* launches) {
+  const int n = n0 + n1 + n2;
+  if (n <= 0) return LOAM_OK;
+  odom_to_end_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(T, sT, imu, in0, out0, n0, in1, out1, n1, in2, out2, n2);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}

@@ -1,0 +1,80 @@
+// The 21 + 6 (+ count) term normal-equation reduction shared by odometry (LO:972-974) and mapping (LM:965-967).
+// The reference forms A (n x 6, fp32), then AtA = At * A and AtB = At * B through OpenCV's GEMM, which accumulates
+// float products in DOUBLE.  A float x float product is exact in double, so summing the exact products in double in
+// any order reproduces the reference's sums to ~1e-16 relative; the result is rounded to fp32 once on the host.
+// Layout of the 28 doubles: upper triangle of AtA row-major (00 01 .. 05 11 12 .. 55), then AtB[0..5], then n_sel.
+#pragma once
+#include "lg_common.cuh"
+
+#ifdef __CUDACC__
+
+struct Acc28 {
+  double v[28];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 28; i++) v[i] = 0.0;
+  }
+  __device__ __forceinline__ void add_row(const float* a, float b) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = i; j < 6; j++) v[t++] += (double)a[i] * (double)a[j];
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[21 + i] += (double)a[i] * (double)b;
+    v[27] += 1.0;
+  }
+};
+
+// Warp shuffle -> shared memory -> per-CTA partial in global memory; the last CTA to arrive (ticket) adds the partials
+// in CTA order (deterministic) and writes the 28 results to out28 (device memory or mapped pinned host memory).
+template <int NT>
+__device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                            double* __restrict__ out28) {
+  __shared__ double s_part[NT / 32][28];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 28; i++) {
+    double x = lg_warp_sum(acc.v[i]);
+    if (lane == 0) s_part[w][i] = x;
+  }
+  __syncthreads();
+  if (tid < 28) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; k++) s += s_part[k][tid];
+    partials[(size_t)blockIdx.x * 28 + tid] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (tid < 28) {
+      double s = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * 28 + tid]);
+      out28[tid] = s;
+    }
+    if (tid == 0) *ticket = 0u;
+  }
+}
+
+#endif  // __CUDACC__
+
+// host: 28 doubles -> AtA (6x6 row-major float), AtB (6 float), n_sel
+static inline void lg_unpack28(const double* r, float* AtA, float* AtB, int* n_sel) {
+  int t = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      float v = (float)r[t++];
+      AtA[i * 6 + j] = v;
+      AtA[j * 6 + i] = v;
+    }
+  for (int i = 0; i < 6; i++) AtB[i] = (float)r[21 + i];
+  *n_sel = (int)(r[27] + 0.5);
+}

@@ -1,0 +1,461 @@
+// K5 — voxel-grid centroid down-sampling, the B200 replacement for pcl::VoxelGrid<PointXYZI>::filter at the
+// reference's call sites SR:677-683 (0.2 m per ring), LM:736-744 (0.2 / 0.4 m stacks), LM:1061-1079 (per valid
+// cube) and LM:1092-1094 (surround).  Semantics (PCL 1.8.0): cell = floor(p * (1/leaf)) - min_b,
+// linear id x-fastest, one output per occupied cell in ascending id, centroid of all four fields, in-cell sums taken
+// in ascending input index (our deterministic choice), index-overflow => input returned unfiltered.
+//
+// Two paths, both batched over independent SEGMENTS (rings / stacks / map cubes):
+//   small: one CTA per segment, keys (cell << 32 | index) bitonic-sorted in shared memory (<= 16384 points);
+//   big  : global LSD radix sort of (segment << 32 | cell, index), 8 bits per pass, any size.
+// HBM roofline: algorithmic bytes 16 (M + V) per call.
+#include <float.h>
+
+#include "lg_voxel.h"
+
+namespace {
+
+__device__ __forceinline__ int f2ord(float f) {
+  int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
+
+// Shared by both paths: PCL's grid set-up from the float bounding box.  Returns false on index overflow.
+struct VoxGrid {
+  int minb0, minb1, minb2, divx, divxy;
+  float inv;
+};
+__device__ __forceinline__ bool vox_grid_setup(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float leaf, VoxGrid& g) {
+  float inv = 1.0f / leaf;
+  g.inv = inv;
+  long long dx = (long long)((mxx - mnx) * inv) + 1;
+  long long dy = (long long)((mxy - mny) * inv) + 1;
+  long long dz = (long long)((mxz - mnz) * inv) + 1;
+  if (dx * dy * dz > 2147483647ll) return false;
+  g.minb0 = (int)floorf(mnx * inv);
+  g.minb1 = (int)floorf(mny * inv);
+  g.minb2 = (int)floorf(mnz * inv);
+  int maxb0 = (int)floorf(mxx * inv), maxb1 = (int)floorf(mxy * inv);
+  g.divx = maxb0 - g.minb0 + 1;
+  g.divxy = g.divx * (maxb1 - g.minb1 + 1);
+  return true;
+}
+__device__ __forceinline__ int vox_cell(const VoxGrid& g, float4 p) {
+  int i0 = (int)(floorf(p.x * g.inv) - (float)g.minb0);
+  int i1 = (int)(floorf(p.y * g.inv) - (float)g.minb1);
+  int i2 = (int)(floorf(p.z * g.inv) - (float)g.minb2);
+  return i0 + i1 * g.divx + i2 * g.divxy;
+}
+
+// ------------------------------------------------------------------------------------------------ small path
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict__ segs, int* __restrict__ overflow) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ float s_red[6][NT / 32];
+  __shared__ int s_cnt[NT / 32];
+  __shared__ int s_scan[NT / 32 + 2];
+  __shared__ float s_bb[6];
+  __shared__ int s_nvalid;
+  const VoxSegD sg = segs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = sg.n;
+  if (n > CAP) {
+    if (tid == 0) {
+      atomicExch(overflow, 1);
+      *sg.out_count = -1;
+    }
+    return;
+  }
+  if (n <= 0) {
+    if (tid == 0) *sg.out_count = 0;
+    return;
+  }
+  float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
+  int cnt = 0;
+  for (int i = tid; i < n; i += NT) {
+    if (sg.valid && !sg.valid[i]) continue;
+    float4 p = sg.in[i];
+    mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
+    mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
+    cnt++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    s_red[0][w] = mn0; s_red[1][w] = mn1; s_red[2][w] = mn2; s_red[3][w] = mx0; s_red[4][w] = mx1; s_red[5][w] = mx2;
+    s_cnt[w] = cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < NT / 32; k++) {
+      s_red[0][0] = fminf(s_red[0][0], s_red[0][k]); s_red[1][0] = fminf(s_red[1][0], s_red[1][k]);
+      s_red[2][0] = fminf(s_red[2][0], s_red[2][k]); s_red[3][0] = fmaxf(s_red[3][0], s_red[3][k]);
+      s_red[4][0] = fmaxf(s_red[4][0], s_red[4][k]); s_red[5][0] = fmaxf(s_red[5][0], s_red[5][k]);
+      s_cnt[0] += s_cnt[k];
+    }
+    for (int k = 0; k < 6; k++) s_bb[k] = s_red[k][0];
+    s_nvalid = s_cnt[0];
+  }
+  __syncthreads();
+  const int nvalid = s_nvalid;
+  if (nvalid == 0) {
+    if (tid == 0) *sg.out_count = 0;
+    return;
+  }
+  VoxGrid g;
+  const bool ok = vox_grid_setup(s_bb[0], s_bb[1], s_bb[2], s_bb[3], s_bb[4], s_bb[5], sg.leaf, g);
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = tid; i < P; i += NT) {
+    unsigned long long key = ~0ull;
+    if (i < n && (!sg.valid || sg.valid[i])) {
+      int cell = ok ? vox_cell(g, sg.in[i]) : i;
+      key = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
+    }
+    skeys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += NT) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int l = i | j;
+        unsigned long long a = skeys[i], b = skeys[l];
+        bool asc = (i & k) == 0;
+        if ((a > b) == asc) {
+          skeys[i] = b;
+          skeys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int per = (nvalid + NT - 1) / NT;
+  const int b = min(tid * per, nvalid), e = min(b + per, nvalid);
+  int local = 0;
+  for (int i = b; i < e; i++) local += (i == 0 || (unsigned int)(skeys[i] >> 32) != (unsigned int)(skeys[i - 1] >> 32)) ? 1 : 0;
+  int V;
+  int r = block_excl_scan<NT>(local, &V, s_scan);
+  for (int i = b; i < e; i++) {
+    unsigned int cell = (unsigned int)(skeys[i] >> 32);
+    if (i == 0 || cell != (unsigned int)(skeys[i - 1] >> 32)) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int j = i;
+      while (j < nvalid && (unsigned int)(skeys[j] >> 32) == cell) {
+        float4 p = sg.in[(unsigned int)(skeys[j] & 0xffffffffull)];
+        sx = sx + p.x; sy = sy + p.y; sz = sz + p.z; si = si + p.w;
+        j++;
+      }
+      float c = (float)(j - i);
+      sg.out[r++] = make_float4(sx / c, sy / c, sz / c, si / c);
+    }
+  }
+  if (tid == 0) *sg.out_count = V;
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort
+constexpr int RS_NT = 256, RS_ITEMS = 8, RS_TILE = RS_NT * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const unsigned long long* __restrict__ keys, int n, int shift,
+                                                         unsigned int* __restrict__ hist, int nblocks) {
+  __shared__ unsigned int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int c = 0; c < RS_ITEMS; c++) {
+    int i = base + c * RS_NT + threadIdx.x;
+    if (i < n) atomicAdd(&h[(unsigned int)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// in-place exclusive scan of `total` counters by one CTA
+__global__ void __launch_bounds__(1024) rs_scan_kernel(unsigned int* __restrict__ a, int total) {
+  __shared__ int s_scan[34];
+  int per = (total + 1023) / 1024;
+  int b = min((int)threadIdx.x * per, total), e = min(b + per, total);
+  int local = 0;
+  for (int i = b; i < e; i++) local += (int)a[i];
+  int tot;
+  int r = block_excl_scan<1024>(local, &tot, s_scan);
+  for (int i = b; i < e; i++) {
+    int v = (int)a[i];
+    a[i] = (unsigned int)r;
+    r += v;
+  }
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const unsigned long long* __restrict__ kin, const unsigned int* __restrict__ vin,
+                                                            unsigned long long* __restrict__ kout, unsigned int* __restrict__ vout, int n,
+                                                            int shift, const unsigned int* __restrict__ hist, int nblocks) {
+  __shared__ unsigned int s_base[256];
+  __shared__ unsigned int s_wcnt[RS_NT / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  s_base[tid] = hist[tid * nblocks + blockIdx.x];
+  int base = blockIdx.x * RS_TILE;
+  for (int c = 0; c < RS_ITEMS; c++) {
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; k++) s_wcnt[k][tid] = 0;
+    __syncthreads();
+    int i = base + c * RS_NT + tid;
+    bool valid = i < n;
+    unsigned long long key = valid ? kin[i] : 0ull;
+    unsigned int d = (unsigned int)(key >> shift) & 255u;
+    unsigned int m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+    unsigned int rank = __popc(m & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wcnt[w][d] = __popc(m);
+    __syncthreads();
+    if (valid) {
+      unsigned int off = s_base[d] + rank;
+      for (int k = 0; k < w; k++) off += s_wcnt[k][d];
+      kout[off] = key;
+      vout[off] = vin[i];
+    }
+    __syncthreads();
+    unsigned int add = 0;
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; k++) add += s_wcnt[k][tid];
+    s_base[tid] += add;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ big path
+__device__ __forceinline__ int find_seg(const int* __restrict__ seg_off, int nseg, int i) {
+  int lo = 0, hi = nseg;  // largest s with seg_off[s] <= i
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void vb_init_kernel(int* __restrict__ bb, int nseg, int* __restrict__ out_start, int* __restrict__ out_end) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nseg * 6) bb[i] = (i % 6) < 3 ? 0x7fffffff : (int)0x80000000;
+  if (i < nseg) {
+    out_start[i] = 0;
+    out_end[i] = 0;
+  }
+}
+
+__global__ void vb_bbox_kernel(const float4* __restrict__ in, const int* __restrict__ seg_off, int nseg, int M, int* __restrict__ bb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int seg = -1;
+  int o[6];
+  if (i < M) {
+    seg = find_seg(seg_off, nseg, i);
+    float4 p = in[i];
+    o[0] = f2ord(p.x); o[1] = f2ord(p.y); o[2] = f2ord(p.z);
+    o[3] = o[0]; o[4] = o[1]; o[5] = o[2];
+  }
+  unsigned int m = __match_any_sync(0xffffffffu, seg);
+  if (seg < 0) return;
+  // reduce inside the group of lanes that share a segment (usually the whole warp)
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  if (m == 0xffffffffu) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        o[k] = min(o[k], __shfl_xor_sync(0xffffffffu, o[k], off));
+        o[k + 3] = max(o[k + 3], __shfl_xor_sync(0xffffffffu, o[k + 3], off));
+      }
+    }
+    if (lane == leader) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        atomicMin(&bb[seg * 6 + k], o[k]);
+        atomicMax(&bb[seg * 6 + 3 + k], o[k + 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&bb[seg * 6 + k], o[k]);
+      atomicMax(&bb[seg * 6 + 3 + k], o[k + 3]);
+    }
+  }
+}
+
+__global__ void vb_key_kernel(const float4* __restrict__ in, const int* __restrict__ seg_off, const float* __restrict__ seg_leaf, int nseg,
+                              int M, const int* __restrict__ bb, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  int seg = find_seg(seg_off, nseg, i);
+  const int* b = bb + seg * 6;
+  VoxGrid g;
+  bool ok = vox_grid_setup(ord2f(b[0]), ord2f(b[1]), ord2f(b[2]), ord2f(b[3]), ord2f(b[4]), ord2f(b[5]), seg_leaf[seg], g);
+  int cell = ok ? vox_cell(g, in[i]) : (i - seg_off[seg]);
+  keys[i] = ((unsigned long long)(unsigned int)seg << 32) | (unsigned int)cell;
+  vals[i] = (unsigned int)i;
+}
+
+constexpr int VC_NT = 256, VC_ITEMS = 4, VC_TILE = VC_NT * VC_ITEMS;
+
+__global__ void __launch_bounds__(VC_NT) vb_count_kernel(const unsigned long long* __restrict__ keys, int M, unsigned int* __restrict__ block_sums) {
+  __shared__ int s_w[VC_NT / 32];
+  int base = blockIdx.x * VC_TILE + threadIdx.x * VC_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < VC_ITEMS; k++) {
+    int i = base + k;
+    if (i < M) c += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < VC_NT / 32; k++) t += s_w[k];
+    block_sums[blockIdx.x] = (unsigned int)t;
+  }
+}
+
+__global__ void __launch_bounds__(VC_NT) vb_centroid_kernel(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
+                                                             const unsigned int* __restrict__ vals, int M, const unsigned int* __restrict__ block_off,
+                                                             const int* __restrict__ seg_off, float4* __restrict__ out,
+                                                             int* __restrict__ out_start, int* __restrict__ out_end) {
+  __shared__ int s_scan[VC_NT / 32 + 2];
+  int base = blockIdx.x * VC_TILE + threadIdx.x * VC_ITEMS;
+  int local = 0;
+  bool head[VC_ITEMS];
+#pragma unroll
+  for (int k = 0; k < VC_ITEMS; k++) {
+    int i = base + k;
+    head[k] = (i < M) && (i == 0 || keys[i] != keys[i - 1]);
+    local += head[k] ? 1 : 0;
+  }
+  int tot;
+  int r = block_excl_scan<VC_NT>(local, &tot, s_scan) + (int)block_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < VC_ITEMS; k++) {
+    int i = base + k;
+    if (i >= M) break;
+    unsigned long long key = keys[i];
+    int seg = (int)(key >> 32);
+    if (head[k]) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int j = i;
+      while (j < M && keys[j] == key) {
+        float4 p = in[vals[j]];
+        sx = sx + p.x; sy = sy + p.y; sz = sz + p.z; si = si + p.w;
+        j++;
+      }
+      float c = (float)(j - i);
+      out[r] = make_float4(sx / c, sy / c, sz / c, si / c);
+      if (i == seg_off[seg]) out_start[seg] = r;
+      r++;
+    }
+    if (i == seg_off[seg + 1] - 1) out_end[seg] = r;  // r = rank of this element's cell + 1
+  }
+}
+
+__global__ void gather_kernel(const CopyEnt* __restrict__ ents, int nent, float4* __restrict__ dst) {
+  // blockIdx.y = entry, blockIdx.x strides over the entry's points
+  for (int e = blockIdx.y; e < nent; e += gridDim.y) {
+    CopyEnt ce = ents[e];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ce.n; i += gridDim.x * blockDim.x) dst[ce.dst_off + i] = ce.src[i];
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- host side
+int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overflow, cudaStream_t st, long long* launches) {
+  if (nseg <= 0) return LOAM_OK;
+  if (max_seg_hint <= 4096) {
+    vox_small_kernel<4096, 256><<<nseg, 256, 4096 * sizeof(unsigned long long), st>>>(d_segs, d_overflow);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(vox_small_kernel<16384, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(unsigned long long));
+      attr_set = true;
+    }
+    vox_small_kernel<16384, 1024><<<nseg, 1024, 16384 * sizeof(unsigned long long), st>>>(d_segs, d_overflow);
+  }
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_radix_sort(RadixWs& ws, int n, int bits, cudaStream_t st, long long* launches, int* result_in_b) {
+  // keys/vals in ws.keysA/valsA; sorted result ends in A or B (result_in_b)
+  int nblocks = lg_div_up(n, RS_TILE);
+  LG_CHECK(ws.hist.ensure((size_t)256 * nblocks * sizeof(unsigned int), st));
+  unsigned long long* ka = ws.keysA.as<unsigned long long>();
+  unsigned long long* kb = ws.keysB.as<unsigned long long>();
+  unsigned int* va = ws.valsA.as<unsigned int>();
+  unsigned int* vb = ws.valsB.as<unsigned int>();
+  int flip = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    rs_hist_kernel<<<nblocks, RS_NT, 0, st>>>(ka, n, shift, ws.hist.as<unsigned int>(), nblocks);
+    rs_scan_kernel<<<1, 1024, 0, st>>>(ws.hist.as<unsigned int>(), 256 * nblocks);
+    rs_scatter_kernel<<<nblocks, RS_NT, 0, st>>>(ka, va, kb, vb, n, shift, ws.hist.as<unsigned int>(), nblocks);
+    (*launches) += 3;
+    std::swap(ka, kb);
+    std::swap(va, vb);
+    flip ^= 1;
+  }
+  LG_CHECK(cudaGetLastError());
+  *result_in_b = flip;
+  return LOAM_OK;
+}
+
+int lg_radix_ensure(RadixWs& ws, int n, cudaStream_t st) {
+  LG_CHECK(ws.keysA.ensure((size_t)n * 8, st));
+  LG_CHECK(ws.keysB.ensure((size_t)n * 8, st));
+  LG_CHECK(ws.valsA.ensure((size_t)n * 4, st));
+  LG_CHECK(ws.valsB.ensure((size_t)n * 4, st));
+  return LOAM_OK;
+}
+
+int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
+               int* d_out_start, int* d_out_end, cudaStream_t st, long long* launches) {
+  if (nseg <= 0) return LOAM_OK;
+  LG_CHECK(ws.bb.ensure((size_t)nseg * 6 * sizeof(int), st));
+  vb_init_kernel<<<lg_div_up(nseg * 6, 256), 256, 0, st>>>(ws.bb.as<int>(), nseg, d_out_start, d_out_end);
+  (*launches)++;
+  if (M <= 0) return LOAM_OK;
+  int rc = lg_radix_ensure(ws.rs, M, st);
+  if (rc) return rc;
+  int nb = lg_div_up(M, 256);
+  vb_bbox_kernel<<<nb, 256, 0, st>>>(d_in, d_seg_off, nseg, M, ws.bb.as<int>());
+  vb_key_kernel<<<nb, 256, 0, st>>>(d_in, d_seg_off, d_seg_leaf, nseg, M, ws.bb.as<int>(), ws.rs.keysA.as<unsigned long long>(),
+                                    ws.rs.valsA.as<unsigned int>());
+  (*launches) += 2;
+  int segbits = 0;
+  while ((1 << segbits) < nseg) segbits++;
+  int bits = nseg > 1 ? 32 + segbits : 31;
+  int in_b = 0;
+  rc = lg_radix_sort(ws.rs, M, bits, st, launches, &in_b);
+  if (rc) return rc;
+  const unsigned long long* keys = in_b ? ws.rs.keysB.as<unsigned long long>() : ws.rs.keysA.as<unsigned long long>();
+  const unsigned int* vals = in_b ? ws.rs.valsB.as<unsigned int>() : ws.rs.valsA.as<unsigned int>();
+  int ncb = lg_div_up(M, VC_TILE);
+  LG_CHECK(ws.block_sums.ensure((size_t)ncb * sizeof(unsigned int), st));
+  vb_count_kernel<<<ncb, VC_NT, 0, st>>>(keys, M, ws.block_sums.as<unsigned int>());
+  rs_scan_kernel<<<1, 1024, 0, st>>>(ws.block_sums.as<unsigned int>(), ncb);
+  vb_centroid_kernel<<<ncb, VC_NT, 0, st>>>(d_in, keys, vals, M, ws.block_sums.as<unsigned int>(), d_seg_off, d_out, d_out_start, d_out_end);
+  (*launches) += 3;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_gather(const CopyEnt* d_ents, int nent, int max_n, float4* d_dst, cudaStream_t st, long long* launches) {
+  if (nent <= 0 || max_n <= 0) return LOAM_OK;
+  dim3 grid(std::max(1, std::min(lg_div_up(max_n, 256), 64)), std::min(nent, 1024));
+  gather_kernel<<<grid, 256, 0, st>>>(d_ents, nent, d_dst);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}

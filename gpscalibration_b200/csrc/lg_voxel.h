@@ -1,0 +1,41 @@
+// Host-side interface of lg_voxel.cu (voxel-grid down-sampling, radix sort, table-driven gather).
+#pragma once
+#include <algorithm>
+
+#include "lg_common.cuh"
+
+struct VoxSegD {               // one independent voxel-grid problem (device-resident descriptor)
+  const float4* in;            // input points
+  const unsigned char* valid;  // optional per-point mask (1 = take part), may be null
+  float4* out;                 // output, capacity >= n
+  int* out_count;              // receives the number of occupied cells (or -1 on small-path capacity overflow)
+  int n;
+  float leaf;
+};
+
+struct CopyEnt {  // table-driven gather: dst[dst_off + i] = src[i], i < n
+  const float4* src;
+  int n;
+  int dst_off;
+};
+
+struct RadixWs {
+  DevBuf keysA, keysB, valsA, valsB, hist;
+  void release() { keysA.release(); keysB.release(); valsA.release(); valsB.release(); hist.release(); }
+};
+struct VoxBigWs {
+  RadixWs rs;
+  DevBuf bb, block_sums;
+  void release() { rs.release(); bb.release(); block_sums.release(); }
+};
+
+// One CTA per segment, shared-memory bitonic sort; max_seg_hint picks the 4096- or 16384-point instantiation.
+int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overflow, cudaStream_t st, long long* launches);
+// Any size: segments are contiguous in d_in, d_seg_off[nseg + 1]; outputs contiguous in d_out, per-segment
+// [d_out_start[s], d_out_end[s]).
+int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
+               int* d_out_start, int* d_out_end, cudaStream_t st, long long* launches);
+int lg_radix_ensure(RadixWs& ws, int n, cudaStream_t st);
+// Stable LSD radix sort of ws.keysA/valsA over the low `bits` bits; *result_in_b tells which buffer holds the result.
+int lg_radix_sort(RadixWs& ws, int n, int bits, cudaStream_t st, long long* launches, int* result_in_b);
+int lg_gather(const CopyEnt* d_ents, int nent, int max_n, float4* d_dst, cudaStream_t st, long long* launches);

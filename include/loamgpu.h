@@ -1,0 +1,182 @@
+/* loamgpu.h — C ABI of the B200-native LiDAR registration hot path for gpsCalibration.
+ *
+ * The reference has no plugin/FFI API: its seams are the bodies of three ROS nodes
+ *   scanRegistration  src/gpsCalibration/src/lidar_slam/loam/scanRegistration.cpp  (SR)
+ *   laserOdometry     src/gpsCalibration/src/lidar_slam/loam/laserOdometry.cpp     (LO)
+ *   laserMapping      src/gpsCalibration/src/lidar_slam/loam/laserMapping.cpp      (LM)
+ * Each entry point below names the reference block (file:line) whose body it replaces.  A maintainer keeps the
+ * node's subscribers/publishers and swaps the body for the call.
+ *
+ * Conventions: plain C, no C++ types, no exceptions across the boundary.  Every function returns 0 (LOAM_OK) or a
+ * negative error code.  The caller owns every host pointer it passes; the library owns all device memory and pinned
+ * staging inside the handle.  A handle is bound to one CUDA device and one stream and is NOT thread-safe (neither
+ * are the reference's nodes); different handles are independent.  Clouds are arrays of float4 {x, y, z, intensity}
+ * (16 B/point; the reference's pcl::PointXYZI payload, CH:49); the raw sweep is packed float xyz with a byte stride.
+ * Poses are float[6] = {rx, ry, rz, tx, ty, tz} exactly like `transformation[6]` (LO:111) / `transformSum[6]`
+ * (LO:112) / `transformTobeMapped[6]` (LM:108).
+ */
+#ifndef LOAMGPU_H
+#define LOAMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOAM_OK 0
+#define LOAM_EINVAL (-1) /* bad argument */
+#define LOAM_ECUDA (-2)  /* CUDA runtime error (loam_last_cuda_error has the text) */
+#define LOAM_ENOSPC (-3) /* caller buffer or internal capacity too small */
+#define LOAM_ESTATE (-4) /* call order violated (e.g. odometry before any extract) */
+
+typedef struct loam_handle loam_handle;
+
+/* Compile-time constants of the reference that are structural rather than numeric.  All
+ * thresholds (0.1, 0.05, 25, 1.0, 3x, 0.2 ...) stay compile-time constants as in the reference. */
+typedef struct loam_params {
+  int n_scans;         /* SR:65 N_SCANS = 16 (max 64) */
+  int ring_mode;       /* 0: the reference's 16-entry ring table SR:301-320; 1: uniform table (HDL-64-shaped) */
+  float ring_ang_min;  /* ring_mode 1: ring = int((angle - ring_ang_min) / ring_ang_step + 0.5) */
+  float ring_ang_step;
+  int skip_frame_num;  /* LO:52 skipFrameNum = 1: clouds go to mapping every (skip+1)-th sweep */
+  int max_points;      /* capacity hint: points per sweep (CH:15 POINTSNUM fence lifted); grows on demand */
+  int max_map_points;  /* capacity hint: points of the gathered local map; grows on demand */
+  int want_registered; /* 1: mapping also produces /velodyne_cloud_registered (LM:1103-1112) */
+  int want_surround;   /* 1: mapping also produces /laser_cloud_surround every mapFrameNum runs (LM:1081-1101) */
+} loam_params;
+
+/* cloud selectors for loam_get_cloud */
+enum {
+  LOAM_CLOUD_FULL = 0,         /* /velodyne_cloud_2          SR:689-693 */
+  LOAM_CLOUD_SHARP = 1,        /* /laser_cloud_sharp         SR:698-702 */
+  LOAM_CLOUD_LESS_SHARP = 2,   /* /laser_cloud_less_sharp    SR:706-710 */
+  LOAM_CLOUD_FLAT = 3,         /* /laser_cloud_flat          SR:714-718 */
+  LOAM_CLOUD_LESS_FLAT = 4,    /* /laser_cloud_less_flat     SR:722-726 */
+  LOAM_CLOUD_CORNER_LAST = 5,  /* /laser_cloud_corner_last   LO:541-545,1129-1133 (current kd-tree target) */
+  LOAM_CLOUD_SURF_LAST = 6,    /* /laser_cloud_surf_last     LO:547-551,1135-1139 */
+  LOAM_CLOUD_FULL_RES3 = 7,    /* /velodyne_cloud_3          LO:1141-1145 (valid after a publishing sweep) */
+  LOAM_CLOUD_CORNER_STACK = 8, /* laserCloudCornerStack      LM:736-739 */
+  LOAM_CLOUD_SURF_STACK = 9,   /* laserCloudSurfStack        LM:741-744 */
+  LOAM_CLOUD_CORNER_MAP = 10,  /* laserCloudCornerFromMap    LM:717-722 */
+  LOAM_CLOUD_SURF_MAP = 11,    /* laserCloudSurfFromMap      LM:717-722 */
+  LOAM_CLOUD_SURROUND = 12,    /* /laser_cloud_surround      LM:1085-1100 */
+  LOAM_CLOUD_REGISTERED = 13   /* /velodyne_cloud_registered LM:1103-1112 */
+};
+
+/* diagnostic selectors for loam_get_diag (parity tests) */
+enum {
+  LOAM_DIAG_CURVATURE = 0,   /* float[n_full]  cloudCurvature       SR:475 */
+  LOAM_DIAG_PICKED_MASK = 1, /* uint8[n_full]  cloudNeighborPicked after SR:492-549, before selection */
+  LOAM_DIAG_LABEL = 2,       /* int8[n_full]   cloudLabel           SR:586-632 */
+  LOAM_DIAG_SCAN_START = 3,  /* int32[n_scans] scanStartInd         SR:484,489 */
+  LOAM_DIAG_SCAN_END = 4     /* int32[n_scans] scanEndInd           SR:485,490 */
+};
+
+typedef struct loam_counts { /* sizes of the five clouds scanRegistration publishes */
+  int n_full, n_sharp, n_less_sharp, n_flat, n_less_flat;
+} loam_counts;
+
+typedef struct loam_odom_result { /* what one laserOdometry loop body publishes (LO:502-1147) */
+  float transform_sum[6];  /* /laser_odom_to_init pose (LO:1059-1064); zeros on the (re)initialisation sweep */
+  float transformation[6]; /* sweep-relative transform after the Gauss-Newton loop */
+  int odom_published;      /* 0 only on the (re)initialisation sweep (LO:519-563) */
+  int clouds_published;    /* corner/surf last published (LO:541-551 or LO:1126-1139) */
+  int fullres_published;   /* /velodyne_cloud_3 published (LO:1141-1145): mapping has a full message set */
+  int iterations;          /* Gauss-Newton iterations executed (<= 25) */
+  int n_corner_last, n_surf_last;
+} loam_odom_result;
+
+typedef struct loam_map_result { /* what one laserMapping loop body publishes (LM:425-1139) */
+  float transform_aft_mapped[6];  /* /aft_mapped_to_init pose            LM:1114-1124 */
+  float transform_bef_mapped[6];  /* carried in the twist fields         LM:1125-1130 */
+  float transform_tobe_mapped[6]; /* pose used for the registered cloud  LM:1103-1106 */
+  int optimised;                  /* local map large enough (LM:749) */
+  int iterations;                 /* Gauss-Newton iterations executed (<= 10) */
+  int surround_published;         /* mapFrameCount hit mapFrameNum (LM:1082) */
+  int n_corner_stack, n_surf_stack, n_corner_map, n_surf_map;
+  int n_surround, n_registered;
+} loam_map_result;
+
+typedef struct loam_sweep_result { /* loam_process_sweep: SR -> LO -> LM for one sweep */
+  loam_counts counts;
+  loam_odom_result odom;
+  loam_map_result map; /* valid when mapping_ran */
+  int mapping_ran;
+} loam_sweep_result;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------------- */
+const char* loam_strerror(int code);
+const char* loam_last_cuda_error(const loam_handle* h);
+void loam_default_params(loam_params* p);
+int loam_create(const loam_params* p, int device, loam_handle** out);
+int loam_destroy(loam_handle* h);
+/* IMControl{systemInited=false} (IN:281-284 -> LO:411-415): the next sweep re-initialises odometry, and mapping
+ * resets when it then sees the zero odometry pose (LM:316-319, 434-461). */
+int loam_reset(loam_handle* h);
+/* cudaStream_t of the handle, for CUDA-event timing by the caller. */
+void* loam_stream(loam_handle* h);
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+long long loam_launch_count(const loam_handle* h);
+
+/* ---- scanRegistration: replaces the body of laserCloudHandler, SR:238-752 ------------------------------------
+ * xyz: n points in the SENSOR frame (x fwd, y left, z up), `stride_bytes` apart (12 for packed xyz, 16 for PointXYZ).
+ * imu_trans: the 12 floats of /imu_trans (SR:730-745), NULL = zeros (IMU branch dormant in the shipped pipeline).
+ * Results stay device-resident for loam_odometry_process; counts are returned; clouds via loam_get_cloud. */
+int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
+/* Same, the sweep already resident in device memory of this handle's GPU. */
+int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
+
+/* ---- laserOdometry: replaces the loop body LO:502-1147 for the message set of the last loam_extract ---------- */
+int loam_odometry_process(loam_handle* h, loam_odom_result* out);
+
+/* ---- laserMapping: replaces laserOdometryHandler's reset test (LM:316-319) and the loop body LM:425-1139 ------
+ * loam_mapping_odometry must be called for every published odometry message (every sweep), loam_mapping_process
+ * only when odometry published the full message set (fullres_published). */
+int loam_mapping_odometry(loam_handle* h, const float transform_sum[6]);
+int loam_mapping_process(loam_handle* h, loam_map_result* out);
+
+/* ---- whole hot path for one sweep (SR -> LO -> LM with device-resident hand-over) -------------- */
+int loam_process_sweep(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, loam_sweep_result* out);
+int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, loam_sweep_result* out);
+
+/* ---- data access ---------------------------------------------------------------------------------------------- */
+/* Copies cloud `which` (float4 per point) into host_buf (capacity `cap` points); *n = point count.  LOAM_ENOSPC when
+ * cap is too small (*n still set).  host_buf may be NULL to query the size. */
+int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n);
+int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int* n_items);
+
+/* ---- stage-level entry points (what the node-level calls are made of; used by the parity tests) --------------- */
+/* pcl::VoxelGrid<PointXYZI>::filter (SR:677-683, LM:736-744,1061-1079,1092-1094) on host clouds. */
+int loam_voxel_grid(loam_handle* h, const float* in4_host, int m, float leaf, float* out4_host, int cap, int* v);
+/* Explicit odometry inputs instead of loam_extract's (tests): current sharp/flat, last corner/surf clouds. */
+int loam_odom_set_inputs(loam_handle* h, const float* sharp, int n_sharp, const float* flat, int n_flat,
+                         const float* corner_last, int n_corner_last, const float* surf_last, int n_surf_last);
+/* One Gauss-Newton iteration body without the solve, LO:586-974: TransformToStart, correspondence refresh when
+ * iter % 5 == 0, point-to-line / point-to-plane coefficients, Jacobian rows, AtA (6x6, row-major) and AtB.
+ * n_sel < 10 => AtA/AtB zeroed, caller skips the solve (LO:904-907). */
+int loam_odom_iter(loam_handle* h, int iter, const float T[6], float AtA[36], float AtB[6], int* n_sel);
+/* pointSearchCornerInd1/2, pointSearchSurfInd1/2/3 (LO:102-109) as int32, -1 = none. */
+int loam_odom_get_corr(loam_handle* h, int* c1, int* c2, int cap_c, int* s1, int* s2, int* s3, int cap_s);
+/* TransformToEnd (LO:156-227) of a host cloud with transform T and imu_trans (NULL = zeros). */
+int loam_transform_to_end(loam_handle* h, const float* in4_host, int n, const float T[6], const float* imu_trans, float* out4_host);
+/* Explicit mapping inputs (tests): down-sampled stacks (sensor frame) and the gathered local map (map frame). */
+int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, const float* surf_stack, int n_ss,
+                        const float* corner_map, int n_cm, const float* surf_map, int n_sm);
+/* One Gauss-Newton iteration body without the solve, LM:754-967: kNN-5, line / plane fit, rows, AtA, AtB.
+ * n_sel < 50 => AtA/AtB zeroed (LM:929-932). */
+int loam_map_iter(loam_handle* h, int iter, const float T[6], float AtA[36], float AtB[6], int* n_sel);
+/* pointSearchInd (LM:760,867): 5 int32 per stack point, -1 x5 when the 5th neighbour is not within 1 m. */
+int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int cap_s);
+/* The 6x6 solve + degeneracy handling the host keeps (LO:975-1004 / LM:968-997).  state37 = matP (36) + isDegenerate. */
+int loam_gn_solve(const float AtA[36], const float AtB[6], int iter, float eig_threshold, float state37[37], float X[6]);
+/* Mapping iterations with the local map sharded over several GPUs: like loam_map_iter but leaves
+ * the 28 partial sums {21 upper-triangle AtA, 6 AtB, n_sel} as doubles in device memory at `partial_dev` for an
+ * all-reduce by the caller; loam_map_finish_reduced turns the reduced sums into AtA/AtB. */
+int loam_map_iter_partial(loam_handle* h, int iter, const float T[6], double* partial_dev28);
+int loam_map_finish_reduced(const double reduced28_host[28], float AtA[36], float AtB[6], int* n_sel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOAMGPU_H */

@@ -1,0 +1,275 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer / index results bit-exact (kNN tie rule: (d2, index) ascending);
+fp32 normal equations within 1e-5 relative; poses within 1e-4 m / 1e-5 rad.
+"""
+import numpy as np
+import pytest
+
+from conftest import ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_cloud(rng, m, extent=30.0):
+    p = np.empty((m, 4), np.float32)
+    p[:, :3] = rng.uniform(-extent, extent, (m, 3))
+    p[:, 3] = rng.uniform(0, 16, m)
+    return p
+
+
+# ------------------------------------------------------------------------------------------------ voxel grid (a5)
+@pytest.mark.parametrize("m,leaf", [(0, 0.2), (1, 0.2), (37, 0.4), (2000, 0.2), (4096, 0.4), (4097, 0.2), (16384, 0.2),
+                                    (20000, 0.4), (150000, 0.2)])
+def test_voxel_grid_bit_exact(gpu, orc, m, leaf):
+    rng = np.random.default_rng(m + 1)
+    pts = _rand_cloud(rng, m, extent=8.0 if m < 50000 else 25.0)
+    ref = orc.voxel_grid(pts, leaf)
+    got = gpu.voxel_grid(pts, leaf)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))  # centroids, order and count bit-exact
+
+
+def test_voxel_grid_overflow_returns_input(gpu, orc):
+    # > INT_MAX cells: PCL warns and hands the input back unfiltered
+    pts = np.array([[0, 0, 0, 1], [3000, 3000, 3000, 2], [1, 1, 1, 3]], np.float32)
+    ref = orc.voxel_grid(pts, 0.2)
+    got = gpu.voxel_grid(pts, 0.2)
+    assert np.array_equal(ref, pts) and np.array_equal(got, pts)
+
+
+def test_voxel_grid_idempotent(gpu):
+    rng = np.random.default_rng(7)
+    once = gpu.voxel_grid(_rand_cloud(rng, 30000, 20.0), 0.4)
+    twice = gpu.voxel_grid(once, 0.4)
+    assert twice.shape[0] <= once.shape[0]
+    thrice = gpu.voxel_grid(twice, 0.4)
+    assert thrice.shape[0] <= twice.shape[0]
+
+
+# ------------------------------------------------------------------------------------------------ extraction (a1-a4)
+def _check_extract(gpu, orc_sr, xyz):
+    ref = orc_sr.extract(xyz)
+    c = gpu.extract(xyz)
+    assert (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat) == tuple(ref[k].shape[0] for k in orc_sr.CLOUDS)
+    full = gpu.cloud("full")
+    assert np.array_equal(full[:, :3], ref["full"][:, :3])  # ring-major order and coordinates bit-exact
+    # intensity = ring + 0.1 * relTime goes through atan2: fp64-rounded on the GPU vs glibc atan2f on the CPU
+    assert ulp_diff(full[:, 3], ref["full"][:, 3]).max() <= 4
+    assert np.array_equal(gpu.diag("scan_start"), orc_sr.ints("scan_start"))
+    assert np.array_equal(gpu.diag("scan_end"), orc_sr.ints("scan_end"))
+    n = c.n_full
+    assert np.array_equal(gpu.diag("curvature")[5:n - 5], orc_sr.curvature()[5:n - 5])
+    assert np.array_equal(gpu.diag("picked_mask")[5:n - 5].astype(np.int32), orc_sr.ints("picked_mask")[5:n - 5])
+    assert np.array_equal(gpu.diag("label")[5:n - 5].astype(np.int32), orc_sr.ints("label")[5:n - 5])
+    for k in ("sharp", "less_sharp", "flat"):
+        got = gpu.cloud(k)
+        assert np.array_equal(got[:, :3], ref[k][:, :3]), k  # same points, same (ring, sector, pick) order
+        assert ulp_diff(got[:, 3], ref[k][:, 3]).max() <= 4
+    lf = gpu.cloud("less_flat")
+    assert np.array_equal(lf[:, :3], ref["less_flat"][:, :3])
+    assert np.abs(lf[:, 3] - ref["less_flat"][:, 3]).max() <= 1e-5
+    return ref
+
+
+def test_extract_vlp16_parity(gpu, orc, sweeps16):
+    sr = orc.ScanRegistration()
+    for k in (0, 1, 5):
+        _check_extract(gpu, sr, sweeps16[k])
+
+
+def test_extract_with_nan_and_ragged_input(gpu, orc, sweeps16):
+    xyz = sweeps16[2].copy()
+    rng = np.random.default_rng(3)
+    bad = rng.choice(xyz.shape[0], 500, replace=False)
+    xyz[bad[:250], 0] = np.nan
+    xyz[bad[250:], 2] = np.inf
+    xyz[0] = np.nan  # first point invalid: start azimuth comes from the first finite point
+    xyz[-1] = np.nan
+    xyz = xyz[:-777]  # ragged tail
+    _check_extract(gpu, orc.ScanRegistration(), xyz)
+
+
+def test_extract_hdl64_parity(orc):
+    from gpscalibration_b200 import LoamGpu, SweepGenerator
+    g = SweepGenerator(sensor=2, scene=0, seed=0xC0FFEE)
+    step = 26.8 / 63.0
+    gpu = LoamGpu(n_scans=64, ring_mode=1, ring_ang_min=-24.8, ring_ang_step=step)
+    sr = orc.ScanRegistration(64, 1, -24.8, step)
+    ref = _check_extract(gpu, sr, g.sweep(0)[0])
+    assert ref["full"].shape[0] > 100000
+    gpu.close()
+
+
+def test_extract_empty_and_tiny(gpu, orc):
+    c = gpu.extract(np.zeros((0, 3), np.float32))
+    assert c.n_full == 0 and c.n_sharp == 0 and c.n_less_flat == 0
+    xyz = np.array([[5, 0, 0], [5, 1, 0], [5, 2, 0.1]], np.float32)
+    ref = orc.ScanRegistration().extract(xyz)
+    c = gpu.extract(xyz)
+    assert c.n_full == ref["full"].shape[0] and c.n_sharp == 0 and c.n_flat == 0
+
+
+# ------------------------------------------------------------------------------------------------ odometry (a6-a12)
+def _odom_pair(orc, sweeps16, a=0, b=1):
+    sr = orc.ScanRegistration()
+    f0 = sr.extract(sweeps16[a])
+    f1 = sr.extract(sweeps16[b])
+    T0 = np.zeros(6, np.float32)
+    return f1, orc.transform_to_end(f0["less_sharp"], T0), orc.transform_to_end(f0["less_flat"], T0)
+
+
+def test_transform_to_end_parity(gpu, orc, sweeps16):
+    f1, _, _ = _odom_pair(orc, sweeps16)
+    T = np.array([0.003, 0.021, -0.002, 0.05, -0.01, 1.02], np.float32)
+    imu = np.array([0.01, -0.02, 0.005, 0.012, -0.018, 0.004, 0.1, -0.05, 0.02, 0.3, 0.1, -0.2], np.float32)
+    for imu_t in (None, imu):
+        ref = orc.transform_to_end(f1["less_flat"], T, imu_t)
+        got = gpu.transform_to_end(f1["less_flat"], T, imu_t)
+        assert np.array_equal(got[:, 3], ref[:, 3])
+        assert np.abs(got[:, :3] - ref[:, :3]).max() <= 2e-5  # sin/cos of per-point angles: fp64-rounded vs glibc sinf
+
+
+def test_odom_iterations_parity(gpu, orc, sweeps16):
+    """cfg 1: one full Gauss-Newton registration of sweep 1 against sweep 0, iteration by iteration."""
+    f1, last_c, last_s = _odom_pair(orc, sweeps16)
+    gpu.odom_set_inputs(f1["sharp"], f1["flat"], last_c, last_s)
+    oi = orc.OdomIter(f1["sharp"], f1["flat"], last_c, last_s, brute=True)
+    ns, nf = f1["sharp"].shape[0], f1["flat"].shape[0]
+    T = np.zeros(6, np.float32)
+    state = np.zeros(37, np.float32)
+    worst = 0.0
+    for it in range(25):
+        rAtA, rAtB, rn = oi.iterate(it, T)
+        AtA, AtB, n = gpu.odom_iter(it, T)
+        assert n == rn, (it, n, rn)
+        if it % 5 == 0:
+            c1, c2, s1, s2, s3 = gpu.odom_corr(ns, nf)
+            assert np.array_equal(c1, oi.c1) and np.array_equal(c2, oi.c2), it  # bit-exact correspondences
+            assert np.array_equal(s1, oi.s1) and np.array_equal(s2, oi.s2) and np.array_equal(s3, oi.s3), it
+        if rn < 10:
+            continue
+        sa, sb = np.abs(rAtA).max(), np.abs(rAtB).max()
+        worst = max(worst, np.abs(AtA - rAtA).max() / sa, np.abs(AtB - rAtB).max() / sb)
+        assert np.abs(AtA - rAtA).max() <= 1e-5 * sa and np.abs(AtB - rAtB).max() <= 1e-5 * sb, it
+        X = orc.gn_solve(rAtA, rAtB, it, 10.0, state)
+        T = (T + X).astype(np.float32)
+    assert abs(T[5]) > 0.5  # the registration actually moved (1 m/sweep forward)
+    print("odom worst rel err", worst)
+
+
+def test_host_gn_solve_matches_oracle(orc):
+    from gpscalibration_b200 import capi
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        A = rng.normal(size=(200, 6)).astype(np.float32)
+        if trial % 3 == 0:
+            A[:, 4] *= 1e-3  # near-degenerate direction -> projection path
+        AtA = (A.T.astype(np.float64) @ A.astype(np.float64)).astype(np.float32)
+        AtB = rng.normal(size=6).astype(np.float32)
+        s1, s2 = np.zeros(37, np.float32), np.zeros(37, np.float32)
+        for it in (0, 1):
+            X1 = capi.gn_solve(AtA, AtB, it, 10.0, s1)
+            X2 = orc.gn_solve(AtA, AtB, it, 10.0, s2)
+            assert np.array_equal(X1, X2) and np.array_equal(s1, s2)
+
+
+# ------------------------------------------------------------------------------------------------ mapping (a13-a18)
+def _run_pipeline(gpu, orc_pipe, sweeps, check=None):
+    out = []
+    for k, xyz in enumerate(sweeps):
+        r = gpu.process_sweep(xyz)
+        o = orc_pipe.process(xyz)
+        out.append((r, o))
+        if check:
+            check(k, r, o)
+    return out
+
+
+def test_map_iteration_parity(gpu, orc, sweeps16):
+    """Correspondences (5-NN) bit-exact and normal equations within 1e-5 on a map built by the pipeline itself."""
+    pipe = orc.Pipeline()
+    _run_pipeline(gpu, pipe, sweeps16[:10])
+    cs, ss = gpu.cloud("corner_stack"), gpu.cloud("surf_stack")
+    cm, sm = gpu.cloud("corner_map"), gpu.cloud("surf_map")
+    assert cm.shape[0] > 1000 and sm.shape[0] > 5000
+    T = np.array([0.001, 0.17, -0.002, 0.6, 0.05, 8.5], np.float32)
+    rAtA, rAtB, rn, rcc, rcs = orc.map_iteration(cs, ss, cm, sm, T, brute=False)
+    gpu.map_set_inputs(cs, ss, cm, sm)
+    AtA, AtB, n = gpu.map_iter(0, T)
+    cc, cs5 = gpu.map_corr(cs.shape[0], ss.shape[0])
+    assert np.array_equal(cc, rcc) and np.array_equal(cs5, rcs)
+    assert (rcs[:, 0] >= 0).sum() > 1000
+    assert n == rn
+    sa, sb = np.abs(rAtA).max(), np.abs(rAtB).max()
+    assert np.abs(AtA - rAtA).max() <= 1e-5 * sa and np.abs(AtB - rAtB).max() <= 1e-5 * sb
+
+
+def test_pipeline_parity_vlp16(gpu, orc, sweeps16):
+    """cfg 2 shape (short): extract -> odometry -> mapping over consecutive sweeps, poses vs the oracle."""
+    pipe = orc.Pipeline()
+    worst = {"t": 0.0, "r": 0.0}
+
+    def check(k, r, o):
+        assert (r.counts.n_full, r.counts.n_sharp, r.counts.n_less_sharp, r.counts.n_flat, r.counts.n_less_flat) == \
+            (o.n_full, o.n_sharp, o.n_less_sharp, o.n_flat, o.n_less_flat), k
+        assert r.odom.odom_published == o.odom_published and r.mapping_ran == o.mapping_ran, k
+        assert r.odom.iterations == o.odom_iters, (k, r.odom.iterations, o.odom_iters)
+        go, ro = np.array(r.odom.transform_sum), np.array(o.odom)
+        assert np.abs(go[:3] - ro[:3]).max() <= 1e-5 and np.abs(go[3:] - ro[3:]).max() <= 1e-4, (k, go, ro)
+        worst["r"] = max(worst["r"], np.abs(go[:3] - ro[:3]).max())
+        worst["t"] = max(worst["t"], np.abs(go[3:] - ro[3:]).max())
+        if r.mapping_ran:
+            assert (r.map.n_corner_stack, r.map.n_surf_stack, r.map.n_corner_map, r.map.n_surf_map) == \
+                (o.n_corner_stack, o.n_surf_stack, o.n_corner_map, o.n_surf_map), k
+            assert r.map.iterations == o.map_iters, (k, r.map.iterations, o.map_iters)
+            gm, rm = np.array(r.map.transform_aft_mapped), np.array(o.mapped)
+            assert np.abs(gm[:3] - rm[:3]).max() <= 1e-5 and np.abs(gm[3:] - rm[3:]).max() <= 1e-4, (k, gm, rm)
+
+    _run_pipeline(gpu, pipe, sweeps16, check)
+    print("pipeline worst pose diff", worst)
+
+
+def test_pipeline_reset_protocol(gpu, orc, sweeps16):
+    """IMControl{false}: odometry re-initialises, mapping resets on the zero pose."""
+    pipe = orc.Pipeline()
+    for k in range(5):
+        gpu.process_sweep(sweeps16[k])
+        pipe.process(sweeps16[k])
+    gpu.reset()
+    pipe.reset()
+    for k in range(5, 10):
+        r = gpu.process_sweep(sweeps16[k])
+        o = pipe.process(sweeps16[k])
+        assert r.odom.odom_published == o.odom_published and r.mapping_ran == o.mapping_ran
+        assert np.abs(np.array(r.odom.transform_sum) - np.array(o.odom)).max() <= 1e-4
+        if r.mapping_ran:
+            assert (r.map.n_corner_map, r.map.n_surf_map) == (o.n_corner_map, o.n_surf_map)
+
+
+def test_nodewise_equals_fused(orc, sweeps16):
+    from gpscalibration_b200 import LoamPipeline
+    a, b = LoamPipeline(), LoamPipeline()
+    for k in range(6):
+        r = a.process(sweeps16[k])
+        o, m = b.process_nodewise(sweeps16[k])
+        assert np.array_equal(np.array(r.odom.transform_sum), np.array(o.transform_sum))
+        assert (m is not None) == bool(r.mapping_ran)
+        if m is not None:
+            assert np.array_equal(np.array(r.map.transform_aft_mapped), np.array(m.transform_aft_mapped))
+
+
+def test_registered_and_surround_clouds(orc, sweeps16):
+    from gpscalibration_b200 import LoamGpu
+    gpu = LoamGpu(want_registered=True, want_surround=True)
+    pipe = orc.Pipeline(keep_clouds=True)
+    for k in range(4):
+        r = gpu.process_sweep(sweeps16[k])
+        o = pipe.process(sweeps16[k])
+        if r.mapping_ran:
+            reg, rreg = gpu.cloud("registered"), pipe.cloud("registered")
+            assert reg.shape == rreg.shape and np.abs(reg - rreg).max() <= 1e-3
+            if r.map.surround_published:
+                s, rs = gpu.cloud("surround"), pipe.cloud("surround")
+                assert s.shape == rs.shape
+    gpu.close()
