@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_extract", "loam_extract_device", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -89,6 +89,9 @@ def load_library():
     lib.loam_stream.argtypes = [vp]
     lib.loam_launch_count.restype = C.c_longlong
     lib.loam_launch_count.argtypes = [vp]
+    lib.loam_stats.argtypes = [vp, vp]
+    lib.loam_profile.argtypes = [vp, C.c_int]
+    lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_odometry_process.argtypes = [vp, C.POINTER(OdomResult)]
@@ -161,6 +164,23 @@ class LoamGpu:
     @property
     def launches(self):
         return int(self.lib.loam_launch_count(self._h))
+
+    def stats(self):
+        out = (C.c_longlong * 4)()
+        self._check(self.lib.loam_stats(self._h, out), "loam_stats")
+        return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
+
+    PROFILE_CLASSES = ("extract", "odom_knn", "odom_iter", "to_end", "map_stack", "voxel", "gather", "grid", "map_knn",
+                       "map_fit", "insert")
+
+    def profile(self, enable):
+        self._check(self.lib.loam_profile(self._h, int(enable)), "loam_profile")
+
+    def profile_read(self):
+        n = len(self.PROFILE_CLASSES)
+        ms, units, scopes = np.zeros(n), np.zeros(n), np.zeros(n, np.int64)
+        self._check(self.lib.loam_profile_read(self._h, ms.ctypes.data, units.ctypes.data, scopes.ctypes.data, n), "loam_profile_read")
+        return {k: dict(ms=float(ms[i]), units=float(units[i]), scopes=int(scopes[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
     # ---- node level
     def extract(self, xyz, stamp=0.0):

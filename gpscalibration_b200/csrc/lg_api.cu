@@ -21,7 +21,11 @@
 #include "lg_voxel.h"
 
 static thread_local char g_cuda_err[512] = "";
+thread_local LgProf* g_lg_prof = nullptr;
 void lg_set_error(const char* msg, const char* file, int line) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s:%d)", msg, file, line); }
+
+#define LG_SYNC(h) do { (h)->syncs++; LG_CHECK(cudaStreamSynchronize((h)->st)); } while (0)
+#define LG_D2H(h, dst, src, bytes) do { (h)->d2h_bytes += (long long)(bytes); LG_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (h)->st)); } while (0)
 
 namespace {
 
@@ -45,6 +49,8 @@ struct loam_handle {
   int device = 0;
   cudaStream_t st = nullptr;
   long long launches = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0, syncs = 0;
+  LgProf prof;
   // pinned host staging
   double* h_mail = nullptr;  // mapped: 28 doubles written by the reduction kernels
   double* d_mail = nullptr;
@@ -96,6 +102,7 @@ struct loam_handle {
 namespace {
 
 int upload(loam_handle* h, DevBuf& dst, const void* src, size_t bytes) {
+  h->h2d_bytes += (long long)bytes;
   LG_CHECK(dst.ensure(bytes + 16, h->st));
   if (bytes) LG_CHECK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->st));
   return LOAM_OK;
@@ -139,7 +146,7 @@ int arena_reserve(loam_handle* h, size_t need) {
     rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, fresh.as<float4>(), h->st, &h->launches);
     if (rc) return rc;
   }
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
   h->arena.release();
   h->arena = fresh;
   h->bump = off;
@@ -215,10 +222,13 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
     for (int i = 0; i < nseg; i++) segs[i].out_count = d_counts + 1 + i;
     int rc = upload(h, h->d_segs, segs.data(), nseg * sizeof(VoxSegD));
     if (rc) return rc;
+    double units = 0;
+    for (auto& sg : segs) units += sg.n;
+    LgProfScope prof_scope(LGK_VOXEL, h->st, units);
     rc = lg_vox_small(h->d_segs.as<VoxSegD>(), nseg, max_n, d_counts, h->st, &h->launches);
     if (rc) return rc;
-    LG_CHECK(cudaMemcpyAsync(h->h_ints, d_counts + 1, nseg * 4, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaStreamSynchronize(h->st));
+    LG_D2H(h, h->h_ints, d_counts + 1, nseg * 4);
+    LG_SYNC(h);
     for (int i = 0; i < nseg; i++) counts[i] = h->h_ints[i];
     return LOAM_OK;
   }
@@ -250,8 +260,8 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
                   d_end, h->st, &h->launches);
   if (rc) return rc;
   if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
-  LG_CHECK(cudaMemcpyAsync(h->h_ints, d_start, nseg * 8, cudaMemcpyDeviceToHost, h->st));
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_D2H(h, h->h_ints, d_start, nseg * 8);
+  LG_SYNC(h);
   for (int i = 0; i < nseg; i++) {
     int s = h->h_ints[i], e = h->h_ints[nseg + i];
     counts[i] = e - s;
@@ -262,8 +272,8 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
 }
 
 int read_sr_counts(loam_handle* h, loam_counts* out) {
-  LG_CHECK(cudaMemcpyAsync(h->h_ints, h->sr.meta.p, 8 * 4, cudaMemcpyDeviceToHost, h->st));
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_D2H(h, h->h_ints, h->sr.meta.p, 8 * 4);
+  LG_SYNC(h);
   if (h->h_ints[SRM_ERR]) return LOAM_ENOSPC;
   if (h->h_ints[SRM_VOX_OVERFLOW]) return LOAM_ENOSPC;
   h->counts.n_full = h->h_ints[SRM_N_FULL];
@@ -300,7 +310,8 @@ int odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, 
                                h->corner_last.as<float4>(), h->n_corner_last, h->surf_last.as<float4>(), h->n_surf_last, h->d_mail, h->st,
                                &h->launches);
   if (rc) return rc;
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
+  h->d2h_bytes += 28 * 8;
   lg_unpack28(h->h_mail, AtA, AtB, n_sel);
   return LOAM_OK;
 }
@@ -313,7 +324,8 @@ int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, floa
                               h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail, h->st, &h->launches);
   if (rc) return rc;
   if (out28_dev) return LOAM_OK;
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
+  h->d2h_bytes += 28 * 8;
   lg_unpack28(h->h_mail, AtA, AtB, n_sel);
   return LOAM_OK;
 }
@@ -397,6 +409,8 @@ int loam_destroy(loam_handle* h) {
   if (!h) return LOAM_EINVAL;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
+  h->prof.resolve(h->st);
+  h->prof.release();
   h->sr.release(); h->od.release(); h->grid_c.release(); h->grid_s.release(); h->mi.release(); h->vb.release();
   DevBuf* all[] = {&h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
@@ -416,12 +430,40 @@ int loam_reset(loam_handle* h) {
   return LOAM_OK;
 }
 void* loam_stream(loam_handle* h) { return h ? (void*)h->st : nullptr; }
+int loam_stats(const loam_handle* h, long long out4[4]) {
+  if (!h || !out4) return LOAM_EINVAL;
+  out4[0] = h->launches;
+  out4[1] = h->h2d_bytes;
+  out4[2] = h->d2h_bytes;
+  out4[3] = h->syncs;
+  return LOAM_OK;
+}
+int loam_profile(loam_handle* h, int enable) {
+  if (!h) return LOAM_EINVAL;
+  cudaSetDevice(h->device);
+  h->prof.resolve(h->st);
+  h->prof.on = enable != 0;
+  for (int i = 0; i < LGK_COUNT; i++) h->prof.ms[i] = h->prof.units[i] = 0.0, h->prof.scopes[i] = 0;
+  return LOAM_OK;
+}
+int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n) {
+  if (!h || n < LGK_COUNT) return LOAM_EINVAL;
+  cudaSetDevice(h->device);
+  h->prof.resolve(h->st);
+  for (int i = 0; i < LGK_COUNT; i++) {
+    if (ms) ms[i] = h->prof.ms[i];
+    if (units) units[i] = h->prof.units[i];
+    if (scopes) scopes[i] = h->prof.scopes[i];
+  }
+  return LOAM_OK;
+}
 long long loam_launch_count(const loam_handle* h) { return h ? h->launches : 0; }
 
 // ============================================================================================ scanRegistration
 int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
   if (!h || (!xyz_host && n > 0)) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = upload(h, h->xyz_in, xyz_host, (size_t)n * stride_bytes);
   if (rc) return rc;
   return extract_common(h, h->xyz_in.as<float>(), n, stride_bytes, imu_trans, out);
@@ -429,6 +471,7 @@ int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes,
 int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
   if (!h || (!xyz_dev && n > 0)) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   return extract_common(h, xyz_dev, n, stride_bytes, imu_trans, out);
 }
 
@@ -437,6 +480,7 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
   if (!h || !out) return LOAM_EINVAL;
   if (!h->have_features) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
   const loam_counts& c = h->counts;
   const float* imu = h->imu;
@@ -541,6 +585,7 @@ int loam_mapping_odometry(loam_handle* h, const float* Tsum) {
 int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (!h || !out) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
   if (!h->lm_inited) {
     h->lm_inited = true;
@@ -675,8 +720,8 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
                             in_b ? h->vb.rs.valsB.as<unsigned int>() : h->vb.rs.valsA.as<unsigned int>(), h->ins_sel.as<float4>(), nins,
                             h->ins_sorted.as<float4>(), d_nruns, d_runs, cap_runs, h->st, &h->launches);
     if (rc) return rc;
-    LG_CHECK(cudaMemcpyAsync(h->h_ints, d_nruns, 8 + (size_t)cap_runs * 8, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaStreamSynchronize(h->st));
+    LG_D2H(h, h->h_ints, d_nruns, 8 + (size_t)cap_runs * 8);
+    LG_SYNC(h);
     int nruns = h->h_ints[0];
     if (nruns > cap_runs) return LOAM_ENOSPC;
     std::vector<std::pair<int, int>> runs(nruns);  // (start, key)
@@ -770,8 +815,8 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
                       &h->launches);
       if (rc) return rc;
       if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
-      LG_CHECK(cudaMemcpyAsync(h->h_ints, d_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, h->st));
-      LG_CHECK(cudaStreamSynchronize(h->st));
+      LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8);
+      LG_SYNC(h);
       int total = 0, s = 0;
       for (int ind : validInd)
         for (int type = 0; type < 2; type++) {
@@ -856,6 +901,7 @@ int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int s
 int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n) {
   if (!h || !n) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   const void* src = nullptr;
   int cnt = 0;
   switch (which) {
@@ -879,8 +925,8 @@ int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n) 
   if (!host_buf) return LOAM_OK;
   if (cap < cnt) return LOAM_ENOSPC;
   if (cnt > 0) {
-    LG_CHECK(cudaMemcpyAsync(host_buf, src, (size_t)cnt * 16, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaStreamSynchronize(h->st));
+    LG_D2H(h, host_buf, src, (size_t)cnt * 16);
+    LG_SYNC(h);
   }
   return LOAM_OK;
 }
@@ -889,6 +935,7 @@ int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int*
   if (!h || !n_items) return LOAM_EINVAL;
   if (!h->sr.meta.p) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   const void* src = nullptr;
   int cnt = 0, esz = 1;
   switch (which) {
@@ -903,8 +950,8 @@ int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int*
   if (!host_buf) return LOAM_OK;
   if (cap_bytes < cnt * esz) return LOAM_ENOSPC;
   if (cnt > 0) {
-    LG_CHECK(cudaMemcpyAsync(host_buf, src, (size_t)cnt * esz, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaStreamSynchronize(h->st));
+    LG_D2H(h, host_buf, src, (size_t)cnt * esz);
+    LG_SYNC(h);
   }
   return LOAM_OK;
 }
@@ -913,6 +960,7 @@ int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int*
 int loam_voxel_grid(loam_handle* h, const float* in4_host, int m, float leaf, float* out4_host, int cap, int* v) {
   if (!h || !v || m < 0 || !(leaf > 0.f)) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   *v = 0;
   if (m == 0) return LOAM_OK;
   int rc = upload(h, h->vg_in, in4_host, (size_t)m * 16);
@@ -943,12 +991,13 @@ int loam_odom_set_inputs(loam_handle* h, const float* sharp, int n_sharp, const 
                          int n_corner_last, const float* surf_last, int n_surf_last) {
   if (!h || n_sharp < 0 || n_flat < 0 || n_corner_last < 0 || n_surf_last < 0) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = upload(h, h->t_sharp, sharp, (size_t)n_sharp * 16);
   if (!rc) rc = upload(h, h->t_flat, flat, (size_t)n_flat * 16);
   if (!rc) rc = upload(h, h->corner_last, corner_last, (size_t)n_corner_last * 16);
   if (!rc) rc = upload(h, h->surf_last, surf_last, (size_t)n_surf_last * 16);
   if (rc) return rc;
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
   h->cur_sharp = h->t_sharp.as<float4>();
   h->cur_flat = h->t_flat.as<float4>();
   h->counts.n_sharp = n_sharp;
@@ -962,6 +1011,7 @@ int loam_odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* 
   if (!h || !T || !AtA || !AtB || !n_sel || iter < 0) return LOAM_EINVAL;
   if (!h->cur_sharp && h->counts.n_sharp > 0) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = odom_iter(h, iter, T, AtA, AtB, n_sel);
   if (rc) return rc;
   if (*n_sel < 10) {
@@ -975,23 +1025,25 @@ int loam_odom_get_corr(loam_handle* h, int* c1, int* c2, int cap_c, int* s1, int
   if (!h) return LOAM_EINVAL;
   if (cap_c < h->counts.n_sharp || cap_s < h->counts.n_flat) return LOAM_ENOSPC;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   size_t bc = (size_t)h->counts.n_sharp * 4, bs = (size_t)h->counts.n_flat * 4;
   if (bc) {
-    LG_CHECK(cudaMemcpyAsync(c1, h->od.c1.p, bc, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaMemcpyAsync(c2, h->od.c2.p, bc, cudaMemcpyDeviceToHost, h->st));
+    LG_D2H(h, c1, h->od.c1.p, bc);
+    LG_D2H(h, c2, h->od.c2.p, bc);
   }
   if (bs) {
-    LG_CHECK(cudaMemcpyAsync(s1, h->od.s1.p, bs, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaMemcpyAsync(s2, h->od.s2.p, bs, cudaMemcpyDeviceToHost, h->st));
-    LG_CHECK(cudaMemcpyAsync(s3, h->od.s3.p, bs, cudaMemcpyDeviceToHost, h->st));
+    LG_D2H(h, s1, h->od.s1.p, bs);
+    LG_D2H(h, s2, h->od.s2.p, bs);
+    LG_D2H(h, s3, h->od.s3.p, bs);
   }
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
   return LOAM_OK;
 }
 
 int loam_transform_to_end(loam_handle* h, const float* in4_host, int n, const float* T, const float* imu_trans, float* out4_host) {
   if (!h || n < 0 || !T) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   if (n == 0) return LOAM_OK;
   float imu[12] = {0};
   if (imu_trans) memcpy(imu, imu_trans, sizeof(imu));
@@ -1003,8 +1055,8 @@ int loam_transform_to_end(loam_handle* h, const float* in4_host, int n, const fl
   rc = lg_odom_to_end_launch(ot, host_sincos3(T), imu_sc(imu), h->vg_in.as<float4>(), h->vg_out.as<float4>(), n, nullptr, nullptr, 0, nullptr,
                              nullptr, 0, h->st, &h->launches);
   if (rc) return rc;
-  LG_CHECK(cudaMemcpyAsync(out4_host, h->vg_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->st));
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_D2H(h, out4_host, h->vg_out.p, (size_t)n * 16);
+  LG_SYNC(h);
   return LOAM_OK;
 }
 
@@ -1012,6 +1064,7 @@ int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, con
                         const float* surf_map, int n_sm) {
   if (!h || n_cs < 0 || n_ss < 0 || n_cm < 0 || n_sm < 0) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = upload(h, h->stack_c, corner_stack, (size_t)n_cs * 16);
   if (!rc) rc = upload(h, h->stack_s, surf_stack, (size_t)n_ss * 16);
   if (!rc) rc = upload(h, h->map_c, corner_map, (size_t)n_cm * 16);
@@ -1021,7 +1074,7 @@ int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, con
   rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), n_cm, h->st, &h->launches);
   if (!rc) rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), n_sm, h->st, &h->launches);
   if (rc) return rc;
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
   h->grids_valid = true;
   return LOAM_OK;
 }
@@ -1030,6 +1083,7 @@ int loam_map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* A
   if (!h || !T || !AtA || !AtB || !n_sel || iter < 0) return LOAM_EINVAL;
   if (!h->grids_valid) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = map_iter(h, T, nullptr, AtA, AtB, n_sel);
   if (rc) return rc;
   if (*n_sel < 50) {
@@ -1044,10 +1098,11 @@ int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int c
   if (cap_c < h->n_stack_c || cap_s < h->n_stack_s) return LOAM_ENOSPC;
   if (!h->mi.nbr.p) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
-  if (h->n_stack_c) LG_CHECK(cudaMemcpyAsync(corner5, h->mi.nbr.p, (size_t)h->n_stack_c * 20, cudaMemcpyDeviceToHost, h->st));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+  if (h->n_stack_c) LG_D2H(h, corner5, h->mi.nbr.p, (size_t)h->n_stack_c * 20);
   if (h->n_stack_s)
-    LG_CHECK(cudaMemcpyAsync(surf5, h->mi.nbr.as<int>() + (size_t)h->n_stack_c * 5, (size_t)h->n_stack_s * 20, cudaMemcpyDeviceToHost, h->st));
-  LG_CHECK(cudaStreamSynchronize(h->st));
+    LG_D2H(h, surf5, h->mi.nbr.as<int>() + (size_t)h->n_stack_c * 5, (size_t)h->n_stack_s * 20);
+  LG_SYNC(h);
   return LOAM_OK;
 }
 
@@ -1066,9 +1121,10 @@ int loam_map_iter_partial(loam_handle* h, int iter, const float* T, double* part
   if (!h || !T || !partial_dev28 || iter < 0) return LOAM_EINVAL;
   if (!h->grids_valid) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = map_iter(h, T, partial_dev28, nullptr, nullptr, nullptr);
   if (rc) return rc;
-  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_SYNC(h);
   return LOAM_OK;
 }
 

@@ -6,8 +6,10 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <vector>
 
 #include "../../include/loamgpu.h"
+#include "lg_libm.cuh"
 
 #define LG_CHECK(expr)                                                         \
   do {                                                                         \
@@ -51,6 +53,67 @@ struct DevBuf {
   T* as() const { return (T*)p; }
 };
 
+
+// ---- optional per-kernel-class CUDA-event timing (bench.py's roofline object); off by default, zero cost when off
+enum LgKernelClass {
+  LGK_EXTRACT = 0,   // K1-K4: every scanRegistration kernel incl. the per-ring voxel grid
+  LGK_ODOM_KNN = 1,  // K8: odom_knn_kernel
+  LGK_ODOM_ITER = 2, // K8/K9: odom_iter_kernel
+  LGK_TO_END = 3,    // K6: odom_to_end_kernel
+  LGK_MAP_STACK = 4, // K6: map_stack_kernel / map_register_kernel
+  LGK_VOXEL = 5,     // K5: voxel grids of stacks, cubes, surround (incl. their sorts)
+  LGK_GATHER = 6,    // K11: table-driven gathers
+  LGK_GRID = 7,      // K7: voxel-hash build
+  LGK_MAP_KNN = 8,   // K10: map_knn_kernel
+  LGK_MAP_FIT = 9,   // K10: map_fit_kernel
+  LGK_INSERT = 10,   // K11: map_insert_kernel + cube sort + runs
+  LGK_COUNT = 11
+};
+struct LgProf {
+  bool on = false;
+  struct Pair { int cls; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> pool;
+  std::vector<Pair> pending;
+  double ms[LGK_COUNT] = {0};
+  double units[LGK_COUNT] = {0};
+  long long scopes[LGK_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void resolve(cudaStream_t st) {
+    if (pending.empty()) return;
+    cudaStreamSynchronize(st);
+    for (auto& p : pending) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, p.a, p.b);
+      ms[p.cls] += t;
+      pool.push_back(p.a);
+      pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+  void release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+extern thread_local LgProf* g_lg_prof;
+struct LgProfScope {
+  LgProf* p; int cls; cudaStream_t st; cudaEvent_t a;
+  LgProfScope(int c, cudaStream_t s, double units) : p(g_lg_prof), cls(c), st(s), a(nullptr) {
+    if (!p) return;
+    a = p->get();
+    cudaEventRecord(a, st);
+    p->units[cls] += units;
+    p->scopes[cls]++;
+  }
+  ~LgProfScope() {
+    if (!p) return;
+    cudaEvent_t b = p->get();
+    cudaEventRecord(b, st);
+    p->pending.push_back({cls, a, b});
+    if (p->pending.size() > 8192) p->resolve(st);
+  }
+};
+
 static inline int lg_div_up(int a, int b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
@@ -68,13 +131,10 @@ __device__ __forceinline__ unsigned long long lg_pack_nbr(float d2, int idx) {
 __device__ __forceinline__ float lg_nbr_d2(unsigned long long k) { return __uint_as_float((unsigned int)(k >> 32)); }
 __device__ __forceinline__ int lg_nbr_idx(unsigned long long k) { return (int)(unsigned int)(k & 0xffffffffull); }
 
-// sin/cos of an fp32 angle evaluated in fp64 and rounded once: the closest a GPU gets to glibc's (almost always
-// correctly rounded) sinf/cosf that the reference's `sin(float)`/`cos(float)` calls resolve to.
+// sin/cos of an fp32 angle exactly as the host libm (glibc sinf / cosf) returns them — see lg_libm.cuh.
 __device__ __forceinline__ void lg_sincosf_cr(float a, float* s, float* c) {
-  double sd, cd;
-  sincos((double)a, &sd, &cd);
-  *s = (float)sd;
-  *c = (float)cd;
+  *s = lgm_sinf(a);
+  *c = lgm_cosf(a);
 }
 
 struct SinCos3 {  // sin/cos of rx, ry, rz evaluated on the HOST with libm (bit-identical to the oracle's calls)

@@ -60,9 +60,9 @@ __device__ __forceinline__ int ring_of(const SrParams& prm, float angle) {
   return r;
 }
 
-// atan / atan2 of fp32 arguments evaluated in fp64 and rounded once (see lg_sincosf_cr).
-__device__ __forceinline__ float atanf_cr(float a) { return (float)atan((double)a); }
-__device__ __forceinline__ float atan2f_cr(float y, float x) { return (float)atan2((double)y, (double)x); }
+// atan / atan2 exactly as the host libm (glibc atanf / atan2f) returns them — see lg_libm.cuh.
+__device__ __forceinline__ float atanf_cr(float a) { return lgm_atanf(a); }
+__device__ __forceinline__ float atan2f_cr(float y, float x) { return lgm_atan2f(y, x); }
 
 // SR:265-278: start / end azimuth from the first / last finite point.  Evaluated by one thread per CTA.
 __device__ void sweep_ori(const float* xyz, int n, int stride_bytes, float* startOri, float* endOri, int* ok) {
@@ -510,6 +510,7 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
     LG_CHECK(cudaMemsetAsync(meta + SRM_N_FULL, 0, 5 * 4, st));
     return LOAM_OK;
   }
+  LgProfScope prof_scope(LGK_EXTRACT, st, (double)n);
   sr_ring_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
                                             ws.hist.as<unsigned int>(), nblocks, meta);
   sr_scan_kernel<<<1, 1024, 0, st>>>(prm, ws.hist.as<unsigned int>(), nblocks, meta);

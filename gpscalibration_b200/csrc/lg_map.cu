@@ -343,6 +343,7 @@ __global__ void map_runs_kernel(const unsigned long long* __restrict__ keys, con
 int lg_map_stack_launch(const MapT& T, const float4* in0, float4* out0, int n0, const float4* in1, float4* out1, int n1, cudaStream_t st,
                         long long* launches) {
   if (n0 + n1 <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_MAP_STACK, st, (double)(n0 + n1));
   map_stack_kernel<<<lg_div_up(n0 + n1, 256), 256, 0, st>>>(T, in0, out0, n0, in1, out1, n1);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
@@ -351,6 +352,7 @@ int lg_map_stack_launch(const MapT& T, const float4* in0, float4* out0, int n0, 
 
 int lg_map_register_launch(const MapT& T, const float4* in, float4* out, int n, cudaStream_t st, long long* launches) {
   if (n <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_MAP_STACK, st, (double)n);
   map_register_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(T, in, out, n);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
@@ -375,6 +377,7 @@ int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long lo
   g.sorted = ws.sorted.as<float4>();
   g.bits = bits;
   g.n = n;
+  LgProfScope prof_scope(LGK_GRID, st, (double)n);
   LG_CHECK(cudaMemsetAsync(g.keys, 0xff, slots * 8, st));
   LG_CHECK(cudaMemsetAsync(g.count, 0, (slots * 3 + 4) * 4, st));
   if (n > 0) {
@@ -398,9 +401,11 @@ int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack,
     LG_CHECK(cudaMemsetAsync(ws.ticket.p, 0, 4, st));
   }
   if (nq > 0) {
+    LgProfScope prof_scope(LGK_MAP_KNN, st, (double)nq);
     map_knn_kernel<<<lg_div_up(nq, KNN_WARPS), KNN_WARPS * 32, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, gc, gs, ws.nbr.as<int>());
     (*launches)++;
   }
+  LgProfScope prof_scope(LGK_MAP_FIT, st, (double)nq);
   map_fit_kernel<<<nb, FIT_NT, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, corner_map, surf_map, ws.nbr.as<int>(), ws.partials.as<double>(),
                                         ws.ticket.as<unsigned int>(), out28);
   (*launches)++;
@@ -412,6 +417,7 @@ int lg_map_insert_launch(const MapT& T, const CubeGeom& cg, const float4* corner
                          float4* sel_out, unsigned long long* keys, unsigned int* vals, cudaStream_t st, long long* launches) {
   const int n = n_cs + n_ss;
   if (n <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_INSERT, st, (double)n);
   map_insert_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(T, cg, corner_stack, n_cs, surf_stack, n_ss, sel_out, keys, vals);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
@@ -422,6 +428,7 @@ int lg_map_runs_launch(const unsigned long long* keys, const unsigned int* vals,
                        int2* runs, int cap_runs, cudaStream_t st, long long* launches) {
   LG_CHECK(cudaMemsetAsync(n_runs, 0, 4, st));
   if (n <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_INSERT, st, 0.0);
   map_runs_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(keys, vals, sel, n, sorted_sel, n_runs, runs, cap_runs);
   (*launches)++;
   LG_CHECK(cudaGetLastError());

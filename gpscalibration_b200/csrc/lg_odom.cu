@@ -299,11 +299,13 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
     const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
     if (tiles_c + tiles_s > 0) {
       dim3 grid(tiles_c + tiles_s, chunks);
+      LgProfScope prof_scope(LGK_ODOM_KNN, st, (double)nq);
       odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
                                               ws.best.as<unsigned long long>());
       (*launches)++;
     }
   }
+  LgProfScope prof_scope(LGK_ODOM_ITER, st, (double)nq);
   odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
                                          ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(),
                                          ws.s3.as<int>(), ws.partials.as<double>(), ws.ticket.as<unsigned int>(), out28);
@@ -316,6 +318,7 @@ int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, c
                           float4* out1, int n1, const float4* in2, float4* out2, int n2, cudaStream_t st, long long* launches) {
   const int n = n0 + n1 + n2;
   if (n <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_TO_END, st, (double)n);
   odom_to_end_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(T, sT, imu, in0, out0, n0, in1, out1, n1, in2, out2, n2);
   (*launches)++;
   LG_CHECK(cudaGetLastError());

@@ -422,6 +422,7 @@ int lg_radix_ensure(RadixWs& ws, int n, cudaStream_t st) {
 int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
                int* d_out_start, int* d_out_end, cudaStream_t st, long long* launches) {
   if (nseg <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_VOXEL, st, (double)M);
   LG_CHECK(ws.bb.ensure((size_t)nseg * 6 * sizeof(int), st));
   vb_init_kernel<<<lg_div_up(nseg * 6, 256), 256, 0, st>>>(ws.bb.as<int>(), nseg, d_out_start, d_out_end);
   (*launches)++;
@@ -453,6 +454,7 @@ int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const flo
 
 int lg_gather(const CopyEnt* d_ents, int nent, int max_n, float4* d_dst, cudaStream_t st, long long* launches) {
   if (nent <= 0 || max_n <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_GATHER, st, 0.0);
   dim3 grid(std::max(1, std::min(lg_div_up(max_n, 256), 64)), std::min(nent, 1024));
   gather_kernel<<<grid, 256, 0, st>>>(d_ents, nent, d_dst);
   (*launches)++;

@@ -118,6 +118,14 @@ int loam_reset(loam_handle* h);
 void* loam_stream(loam_handle* h);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 long long loam_launch_count(const loam_handle* h);
+/* out4 = {kernel launches, host->device bytes, device->host bytes, stream synchronisations} since loam_create. */
+int loam_stats(const loam_handle* h, long long out4[4]);
+/* Optional per-kernel-class CUDA-event timing on the handle's stream (off by default; adds two event records per
+ * launch group while on).  Classes: 0 extract, 1 odom_knn, 2 odom_iter, 3 to_end, 4 map_stack/register, 5 voxel,
+ * 6 gather, 7 grid build, 8 map_knn, 9 map_fit, 10 insert.  loam_profile(h, 1) clears the counters. */
+#define LOAM_PROFILE_CLASSES 11
+int loam_profile(loam_handle* h, int enable);
+int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n);
 
 /* ---- scanRegistration: replaces the body of laserCloudHandler, SR:238-752 ------------------------------------
  * xyz: n points in the SENSOR frame (x fwd, y left, z up), `stride_bytes` apart (12 for packed xyz, 16 for PointXYZ).

@@ -11,6 +11,19 @@ from conftest import ulp_diff
 pytestmark = pytest.mark.gpu
 
 
+def _host_libm_matches_port():
+    import tempfile
+    from test_libm_port import run_check
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            return run_check(d, 2) == [0, 0, 0, 0]
+    except Exception:
+        return False
+
+
+HOST_LIBM_MATCHES_PORT = _host_libm_matches_port()
+
+
 def _rand_cloud(rng, m, extent=30.0):
     p = np.empty((m, 4), np.float32)
     p[:, :3] = rng.uniform(-extent, extent, (m, 3))
@@ -54,8 +67,10 @@ def _check_extract(gpu, orc_sr, xyz):
     assert (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat) == tuple(ref[k].shape[0] for k in orc_sr.CLOUDS)
     full = gpu.cloud("full")
     assert np.array_equal(full[:, :3], ref["full"][:, :3])  # ring-major order and coordinates bit-exact
-    # intensity = ring + 0.1 * relTime goes through atan2: fp64-rounded on the GPU vs glibc atan2f on the CPU
-    assert ulp_diff(full[:, 3], ref["full"][:, 3]).max() <= 4
+    # intensity = ring + 0.1 * relTime goes through atan2f: the device port of glibc's atan2f is bit-identical
+    # (tests/test_libm_port.py) unless this host's libm is a different build -> then allow an ulp
+    exact = HOST_LIBM_MATCHES_PORT
+    assert ulp_diff(full[:, 3], ref["full"][:, 3]).max() <= (0 if exact else 4)
     assert np.array_equal(gpu.diag("scan_start"), orc_sr.ints("scan_start"))
     assert np.array_equal(gpu.diag("scan_end"), orc_sr.ints("scan_end"))
     n = c.n_full
@@ -65,10 +80,10 @@ def _check_extract(gpu, orc_sr, xyz):
     for k in ("sharp", "less_sharp", "flat"):
         got = gpu.cloud(k)
         assert np.array_equal(got[:, :3], ref[k][:, :3]), k  # same points, same (ring, sector, pick) order
-        assert ulp_diff(got[:, 3], ref[k][:, 3]).max() <= 4
+        assert ulp_diff(got[:, 3], ref[k][:, 3]).max() <= (0 if exact else 4)
     lf = gpu.cloud("less_flat")
     assert np.array_equal(lf[:, :3], ref["less_flat"][:, :3])
-    assert np.abs(lf[:, 3] - ref["less_flat"][:, 3]).max() <= 1e-5
+    assert np.abs(lf[:, 3] - ref["less_flat"][:, 3]).max() <= (0 if exact else 1e-5)
     return ref
 
 
@@ -127,7 +142,8 @@ def test_transform_to_end_parity(gpu, orc, sweeps16):
         ref = orc.transform_to_end(f1["less_flat"], T, imu_t)
         got = gpu.transform_to_end(f1["less_flat"], T, imu_t)
         assert np.array_equal(got[:, 3], ref[:, 3])
-        assert np.abs(got[:, :3] - ref[:, :3]).max() <= 2e-5  # sin/cos of per-point angles: fp64-rounded vs glibc sinf
+        # sin/cos of the per-point angles: device port of glibc sinf/cosf, bit-identical on a matching host libm
+        assert np.abs(got[:, :3] - ref[:, :3]).max() <= (0 if HOST_LIBM_MATCHES_PORT else 2e-5)
 
 
 def test_odom_iterations_parity(gpu, orc, sweeps16):
@@ -214,17 +230,20 @@ def test_pipeline_parity_vlp16(gpu, orc, sweeps16):
         assert (r.counts.n_full, r.counts.n_sharp, r.counts.n_less_sharp, r.counts.n_flat, r.counts.n_less_flat) == \
             (o.n_full, o.n_sharp, o.n_less_sharp, o.n_flat, o.n_less_flat), k
         assert r.odom.odom_published == o.odom_published and r.mapping_ran == o.mapping_ran, k
-        assert r.odom.iterations == o.odom_iters, (k, r.odom.iterations, o.odom_iters)
         go, ro = np.array(r.odom.transform_sum), np.array(o.odom)
         assert np.abs(go[:3] - ro[:3]).max() <= 1e-5 and np.abs(go[3:] - ro[3:]).max() <= 1e-4, (k, go, ro)
+        if HOST_LIBM_MATCHES_PORT:
+            assert r.odom.iterations == o.odom_iters, (k, r.odom.iterations, o.odom_iters)
         worst["r"] = max(worst["r"], np.abs(go[:3] - ro[:3]).max())
         worst["t"] = max(worst["t"], np.abs(go[3:] - ro[3:]).max())
         if r.mapping_ran:
             assert (r.map.n_corner_stack, r.map.n_surf_stack, r.map.n_corner_map, r.map.n_surf_map) == \
                 (o.n_corner_stack, o.n_surf_stack, o.n_corner_map, o.n_surf_map), k
-            assert r.map.iterations == o.map_iters, (k, r.map.iterations, o.map_iters)
             gm, rm = np.array(r.map.transform_aft_mapped), np.array(o.mapped)
             assert np.abs(gm[:3] - rm[:3]).max() <= 1e-5 and np.abs(gm[3:] - rm[3:]).max() <= 1e-4, (k, gm, rm)
+            if HOST_LIBM_MATCHES_PORT:
+                assert r.map.iterations == o.map_iters, (k, r.map.iterations, o.map_iters)
+            worst["map"] = max(worst.get("map", 0.0), float(np.abs(gm - rm).max()))
 
     _run_pipeline(gpu, pipe, sweeps16, check)
     print("pipeline worst pose diff", worst)
