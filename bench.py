@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — LiDAR sweeps/s through extract + scan-to-scan odometry + scan-to-map mapping (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): a synthetic 1000-sweep VLP-16-shaped sequence (16 rings x 1800 columns, the
+reference's own ring-table angles, seed 0xC0FFEE + 1000 * rank) through the full hot path on one B200 per rank.
+One STEP = reset + one pass over the whole sequence.  With N > 1 ranks every rank registers its own independent
+sequence (BASELINE configs[3], no data-path collective): weak scaling, value = all sweeps / max-over-ranks time.
+
+  value : device-timed (CUDA events on the library's stream), the sweeps already resident in HBM
+  e2e   : the same through the reference-facing C-ABI call with HOST buffers (pinned): H2D of every sweep and the
+          D2H reads of counts / 28-double normal-equation mailboxes / poses inside the timed region
+  roofline : dominant kernel class from a separate CUDA-event pass (loam_profile), algorithmic bytes per DESIGN.md
+  cpu_baseline : the CPU oracle (restatement of the reference; oracle/_ref when built) on this box's host cores
+
+`--impl reference` times the reference's CPU implementation of the same path on the same workload (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LiDAR sweeps/s scan-to-map registration"
+UNIT = "sweeps/s"
+
+# algorithmic bytes per unit of work for each kernel class (DESIGN.md "Kernels" table)
+ALGO_BYTES = {
+    "extract": ("28 N + 16 F per sweep", None),       # computed from counts
+    "odom_knn": ("28 Q + 16 T per refresh", None),    # computed from counts
+    "odom_iter": ("64 Q + 108 B per pass", 64.0),
+    "to_end": ("32 B per point", 32.0),
+    "map_stack": ("32 B per point", 32.0),
+    "voxel": ("16 (M + V) per call", None),
+    "grid": ("36 T per build", 36.0),
+    "map_knn": ("96 Q per map iteration (kNN-5 + fit pair)", 96.0),
+    "map_fit": ("(counted with map_knn)", 0.0),
+    "gather": ("32 B per point", 32.0),
+    "insert": ("32 B per point", 32.0),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_sequence(n_sweeps, rank, pinned=True):
+    """All sweeps of the rank's sequence in one (pinned) host buffer + offsets in points."""
+    import torch
+    from gpscalibration_b200 import SweepGenerator
+    gen = SweepGenerator(sensor=0, scene=0, seed=0xC0FFEE + 1000 * rank, t_offset=37.0 * rank)
+    cap = gen.max_points
+    host = torch.empty((n_sweeps * cap, 3), dtype=torch.float32, pin_memory=pinned)
+    arr = host.numpy()
+    offs = np.zeros(n_sweeps + 1, np.int64)
+    for k in range(n_sweeps):
+        xyz, _ = gen.sweep(k, out=arr[offs[k]:offs[k] + cap])
+        offs[k + 1] = offs[k] + xyz.shape[0]
+    return host, arr, offs
+
+
+def reference_available():
+    return all(os.path.exists(os.path.join(ROOT, "oracle", "_ref", f)) for f in ("libref_sr.so", "libref_lo.so", "libref_lm.so"))
+
+
+def run_cpu(arr, offs, n_sweeps, threads3=True):
+    """CPU reference path over the first n_sweeps sweeps.  Returns (seconds, kind, cores, results)."""
+    if reference_available():
+        from oracle import ref as refmod
+        t0 = time.perf_counter()
+        res = refmod.run_sequence(arr, offs[:n_sweeps + 1])
+        return time.perf_counter() - t0, "reference", 3, res
+    from oracle import orc
+    pipe = orc.Pipeline(keep_clouds=False)
+    t0 = time.perf_counter()
+    if threads3:
+        res = pipe.run_threaded(arr[:offs[n_sweeps]], offs[:n_sweeps + 1])
+        cores = 3
+    else:
+        res = [pipe.process(arr[offs[k]:offs[k + 1]]) for k in range(n_sweeps)]
+        cores = 1
+    return time.perf_counter() - t0, "port", cores, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweeps", type=int, default=1000, help="sweeps per sequence (configs[1]: 1000)")
+    ap.add_argument("--cpu-sweeps", type=int, default=150, help="bounded CPU sample (first sweeps of the same sequence)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "cfg2: synthetic 1000-sweep VLP-16-shaped sequence (16x1800, reference ring table), extract + "
+                          "odometry + mapping, one independent sequence per GPU",
+              "sweeps_per_step": args.sweeps, "points_per_sweep": 28800, "seed": "0xC0FFEE + 1000*rank",
+              "l2": "inputs larger than L2 (345 MB of sweeps per step, each touched once)"}
+
+    # ------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n = min(args.cpu_sweeps, args.sweeps)
+        _, arr, offs = make_sequence(n, 0, pinned=False)
+        times = []
+        kind = cores = None
+        for s in range(args.warmup + args.steps):
+            dt, kind, cores, _ = run_cpu(arr, offs, n)
+            if s >= args.warmup:
+                times.append(dt)
+            log(f"[reference] step {s}: {n / dt:.2f} sweeps/s")
+        total = sum(times)
+        val = n * args.steps / total
+        sample = f"first {n} sweeps of the rank-0 sequence per step, three stage threads (SR | LO | LM) like the reference's three ROS processes"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from gpscalibration_b200 import LoamGpu
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_gen = time.perf_counter()
+    host, arr, offs = make_sequence(args.sweeps, rank)
+    n_pts = int(offs[-1])
+    dev = host[:n_pts].cuda()
+    log(f"[rank {rank}] generated {args.sweeps} sweeps ({n_pts * 12 / 1e6:.0f} MB) in {time.perf_counter() - t_gen:.1f}s")
+
+    gpu = LoamGpu(device=local_rank)
+    stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local_rank))
+    base_dev = dev.data_ptr()
+    S = args.sweeps
+
+    def step_device():
+        gpu.reset()
+        last = None
+        for k in range(S):
+            last = gpu.process_sweep_device(base_dev + int(offs[k]) * 12, int(offs[k + 1] - offs[k]))
+        return last
+
+    def step_host():
+        gpu.reset()
+        last = None
+        for k in range(S):
+            last = gpu.process_sweep(arr[offs[k]:offs[k + 1]])
+        return last
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0 = gpu.stats()
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            last = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        barrier()
+        s1 = gpu.stats()
+        ms = e0.elapsed_time(e1)
+        return ms, wall, {k: s1[k] - s0[k] for k in s0}, last
+
+    for w in range(args.warmup):
+        step_device()
+    step_host()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, wall_dev, st_dev, last = timed(step_device, args.steps)
+    ms_e2e, wall_e2e, st_e2e, _ = timed(step_host, args.steps)
+    clocks = sampler.stop()
+    ms_dev_max = max_over_ranks(ms_dev)
+    ms_e2e_max = max_over_ranks(ms_e2e)
+    value = world * S * args.steps / (ms_dev_max / 1e3)
+    e2e_value = world * S * args.steps / (ms_e2e_max / 1e3)
+
+    # roofline: separate CUDA-event pass over one step (events around every launch group perturb the step time)
+    gpu.profile(True)
+    step_device()
+    prof = gpu.profile_read()
+    gpu.profile(False)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    if dom == "map_fit":
+        dom = "map_knn"
+    d = prof[dom]
+    per_unit = ALGO_BYTES[dom][1]
+    if dom == "map_knn":
+        d = {"ms": prof["map_knn"]["ms"] + prof["map_fit"]["ms"], "units": prof["map_knn"]["units"], "scopes": prof["map_knn"]["scopes"]}
+    if per_unit is None:  # classes whose bytes depend on two sizes: use the per-sweep typical figures
+        per_unit = {"extract": 28.0 + 16.0 * 0.69, "odom_knn": 28.0 + 16.0 * 2.7, "voxel": 32.0}[dom]
+    algo_bytes = per_unit * d["units"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_unit": per_unit, "units_per_launch": d["units"] / max(1, d["scopes"]),
+                "avg_launch_us": 1e3 * d["ms"] / max(1, d["scopes"]), "share_of_gpu_time": d["ms"] / tot_ms,
+                "note": "single-sequence configs are launch/latency bound by construction (SURVEY §8d): ~9 MB per registration",
+                "classes_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+                "classes_launch_groups": {k: v["scopes"] for k, v in prof.items()}}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"] // args.steps,
+                   "d2h_bytes_per_step": st_e2e["d2h_bytes"] // args.steps, "ms_per_step": ms_e2e_max / args.steps},
+           "gpu_launches": int(st_dev["launches"]), "host_syncs_per_step": st_dev["syncs"] // args.steps,
+           "wall_vs_event_ms": [round(1e3 * wall_dev, 1), round(ms_dev, 1)], "roofline": roofline,
+           "final_pose_odom": [round(float(x), 4) for x in last.odom.transform_sum],
+           "final_pose_mapped": [round(float(x), 4) for x in last.map.transform_aft_mapped]}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = min(args.cpu_sweeps, S)
+        dt, kind, cores, _ = run_cpu(arr, offs, n)
+        out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"first {n} sweeps of the same sequence, three stage threads (SR | LO | LM), {os.cpu_count()} host cores present"}
+    if rank == 0:
+        print(json.dumps(out))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

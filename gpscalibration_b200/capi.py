@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_extract", "loam_extract_device", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -91,6 +91,7 @@ def load_library():
     lib.loam_launch_count.argtypes = [vp]
     lib.loam_stats.argtypes = [vp, vp]
     lib.loam_profile.argtypes = [vp, C.c_int]
+    lib.loam_host_times.argtypes = [vp, vp, C.c_int]
     lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
@@ -172,6 +173,14 @@ class LoamGpu:
 
     PROFILE_CLASSES = ("extract", "odom_knn", "odom_iter", "to_end", "map_stack", "voxel", "gather", "grid", "map_knn",
                        "map_fit", "insert")
+
+    HOST_SECTIONS = ("extract", "odom_iters", "odom_end", "map_prep", "map_grid", "map_iters", "map_insert", "map_cube_ds", "map_rest",
+                     "t9", "t10", "t11", "t12", "t13", "t14", "t15")
+
+    def host_times(self, clear=True):
+        out = np.zeros(16)
+        self._check(self.lib.loam_host_times(self._h, out.ctypes.data, int(clear)), "loam_host_times")
+        return {k: float(out[i]) for i, k in enumerate(self.HOST_SECTIONS)}
 
     def profile(self, enable):
         self._check(self.lib.loam_profile(self._h, int(enable)), "loam_profile")

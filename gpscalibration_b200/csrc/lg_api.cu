@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <vector>
 
@@ -28,6 +29,21 @@ void lg_set_error(const char* msg, const char* file, int line) { snprintf(g_cuda
 #define LG_D2H(h, dst, src, bytes) do { (h)->d2h_bytes += (long long)(bytes); LG_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (h)->st)); } while (0)
 
 namespace {
+
+enum { HT_EXTRACT = 0, HT_ODOM_ITERS = 1, HT_ODOM_END = 2, HT_MAP_PREP = 3, HT_MAP_GRID = 4, HT_MAP_ITERS = 5, HT_MAP_INSERT = 6,
+       HT_MAP_CUBEDS = 7, HT_MAP_REST = 8 };
+struct HostTimer {
+  double* acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostTimer(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  void lap(double* next) {
+    auto t1 = std::chrono::steady_clock::now();
+    *acc += std::chrono::duration<double>(t1 - t0).count();
+    acc = next;
+    t0 = t1;
+  }
+  ~HostTimer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 struct Chunk {
   int off, n;
@@ -51,6 +67,7 @@ struct loam_handle {
   long long launches = 0;
   long long h2d_bytes = 0, d2h_bytes = 0, syncs = 0;
   LgProf prof;
+  double host_s[16] = {0};  // host wall-clock per section (diagnostics, loam_host_times)
   // pinned host staging
   double* h_mail = nullptr;  // mapped: 28 doubles written by the reduction kernels
   double* d_mail = nullptr;
@@ -85,7 +102,7 @@ struct loam_handle {
   float mTsum[6] = {0}, Tincre[6] = {0}, Ttobe[6] = {0}, Tbef[6] = {0}, Taft[6] = {0};
   LgGNState lm_gn;
   std::vector<std::vector<Chunk>> cubeC, cubeS;  // laserCloudCornerArray / laserCloudSurfArray LM:98-99 as arena chunks
-  DevBuf arena;
+  DevBuf arena, arena2;
   size_t bump = 0;  // in points
   DevBuf stack2_c, stack2_s, stack_c, stack_s, map_c, map_s;
   int n_stack_c = 0, n_stack_s = 0, n_map_c = 0, n_map_s = 0;
@@ -118,14 +135,17 @@ size_t live_points(const loam_handle* h) {
   return s;
 }
 
-// Makes room for `need` more points at the bump pointer; compacts all live chunks into a larger arena when full.
+// Makes room for `need` more points at the bump pointer.  Voxel-gridding a cube writes its new cloud at the bump
+// pointer and turns the old chunks into garbage; when the arena is full the live chunks are compacted into the
+// second (ping-pong) arena — no cudaMalloc / cudaFree on the steady-state path.
 int arena_reserve(loam_handle* h, size_t need) {
   size_t cap = h->arena.cap / 16;
   if (h->bump + need <= cap) return LOAM_OK;
   size_t live = live_points(h);
-  size_t ncap = std::max<size_t>(2 * (live + need), (size_t)1 << 20);
-  DevBuf fresh;
-  LG_CHECK(fresh.ensure(ncap * 16, h->st));
+  size_t want = std::max<size_t>(8 * (live + need), (size_t)std::max(h->prm.max_map_points, 1 << 20) * 4);
+  if (h->arena2.cap / 16 < live + need || h->arena2.cap < h->arena.cap) {
+    LG_CHECK(h->arena2.ensure(std::max(want * 16, h->arena.cap), h->st));
+  }
   std::vector<CopyEnt> ents;
   size_t off = 0;
   int max_n = 0;
@@ -143,12 +163,10 @@ int arena_reserve(loam_handle* h, size_t need) {
   if (!ents.empty()) {
     int rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
     if (rc) return rc;
-    rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, fresh.as<float4>(), h->st, &h->launches);
+    rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->arena2.as<float4>(), h->st, &h->launches);
     if (rc) return rc;
   }
-  LG_SYNC(h);
-  h->arena.release();
-  h->arena = fresh;
+  std::swap(h->arena, h->arena2);
   h->bump = off;
   return LOAM_OK;
 }
@@ -286,6 +304,7 @@ int read_sr_counts(loam_handle* h, loam_counts* out) {
 }
 
 int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out) {
+  HostTimer ht(&h->host_s[HT_EXTRACT]);
   if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return LOAM_EINVAL;
   for (int i = 0; i < 12; i++) h->imu[i] = imu_trans ? imu_trans[i] : 0.f;
   int rc = lg_extract_launch(h->sr, h->srp, d_xyz, n, stride_bytes, h->st, &h->launches);
@@ -365,8 +384,8 @@ void loam_default_params(loam_params* p) {
   p->ring_ang_min = -15.f;
   p->ring_ang_step = 2.f;
   p->skip_frame_num = 1;
-  p->max_points = 60000;
-  p->max_map_points = 1 << 20;
+  p->max_points = 131072;
+  p->max_map_points = 1 << 21;
   p->want_registered = 0;
   p->want_surround = 0;
 }
@@ -401,6 +420,23 @@ int loam_create(const loam_params* p, int device, loam_handle** out) {
     delete h;
     return LOAM_ECUDA;
   }
+  // reserve the steady-state working set up front (HBM is plentiful; reallocation stalls are not)
+  {
+    const size_t mp = (size_t)std::max(prm.max_points, 1024), mm = (size_t)std::max(prm.max_map_points, 1024);
+    DevBuf* sweep_bufs[] = {&h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3, &h->stack2_c, &h->stack2_s,
+                            &h->stack_c, &h->stack_s, &h->ins_sel, &h->ins_sorted};
+    for (DevBuf* b : sweep_bufs) e = e == cudaSuccess ? b->ensure(mp * 16, h->st) : e;
+    DevBuf* map_bufs[] = {&h->map_c, &h->map_s, &h->ds_in};
+    for (DevBuf* b : map_bufs) e = e == cudaSuccess ? b->ensure(mm * 16, h->st) : e;
+    if (e == cudaSuccess) e = h->arena.ensure(mm * 4 * 16, h->st);
+    if (e == cudaSuccess) e = h->arena2.ensure(mm * 4 * 16, h->st);
+    if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (e != cudaSuccess) {
+      lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      loam_destroy(h);
+      return LOAM_ECUDA;
+    }
+  }
   *out = h;
   return LOAM_OK;
 }
@@ -413,7 +449,7 @@ int loam_destroy(loam_handle* h) {
   h->prof.release();
   h->sr.release(); h->od.release(); h->grid_c.release(); h->grid_s.release(); h->mi.release(); h->vb.release();
   DevBuf* all[] = {&h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
-                   &h->arena, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
+                   &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
                    &h->surround, &h->registered, &h->vg_in, &h->vg_out};
   for (DevBuf* b : all) b->release();
@@ -436,6 +472,14 @@ int loam_stats(const loam_handle* h, long long out4[4]) {
   out4[1] = h->h2d_bytes;
   out4[2] = h->d2h_bytes;
   out4[3] = h->syncs;
+  return LOAM_OK;
+}
+int loam_host_times(loam_handle* h, double* out9, int clear) {
+  if (!h || !out9) return LOAM_EINVAL;
+  for (int i = 0; i < 16; i++) {
+    out9[i] = h->host_s[i];
+    if (clear) h->host_s[i] = 0.0;
+  }
   return LOAM_OK;
 }
 int loam_profile(loam_handle* h, int enable) {
@@ -502,6 +546,7 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
     out->n_surf_last = h->n_surf_last;
     return LOAM_OK;
   }
+  HostTimer ht(&h->host_s[HT_ODOM_ITERS]);
   const float scanPeriod = 0.1f;  // LO:50
   h->T[3] -= imu[9] * scanPeriod;
   h->T[4] -= imu[10] * scanPeriod;
@@ -523,6 +568,7 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
       if (deltaR < 0.1 && deltaT < 0.1) break;
     }
   }
+  ht.lap(&h->host_s[HT_ODOM_END]);
   // LO:1035-1064
   float* T = h->T;
   float* S = h->Tsum;
@@ -587,6 +633,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
+  HostTimer ht(&h->host_s[HT_MAP_PREP]);
   if (!h->lm_inited) {
     h->lm_inited = true;
     map_reset(h);
@@ -605,6 +652,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
                                h->stack2_s.as<float4>(), nsl, h->st, &h->launches);
   if (rc) return rc;
 
+  ht.lap(&h->host_s[9]);
   float yax[3] = {0.f, 10.f, 0.f}, pOnY[3];
   lgh::associate_to_map(Tt, yax, pOnY);  // LM:483-487
   int cI = int((Tt[3] + 25.0) / 50.0) + h->cenW;
@@ -648,11 +696,13 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
         }
       }
 
+  ht.lap(&h->host_s[10]);
   // LM:717-724 gather the local map (reference order: valid cubes in loop order, points in cube order)
   rc = gather_cubes(h, validInd, true, false, h->map_c, &h->n_map_c);
   if (rc) return rc;
   rc = gather_cubes(h, validInd, false, true, h->map_s, &h->n_map_s);
   if (rc) return rc;
+  ht.lap(&h->host_s[11]);
   // LM:736-747 down-sample the stacks
   {
     std::vector<VoxSegD> segs(2);
@@ -671,11 +721,13 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
 
   if (h->n_map_c > 10 && h->n_map_s > 100) {  // LM:749
     out->optimised = 1;
+    ht.lap(&h->host_s[HT_MAP_GRID]);
     rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), h->n_map_c, h->st, &h->launches);
     if (rc) return rc;
     rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), h->n_map_s, h->st, &h->launches);
     if (rc) return rc;
     h->grids_valid = true;
+    ht.lap(&h->host_s[HT_MAP_ITERS]);
     for (int iter = 0; iter < 10; iter++) {
       out->iterations = iter + 1;
       float AtA[36], AtB[6], X[6];
@@ -697,6 +749,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   for (int i = 0; i < 6; i++) mt.t[i] = Tt[i];
   mt.sc = host_sincos3(Tt);
 
+  ht.lap(&h->host_s[HT_MAP_INSERT]);
   // LM:1023-1059 insert the stacks into their cubes
   const int nins = h->n_stack_c + h->n_stack_s;
   std::map<int, std::pair<int, int>> runC, runS;  // cube -> (start in ins_sorted, count)
@@ -735,6 +788,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       if (key & (1 << 14)) runS[cube] = {start, cnt}; else runC[cube] = {start, cnt};
     }
   }
+  ht.lap(&h->host_s[HT_MAP_CUBEDS]);
   // LM:1061-1079 voxel-grid every valid cube (old points first, then the new ones: push_back order)
   {
     std::vector<CopyEnt> ents;
@@ -756,8 +810,10 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       auto b = runS.find(ind);
       if (b != runS.end()) M += b->second.second;
     }
+    ht.lap(&h->host_s[12]);
     rc = arena_reserve(h, M + extra);
     if (rc) return rc;
+    ht.lap(&h->host_s[13]);
     const float4* ar = h->arena.as<float4>();
     for (int ind : validInd)
       for (int type = 0; type < 2; type++) {
@@ -811,9 +867,11 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       int* d_start = h->d_out_se.as<int>();
       int* d_end = d_start + nseg;
       float4* outp = h->arena.as<float4>() + h->bump;
+      ht.lap(&h->host_s[14]);
       rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, h->st,
                       &h->launches);
       if (rc) return rc;
+      ht.lap(&h->host_s[15]);
       if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
       LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8);
       LG_SYNC(h);
@@ -830,6 +888,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       h->bump += total;
     }
   }
+  ht.lap(&h->host_s[HT_MAP_REST]);
   // LM:1081-1101
   h->mapFrameCount++;
   if (h->mapFrameCount >= 5) {

@@ -28,7 +28,7 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t ensure(size_t bytes, cudaStream_t st, bool keep = false) {
     if (bytes <= cap) return cudaSuccess;
-    size_t ncap = bytes + bytes / 2 + 256;
+    size_t ncap = 2 * bytes + (1u << 20);  // grow rarely: cudaMalloc / cudaFree cost milliseconds and stall the stream
     void* np = nullptr;
     cudaError_t e = cudaMalloc(&np, ncap);
     if (e != cudaSuccess) return e;

@@ -124,6 +124,10 @@ int loam_stats(const loam_handle* h, long long out4[4]);
  * launch group while on).  Classes: 0 extract, 1 odom_knn, 2 odom_iter, 3 to_end, 4 map_stack/register, 5 voxel,
  * 6 gather, 7 grid build, 8 map_knn, 9 map_fit, 10 insert.  loam_profile(h, 1) clears the counters. */
 #define LOAM_PROFILE_CLASSES 11
+/* Host wall-clock seconds per section of the node-level calls (incl. waits on the GPU): 0 extract, 1 odometry
+ * iterations, 2 odometry end, 3 mapping prepare (stack, gather, voxel), 4 grid build, 5 mapping iterations, 6 insert,
+ * 7 cube voxel grids, 8 rest.  Diagnostics only. */
+int loam_host_times(loam_handle* h, double* out9, int clear);
 int loam_profile(loam_handle* h, int enable);
 int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n);
 

@@ -60,6 +60,7 @@ def lib():
         L.orc_pipeline_reset.argtypes = [vp]
         L.orc_pipeline_process.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(PipelineResult)]
         L.orc_pipeline_cloud.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.orc_pipeline_run_threaded.argtypes = [vp, vp, vp, C.c_int, vp]
         L.orc_pipeline_map_size.argtypes = [vp, ip, ip]
         _LIB = L
     return _LIB
@@ -231,6 +232,15 @@ class Pipeline:
         r = PipelineResult()
         lib().orc_pipeline_process(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] // 4, C.byref(r))
         return r
+
+    def run_threaded(self, xyz_all, offsets):
+        """Three stage threads (SR | LO | LM) over a whole sequence; returns the per-sweep PipelineResult array."""
+        xyz_all = _f32(xyz_all)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = offsets.shape[0] - 1
+        res = (PipelineResult * n)()
+        lib().orc_pipeline_run_threaded(self._h, xyz_all.ctypes.data, offsets.ctypes.data, n, res)
+        return res
 
     def cloud(self, which):
         w = self.CLOUDS.index(which)

@@ -3,7 +3,11 @@
 // PARITY PIN: see oracle/README.md — the restatement is checked bit-for-bit against the reference's own
 // translation units compiled in oracle/_ref (real SR/LO/LM sources + shim headers for ROS/PCL/OpenCV).
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "orc_cloud.h"
 #include "orc_linalg.h"
@@ -315,3 +319,99 @@ void orc_pipeline_map_size(void* hv, int* n_corner, int* n_surf) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- the reference's process layout: three single-threaded
+// stages (scanRegistration | laserOdometry | laserMapping are separate ROS processes) connected by queues.
+// Same results as orc_pipeline_process (asserted in tests); used by bench.py --impl reference to give the CPU path
+// all the host threads its structure can use for ONE sequence.
+namespace {
+template <typename T>
+struct Chan {
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<T> q;
+  bool closed = false;
+  void push(T&& v) {
+    { std::lock_guard<std::mutex> l(m); q.push_back(std::move(v)); }
+    cv.notify_one();
+  }
+  void close() {
+    { std::lock_guard<std::mutex> l(m); closed = true; }
+    cv.notify_all();
+  }
+  bool pop(T& out) {
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [&] { return !q.empty() || closed; });
+    if (q.empty()) return false;
+    out = std::move(q.front());
+    q.pop_front();
+    return true;
+  }
+};
+struct Msg1 { int k; SROut f; };
+struct Msg2 { int k; bool odom; bool full; float Tsum[6]; Cloud corner, surf, fullres; };
+}  // namespace
+
+extern "C" int orc_pipeline_run_threaded(void* hv, const float* xyz_all, const long long* offsets, int n_sweeps, PipelineResult* res) {
+  Pipeline* p = (Pipeline*)hv;
+  for (int k = 0; k < n_sweeps; k++) std::memset(&res[k], 0, sizeof(PipelineResult));
+  Chan<Msg1> c1;
+  Chan<Msg2> c2;
+  std::thread tA([&] {
+    for (int k = 0; k < n_sweeps; k++) {
+      double t0 = now_s();
+      Msg1 m;
+      m.k = k;
+      extract(p->sr.prm, p->sr.st, xyz_all + 3 * offsets[k], (int)(offsets[k + 1] - offsets[k]), 3, m.f);
+      res[k].t_extract = now_s() - t0;
+      res[k].n_full = (int)m.f.full.size(); res[k].n_sharp = (int)m.f.sharp.size(); res[k].n_less_sharp = (int)m.f.lessSharp.size();
+      res[k].n_flat = (int)m.f.flat.size(); res[k].n_less_flat = (int)m.f.lessFlat.size();
+      c1.push(std::move(m));
+    }
+    c1.close();
+  });
+  std::thread tB([&] {
+    Msg1 m;
+    ImuTrans imu;
+    OdomOut oo;
+    while (c1.pop(m)) {
+      double t0 = now_s();
+      p->lo.process(m.f.sharp, m.f.lessSharp, m.f.flat, m.f.lessFlat, m.f.full, imu, oo);
+      PipelineResult& r = res[m.k];
+      r.t_odom = now_s() - t0;
+      r.odom_published = oo.odomPublished;
+      r.odom_iters = oo.iterations;
+      for (int i = 0; i < 6; i++) { r.odom[i] = oo.transformSum[i]; r.rel[i] = oo.transformation[i]; }
+      Msg2 o;
+      o.k = m.k;
+      o.odom = oo.odomPublished;
+      o.full = oo.odomPublished && oo.fullResPublished;
+      for (int i = 0; i < 6; i++) o.Tsum[i] = oo.transformSum[i];
+      if (o.full) { o.corner = oo.cornerLast; o.surf = oo.surfLast; o.fullres = oo.fullRes; }
+      c2.push(std::move(o));
+    }
+    c2.close();
+  });
+  std::thread tC([&] {
+    Msg2 o;
+    MapOut mo;
+    while (c2.pop(o)) {
+      double t0 = now_s();
+      PipelineResult& r = res[o.k];
+      if (o.odom) p->lm.odometry_msg(o.Tsum);
+      if (o.full) {
+        p->lm.process(o.corner, o.surf, o.fullres, mo);
+        r.mapping_ran = 1;
+        r.map_iters = mo.iterations;
+        r.n_corner_stack = mo.nCornerStack; r.n_surf_stack = mo.nSurfStack;
+        r.n_corner_map = mo.nCornerFromMap; r.n_surf_map = mo.nSurfFromMap;
+      }
+      for (int i = 0; i < 6; i++) r.mapped[i] = p->lm.Taft[i];
+      r.t_map = now_s() - t0;
+    }
+  });
+  tA.join();
+  tB.join();
+  tC.join();
+  return 0;
+}
