@@ -8,6 +8,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <immintrin.h>
+
 #include <algorithm>
 #include <chrono>
 #include <map>
@@ -66,6 +68,7 @@ struct loam_handle {
   cudaStream_t st = nullptr;
   long long launches = 0;
   long long h2d_bytes = 0, d2h_bytes = 0, syncs = 0;
+  unsigned long long mail_seq = 0;  // sequence number the reduction kernels publish into the mapped mailbox
   LgProf prof;
   double host_s[16] = {0};  // host wall-clock per section (diagnostics, loam_host_times)
   // pinned host staging
@@ -320,16 +323,41 @@ int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, 
   return LOAM_OK;
 }
 
+// Waits until the reduction kernel has published sequence number h->mail_seq next to the 28 sums in the mapped pinned
+// mailbox.  Spinning on host memory the GPU writes over PCIe costs ~2 us; cudaStreamSynchronize costs 10-20 us, and
+// there is one such hand-over per Gauss-Newton iteration (the 6x6 solve stays on the host).
+int mailbox_wait(loam_handle* h) {
+  volatile unsigned long long* flag = (volatile unsigned long long*)(h->h_mail + 31);
+  h->syncs++;
+  for (long spin = 0;; spin++) {
+    if (*flag == h->mail_seq) return LOAM_OK;
+    _mm_pause();
+    if ((spin & 0xffff) == 0xffff) {  // every ~65k polls make sure the stream has not died
+      cudaError_t e = cudaStreamQuery(h->st);
+      if (e != cudaSuccess && e != cudaErrorNotReady) {
+        lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+        return LOAM_ECUDA;
+      }
+      if (e == cudaSuccess && *flag != h->mail_seq) {  // stream drained but no flag: should not happen
+        if (*flag == h->mail_seq) return LOAM_OK;
+        lg_set_error("mailbox sequence never arrived", __FILE__, __LINE__);
+        return LOAM_ECUDA;
+      }
+    }
+  }
+}
+
 // One odometry iteration: launch, wait for the 28-double mailbox, unpack.
 int odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel) {
   OdomT ot;
   for (int i = 0; i < 6; i++) ot.t[i] = T[i];
   SinCos3 sc = host_sincos3(T);
   int rc = lg_odom_iter_launch(h->od, ot, sc, iter, h->cur_sharp, h->counts.n_sharp, h->cur_flat, h->counts.n_flat,
-                               h->corner_last.as<float4>(), h->n_corner_last, h->surf_last.as<float4>(), h->n_surf_last, h->d_mail, h->st,
-                               &h->launches);
+                               h->corner_last.as<float4>(), h->n_corner_last, h->surf_last.as<float4>(), h->n_surf_last, h->d_mail,
+                               ++h->mail_seq, h->st, &h->launches);
   if (rc) return rc;
-  LG_SYNC(h);
+  rc = mailbox_wait(h);
+  if (rc) return rc;
   h->d2h_bytes += 28 * 8;
   lg_unpack28(h->h_mail, AtA, AtB, n_sel);
   return LOAM_OK;
@@ -340,10 +368,12 @@ int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, floa
   for (int i = 0; i < 6; i++) mt.t[i] = T[i];
   mt.sc = host_sincos3(T);
   int rc = lg_map_iter_launch(h->mi, mt, h->stack_c.as<float4>(), h->n_stack_c, h->stack_s.as<float4>(), h->n_stack_s, h->grid_c.d, h->grid_s.d,
-                              h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail, h->st, &h->launches);
+                              h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail,
+                              out28_dev ? 0ull : ++h->mail_seq, h->st, &h->launches);
   if (rc) return rc;
   if (out28_dev) return LOAM_OK;
-  LG_SYNC(h);
+  rc = mailbox_wait(h);
+  if (rc) return rc;
   h->d2h_bytes += 28 * 8;
   lg_unpack28(h->h_mail, AtA, AtB, n_sel);
   return LOAM_OK;

@@ -298,40 +298,61 @@ __device__ __forceinline__ unsigned char mask_at(const unsigned char* __restrict
   return r;
 }
 
-constexpr int SEL_CAP = 4096;  // points per sector the shared-memory sort accepts (ring <= 6 * 4096 points)
+constexpr int SEL_CAP = 2048;   // points per sector the shared-memory sort accepts
+constexpr int RING_CAP = 8192;  // points per ring whose flags are staged in shared memory
 
-// SR:597-622 / 641-666 with FENCE (iv) (bounds) — see oracle/orc_sr.h suppress_neighbours
-__device__ __forceinline__ void suppress(unsigned char* picked, const unsigned char* __restrict__ cond, int ind, int n) {
+// SR:597-622 / 641-666: how far the suppression of a pick at `ind` reaches forwards / backwards (0..5 each), from the
+// gap flags alone — independent of the pick state, which is what lets a warp resolve 32 candidates at once.
+// FENCE (iv) (bounds) as in oracle/orc_sr.h suppress_neighbours.
+__device__ __forceinline__ void suppress_reach(const unsigned char* s_cond, int li, int len, int& nf, int& nb) {
+  nf = 0;
   for (int l = 1; l <= 5; l++) {
-    if (ind + l >= n || ind + l - 1 < 0) break;
-    if (cond[ind + l] & C_GAP) break;
-    picked[ind + l] = 1;
+    if (li + l >= len) break;
+    if (s_cond[li + l] & C_GAP) break;
+    nf = l;
   }
-  for (int l = -1; l >= -5; l--) {
-    if (ind + l < 0 || ind + l + 1 >= n) break;
-    if (cond[ind + l + 1] & C_GAP) break;
-    picked[ind + l] = 1;
+  nb = 0;
+  for (int l = 1; l <= 5; l++) {
+    if (li - l < 0) break;
+    if (s_cond[li - l + 1] & C_GAP) break;
+    nb = l;
   }
 }
 
+// One CTA per ring.  Per sector: bitonic sort of (curvature, index) keys by the whole CTA, then warp 0 replays the
+// reference's greedy walk 32 candidates at a time: every lane knows its candidate's suppression interval, and the
+// sequential "picked earlier => suppress neighbours" dependency inside a batch is resolved with ballots.
 __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                          const float* __restrict__ curv, const unsigned char* __restrict__ cond,
                                                          unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
                                                          signed char* __restrict__ label, int* __restrict__ picks) {
   __shared__ unsigned long long skeys[SEL_CAP];
-  const int r = blockIdx.x, tid = threadIdx.x;
+  __shared__ unsigned char s_cond[RING_CAP];
+  __shared__ unsigned char s_picked[RING_CAP];
+  __shared__ signed char s_label[RING_CAP];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int n = meta[SRM_N_FULL];
   const int R = prm.n_scans;
-  const int S = (r == 0) ? 5 : meta[SRM_SCAN_START + r];            // SR:489
-  const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];     // SR:490
+  const int S = (r == 0) ? 5 : meta[SRM_SCAN_START + r];         // SR:489
+  const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];  // SR:490
   int* my_picks = picks + r * SR_PICKS_PER_RING;
   int* cnt = meta + SRM_PICK_CNT + r * 3;
   // this ring's points: [S - 5, E + 5)
   const int a = max(S - 5, 0), b = min(E + 5, n);
-  for (int i = a + tid; i < b; i += blockDim.x) {
-    unsigned char m = mask_at(cond, i, n);
-    picked[i] = m;
-    mask_diag[i] = m;
+  const int len = b - a;
+  if (len > RING_CAP) {
+    if (tid == 0) {
+      cnt[0] = cnt[1] = cnt[2] = 0;
+      atomicExch(&meta[SRM_ERR], 1);
+    }
+    return;
+  }
+  for (int li = tid; li < len; li += blockDim.x) {
+    unsigned char m = mask_at(cond, a + li, n);
+    s_cond[li] = cond[a + li];
+    s_picked[li] = m;
+    s_label[li] = 0;
+    mask_diag[a + li] = m;
   }
   int nsharp = 0, nless = 0, nflat = 0;
   bool too_big = false;
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
     const int ep = (S * (5 - j) + E * (j + 1)) / 6 - 1;
     const int m = ep - sp + 1;
     if (m <= 0) continue;
-    if (m > SEL_CAP || sp < 0 || ep >= n) {
+    if (m > SEL_CAP || sp < a || ep >= b) {
       too_big = true;
       continue;
     }
@@ -364,47 +385,98 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
         }
         __syncthreads();
       }
-    if (tid == 0) {
-      // SR:578-624, walking down from the largest curvature; everything below the first c <= 0.1 can never pass
-      int largest = 0;
-      for (int k = m - 1; k >= 0; k--) {
-        float cv = __uint_as_float((unsigned int)(skeys[k] >> 32));
-        if (!(cv > 0.1)) break;
-        int ind = (int)(unsigned int)(skeys[k] & 0xffffffffull);
-        if (picked[ind] == 0) {
-          largest++;
-          if (largest <= 16) {
-            label[ind] = 2;
-            my_picks[SR_PICK_SHARP + nsharp++] = ind;
-            my_picks[SR_PICK_LESS + nless++] = ind;
-          } else if (largest <= 20) {
-            label[ind] = 1;
-            my_picks[SR_PICK_LESS + nless++] = ind;
-          } else {
+    if (tid < 32) {
+      // ---- SR:578-624: walk down from the largest curvature
+      int count = 0;
+      bool done = false;
+      for (int k = m - 1; k >= 0 && !done; k -= 32) {
+        const int kk = k - lane;
+        const bool have = kk >= 0;
+        const unsigned long long key = have ? skeys[kk] : 0ull;
+        const float cv = __uint_as_float((unsigned int)(key >> 32));
+        const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
+        const bool pass = have && (cv > 0.1);
+        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+        int nf = 0, nb = 0;
+        if (pass) suppress_reach(s_cond, li, len, nf, nb);
+        const bool alive = pass && s_picked[li] == 0;
+        unsigned int am = __ballot_sync(0xffffffffu, alive);
+        int mynum = 0;
+        while (am) {
+          const int p = __ffs(am) - 1;
+          am &= ~(1u << p);
+          count++;
+          if (count > 20) {  // SR:592-594: the 21st candidate only ends the walk
+            done = true;
             break;
           }
-          picked[ind] = 1;
-          suppress(picked, cond, ind, n);
+          if (lane == p) mynum = count;
+          const int pli = __shfl_sync(0xffffffffu, li, p);
+          const int plo = pli - __shfl_sync(0xffffffffu, nb, p), phi = pli + __shfl_sync(0xffffffffu, nf, p);
+          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
         }
-      }
-      // SR:626-668, walking up from the smallest curvature
-      int smallest = 0;
-      for (int k = 0; k < m; k++) {
-        float cv = __uint_as_float((unsigned int)(skeys[k] >> 32));
-        if (!(cv < 0.1)) break;
-        int ind = (int)(unsigned int)(skeys[k] & 0xffffffffull);
-        if (picked[ind] == 0) {
-          label[ind] = -1;
-          my_picks[SR_PICK_FLAT + nflat++] = ind;
-          smallest++;
-          if (smallest >= 32) break;
-          picked[ind] = 1;
-          suppress(picked, cond, ind, n);
+        if (mynum > 0) {
+          const int ind = li + a;
+          if (mynum <= 16) {
+            s_label[li] = 2;
+            my_picks[SR_PICK_SHARP + nsharp + mynum - 1] = ind;
+          } else {
+            s_label[li] = 1;
+          }
+          my_picks[SR_PICK_LESS + nless + mynum - 1] = ind;
+          for (int l = -nb; l <= nf; l++) s_picked[li + l] = 1;
         }
+        __syncwarp();
+        if (pm != 0xffffffffu) done = true;  // sorted: nothing below the first c <= 0.1 can pass
       }
+      const int npick = min(count, 20);
+      nsharp += min(npick, 16);
+      nless += npick;
+      // ---- SR:626-668: walk up from the smallest curvature
+      count = 0;
+      done = false;
+      for (int k = 0; k < m && !done; k += 32) {
+        const int kk = k + lane;
+        const bool have = kk < m;
+        const unsigned long long key = have ? skeys[kk] : 0ull;
+        const float cv = __uint_as_float((unsigned int)(key >> 32));
+        const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
+        const bool pass = have && (cv < 0.1);
+        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+        int nf = 0, nb = 0;
+        if (pass) suppress_reach(s_cond, li, len, nf, nb);
+        const bool alive = pass && s_picked[li] == 0;
+        unsigned int am = __ballot_sync(0xffffffffu, alive);
+        int mynum = 0;
+        bool last32 = false;
+        while (am) {
+          const int p = __ffs(am) - 1;
+          am &= ~(1u << p);
+          count++;
+          if (lane == p) mynum = count;
+          if (count >= 32) {  // SR:635-638: the 32nd flat point is kept but neither marked nor suppressing
+            if (lane == p) last32 = true;
+            done = true;
+            break;
+          }
+          const int pli = __shfl_sync(0xffffffffu, li, p);
+          const int plo = pli - __shfl_sync(0xffffffffu, nb, p), phi = pli + __shfl_sync(0xffffffffu, nf, p);
+          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
+        }
+        if (mynum > 0) {
+          s_label[li] = -1;
+          my_picks[SR_PICK_FLAT + nflat + mynum - 1] = li + a;
+          if (!last32)
+            for (int l = -nb; l <= nf; l++) s_picked[li + l] = 1;
+        }
+        __syncwarp();
+        if (pm != 0xffffffffu) done = true;
+      }
+      nflat += count;
     }
     __syncthreads();
   }
+  for (int li = tid; li < len; li += blockDim.x) label[a + li] = s_label[li];
   if (tid == 0) {
     cnt[0] = nsharp;
     cnt[1] = nless;

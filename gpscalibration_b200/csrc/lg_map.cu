@@ -219,7 +219,8 @@ constexpr int FIT_NT = 128;
 __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* __restrict__ corner_stack, int n_cs,
                                                           const float4* __restrict__ surf_stack, int n_ss, const float4* __restrict__ corner_map,
                                                           const float4* __restrict__ surf_map, const int* __restrict__ nbr,
-                                                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28) {
+                                                          double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28,
+                                                          unsigned long long seq) {
   Acc28 acc;
   acc.clear();
   const int q = blockIdx.x * FIT_NT + threadIdx.x;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* _
     a[5] = c.z;
     acc.add_row(a, -c.w);
   }
-  lg_reduce28<FIT_NT>(acc, partials, ticket, out28);
+  lg_reduce28<FIT_NT>(acc, partials, ticket, out28, seq);
 }
 
 // LM:1023-1059: map-frame point and cube index; key 0xFFFFFFFF.. sorts dropped points to the end.
@@ -391,7 +392,8 @@ int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long lo
 }
 
 int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
-                       const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, cudaStream_t st, long long* launches) {
+                       const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
+                       long long* launches) {
   const int nq = n_cs + n_ss;
   const int nb = std::max(1, lg_div_up(nq, FIT_NT));
   LG_CHECK(ws.nbr.ensure((size_t)(nq + 1) * 5 * 4, st));
@@ -407,7 +409,7 @@ int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack,
   }
   LgProfScope prof_scope(LGK_MAP_FIT, st, (double)nq);
   map_fit_kernel<<<nb, FIT_NT, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, corner_map, surf_map, ws.nbr.as<int>(), ws.partials.as<double>(),
-                                        ws.ticket.as<unsigned int>(), out28);
+                                        ws.ticket.as<unsigned int>(), out28, seq);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;

@@ -2,9 +2,9 @@
 //   odom_knn_kernel     LO:603,758   exact nearest neighbour of every de-skewed feature in the previous sweep's
 //                                    corner / surf cloud (replaces KdTreeFLANN::nearestKSearch(k = 1)); brute force over
 //                                    shared-memory target tiles, (d2, index) packed into one 64-bit atomicMin key
-//   odom_iter_kernel    LO:595-971   TransformToStart, the +-1-ring scans for the 2nd / 3rd point on refresh
-//                                    iterations, point-to-line / point-to-plane coefficients, Jacobian row, and the
-//                                    21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
+//   odom_corr_kernel    LO:604-677,760-844  the +-1-ring scans for the 2nd / 3rd point, one warp per feature
+//   odom_iter_kernel    LO:595,680-971  TransformToStart, point-to-line / point-to-plane coefficients, Jacobian row,
+//                                    and the 21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
 //   odom_to_end_kernel  LO:1087-1106 TransformToEnd over less-sharp, less-flat and (every 2nd sweep) the full cloud
 // The 6x6 solve, degeneracy projection, convergence test and pose accumulation stay on the host (lg_api.cu).
 #include "lg_odom.h"
@@ -88,54 +88,126 @@ __device__ __forceinline__ void line_coeff(float x0, float y0, float z0, float x
   ld2 = a012 / l12;
 }
 
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)v, o);
+    unsigned int hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(v >> 32), o);
+    unsigned long long t = ((unsigned long long)hi << 32) | lo;
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+constexpr int CORR_WARPS = 8;
+constexpr unsigned long long NONE64 = ~0ull;
+
+// LO:604-677 / LO:760-844, one WARP per feature: the sequential +-1-ring scans of the reference become 32-wide
+// chunks.  The reference's `break` (first j whose ring leaves the window) is reproduced literally: lanes before the
+// first breaking lane of a chunk are candidates, the chunk containing it is the last one.  Tie rule of the
+// reference's strict '<' updates: forward scan first (smallest j wins ties), backward scan only replaces on a strictly
+// smaller distance (largest j wins ties among backward candidates).
+__global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
+                                                                     const float4* __restrict__ flat, int n_flat,
+                                                                     const float4* __restrict__ corner_last, int n_cl,
+                                                                     const float4* __restrict__ surf_last, int n_sl,
+                                                                     const unsigned long long* __restrict__ best, int* __restrict__ c1,
+                                                                     int* __restrict__ c2, int* __restrict__ s1, int* __restrict__ s2,
+                                                                     int* __restrict__ s3) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * CORR_WARPS + (threadIdx.x >> 5);
+  if (q >= n_sharp + n_flat) return;
+  const bool is_c = q < n_sharp;
+  const int f = is_c ? q : q - n_sharp;
+  const float4* pts = is_c ? corner_last : surf_last;
+  const int nlast = is_c ? n_cl : n_sl;
+  const int bound = min(is_c ? n_sharp : n_flat, nlast);  // FENCE (i): LO:620 / LO:776 bound by the CURRENT feature count
+  const float4 sel = transform_to_start(T, is_c ? sharp[f] : flat[f]);
+  const unsigned long long b = best[q];
+  int closest = -1, r2 = -1, r3 = -1;
+  if (b != NONE64 && lg_nbr_d2(b) < 25) {
+    closest = lg_nbr_idx(b);
+    const int scan = int(pts[closest].w);
+    unsigned long long f2 = NONE64, f3 = NONE64, b2 = NONE64, b3 = NONE64;
+    for (int base = closest + 1; base < bound; base += 32) {
+      const int j = base + lane;
+      const bool valid = j < bound;
+      float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = int(t.w);
+      const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r > scan + 1.5));
+      const bool live = valid && (bm == 0u || lane < (__ffs(bm) - 1));
+      if (live) {
+        float d = sqd(t, sel);
+        if (d < 25) {
+          unsigned long long key = lg_pack_nbr(d, j);
+          if (is_c) {
+            if (r > scan) f2 = min(f2, key);
+          } else {
+            if (r <= scan) f2 = min(f2, key); else f3 = min(f3, key);
+          }
+        }
+      }
+      if (bm != 0u) break;
+    }
+    for (int base = closest - 1; base >= 0; base -= 32) {
+      const int j = base - lane;
+      const bool valid = j >= 0;
+      float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = int(t.w);
+      const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r < scan - 1.5));
+      const bool live = valid && (bm == 0u || lane < (__ffs(bm) - 1));
+      if (live) {
+        float d = sqd(t, sel);
+        if (d < 25) {
+          unsigned long long key = lg_pack_nbr(d, 0x7fffffff - j);  // first met (largest j) wins ties
+          if (is_c) {
+            if (r < scan) b2 = min(b2, key);
+          } else {
+            if (r >= scan) b2 = min(b2, key); else b3 = min(b3, key);
+          }
+        }
+      }
+      if (bm != 0u) break;
+    }
+    f2 = warp_min_u64(f2); b2 = warp_min_u64(b2);
+    if (f2 != NONE64 && (b2 == NONE64 || !(lg_nbr_d2(b2) < lg_nbr_d2(f2)))) r2 = lg_nbr_idx(f2);
+    else if (b2 != NONE64) r2 = 0x7fffffff - lg_nbr_idx(b2);
+    if (!is_c) {
+      f3 = warp_min_u64(f3); b3 = warp_min_u64(b3);
+      if (f3 != NONE64 && (b3 == NONE64 || !(lg_nbr_d2(b3) < lg_nbr_d2(f3)))) r3 = lg_nbr_idx(f3);
+      else if (b3 != NONE64) r3 = 0x7fffffff - lg_nbr_idx(b3);
+    }
+  }
+  if (lane == 0) {
+    if (is_c) {
+      c1[f] = closest;
+      c2[f] = r2;
+    } else {
+      s1[f] = closest;
+      s2[f] = r2;
+      s3[f] = r3;
+    }
+  }
+}
+
 constexpr int IT_NT = 128;
 
 __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp,
                                                            const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
                                                            int n_cl, const float4* __restrict__ surf_last, int n_sl,
-                                                           const unsigned long long* __restrict__ best, int* __restrict__ c1, int* __restrict__ c2,
-                                                           int* __restrict__ s1, int* __restrict__ s2, int* __restrict__ s3,
-                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28) {
+                                                           const int* __restrict__ c1, const int* __restrict__ c2,
+                                                           const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
+                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28,
+                                                           unsigned long long seq) {
   Acc28 acc;
   acc.clear();
   const int q = blockIdx.x * IT_NT + threadIdx.x;
-  const bool refresh = (iter % 5) == 0;
   float4 ori, coef;
   bool keep = false;
   if (q < n_sharp) {
     ori = sharp[q];
     const float4 sel = transform_to_start(T, ori);
-    if (refresh) {  // LO:598-677
-      unsigned long long b = best[q];
-      int closest = -1, min2 = -1;
-      if (b != ~0ull && lg_nbr_d2(b) < 25) {
-        closest = lg_nbr_idx(b);
-        int scan = int(corner_last[closest].w);
-        float minD2 = 25;
-        // FENCE (i): the reference bounds this scan by cornerPointsSharpNum (LO:620); clamp to the cloud
-        int bound = min(n_sharp, n_cl);
-        for (int j = closest + 1; j < bound; j++) {
-          float4 t = corner_last[j];
-          if (int(t.w) > scan + 1.5) break;
-          float d = sqd(t, sel);
-          if (int(t.w) > scan && d < minD2) {
-            minD2 = d;
-            min2 = j;
-          }
-        }
-        for (int j = closest - 1; j >= 0; j--) {
-          float4 t = corner_last[j];
-          if (int(t.w) < scan - 1.5) break;
-          float d = sqd(t, sel);
-          if (int(t.w) < scan && d < minD2) {
-            minD2 = d;
-            min2 = j;
-          }
-        }
-      }
-      c1[q] = closest;
-      c2[q] = min2;
-    }
     const int i2 = c2[q];
     if (i2 >= 0) {  // LO:680-746
       float4 t1 = corner_last[c1[q]], t2 = corner_last[i2];
@@ -150,39 +222,6 @@ __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, i
     const int f = q - n_sharp;
     ori = flat[f];
     const float4 sel = transform_to_start(T, ori);
-    if (refresh) {  // LO:756-844
-      unsigned long long b = best[q];
-      int closest = -1, min2 = -1, min3 = -1;
-      if (b != ~0ull && lg_nbr_d2(b) < 25) {
-        closest = lg_nbr_idx(b);
-        int scan = int(surf_last[closest].w);
-        float minD2 = 25, minD3 = 25;
-        int bound = min(n_flat, n_sl);  // FENCE (i), LO:776
-        for (int j = closest + 1; j < bound; j++) {
-          float4 t = surf_last[j];
-          if (int(t.w) > scan + 1.5) break;
-          float d = sqd(t, sel);
-          if (int(t.w) <= scan) {
-            if (d < minD2) { minD2 = d; min2 = j; }
-          } else {
-            if (d < minD3) { minD3 = d; min3 = j; }
-          }
-        }
-        for (int j = closest - 1; j >= 0; j--) {
-          float4 t = surf_last[j];
-          if (int(t.w) < scan - 1.5) break;
-          float d = sqd(t, sel);
-          if (int(t.w) >= scan) {
-            if (d < minD2) { minD2 = d; min2 = j; }
-          } else {
-            if (d < minD3) { minD3 = d; min3 = j; }
-          }
-        }
-      }
-      s1[f] = closest;
-      s2[f] = min2;
-      s3[f] = min3;
-    }
     const int i2 = s2[f], i3 = s3[f];
     if (i2 >= 0 && i3 >= 0) {  // LO:847-901
       float4 t1 = surf_last[s1[f]], t2 = surf_last[i2], t3 = surf_last[i3];
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, i
     float b = (float)(-0.05 * c.w);
     acc.add_row(a, b);
   }
-  lg_reduce28<IT_NT>(acc, partials, ticket, out28);
+  lg_reduce28<IT_NT>(acc, partials, ticket, out28, seq);
 }
 
 // LO:156-227.  sT = sin/cos of the full transform, imu sin/cos evaluated on the host.
@@ -279,7 +318,8 @@ __global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, I
 }  // namespace
 
 int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
-                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, cudaStream_t st, long long* launches) {
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, unsigned long long seq, cudaStream_t st,
+                        long long* launches) {
   const int nq = n_sharp + n_flat;
   const int nb = std::max(1, lg_div_up(nq, IT_NT));
   LG_CHECK(ws.best.ensure((size_t)(nq + 1) * 8, st));
@@ -302,13 +342,15 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
       LgProfScope prof_scope(LGK_ODOM_KNN, st, (double)nq);
       odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
                                               ws.best.as<unsigned long long>());
-      (*launches)++;
+      odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
+                                                                              ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
+                                                                              ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
+      (*launches) += 2;
     }
   }
   LgProfScope prof_scope(LGK_ODOM_ITER, st, (double)nq);
-  odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
-                                         ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(),
-                                         ws.s3.as<int>(), ws.partials.as<double>(), ws.ticket.as<unsigned int>(), out28);
+  odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(),
+                                         ws.s3.as<int>(), ws.partials.as<double>(), ws.ticket.as<unsigned int>(), out28, seq);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;

@@ -25,6 +25,7 @@ struct OdomWs {
 };
 
 int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
-                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, cudaStream_t st, long long* launches);
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, unsigned long long seq, cudaStream_t st,
+                        long long* launches);
 int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, const float4* in0, float4* out0, int n0, const float4* in1,
                           float4* out1, int n1, const float4* in2, float4* out2, int n2, cudaStream_t st, long long* launches);

@@ -30,7 +30,7 @@ struct Acc28 {
 // in CTA order (deterministic) and writes the 28 results to out28 (device memory or mapped pinned host memory).
 template <int NT>
 __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                            double* __restrict__ out28) {
+                                            double* __restrict__ out28, unsigned long long seq = 0ull) {
   __shared__ double s_part[NT / 32][28];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -61,6 +61,14 @@ __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ par
       out28[tid] = s;
     }
     if (tid == 0) *ticket = 0u;
+    if (seq != 0ull) {  // host mailbox: publish the sequence number after the 28 values are visible system-wide
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        *((volatile unsigned long long*)(out28 + 31)) = seq;
+        __threadfence_system();
+      }
+    }
   }
 }
 

@@ -1,0 +1,11 @@
+"""Short fused-pipeline run used as the ncu target (N sweeps, host buffers)."""
+import sys
+sys.path.insert(0, '.')
+from gpscalibration_b200 import LoamGpu, SweepGenerator
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+gen = SweepGenerator()
+sw = [gen.sweep(k)[0].copy() for k in range(N)]
+gpu = LoamGpu()
+for k in range(N):
+    r = gpu.process_sweep(sw[k])
+print("ok", list(r.odom.transform_sum), gpu.stats())
