@@ -5,6 +5,6 @@ Only what the hot path needs lives here: ``csrc/`` holds the hand-w
 (scanRegistration / laserOdometry / laserMapping handler interfaces) on top of it; ``synth`` is the synthetic sweep
 generator used by tests and bench.  There is no CPU fallback: without libloamgpu.so or a CUDA device, calls fail.
 """
-from .capi import LoamGpu, LoamError, load_library, library_path  # noqa: F401
+from .capi import LoamGpu, LoamGpuPipeline, LoamError, load_library, library_path  # noqa: F401
 from .nodes import ScanRegistration, LaserOdometry, LaserMapping, LoamPipeline  # noqa: F401
 from .synth import SweepGenerator  # noqa: F401

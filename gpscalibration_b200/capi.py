@@ -59,7 +59,9 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_mapping_odometry", "loam_mapping_process", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
-           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced"]
+           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
+           "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_stats"]
 
 
 def library_path():
@@ -113,6 +115,14 @@ def load_library():
     lib.loam_gn_solve.argtypes = [vp, vp, C.c_int, C.c_float, vp, vp]
     lib.loam_map_iter_partial.argtypes = [vp, C.c_int, vp, vp]
     lib.loam_map_finish_reduced.argtypes = [vp, vp, vp, ip]
+    lib.loam_pipeline_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
+    lib.loam_pipeline_destroy.argtypes = [vp]
+    lib.loam_pipeline_reset.argtypes = [vp]
+    lib.loam_pipeline_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
+    lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
+    lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
+    lib.loam_pipeline_pending.argtypes = [vp]
+    lib.loam_pipeline_stats.argtypes = [vp, vp]
     _LIB = lib
     return lib
 
@@ -306,6 +316,61 @@ class LoamGpu:
     def map_iter_partial(self, it, T, dev_ptr28):
         T = _f32(T)
         self._check(self.lib.loam_map_iter_partial(self._h, it, T.ctypes.data, dev_ptr28), "loam_map_iter_partial")
+
+
+class LoamGpuPipeline:
+    """Pipelined mode (loam_pipeline_*): submit sweeps, collect results in order; same results as LoamGpu.process_sweep."""
+
+    def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1):
+        self.lib = load_library()
+        p = Params()
+        self.lib.loam_default_params(C.byref(p))
+        p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
+        p.skip_frame_num = skip_frame_num
+        self._h = C.c_void_p()
+        rc = self.lib.loam_pipeline_create(C.byref(p), device, C.byref(self._h))
+        if rc:
+            raise LoamError(rc, "loam_pipeline_create", self.lib.loam_strerror(rc).decode())
+
+    def _check(self, rc, where):
+        if rc != 0:
+            raise LoamError(rc, where, self.lib.loam_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.loam_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(self.lib.loam_pipeline_reset(self._h), "loam_pipeline_reset")
+
+    def submit(self, xyz, stamp=0.0):
+        xyz = _f32(xyz)
+        self._check(self.lib.loam_pipeline_submit(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] if xyz.shape[0] > 1 else 12, stamp),
+                    "loam_pipeline_submit")
+
+    def submit_device(self, dev_ptr, n, stride_bytes=12, stamp=0.0):
+        self._check(self.lib.loam_pipeline_submit_device(self._h, dev_ptr, n, stride_bytes, stamp), "loam_pipeline_submit_device")
+
+    def wait(self):
+        r = SweepResult()
+        self._check(self.lib.loam_pipeline_wait(self._h, C.byref(r)), "loam_pipeline_wait")
+        return r
+
+    @property
+    def pending(self):
+        return self.lib.loam_pipeline_pending(self._h)
+
+    def stats(self):
+        out = (C.c_longlong * 4)()
+        self._check(self.lib.loam_pipeline_stats(self._h, out), "loam_pipeline_stats")
+        return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
 
 
 def gn_solve(AtA, AtB, it, eig_threshold, state37):

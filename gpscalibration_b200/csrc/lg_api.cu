@@ -420,7 +420,8 @@ void loam_default_params(loam_params* p) {
   p->want_surround = 0;
 }
 
-int loam_create(const loam_params* p, int device, loam_handle** out) {
+// role bits: 1 = needs the per-sweep odometry buffers, 2 = needs the map storage (arena, sort workspace)
+static int create_internal(const loam_params* p, int device, int role, loam_handle** out) {
   if (!out) return LOAM_EINVAL;
   *out = nullptr;
   loam_params prm;
@@ -455,12 +456,15 @@ int loam_create(const loam_params* p, int device, loam_handle** out) {
     const size_t mp = (size_t)std::max(prm.max_points, 1024), mm = (size_t)std::max(prm.max_map_points, 1024);
     DevBuf* sweep_bufs[] = {&h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3, &h->stack2_c, &h->stack2_s,
                             &h->stack_c, &h->stack_s, &h->ins_sel, &h->ins_sorted};
-    for (DevBuf* b : sweep_bufs) e = e == cudaSuccess ? b->ensure(mp * 16, h->st) : e;
+    if (role & 1)
+      for (DevBuf* b : sweep_bufs) e = e == cudaSuccess ? b->ensure(mp * 16, h->st) : e;
     DevBuf* map_bufs[] = {&h->map_c, &h->map_s, &h->ds_in};
-    for (DevBuf* b : map_bufs) e = e == cudaSuccess ? b->ensure(mm * 16, h->st) : e;
-    if (e == cudaSuccess) e = h->arena.ensure(mm * 4 * 16, h->st);
-    if (e == cudaSuccess) e = h->arena2.ensure(mm * 4 * 16, h->st);
-    if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (role & 2) {
+      for (DevBuf* b : map_bufs) e = e == cudaSuccess ? b->ensure(mm * 16, h->st) : e;
+      if (e == cudaSuccess) e = h->arena.ensure(mm * 4 * 16, h->st);
+      if (e == cudaSuccess) e = h->arena2.ensure(mm * 4 * 16, h->st);
+      if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
+    }
     if (e != cudaSuccess) {
       lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       loam_destroy(h);
@@ -470,6 +474,8 @@ int loam_create(const loam_params* p, int device, loam_handle** out) {
   *out = h;
   return LOAM_OK;
 }
+
+int loam_create(const loam_params* p, int device, loam_handle** out) { return create_internal(p, device, 3, out); }
 
 int loam_destroy(loam_handle* h) {
   if (!h) return LOAM_EINVAL;
@@ -1223,6 +1229,379 @@ int loam_map_finish_reduced(const double* reduced28_host, float* AtA, float* AtB
   if (*n_sel < 50) {
     memset(AtA, 0, 36 * sizeof(float));
     memset(AtB, 0, 6 * sizeof(float));
+  }
+  return LOAM_OK;
+}
+
+}  // extern "C"
+
+// ===================================================================================================== pipelined mode
+// The reference runs scanRegistration, laserOdometry and laserMapping as three processes connected by ROS queues
+// (SURVEY §1): while mapping works on sweep k, odometry registers sweep k+1 and scanRegistration extracts sweep k+2.
+// loam_pipeline_* is the same structure on one GPU: three stage threads, each with its own handle (state + CUDA
+// stream), device-resident hand-over through small rings of slots ordered by CUDA events.  Results are identical to
+// loam_process_sweep (same kernels, same order of operations per stage); only the latency/throughput trade changes.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+namespace {
+
+template <typename T>
+struct BQueue {
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<T> q;
+  void push(const T& v) {
+    { std::lock_guard<std::mutex> l(m); q.push_back(v); }
+    cv.notify_one();
+  }
+  T pop() {
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [&] { return !q.empty(); });
+    T v = q.front();
+    q.pop_front();
+    return v;
+  }
+};
+struct Sem {
+  std::mutex m;
+  std::condition_variable cv;
+  int n;
+  explicit Sem(int v) : n(v) {}
+  void acquire() {
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [&] { return n > 0; });
+    n--;
+  }
+  void release() {
+    { std::lock_guard<std::mutex> l(m); n++; }
+    cv.notify_one();
+  }
+};
+enum { JOB_SWEEP = 0, JOB_RESET = 1, JOB_STOP = 2 };
+struct Job {
+  long long k;
+  int kind;
+  int slot;           // input slot (stage A), feature slot (stage B), map slot or -1 (stage C)
+  const float* xyz;   // device pointer of the sweep (stage A)
+  int n, stride;
+  int odom_published, full;
+  float Tsum[6];
+};
+constexpr int PNS = 4;  // slots per ring
+
+}  // namespace
+
+struct loam_pipeline {
+  loam_handle *hA = nullptr, *hB = nullptr, *hC = nullptr;
+  int device = 0;
+  cudaStream_t copy_st = nullptr;
+  DevBuf in_xyz[PNS];
+  cudaEvent_t in_copied[PNS];
+  struct Feat {
+    DevBuf b[5];
+    loam_counts c;
+    cudaEvent_t ready, consumed;
+  } feat[PNS];
+  struct MapIn {
+    DevBuf corner, surf, full;
+    int nc, ns, nf;
+    cudaEvent_t ready, consumed;
+  } mapin[PNS];
+  Sem in_free{PNS}, feat_free{PNS}, map_free{PNS};
+  BQueue<Job> qA, qB, qC;
+  std::mutex rm;
+  std::condition_variable rcv;
+  std::map<long long, loam_sweep_result> partial, done;
+  long long next_submit = 0, next_wait = 0, in_count = 0, feat_count = 0, map_count = 0;
+  std::atomic<int> error{0};
+  std::thread tA, tB, tC;
+};
+
+namespace {
+
+void pipe_fail(loam_pipeline* p, int rc) {
+  int expected = 0;
+  p->error.compare_exchange_strong(expected, rc);
+  p->rcv.notify_all();
+}
+
+void stage_a(loam_pipeline* p) {
+  cudaSetDevice(p->device);
+  loam_handle* h = p->hA;
+  for (;;) {
+    Job j = p->qA.pop();
+    if (j.kind != JOB_SWEEP) {
+      p->qB.push(j);
+      if (j.kind == JOB_STOP) return;
+      continue;
+    }
+    loam_counts c = {0, 0, 0, 0, 0};
+    int rc = p->error.load();
+    if (!rc) {
+      if (j.slot >= 0) cudaStreamWaitEvent(h->st, p->in_copied[j.slot], 0);
+      g_lg_prof = h->prof.on ? &h->prof : nullptr;
+      rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c);
+    }
+    if (j.slot >= 0) p->in_free.release();  // extract_common synchronised: the input slot is free again
+    p->feat_free.acquire();
+    const int fs = (int)(p->feat_count++ % PNS);
+    loam_pipeline::Feat& f = p->feat[fs];
+    if (!rc) {
+      f.c = c;
+      const void* src[5] = {h->cur_full, h->cur_sharp, h->cur_less_sharp, h->cur_flat, h->cur_less_flat};
+      const int cnt[5] = {c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat};
+      cudaStreamWaitEvent(h->st, f.consumed, 0);  // odometry of the sweep that used this slot has finished reading it
+      for (int i = 0; i < 5 && !rc; i++) {
+        if (f.b[i].ensure((size_t)(cnt[i] + 16) * 16, h->st) != cudaSuccess) rc = LOAM_ECUDA;
+        else if (cnt[i]) cudaMemcpyAsync(f.b[i].p, src[i], (size_t)cnt[i] * 16, cudaMemcpyDeviceToDevice, h->st);
+      }
+      cudaEventRecord(f.ready, h->st);
+    }
+    if (rc) pipe_fail(p, rc);
+    {
+      std::lock_guard<std::mutex> l(p->rm);
+      p->partial[j.k].counts = c;
+    }
+    j.slot = fs;
+    p->qB.push(j);
+  }
+}
+
+void stage_b(loam_pipeline* p) {
+  cudaSetDevice(p->device);
+  loam_handle* h = p->hB;
+  for (;;) {
+    Job j = p->qB.pop();
+    if (j.kind == JOB_RESET) h->lo_inited = false;
+    if (j.kind != JOB_SWEEP) {
+      p->qC.push(j);
+      if (j.kind == JOB_STOP) return;
+      continue;
+    }
+    loam_pipeline::Feat& f = p->feat[j.slot];
+    loam_odom_result o;
+    memset(&o, 0, sizeof(o));
+    int rc = p->error.load();
+    int ms = -1;
+    if (!rc) {
+      cudaStreamWaitEvent(h->st, f.ready, 0);
+      h->counts = f.c;
+      h->cur_full = f.b[0].as<float4>();
+      h->cur_sharp = f.b[1].as<float4>();
+      h->cur_less_sharp = f.b[2].as<float4>();
+      h->cur_flat = f.b[3].as<float4>();
+      h->cur_less_flat = f.b[4].as<float4>();
+      h->have_features = true;
+      rc = loam_odometry_process(h, &o);
+      cudaEventRecord(f.consumed, h->st);
+    }
+    p->feat_free.release();
+    if (!rc && o.odom_published && o.fullres_published) {
+      p->map_free.acquire();
+      ms = (int)(p->map_count++ % PNS);
+      loam_pipeline::MapIn& m = p->mapin[ms];
+      m.nc = h->n_corner_last; m.ns = h->n_surf_last; m.nf = h->n_fullres3;
+      cudaStreamWaitEvent(h->st, m.consumed, 0);
+      cudaError_t e = m.corner.ensure((size_t)(m.nc + 16) * 16, h->st);
+      if (e == cudaSuccess) e = m.surf.ensure((size_t)(m.ns + 16) * 16, h->st);
+      if (e == cudaSuccess) e = m.full.ensure((size_t)(m.nf + 16) * 16, h->st);
+      if (e != cudaSuccess) rc = LOAM_ECUDA;
+      else {
+        if (m.nc) cudaMemcpyAsync(m.corner.p, h->corner_last.p, (size_t)m.nc * 16, cudaMemcpyDeviceToDevice, h->st);
+        if (m.ns) cudaMemcpyAsync(m.surf.p, h->surf_last.p, (size_t)m.ns * 16, cudaMemcpyDeviceToDevice, h->st);
+        if (m.nf) cudaMemcpyAsync(m.full.p, h->fullres3.p, (size_t)m.nf * 16, cudaMemcpyDeviceToDevice, h->st);
+        cudaEventRecord(m.ready, h->st);
+      }
+    }
+    if (rc) pipe_fail(p, rc);
+    {
+      std::lock_guard<std::mutex> l(p->rm);
+      p->partial[j.k].odom = o;
+    }
+    j.slot = ms;
+    j.odom_published = o.odom_published;
+    j.full = ms >= 0;
+    for (int i = 0; i < 6; i++) j.Tsum[i] = o.transform_sum[i];
+    p->qC.push(j);
+  }
+}
+
+void stage_c(loam_pipeline* p) {
+  cudaSetDevice(p->device);
+  loam_handle* h = p->hC;
+  for (;;) {
+    Job j = p->qC.pop();
+    if (j.kind == JOB_STOP) return;
+    if (j.kind != JOB_SWEEP) continue;
+    loam_map_result mr;
+    memset(&mr, 0, sizeof(mr));
+    int rc = p->error.load();
+    int ran = 0;
+    if (!rc && j.odom_published) rc = loam_mapping_odometry(h, j.Tsum);
+    if (j.full) {
+      loam_pipeline::MapIn& m = p->mapin[j.slot];
+      if (!rc) {
+        cudaStreamWaitEvent(h->st, m.ready, 0);
+        std::swap(h->corner_last, m.corner);
+        std::swap(h->surf_last, m.surf);
+        std::swap(h->fullres3, m.full);
+        h->n_corner_last = m.nc; h->n_surf_last = m.ns; h->n_fullres3 = m.nf;
+        rc = loam_mapping_process(h, &mr);
+        cudaEventRecord(m.consumed, h->st);
+        std::swap(h->corner_last, m.corner);
+        std::swap(h->surf_last, m.surf);
+        std::swap(h->fullres3, m.full);
+        ran = 1;
+      }
+      p->map_free.release();
+    }
+    if (rc) pipe_fail(p, rc);
+    {
+      std::lock_guard<std::mutex> l(p->rm);
+      loam_sweep_result r = p->partial[j.k];
+      p->partial.erase(j.k);
+      r.map = mr;
+      r.mapping_ran = ran;
+      p->done[j.k] = r;
+    }
+    p->rcv.notify_all();
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int loam_pipeline_create(const loam_params* prm, int device, loam_pipeline** out) {
+  if (!out) return LOAM_EINVAL;
+  *out = nullptr;
+  loam_pipeline* p = new loam_pipeline;
+  p->device = device;
+  int rc = create_internal(prm, device, 0, &p->hA);
+  if (!rc) rc = create_internal(prm, device, 1, &p->hB);
+  if (!rc) rc = create_internal(prm, device, 2, &p->hC);
+  if (rc) {
+    if (p->hA) loam_destroy(p->hA);
+    if (p->hB) loam_destroy(p->hB);
+    if (p->hC) loam_destroy(p->hC);
+    delete p;
+    return rc;
+  }
+  cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking);
+  for (int i = 0; i < PNS; i++) {
+    cudaEventCreateWithFlags(&p->in_copied[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->feat[i].ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->feat[i].consumed, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->mapin[i].ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->mapin[i].consumed, cudaEventDisableTiming);
+  }
+  p->tA = std::thread(stage_a, p);
+  p->tB = std::thread(stage_b, p);
+  p->tC = std::thread(stage_c, p);
+  *out = p;
+  return LOAM_OK;
+}
+
+int loam_pipeline_destroy(loam_pipeline* p) {
+  if (!p) return LOAM_EINVAL;
+  Job j;
+  memset(&j, 0, sizeof(j));
+  j.kind = JOB_STOP;
+  p->qA.push(j);
+  p->tA.join();
+  p->tB.join();
+  p->tC.join();
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < PNS; i++) {
+    p->in_xyz[i].release();
+    for (auto& b : p->feat[i].b) b.release();
+    p->mapin[i].corner.release(); p->mapin[i].surf.release(); p->mapin[i].full.release();
+    cudaEventDestroy(p->in_copied[i]);
+    cudaEventDestroy(p->feat[i].ready); cudaEventDestroy(p->feat[i].consumed);
+    cudaEventDestroy(p->mapin[i].ready); cudaEventDestroy(p->mapin[i].consumed);
+  }
+  cudaStreamDestroy(p->copy_st);
+  loam_destroy(p->hA);
+  loam_destroy(p->hB);
+  loam_destroy(p->hC);
+  delete p;
+  return LOAM_OK;
+}
+
+int loam_pipeline_reset(loam_pipeline* p) {
+  if (!p) return LOAM_EINVAL;
+  Job j;
+  memset(&j, 0, sizeof(j));
+  j.kind = JOB_RESET;
+  p->qA.push(j);
+  return LOAM_OK;
+}
+
+static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride_bytes, bool host) {
+  if (!p || n < 0 || (!xyz && n > 0) || stride_bytes < 12 || (stride_bytes & 3)) return LOAM_EINVAL;
+  if (int e = p->error.load()) return e;
+  LG_CHECK(cudaSetDevice(p->device));
+  Job j;
+  memset(&j, 0, sizeof(j));
+  j.kind = JOB_SWEEP;
+  j.n = n;
+  j.stride = stride_bytes;
+  j.slot = -1;
+  j.xyz = xyz;
+  if (host) {
+    p->in_free.acquire();
+    const int s = (int)(p->in_count++ % PNS);
+    LG_CHECK(p->in_xyz[s].ensure((size_t)n * stride_bytes + 64, p->copy_st));
+    if (n) LG_CHECK(cudaMemcpyAsync(p->in_xyz[s].p, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, p->copy_st));
+    LG_CHECK(cudaEventRecord(p->in_copied[s], p->copy_st));
+    LG_CHECK(cudaEventSynchronize(p->in_copied[s]));  // the caller may reuse its buffer as soon as we return
+    p->hA->h2d_bytes += (long long)n * stride_bytes;
+    j.slot = s;
+    j.xyz = p->in_xyz[s].as<float>();
+  }
+  {
+    std::lock_guard<std::mutex> l(p->rm);
+    j.k = p->next_submit++;
+    memset(&p->partial[j.k], 0, sizeof(loam_sweep_result));
+  }
+  p->qA.push(j);
+  return LOAM_OK;
+}
+int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double) {
+  return pipeline_submit(p, xyz_host, n, stride_bytes, true);
+}
+int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double) {
+  return pipeline_submit(p, xyz_dev, n, stride_bytes, false);
+}
+
+int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out) {
+  if (!p || !out) return LOAM_EINVAL;
+  std::unique_lock<std::mutex> l(p->rm);
+  if (p->next_wait >= p->next_submit) return LOAM_ESTATE;
+  const long long k = p->next_wait;
+  p->rcv.wait(l, [&] { return p->done.count(k) > 0; });
+  *out = p->done[k];
+  p->done.erase(k);
+  p->next_wait++;
+  return p->error.load();
+}
+
+int loam_pipeline_pending(loam_pipeline* p) {
+  if (!p) return LOAM_EINVAL;
+  std::lock_guard<std::mutex> l(p->rm);
+  return (int)(p->next_submit - p->next_wait);
+}
+
+int loam_pipeline_stats(loam_pipeline* p, long long out4[4]) {
+  if (!p || !out4) return LOAM_EINVAL;
+  for (int i = 0; i < 4; i++) out4[i] = 0;
+  for (loam_handle* h : {p->hA, p->hB, p->hC}) {
+    out4[0] += h->launches; out4[1] += h->h2d_bytes; out4[2] += h->d2h_bytes; out4[3] += h->syncs;
   }
   return LOAM_OK;
 }

@@ -188,6 +188,21 @@ int loam_gn_solve(const float AtA[36], const float AtB[6], int iter, float eig_t
 int loam_map_iter_partial(loam_handle* h, int iter, const float T[6], double* partial_dev28);
 int loam_map_finish_reduced(const double reduced28_host[28], float AtA[36], float AtB[6], int* n_sel);
 
+/* ---- pipelined mode: the reference's three-process layout (SR | LO | LM connected by queues) on one GPU ----------
+ * Three stage threads inside the library, one handle (state + stream) per stage, device-resident hand-over.  Results
+ * are identical to loam_process_sweep; sweep k+2 is extracted while k+1 is registered and k is mapped.
+ * submit returns as soon as the host buffer may be reused; wait returns the results in submission order (blocking). */
+typedef struct loam_pipeline loam_pipeline;
+int loam_pipeline_create(const loam_params* p, int device, loam_pipeline** out);
+int loam_pipeline_destroy(loam_pipeline* p);
+int loam_pipeline_reset(loam_pipeline* p); /* IMControl{false}, ordered with the submitted sweeps */
+int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double stamp);
+/* device-resident sweep: the buffer must stay valid until the sweep's result has been returned */
+int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp);
+int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out);
+int loam_pipeline_pending(loam_pipeline* p);
+int loam_pipeline_stats(loam_pipeline* p, long long out4[4]);
+
 #ifdef __cplusplus
 }
 #endif

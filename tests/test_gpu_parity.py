@@ -292,3 +292,27 @@ def test_registered_and_surround_clouds(orc, sweeps16):
                 s, rs = gpu.cloud("surround"), pipe.cloud("surround")
                 assert s.shape == rs.shape
     gpu.close()
+
+
+def test_pipelined_mode_equals_fused(sweeps16):
+    """loam_pipeline_* (three stage threads, SR | LO | LM) must give exactly the results of loam_process_sweep."""
+    from gpscalibration_b200 import LoamGpu, LoamGpuPipeline
+    a = LoamGpu()
+    ref = [a.process_sweep(x) for x in sweeps16]
+    a.close()
+    p = LoamGpuPipeline()
+    for rep in range(2):  # second pass after an ordered reset
+        for x in sweeps16:
+            p.submit(x)
+        got = [p.wait() for _ in sweeps16]
+        assert p.pending == 0
+        if rep == 0:
+            for k, (r, g) in enumerate(zip(ref, got)):
+                assert (r.counts.n_full, r.counts.n_less_flat) == (g.counts.n_full, g.counts.n_less_flat), k
+                assert list(r.odom.transform_sum) == list(g.odom.transform_sum), k
+                assert r.odom.iterations == g.odom.iterations and r.mapping_ran == g.mapping_ran, k
+                if r.mapping_ran:
+                    assert list(r.map.transform_aft_mapped) == list(g.map.transform_aft_mapped), k
+                    assert (r.map.n_corner_map, r.map.n_surf_map, r.map.iterations) == (g.map.n_corner_map, g.map.n_surf_map, g.map.iterations)
+        p.reset()
+    p.close()
