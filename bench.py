@@ -6,9 +6,10 @@ reference's own ring-table angles, seed 0xC0FFEE + 1000 * rank) through the full
 One STEP = reset + one pass over the whole sequence.  With N > 1 ranks every rank registers its own independent
 sequence (BASELINE configs[3], no data-path collective): weak scaling, value = all sweeps / max-over-ranks time.
 
-  value : device-timed (CUDA events on the library's stream), the sweeps already resident in HBM
+  value : device-timed (CUDA events bracketing all stage streams), the sweeps already resident in HBM, pipelined C ABI
   e2e   : the same through the reference-facing C-ABI call with HOST buffers (pinned): H2D of every sweep and the
           D2H reads of counts / 28-double normal-equation mailboxes / poses inside the timed region
+  sync_api : both numbers again through the blocking one-call-per-sweep entry point (loam_process_sweep)
   roofline : dominant kernel class from a separate CUDA-event pass (loam_profile), algorithmic bytes per DESIGN.md
   cpu_baseline : the CPU oracle (restatement of the reference; oracle/_ref when built) on this box's host cores
 
@@ -207,57 +208,85 @@ def main():
     dev = host[:n_pts].cuda()
     log(f"[rank {rank}] generated {args.sweeps} sweeps ({n_pts * 12 / 1e6:.0f} MB) in {time.perf_counter() - t_gen:.1f}s")
 
-    gpu = LoamGpu(device=local_rank)
-    stream = torch.cuda.ExternalStream(gpu.stream, device=torch.device("cuda", local_rank))
+    from gpscalibration_b200 import LoamGpuPipeline
+    dev_t = torch.device("cuda", local_rank)
+    gpu = LoamGpu(device=local_rank)          # synchronous per-sweep call (loam_process_sweep)
+    pipe = LoamGpuPipeline(device=local_rank)  # pipelined mode (loam_pipeline_*): the reference's SR | LO | LM layout
+    sync_stream = torch.cuda.ExternalStream(gpu.stream, device=dev_t)
+    stage_streams = [torch.cuda.ExternalStream(pipe.stream(i), device=dev_t) for i in range(3)]
+    join_stream = torch.cuda.Stream(device=dev_t)
     base_dev = dev.data_ptr()
     S = args.sweeps
+    DEPTH = 6  # sweeps in flight before the caller starts collecting results
 
-    def step_device():
+    def step_pipe(host_buffers):
+        pipe.reset()
+        last = None
+        for k in range(S):
+            if host_buffers:
+                pipe.submit(arr[offs[k]:offs[k + 1]])
+            else:
+                pipe.submit_device(base_dev + int(offs[k]) * 12, int(offs[k + 1] - offs[k]))
+            if k >= DEPTH:
+                last = pipe.wait()
+        while pipe.pending:
+            last = pipe.wait()
+        return last
+
+    def step_sync(host_buffers):
         gpu.reset()
         last = None
         for k in range(S):
-            last = gpu.process_sweep_device(base_dev + int(offs[k]) * 12, int(offs[k + 1] - offs[k]))
+            if host_buffers:
+                last = gpu.process_sweep(arr[offs[k]:offs[k + 1]])
+            else:
+                last = gpu.process_sweep_device(base_dev + int(offs[k]) * 12, int(offs[k + 1] - offs[k]))
         return last
 
-    def step_host():
-        gpu.reset()
-        last = None
-        for k in range(S):
-            last = gpu.process_sweep(arr[offs[k]:offs[k + 1]])
-        return last
-
-    def timed(fn, steps):
+    def timed(fn, steps, streams, stats_fn):
+        """K steps bracketed by barrier + synchronize; device time from CUDA events that bracket every stage stream."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0 = gpu.stats()
+        s0 = stats_fn()
         w0 = time.perf_counter()
-        e0.record(stream)
+        e0.record(join_stream)
+        for st in streams:
+            st.wait_event(e0)
         for _ in range(steps):
             last = fn()
-        e1.record(stream)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            join_stream.wait_event(ev)
+        e1.record(join_stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - w0
         barrier()
-        s1 = gpu.stats()
-        ms = e0.elapsed_time(e1)
-        return ms, wall, {k: s1[k] - s0[k] for k in s0}, last
+        s1 = stats_fn()
+        return e0.elapsed_time(e1), wall, {k: s1[k] - s0[k] for k in s0}, last
 
     for w in range(args.warmup):
-        step_device()
-    step_host()
+        step_pipe(False)
+    step_pipe(True)
+    step_sync(True)
+    step_sync(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, wall_dev, st_dev, last = timed(step_device, args.steps)
-    ms_e2e, wall_e2e, st_e2e, _ = timed(step_host, args.steps)
+    ms_dev, wall_dev, st_dev, last = timed(lambda: step_pipe(False), args.steps, stage_streams, pipe.stats)
+    ms_e2e, wall_e2e, st_e2e, _ = timed(lambda: step_pipe(True), args.steps, stage_streams, pipe.stats)
     clocks = sampler.stop()
+    ms_sync_dev, _, _, last_sync = timed(lambda: step_sync(False), args.steps, [sync_stream], gpu.stats)
+    ms_sync_e2e, _, st_sync_e2e, _ = timed(lambda: step_sync(True), args.steps, [sync_stream], gpu.stats)
     ms_dev_max = max_over_ranks(ms_dev)
     ms_e2e_max = max_over_ranks(ms_e2e)
     value = world * S * args.steps / (ms_dev_max / 1e3)
     e2e_value = world * S * args.steps / (ms_e2e_max / 1e3)
+    sync_value = world * S * args.steps / (max_over_ranks(ms_sync_dev) / 1e3)
+    sync_e2e_value = world * S * args.steps / (max_over_ranks(ms_sync_e2e) / 1e3)
 
     # roofline: separate CUDA-event pass over one step (events around every launch group perturb the step time)
     gpu.profile(True)
-    step_device()
+    step_sync(False)
     prof = gpu.profile_read()
     gpu.profile(False)
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -291,10 +320,13 @@ def main():
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"] // args.steps,
                    "d2h_bytes_per_step": st_e2e["d2h_bytes"] // args.steps, "ms_per_step": ms_e2e_max / args.steps},
-           "gpu_launches": int(st_dev["launches"]), "host_syncs_per_step": st_dev["syncs"] // args.steps,
-           "wall_vs_event_ms": [round(1e3 * wall_dev, 1), round(ms_dev, 1)], "roofline": roofline,
+           "gpu_launches": int(st_dev["launches"]), "host_handovers_per_step": st_dev["syncs"] // args.steps,
+           "wall_vs_event_ms": [round(1e3 * wall_dev, 1), round(ms_dev, 1)],
+           "mode": "pipelined C ABI (loam_pipeline_submit / loam_pipeline_wait): stage threads SR | LO | LM like the reference's three processes",
+           "sync_api": {"call": "loam_process_sweep (one blocking call per sweep)", "value": sync_value, "e2e": sync_e2e_value, "unit": UNIT},
+           "roofline": roofline,
            "final_pose_odom": [round(float(x), 4) for x in last.odom.transform_sum],
-           "final_pose_mapped": [round(float(x), 4) for x in last.map.transform_aft_mapped]}
+           "results_identical_sync_vs_pipelined": list(last.odom.transform_sum) == list(last_sync.odom.transform_sum)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(args.cpu_sweeps, S)
@@ -304,6 +336,7 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     gpu.close()
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

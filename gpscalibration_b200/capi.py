@@ -61,6 +61,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_stream",
            "loam_pipeline_stats"]
 
 
@@ -122,6 +123,8 @@ def load_library():
     lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
     lib.loam_pipeline_pending.argtypes = [vp]
+    lib.loam_pipeline_stream.restype = vp
+    lib.loam_pipeline_stream.argtypes = [vp, C.c_int]
     lib.loam_pipeline_stats.argtypes = [vp, vp]
     _LIB = lib
     return lib
@@ -366,6 +369,9 @@ class LoamGpuPipeline:
     @property
     def pending(self):
         return self.lib.loam_pipeline_pending(self._h)
+
+    def stream(self, which):
+        return self.lib.loam_pipeline_stream(self._h, which)
 
     def stats(self):
         out = (C.c_longlong * 4)()

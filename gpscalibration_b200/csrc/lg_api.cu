@@ -1591,6 +1591,12 @@ int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out) {
   return p->error.load();
 }
 
+void* loam_pipeline_stream(loam_pipeline* p, int which) {
+  if (!p || which < 0 || which > 2) return nullptr;
+  loam_handle* hs[3] = {p->hA, p->hB, p->hC};
+  return (void*)hs[which]->st;
+}
+
 int loam_pipeline_pending(loam_pipeline* p) {
   if (!p) return LOAM_EINVAL;
   std::lock_guard<std::mutex> l(p->rm);

@@ -201,6 +201,8 @@ int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int str
 int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp);
 int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out);
 int loam_pipeline_pending(loam_pipeline* p);
+/* cudaStream_t of stage `which` (0 extract, 1 odometry, 2 mapping), for CUDA-event timing by the caller */
+void* loam_pipeline_stream(loam_pipeline* p, int which);
 int loam_pipeline_stats(loam_pipeline* p, long long out4[4]);
 
 #ifdef __cplusplus

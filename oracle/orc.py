@@ -58,6 +58,8 @@ def lib():
         L.orc_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_pipeline_destroy.argtypes = [vp]
         L.orc_pipeline_reset.argtypes = [vp]
+        L.orc_pipeline_set_ros_hop.argtypes = [vp, C.c_int]
+        L.orc_odometry_ros_hop.argtypes = [vp, vp]
         L.orc_pipeline_process.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(PipelineResult)]
         L.orc_pipeline_cloud.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_pipeline_run_threaded.argtypes = [vp, vp, vp, C.c_int, vp]
@@ -226,6 +228,10 @@ class Pipeline:
 
     def reset(self):
         lib().orc_pipeline_reset(self._h)
+
+    def set_ros_hop(self, on=True):
+        """Route the odometry pose through the quaternion message like the reference's ROS nodes do (LO:1066-1078, LM:322-332)."""
+        lib().orc_pipeline_set_ros_hop(self._h, int(on))
 
     def process(self, xyz):
         xyz = _f32(xyz)

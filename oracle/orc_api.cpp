@@ -59,6 +59,7 @@ struct PipelineResult {  // mirrored by ctypes in tests/bench
 };
 
 struct Pipeline {
+  bool ros_hop = false;  // route the odometry pose through the quaternion message like the ROS nodes do
   SRH sr;
   LaserOdometry lo;
   LaserMapping lm;
@@ -256,6 +257,8 @@ void* orc_pipeline_create(int n_scans, int ring_mode, float ang_min, float ang_s
   return p;
 }
 void orc_pipeline_destroy(void* h) { delete (Pipeline*)h; }
+void orc_pipeline_set_ros_hop(void* h, int on) { ((Pipeline*)h)->ros_hop = on != 0; }
+void orc_odometry_ros_hop(const float* in6, float* out6) { odometry_ros_hop(in6, out6); }
 // IMControl{systemInited=false} (IN:281-284): odometry re-initialises on the next sweep, mapping when it sees zero odometry.
 void orc_pipeline_reset(void* h) { ((Pipeline*)h)->lo.control(false); }
 
@@ -270,7 +273,11 @@ int orc_pipeline_process(void* hv, const float* xyz, int n, int stride_floats, P
   p->lo.process(f.sharp, f.lessSharp, f.flat, f.lessFlat, f.full, imu, p->oo);
   double t2 = now_s();
   r->odom_published = p->oo.odomPublished;
-  if (p->oo.odomPublished) p->lm.odometry_msg(p->oo.transformSum);
+  if (p->oo.odomPublished) {
+    float ts[6];
+    if (p->ros_hop) odometry_ros_hop(p->oo.transformSum, ts); else std::memcpy(ts, p->oo.transformSum, sizeof(ts));
+    p->lm.odometry_msg(ts);
+  }
   if (p->oo.odomPublished && p->oo.fullResPublished) {
     p->lm.process(p->oo.cornerLast, p->oo.surfLast, p->oo.fullRes, p->mo);
     r->mapping_ran = 1;

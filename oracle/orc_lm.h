@@ -92,6 +92,38 @@ inline void transform_associate_to_map(const float* Tsum, const float* Tbef, con
   Ttobe[5] = Taft[5] - (-sinf(Ttobe[1]) * x2 + cosf(Ttobe[1]) * z2);
 }
 
+// The ROS hop between the two nodes: laserOdometry publishes transformSum as a quaternion built from
+// (rz, -rx, -ry) with the axes permuted (LO:1066-1078) and laserMapping's handler turns it back into
+// (-pitch, -yaw, roll) (LM:322-332), all in double.  Identity up to an ulp; restated so the oracle can be compared
+// bit-for-bit with the reference's own nodes wired through messages.
+inline void odometry_ros_hop(const float* Tsum_in, float* Tsum_out) {
+  double roll = Tsum_in[2], pitch = -Tsum_in[0], yaw = -Tsum_in[1];
+  double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+  double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+  double gx = sr * cp * cy - cr * sp * sy, gy = cr * sp * cy + sr * cp * sy, gz = cr * cp * sy - sr * sp * cy, gw = cr * cp * cy + sr * sp * sy;
+  double ox = -gy, oy = -gz, oz = gx, ow = gw;   // published orientation
+  double qx = oz, qy = -ox, qz = -oy, qw = ow;   // tf::Quaternion(geoQuat.z, -geoQuat.x, -geoQuat.y, geoQuat.w)
+  double d = qx * qx + qy * qy + qz * qz + qw * qw, s = 2.0 / d;
+  double xs = qx * s, ys = qy * s, zs = qz * s;
+  double wx = qw * xs, wy = qw * ys, wz = qw * zs, xx = qx * xs, xy = qx * ys, xz = qx * zs, yy = qy * ys, yz = qy * zs, zz = qz * zs;
+  double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy), m01 = xy - wz, m02 = xz + wy;
+  double r, p, y;
+  if (std::fabs(m20) >= 1) {
+    y = 0;
+    if (m20 < 0) { p = M_PI / 2.0; r = std::atan2(m01, m02); } else { p = -M_PI / 2.0; r = std::atan2(-m01, -m02); }
+  } else {
+    p = -std::asin(m20);
+    r = std::atan2(m21 / std::cos(p), m22 / std::cos(p));
+    y = std::atan2(m10 / std::cos(p), m00 / std::cos(p));
+  }
+  Tsum_out[0] = (float)-p;
+  Tsum_out[1] = (float)-y;
+  Tsum_out[2] = (float)r;
+  Tsum_out[3] = (float)(double)Tsum_in[3];
+  Tsum_out[4] = (float)(double)Tsum_in[4];
+  Tsum_out[5] = (float)(double)Tsum_in[5];
+}
+
 struct MapCorr {  // 5 neighbour indices per stack point, -1 when the 5th neighbour is not within 1 m (diagnostic)
   std::vector<int> corner, surf;
 };

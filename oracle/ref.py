@@ -1,0 +1,172 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes driver of oracle/_ref/*.so: the reference's OWN scanRegistration.cpp,
+laserOdometry.cpp and laserMapping.cpp, compiled unmodified from /root/reference against the shim headers in
+oracle/ref_build/shim (recipe: oracle/ref_build/Makefile).  The three nodes are wired the way gpsCalibration.launch
+wires them: clouds and the odometry message (position + quaternion) are passed from node to node.
+
+Each node's file-scope state lives in its shared object, so there is ONE pipeline per process.
+"""
+import atexit
+import ctypes as C
+import os
+import queue
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "_ref")
+_LIBS = None
+
+
+def available():
+    return all(os.path.exists(os.path.join(_DIR, f)) for f in ("libref_sr.so", "libref_lo.so", "libref_lm.so"))
+
+
+def _libs():
+    global _LIBS
+    if _LIBS is None:
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        sr = C.CDLL(os.path.join(_DIR, "libref_sr.so"))
+        lo = C.CDLL(os.path.join(_DIR, "libref_lo.so"))
+        lm = C.CDLL(os.path.join(_DIR, "libref_lm.so"))
+        sr.ref_sr_process.argtypes = [vp, C.c_int, C.c_double]
+        sr.ref_sr_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lo.ref_lo_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
+        lo.ref_lo_control.argtypes = [C.c_int]
+        lo.ref_lo_odometry.argtypes = [vp]
+        lo.ref_lo_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lm.ref_lm_odometry_only.argtypes = [vp, C.c_double]
+        lm.ref_lm_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
+        lm.ref_lm_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lm.ref_lm_map_size.argtypes = [ip, ip]
+        lo.ref_lo_start()
+        lm.ref_lm_start()
+        _LIBS = (sr, lo, lm)
+        atexit.register(shutdown)
+    return _LIBS
+
+
+def shutdown():
+    """Stops the two node loop threads (must run before the interpreter exits)."""
+    global _LIBS
+    if _LIBS is not None:
+        _LIBS[1].ref_lo_stop()
+        _LIBS[2].ref_lm_stop()
+        _LIBS = None
+
+
+def _cloud(fn, which):
+    n = fn(which, None, 0)
+    out = np.empty((n, 4), np.float32)
+    if n:
+        fn(which, out.ctypes.data, n)
+    return out
+
+
+class SweepOut:
+    __slots__ = ("features", "odom", "rel", "odom_published", "clouds_published", "fullres_published", "mapping_ran", "mapped",
+                 "bef_mapped", "tobe_mapped")
+
+
+def sr_process(xyz, stamp):
+    sr, _, _ = _libs()
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    sr.ref_sr_process(xyz.ctypes.data, xyz.shape[0], float(stamp))
+    return [_cloud(sr.ref_sr_cloud, w) for w in range(5)]  # full, sharp, less sharp, flat, less flat
+
+
+def lo_step(feat, stamp):
+    _, lo, _ = _libs()
+    full, sharp, less_sharp, flat, less_flat = feat
+    out = np.zeros(18, np.float32)
+    lo.ref_lo_step(sharp.ctypes.data, sharp.shape[0], less_sharp.ctypes.data, less_sharp.shape[0], flat.ctypes.data, flat.shape[0],
+                   less_flat.ctypes.data, less_flat.shape[0], full.ctypes.data, full.shape[0], None, float(stamp), out.ctypes.data)
+    pose7 = np.zeros(7, np.float64)
+    lo.ref_lo_odometry(pose7.ctypes.data)
+    clouds = None
+    if out[13] > 0:
+        clouds = [_cloud(lo.ref_lo_cloud, w) for w in range(3)]
+    return out, pose7, clouds
+
+
+def lm_step(clouds, pose7, stamp, full_set):
+    _, _, lm = _libs()
+    if not full_set:
+        lm.ref_lm_odometry_only(pose7.ctypes.data, float(stamp))
+        return None
+    out = np.zeros(24, np.float32)
+    c, s, f = clouds
+    lm.ref_lm_step(c.ctypes.data, c.shape[0], s.ctypes.data, s.shape[0], f.ctypes.data, f.shape[0], pose7.ctypes.data, float(stamp),
+                   out.ctypes.data)
+    return out
+
+
+def control_reset():
+    """IMControl{systemInited=false} to laserOdometry (IN:281-284)."""
+    _libs()[1].ref_lo_control(0)
+
+
+def process(xyz, stamp):
+    """One sweep through the three reference nodes, sequentially."""
+    r = SweepOut()
+    feat = sr_process(xyz, stamp)
+    r.features = feat
+    o, pose7, clouds = lo_step(feat, stamp)
+    r.odom, r.rel = o[:6].copy(), o[6:12].copy()
+    r.odom_published, r.clouds_published, r.fullres_published = bool(o[12] > 0), bool(o[13] > 0), bool(o[14] > 0)
+    r.mapping_ran = False
+    r.mapped = r.bef_mapped = r.tobe_mapped = None
+    if r.odom_published:
+        m = lm_step(clouds, pose7, stamp, r.fullres_published)
+        if m is not None:
+            r.mapping_ran = True
+            r.mapped, r.bef_mapped, r.tobe_mapped = m[:6].copy(), m[6:12].copy(), m[12:18].copy()
+    return r
+
+
+def map_size():
+    a, b = C.c_int(), C.c_int()
+    _libs()[2].ref_lm_map_size(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def run_sequence(arr, offs, t0=100.0):
+    """A whole sequence with the three nodes running concurrently (three Python threads; ctypes releases the GIL),
+    which is how the reference runs them as three ROS processes.  Returns the list of final poses per sweep."""
+    control_reset()
+    n = len(offs) - 1
+    q1, q2 = queue.Queue(maxsize=8), queue.Queue(maxsize=8)
+    res = [None] * n
+
+    def a():
+        for k in range(n):
+            q1.put((k, sr_process(arr[offs[k]:offs[k + 1]], t0 + 0.1 * k)))
+        q1.put(None)
+
+    def b():
+        while True:
+            it = q1.get()
+            if it is None:
+                q2.put(None)
+                return
+            k, feat = it
+            o, pose7, clouds = lo_step(feat, t0 + 0.1 * k)
+            q2.put((k, o, pose7, clouds))
+
+    def c():
+        while True:
+            it = q2.get()
+            if it is None:
+                return
+            k, o, pose7, clouds = it
+            m = None
+            if o[12] > 0:
+                m = lm_step(clouds, pose7, t0 + 0.1 * k, o[14] > 0)
+            res[k] = (o[:6].copy(), None if m is None else m[:6].copy())
+
+    ts = [threading.Thread(target=f) for f in (a, b, c)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return res

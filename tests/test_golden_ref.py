@@ -1,0 +1,107 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE (tests/golden/make_golden.py ran scanRegistration.cpp,
+laserOdometry.cpp and laserMapping.cpp, compiled unmodified from /root/reference, on the seeded sequence).
+
+CPU: the oracle restatement must reproduce them bit-for-bit; where oracle/_ref is present the reference itself is
+re-run against the oracle.  GPU (marked): the CUDA path through the C ABI must reproduce them bit-for-bit as well.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = ("full", "sharp", "less_sharp", "flat", "less_flat")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_vlp16_seq.npz"))
+
+
+@pytest.fixture(scope="module")
+def seq(golden):
+    from gpscalibration_b200 import SweepGenerator
+    gen = SweepGenerator(sensor=0, scene=0, seed=0xC0FFEE)
+    sweeps = [gen.sweep(k)[0].copy() for k in range(int(golden["n_sweeps"]))]
+    for k, x in enumerate(sweeps):  # the generator must still produce the sweeps the fixture was made from
+        assert sha(x) == str(golden["in_hash"][k]), k
+    return sweeps
+
+
+def test_oracle_reproduces_reference_golden(orc, golden, seq):
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    head = int(golden["head"])
+    for k, x in enumerate(seq):
+        r = pipe.process(x)
+        assert [r.n_full, r.n_sharp, r.n_less_sharp, r.n_flat, r.n_less_flat] == golden["counts"][k].tolist(), k
+        for i, nm in enumerate(NAMES):
+            c = pipe.cloud(nm)
+            assert sha(c) == str(golden["cloud_hash"][k][i]), (k, nm)  # every feature cloud bit-exact
+            assert np.array_equal(c[:head], golden["head_" + nm][k][:c[:head].shape[0]])
+        assert [r.odom_published, r.mapping_ran] == [golden["flags"][k][0], golden["flags"][k][2]], k
+        assert np.array_equal(np.array(r.odom, np.float32), golden["odom"][k]), k
+        assert np.array_equal(np.array(r.rel, np.float32), golden["rel"][k]), k
+        if r.mapping_ran:
+            assert np.array_equal(np.array(r.mapped, np.float32), golden["mapped"][k]), k
+    assert list(pipe.map_size()) == golden["map_size"].tolist()
+
+
+def test_reference_itself_matches_oracle(orc, seq):
+    """Re-runs the reference's own translation units (oracle/_ref) next to the oracle; skipped where they are absent."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    ref.control_reset()
+    try:
+        for k, x in enumerate(seq[:8]):
+            r = ref.process(x, 200.0 + 0.1 * k)
+            o = pipe.process(x)
+            for i, nm in enumerate(NAMES):
+                assert np.array_equal(r.features[i].view(np.uint32), pipe.cloud(nm).view(np.uint32)), (k, nm)
+            assert np.array_equal(r.odom, np.array(o.odom, np.float32)), k
+            assert r.mapping_ran == bool(o.mapping_ran)
+            if r.mapping_ran:
+                assert np.array_equal(r.mapped, np.array(o.mapped, np.float32)), k
+    finally:
+        ref.shutdown()
+
+
+def test_ros_pose_hop_is_identity_on_the_sequence(orc, golden):
+    """LO:1066-1078 -> LM:322-332 (pose through a quaternion message) returns the same floats on this sequence."""
+    import ctypes as C
+    L = orc.lib()
+    for k in range(int(golden["n_sweeps"])):
+        a = np.ascontiguousarray(golden["odom"][k], np.float32)
+        b = np.zeros(6, np.float32)
+        L.orc_odometry_ros_hop(a.ctypes.data, b.ctypes.data)
+        assert np.abs(a - b).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_reference_golden(golden, seq):
+    from gpscalibration_b200 import LoamGpu
+    gpu = LoamGpu()
+    head = int(golden["head"])
+    for k, x in enumerate(seq):
+        r = gpu.process_sweep(x)
+        c = r.counts
+        assert [c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat] == golden["counts"][k].tolist(), k
+        if k < 6:
+            for nm in NAMES:
+                cl = gpu.cloud(nm)
+                assert sha(cl) == str(golden["cloud_hash"][k][NAMES.index(nm)]), (k, nm)
+                assert np.array_equal(cl[:head], golden["head_" + nm][k][:cl[:head].shape[0]])
+        assert [r.odom.odom_published, r.mapping_ran] == [golden["flags"][k][0], golden["flags"][k][2]], k
+        assert np.array_equal(np.array(r.odom.transform_sum, np.float32), golden["odom"][k]), k
+        assert np.array_equal(np.array(r.odom.transformation, np.float32), golden["rel"][k]), k
+        if r.mapping_ran:
+            assert np.array_equal(np.array(r.map.transform_aft_mapped, np.float32), golden["mapped"][k]), k
+    gpu.close()
