@@ -156,7 +156,7 @@ def main():
     config = {"workload": "cfg2: synthetic 1000-sweep VLP-16-shaped sequence (16x1800, reference ring table), extract + "
                           "odometry + mapping, one independent sequence per GPU",
               "sweeps_per_step": args.sweeps, "points_per_sweep": 28800, "seed": "0xC0FFEE + 1000*rank",
-              "l2": "inputs larger than L2 (345 MB of sweeps per step, each touched once)"}
+              "l2": "inputs larger than L2 (%d MB of sweeps per step, each touched once)" % (args.sweeps * 28800 * 12 // 1000000)}
 
     # ------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
