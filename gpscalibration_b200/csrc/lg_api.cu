@@ -106,6 +106,8 @@ struct loam_handle {
   LgGNState lm_gn;
   std::vector<std::vector<Chunk>> cubeC, cubeS;  // laserCloudCornerArray / laserCloudSurfArray LM:98-99 as arena chunks
   DevBuf arena, arena2;
+  bool use_merge_path = true;   // voxel-grid valid cubes by merging sorted old clouds with the sorted new points
+  long long merge_fallbacks = 0;  // times the merge path's sortedness check failed and the full sort ran instead
   size_t bump = 0;  // in points
   DevBuf stack2_c, stack2_s, stack_c, stack_s, map_c, map_s;
   int n_stack_c = 0, n_stack_s = 0, n_map_c = 0, n_map_s = 0;
@@ -851,23 +853,42 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
     if (rc) return rc;
     ht.lap(&h->host_s[13]);
     const float4* ar = h->arena.as<float4>();
+    // Two layouts of the same input: segment-major [old chunks, new run] per segment (full sort path) and
+    // [all old | all new] (merge path: old clouds are already voxel-gridded, only the new points get sorted).
+    std::vector<CopyEnt> ents_m;
+    std::vector<int> off_old(1, 0), off_new(1, 0);
+    bool merge_ok = true;
     for (int ind : validInd)
       for (int type = 0; type < 2; type++) {
         auto& cube = type == 0 ? h->cubeC[ind] : h->cubeS[ind];
         auto& runs = type == 0 ? runC : runS;
-        int off = seg_off.back();
+        int off = seg_off.back(), oo = off_old.back(), on = off_new.back();
+        int nchunks = 0;
         for (auto& c : cube)
-          if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+          if (c.n > 0) {
+            ents.push_back(CopyEnt{ar + c.off, c.n, off});
+            ents_m.push_back(CopyEnt{ar + c.off, c.n, oo});
+            off += c.n; oo += c.n;
+            max_n = std::max(max_n, c.n);
+            nchunks++;
+          }
+        if (nchunks > 1) merge_ok = false;  // raw appended chunks: the old cloud is not a voxel-grid output
         auto it = runs.find(ind);
         if (it != runs.end()) {
           ents.push_back(CopyEnt{ins + it->second.first, it->second.second, off});
-          off += it->second.second;
+          ents_m.push_back(CopyEnt{ins + it->second.first, it->second.second, -1 - on});  // patched below: M_old + on
+          off += it->second.second; on += it->second.second;
           max_n = std::max(max_n, it->second.second);
           runs.erase(it);
         }
         seg_off.push_back(off);
+        off_old.push_back(oo);
+        off_new.push_back(on);
         leaf.push_back(type == 0 ? 0.2f : 0.4f);
       }
+    const int n_old = off_old.back(), n_new = off_new.back();
+    for (auto& e : ents_m)
+      if (e.dst_off < 0) e.dst_off = n_old + (-1 - e.dst_off);
     // runs left over belong to cubes that are not voxel-gridded this time: append raw (push_back semantics)
     {
       std::vector<CopyEnt> app;
@@ -891,26 +912,52 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
     const int Mtot = seg_off.back();
     if (nseg > 0 && Mtot > 0) {
       LG_CHECK(h->ds_in.ensure((size_t)(Mtot + 16) * 16, h->st));
-      rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
-      if (rc) return rc;
-      rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
-      if (rc) return rc;
-      rc = upload(h, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
-      if (rc) return rc;
-      rc = upload(h, h->d_seg_leaf, leaf.data(), nseg * 4);
-      if (rc) return rc;
-      LG_CHECK(h->d_out_se.ensure((size_t)nseg * 8 + 16, h->st));
+      LG_CHECK(h->d_out_se.ensure((size_t)nseg * 8 + 64, h->st));
       int* d_start = h->d_out_se.as<int>();
       int* d_end = d_start + nseg;
+      int* d_flags = d_end + nseg;
       float4* outp = h->arena.as<float4>() + h->bump;
-      ht.lap(&h->host_s[14]);
-      rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, h->st,
-                      &h->launches);
+      rc = upload(h, h->d_seg_leaf, leaf.data(), nseg * 4);
       if (rc) return rc;
-      ht.lap(&h->host_s[15]);
-      if (2 * nseg > loam_handle::H_INTS) return LOAM_ENOSPC;
-      LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8);
-      LG_SYNC(h);
+      if (2 * nseg + 1 > loam_handle::H_INTS) return LOAM_ENOSPC;
+      bool done = false;
+      if (merge_ok && h->use_merge_path) {
+        std::vector<int> offs3;  // [old | new | merged] offset tables in one upload
+        offs3.insert(offs3.end(), off_old.begin(), off_old.end());
+        offs3.insert(offs3.end(), off_new.begin(), off_new.end());
+        offs3.insert(offs3.end(), seg_off.begin(), seg_off.end());
+        rc = upload(h, h->d_ents, ents_m.data(), ents_m.size() * sizeof(CopyEnt));
+        if (rc) return rc;
+        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents_m.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+        if (rc) return rc;
+        rc = upload(h, h->d_seg_off, offs3.data(), offs3.size() * 4);
+        if (rc) return rc;
+        const int* d_off = h->d_seg_off.as<int>();
+        ht.lap(&h->host_s[14]);
+        rc = lg_vox_merge(h->vb, h->ds_in.as<float4>(), d_off, d_off + (nseg + 1), d_off + 2 * (nseg + 1), h->d_seg_leaf.as<float>(), nseg,
+                          n_old, n_new, outp, d_start, d_end, d_flags, h->st, &h->launches);
+        if (rc) return rc;
+        ht.lap(&h->host_s[15]);
+        LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8 + 4);
+        LG_SYNC(h);
+        done = h->h_ints[2 * nseg] == 0;
+        if (!done) h->merge_fallbacks++;
+      }
+      if (!done) {
+        rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+        if (rc) return rc;
+        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+        if (rc) return rc;
+        rc = upload(h, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
+        if (rc) return rc;
+        ht.lap(&h->host_s[14]);
+        rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, h->st,
+                        &h->launches);
+        if (rc) return rc;
+        ht.lap(&h->host_s[15]);
+        LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8);
+        LG_SYNC(h);
+      }
       int total = 0, s = 0;
       for (int ind : validInd)
         for (int type = 0; type < 2; type++) {

@@ -299,6 +299,61 @@ __global__ void vb_key_kernel(const float4* __restrict__ in, const int* __restri
   vals[i] = (unsigned int)i;
 }
 
+
+// ------------------------------------------------------------------------------------------------ merge path
+// Voxel-gridding a cube whose OLD cloud is the output of the previous voxel grid (one point per cell, ascending
+// cell id) plus a few NEW points: only the new points are sorted; the two sorted key sequences are merged by rank
+// (old before new on equal keys = ascending input index, exactly the order the full sort would produce) and the
+// usual head / centroid kernels run on the merged sequence.  The old part is CHECKED to be strictly ascending under
+// the new bounding box (a centroid can drift across a cell face by an ulp); if not, the caller falls back to the
+// full sort.  Keys: (segment << 32) | cell with cell < 2^24 (cube-sized segments), so the radix sort of the new part
+// skips bits 24..31.
+__global__ void vm_key_kernel(const float4* __restrict__ in, const int* __restrict__ seg_off, const float* __restrict__ seg_leaf, int nseg,
+                              int n, int val_base, const int* __restrict__ bb, unsigned long long* __restrict__ keys,
+                              unsigned int* __restrict__ vals, int check_sorted, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int seg = find_seg(seg_off, nseg, i);
+  const int* b = bb + seg * 6;
+  VoxGrid g;
+  bool ok = vox_grid_setup(ord2f(b[0]), ord2f(b[1]), ord2f(b[2]), ord2f(b[3]), ord2f(b[4]), ord2f(b[5]), seg_leaf[seg], g);
+  int cell = ok ? vox_cell(g, in[i]) : 0;
+  if (!ok || cell >= (1 << 24) || cell < 0) atomicOr(&flags[0], 1);  // not a cube-sized segment: full path needed
+  unsigned long long key = ((unsigned long long)(unsigned int)seg << 32) | (unsigned int)cell;
+  keys[i] = key;
+  vals[i] = (unsigned int)(val_base + i);
+  if (check_sorted && i > seg_off[seg]) {  // strictly ascending inside the segment (segments ascend by construction)
+    int pc = vox_cell(g, in[i - 1]);
+    if (pc >= cell) atomicOr(&flags[0], 2);
+  }
+}
+
+__global__ void vm_merge_kernel(const unsigned long long* __restrict__ ko, const unsigned int* __restrict__ vo, int n_old,
+                                const unsigned long long* __restrict__ kn, const unsigned int* __restrict__ vn, int n_new,
+                                unsigned long long* __restrict__ km, unsigned int* __restrict__ vm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_old) {
+    unsigned long long key = ko[i];
+    int lo = 0, hi = n_new;  // number of new keys < key
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (kn[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    km[i + lo] = key;
+    vm[i + lo] = vo[i];
+  } else if (i < n_old + n_new) {
+    int j = i - n_old;
+    unsigned long long key = kn[j];
+    int lo = 0, hi = n_old;  // number of old keys <= key
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (ko[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    km[j + lo] = key;
+    vm[j + lo] = vn[j];
+  }
+}
+
 constexpr int VC_NT = 256, VC_ITEMS = 4, VC_TILE = VC_NT * VC_ITEMS;
 
 __global__ void __launch_bounds__(VC_NT) vb_count_kernel(const unsigned long long* __restrict__ keys, int M, unsigned int* __restrict__ block_sums) {
@@ -448,6 +503,82 @@ int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const flo
   rs_scan_kernel<<<1, 1024, 0, st>>>(ws.block_sums.as<unsigned int>(), ncb);
   vb_centroid_kernel<<<ncb, VC_NT, 0, st>>>(d_in, keys, vals, M, ws.block_sums.as<unsigned int>(), d_seg_off, d_out, d_out_start, d_out_end);
   (*launches) += 3;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+
+int lg_radix_sort_shifts(RadixWs& ws, int n, const int* shifts, int nshifts, cudaStream_t st, long long* launches, int* result_in_b) {
+  int nblocks = lg_div_up(n, RS_TILE);
+  LG_CHECK(ws.hist.ensure((size_t)256 * nblocks * sizeof(unsigned int), st));
+  unsigned long long* ka = ws.keysA.as<unsigned long long>();
+  unsigned long long* kb = ws.keysB.as<unsigned long long>();
+  unsigned int* va = ws.valsA.as<unsigned int>();
+  unsigned int* vb = ws.valsB.as<unsigned int>();
+  int flip = 0;
+  for (int p = 0; p < nshifts; p++) {
+    rs_hist_kernel<<<nblocks, RS_NT, 0, st>>>(ka, n, shifts[p], ws.hist.as<unsigned int>(), nblocks);
+    rs_scan_kernel<<<1, 1024, 0, st>>>(ws.hist.as<unsigned int>(), 256 * nblocks);
+    rs_scatter_kernel<<<nblocks, RS_NT, 0, st>>>(ka, va, kb, vb, n, shifts[p], ws.hist.as<unsigned int>(), nblocks);
+    (*launches) += 3;
+    std::swap(ka, kb);
+    std::swap(va, vb);
+    flip ^= 1;
+  }
+  LG_CHECK(cudaGetLastError());
+  *result_in_b = flip;
+  return LOAM_OK;
+}
+
+// d_in = [old points of all segments (segment-major) | new points of all segments]; d_flags[0] != 0 afterwards means
+// the fast path does not apply (caller re-runs lg_vox_big on the same input).  d_seg_off = merged offsets.
+int lg_vox_merge(VoxBigWs& ws, const float4* d_in, const int* d_seg_off_old, const int* d_seg_off_new, const int* d_seg_off,
+                 const float* d_seg_leaf, int nseg, int n_old, int n_new, float4* d_out, int* d_out_start, int* d_out_end, int* d_flags,
+                 cudaStream_t st, long long* launches) {
+  const int M = n_old + n_new;
+  if (nseg <= 0) return LOAM_OK;
+  LgProfScope prof_scope(LGK_VOXEL, st, (double)M);
+  LG_CHECK(ws.bb.ensure((size_t)nseg * 6 * sizeof(int), st));
+  LG_CHECK(cudaMemsetAsync(d_flags, 0, 4, st));
+  vb_init_kernel<<<lg_div_up(nseg * 6, 256), 256, 0, st>>>(ws.bb.as<int>(), nseg, d_out_start, d_out_end);
+  (*launches)++;
+  if (M <= 0) return LOAM_OK;
+  int rc = lg_radix_ensure(ws.rs, std::max(n_new, 1), st);
+  if (rc) return rc;
+  LG_CHECK(ws.keys_old.ensure((size_t)(n_old + 1) * 8, st));
+  LG_CHECK(ws.vals_old.ensure((size_t)(n_old + 1) * 4, st));
+  LG_CHECK(ws.keys_m.ensure((size_t)(M + 1) * 8, st));
+  LG_CHECK(ws.vals_m.ensure((size_t)(M + 1) * 4, st));
+  if (n_old > 0) vb_bbox_kernel<<<lg_div_up(n_old, 256), 256, 0, st>>>(d_in, d_seg_off_old, nseg, n_old, ws.bb.as<int>());
+  if (n_new > 0) vb_bbox_kernel<<<lg_div_up(n_new, 256), 256, 0, st>>>(d_in + n_old, d_seg_off_new, nseg, n_new, ws.bb.as<int>());
+  if (n_old > 0)
+    vm_key_kernel<<<lg_div_up(n_old, 256), 256, 0, st>>>(d_in, d_seg_off_old, d_seg_leaf, nseg, n_old, 0, ws.bb.as<int>(),
+                                                         ws.keys_old.as<unsigned long long>(), ws.vals_old.as<unsigned int>(), 1, d_flags);
+  if (n_new > 0)
+    vm_key_kernel<<<lg_div_up(n_new, 256), 256, 0, st>>>(d_in + n_old, d_seg_off_new, d_seg_leaf, nseg, n_new, n_old, ws.bb.as<int>(),
+                                                         ws.rs.keysA.as<unsigned long long>(), ws.rs.valsA.as<unsigned int>(), 0, d_flags);
+  (*launches) += 4;
+  int in_b = 0;
+  if (n_new > 1) {
+    int segbits = 0;
+    while ((1 << segbits) < nseg) segbits++;
+    int shifts[8], ns = 0;
+    for (int s = 0; s < 24; s += 8) shifts[ns++] = s;
+    for (int s = 0; s < segbits; s += 8) shifts[ns++] = 32 + s;
+    rc = lg_radix_sort_shifts(ws.rs, n_new, shifts, ns, st, launches, &in_b);
+    if (rc) return rc;
+  }
+  const unsigned long long* kn = in_b ? ws.rs.keysB.as<unsigned long long>() : ws.rs.keysA.as<unsigned long long>();
+  const unsigned int* vn = in_b ? ws.rs.valsB.as<unsigned int>() : ws.rs.valsA.as<unsigned int>();
+  vm_merge_kernel<<<lg_div_up(M, 256), 256, 0, st>>>(ws.keys_old.as<unsigned long long>(), ws.vals_old.as<unsigned int>(), n_old, kn, vn, n_new,
+                                                     ws.keys_m.as<unsigned long long>(), ws.vals_m.as<unsigned int>());
+  int ncb = lg_div_up(M, VC_TILE);
+  LG_CHECK(ws.block_sums.ensure((size_t)ncb * sizeof(unsigned int), st));
+  vb_count_kernel<<<ncb, VC_NT, 0, st>>>(ws.keys_m.as<unsigned long long>(), M, ws.block_sums.as<unsigned int>());
+  rs_scan_kernel<<<1, 1024, 0, st>>>(ws.block_sums.as<unsigned int>(), ncb);
+  vb_centroid_kernel<<<ncb, VC_NT, 0, st>>>(d_in, ws.keys_m.as<unsigned long long>(), ws.vals_m.as<unsigned int>(), M,
+                                            ws.block_sums.as<unsigned int>(), d_seg_off, d_out, d_out_start, d_out_end);
+  (*launches) += 4;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;
 }

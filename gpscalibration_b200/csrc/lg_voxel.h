@@ -25,8 +25,10 @@ struct RadixWs {
 };
 struct VoxBigWs {
   RadixWs rs;
-  DevBuf bb, block_sums;
-  void release() { rs.release(); bb.release(); block_sums.release(); }
+  DevBuf bb, block_sums, keys_old, vals_old, keys_m, vals_m;
+  void release() {
+    rs.release(); bb.release(); block_sums.release(); keys_old.release(); vals_old.release(); keys_m.release(); vals_m.release();
+  }
 };
 
 // One CTA per segment, shared-memory bitonic sort; max_seg_hint picks the 4096- or 16384-point instantiation.
@@ -35,6 +37,10 @@ int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overf
 // [d_out_start[s], d_out_end[s]).
 int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
                int* d_out_start, int* d_out_end, cudaStream_t st, long long* launches);
+// Merge path for cube-sized segments whose old cloud is already voxel-gridded (see lg_voxel.cu): d_in = [old | new].
+int lg_vox_merge(VoxBigWs& ws, const float4* d_in, const int* d_seg_off_old, const int* d_seg_off_new, const int* d_seg_off,
+                 const float* d_seg_leaf, int nseg, int n_old, int n_new, float4* d_out, int* d_out_start, int* d_out_end, int* d_flags,
+                 cudaStream_t st, long long* launches);
 int lg_radix_ensure(RadixWs& ws, int n, cudaStream_t st);
 // Stable LSD radix sort of ws.keysA/valsA over the low `bits` bits; *result_in_b tells which buffer holds the result.
 int lg_radix_sort(RadixWs& ws, int n, int bits, cudaStream_t st, long long* launches, int* result_in_b);
