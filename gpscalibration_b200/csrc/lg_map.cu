@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* _
                                                           unsigned long long seq) {
   Acc28 acc;
   acc.clear();
-  const int q = blockIdx.x * FIT_NT + threadIdx.x;
+  // grid-stride over the queries: the grid is capped (a few CTAs per SM) so the last-CTA reduction stays short
+  for (int q = blockIdx.x * FIT_NT + threadIdx.x; q < n_cs + n_ss; q += gridDim.x * FIT_NT) {
   float4 ori, coef;
   bool keep = false;
-  if (q < n_cs + n_ss && nbr[(size_t)q * 5] >= 0) {
+  if (nbr[(size_t)q * 5] >= 0) {
     const bool is_c = q < n_cs;
     ori = is_c ? corner_stack[q] : surf_stack[q - n_cs];
     const float4 sel = assoc_to_map(T, ori);
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* _
     a[4] = c.y;
     a[5] = c.z;
     acc.add_row(a, -c.w);
+  }
   }
   lg_reduce28<FIT_NT>(acc, partials, ticket, out28, seq);
 }
@@ -395,7 +397,7 @@ int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack,
                        const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
                        long long* launches) {
   const int nq = n_cs + n_ss;
-  const int nb = std::max(1, lg_div_up(nq, FIT_NT));
+  const int nb = std::max(1, std::min(lg_div_up(nq, FIT_NT), 148 * 8));
   LG_CHECK(ws.nbr.ensure((size_t)(nq + 1) * 5 * 4, st));
   LG_CHECK(ws.partials.ensure((size_t)nb * 28 * 8, st));
   if (!ws.ticket.p) {

@@ -54,6 +54,7 @@ def lib():
         L.orc_associate_tobe_mapped.argtypes = [vp, C.c_int, vp, vp]
         L.orc_transform_associate_to_map.argtypes = [vp, vp, vp, vp, vp]
         L.orc_map_iteration.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, ip]
+        L.orc_map_iteration_sums28.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
         L.orc_pipeline_create.restype = vp
         L.orc_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_pipeline_destroy.argtypes = [vp]
@@ -212,6 +213,14 @@ def map_iteration(corner_stack, surf_stack, corner_map, surf_map, T, brute=False
                             d.shape[0], T.ctypes.data, int(brute), cc.ctypes.data, cs.ctypes.data, AtA.ctypes.data,
                             AtB.ctypes.data, C.byref(n))
     return AtA, AtB, n.value, cc, cs
+
+
+def map_iteration_sums28(corner_stack, surf_stack, corner_map, surf_map, T):
+    a, b, c, d, T = _f32(corner_stack), _f32(surf_stack), _f32(corner_map), _f32(surf_map), _f32(T)
+    out = np.zeros(28, np.float64)
+    lib().orc_map_iteration_sums28(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], c.ctypes.data, c.shape[0], d.ctypes.data,
+                                   d.shape[0], T.ctypes.data, out.ctypes.data)
+    return out
 
 
 class Pipeline:

@@ -228,6 +228,36 @@ int orc_map_iteration(const float* cornerStack, int n_cs, const float* surfStack
   return 0;
 }
 
+// Same iteration, returning the 28 exact double sums {21 upper-triangle AtA, 6 AtB, n_sel} instead of the rounded
+// matrices (what a rank contributes to the all-reduce when the map is sharded).
+int orc_map_iteration_sums28(const float* cornerStack, int n_cs, const float* surfStack, int n_ss, const float* cornerMap, int n_cm,
+                             const float* surfMap, int n_sm, const float* T, double* out28) {
+  Cloud a, b, c, d;
+  to_cloud(cornerStack, n_cs, a);
+  to_cloud(surfStack, n_ss, b);
+  to_cloud(cornerMap, n_cm, c);
+  to_cloud(surfMap, n_sm, d);
+  KnnIndex kc, ks;
+  kc.set(c, false);
+  ks.set(d, false);
+  NormalEq ne;
+  map_iteration(a, b, c, d, kc, ks, T, nullptr, ne, /*min_rows=*/0);
+  int t = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      double s = 0.0;
+      for (int r = 0; r < ne.n_sel; r++) s += (double)ne.A[r * 6 + i] * (double)ne.A[r * 6 + j];
+      out28[t++] = s;
+    }
+  for (int i = 0; i < 6; i++) {
+    double s = 0.0;
+    for (int r = 0; r < ne.n_sel; r++) s += (double)ne.A[r * 6 + i] * (double)ne.B[r];
+    out28[21 + i] = s;
+  }
+  out28[27] = (double)ne.n_sel;
+  return 0;
+}
+
 // ---------------------------------------------------------------- node level
 void* orc_lo_create(int brute) {
   LaserOdometry* h = new LaserOdometry;

@@ -130,7 +130,8 @@ struct MapCorr {  // 5 neighbour indices per stack point, -1 when the 5th neighb
 
 // One pass of the iteration body LM:754-964 (no solve).
 inline void map_iteration(const Cloud& cornerStack, const Cloud& surfStack, const Cloud& cornerMap, const Cloud& surfMap,
-                          const KnnIndex& kCorner, const KnnIndex& kSurf, const float* T, MapCorr* corr, NormalEq& ne) {
+                          const KnnIndex& kCorner, const KnnIndex& kSurf, const float* T, MapCorr* corr, NormalEq& ne,
+                          int min_rows = 50) {
   std::vector<P4> ori, coef;
   P4 sel;
   Nbr nb[5];
@@ -219,7 +220,7 @@ inline void map_iteration(const Cloud& cornerStack, const Cloud& surfStack, cons
   ne.B.assign(n, 0.f);
   std::memset(ne.AtA, 0, sizeof(ne.AtA));
   std::memset(ne.AtB, 0, sizeof(ne.AtB));
-  if (n < 50) return;  // LM:929-932
+  if (n < min_rows) return;  // LM:929-932 (min_rows = 50 in the reference; 0 for a shard's partial sums)
   for (int i = 0; i < n; i++) {  // LM:940-964
     const P4& p = ori[i];
     const P4& c = coef[i];
