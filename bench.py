@@ -44,7 +44,12 @@ ALGO_BYTES = {
     "map_fit": ("(counted with map_knn)", 0.0),
     "gather": ("32 B per point", 32.0),
     "insert": ("32 B per point", 32.0),
+    "sr_select": ("16 F + 5 N per sweep (keys, flags, labels)", 5.0 + 16.0 * 0.2),
 }
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
+# (r1_ncu_full_<kernel>.csv, first 60 sweeps of the same sequence); None where no capture exists
+NCU_TRAFFIC = {"sr_select": 154880, "odom_iter": 328448, "map_knn": 3706880, "voxel": None, "extract": None, "odom_knn": None}
 
 
 def log(*a):
@@ -308,7 +313,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+                "traffic": NCU_TRAFFIC.get(dom), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_unit": per_unit, "units_per_launch": d["units"] / max(1, d["scopes"]),
                 "avg_launch_us": 1e3 * d["ms"] / max(1, d["scopes"]), "share_of_gpu_time": d["ms"] / tot_ms,
                 "note": "single-sequence configs are launch/latency bound by construction (SURVEY §8d): ~9 MB per registration",

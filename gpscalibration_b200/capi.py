@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-LOAM_OK, LOAM_EINVAL, LOAM_ECUDA, LOAM_ENOSPC, LOAM_ESTATE = 0, -1, -2, -3, -4
+LOAM_OK, LOAM_EINVAL, LOAM_ECUDA, LOAM_ENOSPC, LOAM_ESTATE, LOAM_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 CLOUD = dict(full=0, sharp=1, less_sharp=2, flat=3, less_flat=4, corner_last=5, surf_last=6, full_res3=7, corner_stack=8,
              surf_stack=9, corner_map=10, surf_map=11, surround=12, registered=13)
@@ -185,7 +185,7 @@ class LoamGpu:
         return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
 
     PROFILE_CLASSES = ("extract", "odom_knn", "odom_iter", "to_end", "map_stack", "voxel", "gather", "grid", "map_knn",
-                       "map_fit", "insert")
+                       "map_fit", "insert", "sr_select")
 
     HOST_SECTIONS = ("extract", "odom_iters", "odom_end", "map_prep", "map_grid", "map_iters", "map_insert", "map_cube_ds", "map_rest",
                      "t9", "t10", "t11", "t12", "t13", "t14", "t15")

@@ -295,8 +295,9 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
 }
 
 int read_sr_counts(loam_handle* h, loam_counts* out) {
-  LG_D2H(h, h->h_ints, h->sr.meta.p, 8 * 4);
+  LG_D2H(h, h->h_ints, h->sr.meta.p, 9 * 4);
   LG_SYNC(h);
+  if (h->h_ints[SRM_EMPTY_RING]) return LOAM_EUNSUPPORTED;
   if (h->h_ints[SRM_ERR]) return LOAM_ENOSPC;
   if (h->h_ints[SRM_VOX_OVERFLOW]) return LOAM_ENOSPC;
   h->counts.n_full = h->h_ints[SRM_N_FULL];
@@ -405,6 +406,7 @@ const char* loam_strerror(int code) {
     case LOAM_ECUDA: return "CUDA error";
     case LOAM_ENOSPC: return "buffer or capacity too small";
     case LOAM_ESTATE: return "call order violated";
+    case LOAM_EUNSUPPORTED: return "unsupported input: a ring of the sweep is empty";
   }
   return "unknown error";
 }

@@ -67,7 +67,8 @@ enum LgKernelClass {
   LGK_MAP_KNN = 8,   // K10: map_knn_kernel
   LGK_MAP_FIT = 9,   // K10: map_fit_kernel
   LGK_INSERT = 10,   // K11: map_insert_kernel + cube sort + runs
-  LGK_COUNT = 11
+  LGK_SR_SELECT = 11,  // K4: sr_select_kernel alone (the largest single launch of a sweep)
+  LGK_COUNT = 12
 };
 struct LgProf {
   bool on = false;

@@ -167,6 +167,10 @@ __global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned in
     meta[SRM_N_FULL] = tot;
     meta[SRM_VOX_OVERFLOW] = 0;
     meta[SRM_ERR] = 0;
+    int empty = 0;
+    for (int r = 0; r < prm.n_scans; r++)
+      if (hist[r * nblocks] == ((r + 1 < prm.n_scans) ? hist[(r + 1) * nblocks] : (unsigned int)tot)) empty = 1;
+    meta[SRM_EMPTY_RING] = (tot >= 11) ? empty : 0;  // below 11 points the reference selects nothing at all (SR:454 loop is empty)
   }
 }
 
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
   // this ring's points: [S - 5, E + 5)
   const int a = max(S - 5, 0), b = min(E + 5, n);
   const int len = b - a;
-  if (len > RING_CAP) {
+  if (len > RING_CAP || meta[SRM_EMPTY_RING]) {
     if (tid == 0) {
       cnt[0] = cnt[1] = cnt[2] = 0;
       atomicExch(&meta[SRM_ERR], 1);
@@ -582,6 +586,7 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
     LG_CHECK(cudaMemsetAsync(meta + SRM_N_FULL, 0, 5 * 4, st));
     return LOAM_OK;
   }
+  {
   LgProfScope prof_scope(LGK_EXTRACT, st, (double)n);
   sr_ring_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
                                             ws.hist.as<unsigned int>(), nblocks, meta);
@@ -590,9 +595,14 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
                                                ws.hist.as<unsigned int>(), nblocks, meta, ws.full.as<float4>());
   sr_curv_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
                                                     ws.label.as<signed char>());
+  }
+  {
+  LgProfScope prof_scope(LGK_SR_SELECT, st, (double)n);
   sr_select_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
                                       ws.picked.as<unsigned char>(), ws.mask_diag.as<unsigned char>(), ws.label.as<signed char>(),
                                       ws.picks.as<int>());
+  }
+  LgProfScope prof_scope(LGK_EXTRACT, st, 0.0);
   sr_collect_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.label.as<signed char>(), ws.picks.as<int>(),
                                        ws.sharp.as<float4>(), ws.less_sharp.as<float4>(), ws.flat.as<float4>(),
                                        ws.lf_valid.as<unsigned char>(), ws.lf_tmp.as<float4>(), ws.segs.as<VoxSegD>());

@@ -20,6 +20,7 @@ enum {
   SRM_N_LESS_FLAT = 5,
   SRM_VOX_OVERFLOW = 6,  // a ring exceeded the shared-memory voxel capacity
   SRM_ERR = 7,           // a sector exceeded the shared-memory sort capacity
+  SRM_EMPTY_RING = 8,    // some ring received no point: scanStartInd/EndInd overlap in the reference (SR:480-490)
   SRM_RING_START = 16,   // [n_scans + 1] first index of every ring in the ring-major cloud
   SRM_SCAN_START = 96,   // [n_scans] scanStartInd (SR:484,489)
   SRM_SCAN_END = 160,    // [n_scans] scanEndInd   (SR:485,490)

@@ -29,6 +29,7 @@ extern "C" {
 #define LOAM_ECUDA (-2)  /* CUDA runtime error (loam_last_cuda_error has the text) */
 #define LOAM_ENOSPC (-3) /* caller buffer or internal capacity too small */
 #define LOAM_ESTATE (-4) /* call order violated (e.g. odometry before any extract) */
+#define LOAM_EUNSUPPORTED (-5) /* input the CUDA path does not handle: a sweep with an EMPTY ring (fence iii) */
 
 typedef struct loam_handle loam_handle;
 
@@ -122,8 +123,9 @@ long long loam_launch_count(const loam_handle* h);
 int loam_stats(const loam_handle* h, long long out4[4]);
 /* Optional per-kernel-class CUDA-event timing on the handle's stream (off by default; adds two event records per
  * launch group while on).  Classes: 0 extract, 1 odom_knn, 2 odom_iter, 3 to_end, 4 map_stack/register, 5 voxel,
- * 6 gather, 7 grid build, 8 map_knn, 9 map_fit, 10 insert.  loam_profile(h, 1) clears the counters. */
-#define LOAM_PROFILE_CLASSES 11
+ * 6 gather, 7 grid build, 8 map_knn, 9 map_fit, 10 insert, 11 sr_select (not counted in 0).  loam_profile(h, 1) clears
+ * the counters. */
+#define LOAM_PROFILE_CLASSES 12
 /* Host wall-clock seconds per section of the node-level calls (incl. waits on the GPU): 0 extract, 1 odometry
  * iterations, 2 odometry end, 3 mapping prepare (stack, gather, voxel), 4 grid build, 5 mapping iterations, 6 insert,
  * 7 cube voxel grids, 8 rest.  Diagnostics only. */

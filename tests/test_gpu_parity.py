@@ -125,6 +125,18 @@ def test_extract_empty_and_tiny(gpu, orc):
     assert c.n_full == ref["full"].shape[0] and c.n_sharp == 0 and c.n_flat == 0
 
 
+def test_extract_empty_ring_fails_loudly(gpu):
+    """Fence (iii): true VLP-16 angles leave rings 6/8/10 of the reference's table empty; the reference then indexes with
+    overlapping, partly uninitialised ranges (SR:480-490).  The CUDA path refuses such a sweep instead of guessing."""
+    from gpscalibration_b200 import SweepGenerator, LoamError, capi
+    xyz = SweepGenerator(sensor=1).sweep(0)[0]
+    with pytest.raises(LoamError) as e:
+        gpu.extract(xyz)
+    assert e.value.code == capi.LOAM_EUNSUPPORTED
+    c = gpu.extract(SweepGenerator(sensor=0).sweep(0)[0])  # the handle stays usable
+    assert c.n_full == 28800
+
+
 # ------------------------------------------------------------------------------------------------ odometry (a6-a12)
 def _odom_pair(orc, sweeps16, a=0, b=1):
     sr = orc.ScanRegistration()
