@@ -155,6 +155,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # exactly ONE line on stdout (the JSON): libraries that print banners to fd 1 (NCCL version line) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +186,7 @@ def main():
         total = sum(times)
         val = n * args.steps / total
         sample = f"first {n} sweeps of the rank-0 sequence per step, three stage threads (SR | LO | LM) like the reference's three ROS processes"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -339,7 +346,7 @@ def main():
         out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": f"first {n} sweeps of the same sequence, three stage threads (SR | LO | LM), {os.cpu_count()} host cores present"}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     gpu.close()
     pipe.close()
     if world > 1:
