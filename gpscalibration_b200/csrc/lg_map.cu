@@ -76,6 +76,17 @@ __device__ __forceinline__ unsigned long long cell_key(int ix, int iy, int iz) {
 }
 __device__ __forceinline__ unsigned int cell_hash(unsigned long long k, int bits) { return (unsigned int)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
 
+// Bucket = one 128-byte line per occupied cell: key, count, start and the first GRID_INLINE points inline, so a query
+// lane resolves a cell with ONE memory round trip (two 16-byte loads of the first sector, the rest of the line only
+// when the cell holds more than one point); cells with more points continue in the cell-sorted array.
+__global__ void grid_init_kernel(GridD g) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (1 << g.bits)) return;
+  g.buckets[s].key = EMPTY;
+  g.buckets[s].count = 0;
+  g.buckets[s].start = 0;
+  g.fill[s] = 0;
+}
 __global__ void grid_count_kernel(GridD g, const float4* __restrict__ pts, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -84,26 +95,28 @@ __global__ void grid_count_kernel(GridD g, const float4* __restrict__ pts, int n
   unsigned int h = cell_hash(key, g.bits);
   const unsigned int mask = (1u << g.bits) - 1u;
   while (true) {
-    unsigned long long prev = atomicCAS(&g.keys[h], EMPTY, key);
+    unsigned long long prev = atomicCAS(&g.buckets[h].key, EMPTY, key);
     if (prev == EMPTY || prev == key) break;
     h = (h + 1) & mask;
   }
-  atomicAdd(&g.count[h], 1);
+  atomicAdd(&g.buckets[h].count, 1);
   g.slot_of[i] = (int)h;
 }
 __global__ void grid_alloc_kernel(GridD g) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= (1 << g.bits)) return;
-  int c = g.count[s];
-  if (c > 0) g.start[s] = atomicAdd(g.cursor, c);
+  int c = g.buckets[s].count;
+  if (c > GRID_INLINE) g.buckets[s].start = atomicAdd(g.cursor, c);
 }
 __global__ void grid_fill_kernel(GridD g, const float4* __restrict__ pts, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int s = g.slot_of[i];
-  int pos = g.start[s] + atomicAdd(&g.fill[s], 1);
+  int pos = atomicAdd(&g.fill[s], 1);
   float4 p = pts[i];
-  g.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  float4 e = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  if (pos < GRID_INLINE) g.buckets[s].pts[pos] = e;
+  if (g.buckets[s].count > GRID_INLINE) g.sorted[g.buckets[s].start + pos] = e;
 }
 
 // ---------------------------------------------------------------------------------------------- exact 5-NN
@@ -142,19 +155,25 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
     unsigned long long key = cell_key(ix, iy, iz);
     unsigned int h = cell_hash(key, g.bits);
     const unsigned int mask = (1u << g.bits) - 1u;
+    const float4* line = nullptr;
     int cnt = 0, start = 0;
+    float4 first = make_float4(0.f, 0.f, 0.f, 0.f);
     while (true) {
-      unsigned long long kk = g.keys[h];
+      // first sector of the bucket: {key, count, start} + point 0, two independent 16-byte loads
+      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(&g.buckets[h]));
+      const float4 p0 = __ldg(&g.buckets[h].pts[0]);
+      unsigned long long kk = ((unsigned long long)hd.y << 32) | hd.x;
       if (kk == key) {
-        cnt = g.count[h];
-        start = g.start[h];
+        cnt = (int)hd.z;
+        start = (int)hd.w;
+        first = p0;
+        line = g.buckets[h].pts;
         break;
       }
       if (kk == EMPTY) break;
       h = (h + 1) & mask;
     }
-    for (int j = 0; j < cnt; j++) {
-      float4 p = g.sorted[start + j];
+    auto offer = [&](float4 p) {
       float d2 = lg_sqdist(p.x, p.y, p.z, sel.x, sel.y, sel.z);
       if (d2 < 1.0f) {
         unsigned long long c = lg_pack_nbr(d2, __float_as_int(p.w));
@@ -182,6 +201,18 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
           }
         }
       }
+    };
+    if (cnt > 0) offer(first);
+    if (cnt > 1) {
+      const int ninl = min(cnt, GRID_INLINE);
+      float4 rest[GRID_INLINE - 1];
+#pragma unroll
+      for (int j = 1; j < GRID_INLINE; j++)
+        if (j < ninl) rest[j - 1] = __ldg(&line[j]);  // issued back to back: one more round trip for the whole line
+#pragma unroll
+      for (int j = 1; j < GRID_INLINE; j++)
+        if (j < ninl) offer(rest[j - 1]);
+      for (int j = GRID_INLINE; j < cnt; j++) offer(g.sorted[start + j]);
     }
   }
   // warp merge: five rounds of "global minimum of the lanes' heads"; keys are unique (they embed the index)
@@ -366,23 +397,22 @@ int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long lo
   int bits = 10;
   while ((1 << bits) < 2 * n) bits++;
   const size_t slots = (size_t)1 << bits;
-  LG_CHECK(ws.keys.ensure(slots * 8, st));
-  LG_CHECK(ws.ints.ensure((slots * 3 + 4) * 4, st));
+  LG_CHECK(ws.keys.ensure(slots * sizeof(GridBucket), st));
+  LG_CHECK(ws.ints.ensure((slots + 8) * 4, st));
   LG_CHECK(ws.slot_of.ensure((size_t)(n + 1) * 4, st));
   LG_CHECK(ws.sorted.ensure((size_t)(n + 1) * 16, st));
   GridD& g = ws.d;
-  g.keys = ws.keys.as<unsigned long long>();
-  g.count = ws.ints.as<int>();
-  g.start = g.count + slots;
-  g.fill = g.start + slots;
+  g.buckets = ws.keys.as<GridBucket>();
+  g.fill = ws.ints.as<int>();
   g.cursor = g.fill + slots;
   g.slot_of = ws.slot_of.as<int>();
   g.sorted = ws.sorted.as<float4>();
   g.bits = bits;
   g.n = n;
   LgProfScope prof_scope(LGK_GRID, st, (double)n);
-  LG_CHECK(cudaMemsetAsync(g.keys, 0xff, slots * 8, st));
-  LG_CHECK(cudaMemsetAsync(g.count, 0, (slots * 3 + 4) * 4, st));
+  grid_init_kernel<<<lg_div_up((int)slots, 256), 256, 0, st>>>(g);
+  LG_CHECK(cudaMemsetAsync(g.cursor, 0, 16, st));
+  (*launches)++;
   if (n > 0) {
     grid_count_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(g, pts, n);
     grid_alloc_kernel<<<lg_div_up((int)slots, 256), 256, 0, st>>>(g);

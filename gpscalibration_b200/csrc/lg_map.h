@@ -13,15 +13,22 @@ struct CubeGeom {  // LM:69-75
   int W, H, D, cenW, cenH, cenD;
 };
 
-struct GridD {  // voxel hash over one map cloud (cell = 1 m)
-  unsigned long long* keys;  // cell key per slot, ~0 = empty
-  int* count;                // points in the cell
-  int* start;                // first position in `sorted`
-  int* fill;                 // scatter cursor
-  int* cursor;               // global allocation cursor
-  int* slot_of;              // slot of every map point
-  float4* sorted;            // cell-sorted copy {x, y, z, original index as int bits}
-  int bits;                  // log2(slots)
+constexpr int GRID_INLINE = 7;  // points stored inside a bucket
+
+struct alignas(128) GridBucket {  // one 128-byte line per occupied 1 m cell
+  unsigned long long key;        // cell key, ~0 = empty
+  int count;                     // points in the cell
+  int start;                     // first position in `sorted` (only when count > GRID_INLINE)
+  float4 pts[GRID_INLINE];       // {x, y, z, original index as int bits}
+};
+
+struct GridD {  // voxel hash over one map cloud (cell = 1 m), open addressing over 128-byte buckets
+  GridBucket* buckets;
+  int* fill;       // build-time scatter cursor per slot
+  int* cursor;     // global allocation cursor into `sorted`
+  int* slot_of;    // slot of every map point
+  float4* sorted;  // cells with more than GRID_INLINE points: all their points, contiguous
+  int bits;        // log2(slots)
   int n;
 };
 
