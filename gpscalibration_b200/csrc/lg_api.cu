@@ -117,7 +117,7 @@ struct loam_handle {
   DevBuf d_ents, d_segs, d_ints, d_seg_off, d_seg_leaf, d_out_se;
   VoxBigWs vb;
   DevBuf ds_in, ins_sel, ins_sorted, d_runs;
-  DevBuf surround, registered, vg_in, vg_out;
+  DevBuf surround, registered, vg_in, vg_out, vs_staging, vs_counts;
   int n_surround = 0, n_registered = 0;
 };
 
@@ -248,6 +248,19 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
     double units = 0;
     for (auto& sg : segs) units += sg.n;
     LgProfScope prof_scope(LGK_VOXEL, h->st, units);
+    bool split = max_n > 4096;
+    for (auto& sg : segs) split = split && sg.valid == nullptr;
+    if (split) {  // sweep-sized stacks: 32 CTAs per segment instead of one
+      LG_CHECK(cudaMemsetAsync(d_counts, 0, 4, h->st));
+      rc = lg_vox_split(h->vs_staging, h->vs_counts, h->d_segs.as<VoxSegD>(), nseg, d_counts, h->st, &h->launches);
+      if (rc) return rc;
+      LG_D2H(h, h->h_ints, d_counts, (nseg + 1) * 4);
+      LG_SYNC(h);
+      if (h->h_ints[0] == 0) {
+        for (int i = 0; i < nseg; i++) counts[i] = h->h_ints[1 + i];
+        return LOAM_OK;
+      }
+    }
     rc = lg_vox_small(h->d_segs.as<VoxSegD>(), nseg, max_n, d_counts, h->st, &h->launches);
     if (rc) return rc;
     LG_D2H(h, h->h_ints, d_counts + 1, nseg * 4);
@@ -491,7 +504,7 @@ int loam_destroy(loam_handle* h) {
   DevBuf* all[] = {&h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
-                   &h->surround, &h->registered, &h->vg_in, &h->vg_out};
+                   &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts};
   for (DevBuf* b : all) b->release();
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_ints) cudaFreeHost(h->h_ints);

@@ -7,6 +7,8 @@
 //                                    and the 21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
 //   odom_to_end_kernel  LO:1087-1106 TransformToEnd over less-sharp, less-flat and (every 2nd sweep) the full cloud
 // The 6x6 solve, degeneracy projection, convergence test and pose accumulation stay on the host (lg_api.cu).
+#include <cooperative_groups.h>
+
 #include "lg_odom.h"
 #include "lg_reduce.cuh"
 
@@ -193,16 +195,12 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_kernel(OdomT T, con
 
 constexpr int IT_NT = 128;
 
-__global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp,
-                                                           const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
-                                                           int n_cl, const float4* __restrict__ surf_last, int n_sl,
-                                                           const int* __restrict__ c1, const int* __restrict__ c2,
-                                                           const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
-                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28,
-                                                           unsigned long long seq) {
-  Acc28 acc;
-  acc.clear();
-  const int q = blockIdx.x * IT_NT + threadIdx.x;
+// One feature's contribution to the normal equations: TransformToStart, coefficients (LO:680-746 / LO:847-901), Jacobian
+// row (LO:915-971) accumulated into `acc`.
+__device__ __forceinline__ void odom_row(int q, const OdomT& T, const SinCos3& sc, int iter, const float4* __restrict__ sharp, int n_sharp,
+                                         const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
+                                         const float4* __restrict__ surf_last, const int* __restrict__ c1, const int* __restrict__ c2,
+                                         const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3, Acc28& acc) {
   float4 ori, coef;
   bool keep = false;
   if (q < n_sharp) {
@@ -261,8 +259,70 @@ __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, i
     float b = (float)(-0.05 * c.w);
     acc.add_row(a, b);
   }
+}
+
+__global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp,
+                                                           const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
+                                                           int n_cl, const float4* __restrict__ surf_last, int n_sl,
+                                                           const int* __restrict__ c1, const int* __restrict__ c2,
+                                                           const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
+                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28,
+                                                           unsigned long long seq) {
+  Acc28 acc;
+  acc.clear();
+  const int q = blockIdx.x * IT_NT + threadIdx.x;
+  odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
   lg_reduce28<IT_NT>(acc, partials, ticket, out28, seq);
 }
+
+// Same iteration as ONE thread-block cluster (8 CTAs x 256 threads): every CTA reduces its rows to 28 doubles in shared
+// memory, the cluster synchronises once and CTA 0 adds the eight partials straight out of its peers' shared memory
+// (DSMEM) in rank order before publishing to the host mailbox — no global partials, no ticket atomic, no second
+// pass.  Used whenever the features fit one cluster's grid-stride budget (any VLP-16-sized sweep).
+constexpr int CL_CTAS = 8, CL_NT = 512;
+__global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
+    odom_iter_cluster_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
+                             int n_flat, const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
+                             const int* __restrict__ c1, const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2,
+                             const int* __restrict__ s3, double* __restrict__ out28, unsigned long long seq) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double s_part[CL_NT / 32][28];
+  __shared__ double s_cta[28];
+  Acc28 acc;
+  acc.clear();
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int q = blockIdx.x * CL_NT + tid; q < n_sharp + n_flat; q += CL_CTAS * CL_NT)
+    odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
+#pragma unroll
+  for (int i = 0; i < 28; i++) {
+    double x = lg_warp_sum(acc.v[i]);
+    if (lane == 0) s_part[w][i] = x;
+  }
+  __syncthreads();
+  if (tid < 28) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < CL_NT / 32; k++) s += s_part[k][tid];
+    s_cta[tid] = s;
+  }
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    if (tid < 28) {
+      double s = 0.0;
+      for (int r = 0; r < CL_CTAS; r++) s += cluster.map_shared_rank(s_cta, r)[tid];
+      out28[tid] = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      *((volatile unsigned long long*)(out28 + 31)) = seq;
+      __threadfence_system();
+    }
+  }
+  cluster.sync();  // peers must not exit (and release their shared memory) before CTA 0 has read it
+}
+
 
 // LO:156-227.  sT = sin/cos of the full transform, imu sin/cos evaluated on the host.
 __global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
@@ -349,8 +409,14 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
     }
   }
   LgProfScope prof_scope(LGK_ODOM_ITER, st, (double)nq);
-  odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(),
-                                         ws.s3.as<int>(), ws.partials.as<double>(), ws.ticket.as<unsigned int>(), out28, seq);
+  if (nq <= CL_CTAS * CL_NT * 3) {
+    odom_iter_cluster_kernel<<<CL_CTAS, CL_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, ws.c1.as<int>(),
+                                                        ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>(), out28, seq);
+  } else {
+    odom_iter_kernel<<<nb, IT_NT, 0, st>>>(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.c1.as<int>(),
+                                           ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>(), ws.partials.as<double>(),
+                                           ws.ticket.as<unsigned int>(), out28, seq);
+  }
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;

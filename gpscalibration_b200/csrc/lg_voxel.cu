@@ -158,6 +158,145 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
   if (tid == 0) *sg.out_count = V;
 }
 
+
+// ------------------------------------------------------------------------------------------------ split path
+// Medium segments (a sweep-sized stack, 4 k .. 64 k points): the cell-id range of the segment is cut into `gridDim.x`
+// equal sub-ranges, one CTA each.  Every CTA scans the whole segment (L2-resident), keeps the points of its
+// sub-range, sorts them in shared memory and writes their centroids to its staging slice; a second kernel
+// concatenates the slices in range order, which is ascending cell id.  Same results as vox_small_kernel.
+constexpr int VS_CAP = 4096, VS_NT = 256;
+__global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restrict__ segs, float4* __restrict__ staging,
+                                                           int* __restrict__ range_counts, int* __restrict__ overflow) {
+  __shared__ unsigned long long skeys[VS_CAP];
+  __shared__ float s_red[6][VS_NT / 32];
+  __shared__ int s_scan[VS_NT / 32 + 2];
+  __shared__ float s_bb[6];
+  __shared__ int s_n;
+  const VoxSegD sg = segs[blockIdx.y];
+  const int C = gridDim.x, c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int* my_count = range_counts + blockIdx.y * C + c;
+  float4* my_out = staging + ((size_t)blockIdx.y * C + c) * VS_CAP;
+  const int n = sg.n;
+  if (n <= 0) {
+    if (tid == 0) *my_count = 0;
+    return;
+  }
+  float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
+  for (int i = tid; i < n; i += VS_NT) {
+    float4 p = sg.in[i];
+    mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
+    mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+  }
+  if (lane == 0) {
+    s_red[0][w] = mn0; s_red[1][w] = mn1; s_red[2][w] = mn2; s_red[3][w] = mx0; s_red[4][w] = mx1; s_red[5][w] = mx2;
+  }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < VS_NT / 32; k++) {
+      s_red[0][0] = fminf(s_red[0][0], s_red[0][k]); s_red[1][0] = fminf(s_red[1][0], s_red[1][k]);
+      s_red[2][0] = fminf(s_red[2][0], s_red[2][k]); s_red[3][0] = fmaxf(s_red[3][0], s_red[3][k]);
+      s_red[4][0] = fmaxf(s_red[4][0], s_red[4][k]); s_red[5][0] = fmaxf(s_red[5][0], s_red[5][k]);
+    }
+    for (int k = 0; k < 6; k++) s_bb[k] = s_red[k][0];
+  }
+  __syncthreads();
+  VoxGrid g;
+  const bool ok = vox_grid_setup(s_bb[0], s_bb[1], s_bb[2], s_bb[3], s_bb[4], s_bb[5], sg.leaf, g);
+  if (!ok) {  // PCL would hand the input back unfiltered: leave that to the single-CTA / big paths
+    if (tid == 0) {
+      atomicExch(overflow, 1);
+      *my_count = 0;
+    }
+    return;
+  }
+  const int maxb2 = (int)floorf(s_bb[5] * g.inv);
+  const long long total = (long long)g.divxy * (maxb2 - g.minb2 + 1);
+  const long long wdt = (total + C - 1) / C;
+  const long long lo = wdt * c, hi = lo + wdt;
+  for (int i = tid; i < n; i += VS_NT) {
+    int cell = vox_cell(g, sg.in[i]);
+    if (cell >= lo && cell < hi) {
+      int pos = atomicAdd(&s_n, 1);
+      if (pos < VS_CAP) skeys[pos] = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
+    }
+  }
+  __syncthreads();
+  const int m = s_n;
+  if (m > VS_CAP) {
+    if (tid == 0) {
+      atomicExch(overflow, 1);
+      *my_count = 0;
+    }
+    return;
+  }
+  if (m == 0) {
+    if (tid == 0) *my_count = 0;
+    return;
+  }
+  int P = 2;
+  while (P < m) P <<= 1;
+  for (int i = m + tid; i < P; i += VS_NT) skeys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += VS_NT) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int l = i | j;
+        unsigned long long a = skeys[i], b = skeys[l];
+        bool asc = (i & k) == 0;
+        if ((a > b) == asc) {
+          skeys[i] = b;
+          skeys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  const int per = (m + VS_NT - 1) / VS_NT;
+  const int b0 = min(tid * per, m), e0 = min(b0 + per, m);
+  int local = 0;
+  for (int i = b0; i < e0; i++) local += (i == 0 || (unsigned int)(skeys[i] >> 32) != (unsigned int)(skeys[i - 1] >> 32)) ? 1 : 0;
+  int V;
+  int r = block_excl_scan<VS_NT>(local, &V, s_scan);
+  for (int i = b0; i < e0; i++) {
+    unsigned int cell = (unsigned int)(skeys[i] >> 32);
+    if (i == 0 || cell != (unsigned int)(skeys[i - 1] >> 32)) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int j = i;
+      while (j < m && (unsigned int)(skeys[j] >> 32) == cell) {
+        float4 p = sg.in[(unsigned int)(skeys[j] & 0xffffffffull)];
+        sx = sx + p.x; sy = sy + p.y; sz = sz + p.z; si = si + p.w;
+        j++;
+      }
+      float cc = (float)(j - i);
+      my_out[r++] = make_float4(sx / cc, sy / cc, sz / cc, si / cc);
+    }
+  }
+  if (tid == 0) *my_count = V;
+}
+
+__global__ void __launch_bounds__(256) vox_split_concat_kernel(const VoxSegD* __restrict__ segs, const float4* __restrict__ staging,
+                                                                const int* __restrict__ range_counts, int C) {
+  const int s = blockIdx.y, c = blockIdx.x;
+  const int* cnt = range_counts + s * C;
+  int off = 0, tot = 0;
+  for (int k = 0; k < C; k++) {
+    if (k < c) off += cnt[k];
+    tot += cnt[k];
+  }
+  const float4* src = staging + ((size_t)s * C + c) * VS_CAP;
+  float4* dst = segs[s].out + off;
+  for (int i = threadIdx.x; i < cnt[c]; i += blockDim.x) dst[i] = src[i];
+  if (c == 0 && threadIdx.x == 0) *segs[s].out_count = tot;
+}
+
 // ------------------------------------------------------------------------------------------------ radix sort
 constexpr int RS_NT = 256, RS_ITEMS = 8, RS_TILE = RS_NT * RS_ITEMS;
 
@@ -439,6 +578,20 @@ int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overf
     vox_small_kernel<16384, 1024><<<nseg, 1024, 16384 * sizeof(unsigned long long), st>>>(d_segs, d_overflow);
   }
   (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+
+int lg_vox_split(DevBuf& staging, DevBuf& counts, const VoxSegD* d_segs, int nseg, int* d_overflow, cudaStream_t st, long long* launches) {
+  if (nseg <= 0) return LOAM_OK;
+  const int C = 32;
+  LG_CHECK(staging.ensure((size_t)nseg * C * VS_CAP * sizeof(float4), st));
+  LG_CHECK(counts.ensure((size_t)nseg * C * sizeof(int), st));
+  dim3 grid(C, nseg);
+  vox_split_kernel<<<grid, VS_NT, 0, st>>>(d_segs, staging.as<float4>(), counts.as<int>(), d_overflow);
+  vox_split_concat_kernel<<<grid, 256, 0, st>>>(d_segs, staging.as<float4>(), counts.as<int>(), C);
+  (*launches) += 2;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;
 }

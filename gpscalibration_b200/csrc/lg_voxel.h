@@ -33,6 +33,9 @@ struct VoxBigWs {
 
 // One CTA per segment, shared-memory bitonic sort; max_seg_hint picks the 4096- or 16384-point instantiation.
 int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overflow, cudaStream_t st, long long* launches);
+// 4 k .. 64 k points per segment (no `valid` mask): the cell-id range is split over 32 CTAs per segment; sets *d_overflow
+// when a sub-range exceeds its shared-memory capacity (caller falls back to lg_vox_small / lg_vox_big).
+int lg_vox_split(DevBuf& staging, DevBuf& counts, const VoxSegD* d_segs, int nseg, int* d_overflow, cudaStream_t st, long long* launches);
 // Any size: segments are contiguous in d_in, d_seg_off[nseg + 1]; outputs contiguous in d_out, per-segment
 // [d_out_start[s], d_out_end[s]).
 int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
