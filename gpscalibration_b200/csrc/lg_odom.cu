@@ -132,45 +132,68 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_kernel(OdomT T, con
     closest = lg_nbr_idx(b);
     const int scan = int(pts[closest].w);
     unsigned long long f2 = NONE64, f3 = NONE64, b2 = NONE64, b3 = NONE64;
-    for (int base = closest + 1; base < bound; base += 32) {
-      const int j = base + lane;
-      const bool valid = j < bound;
-      float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r = int(t.w);
-      const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r > scan + 1.5));
-      const bool live = valid && (bm == 0u || lane < (__ffs(bm) - 1));
-      if (live) {
-        float d = sqd(t, sel);
-        if (d < 25) {
-          unsigned long long key = lg_pack_nbr(d, j);
-          if (is_c) {
-            if (r > scan) f2 = min(f2, key);
-          } else {
-            if (r <= scan) f2 = min(f2, key); else f3 = min(f3, key);
+    // four 32-wide chunks per step: the loads of a step are independent, so four L2 round trips overlap
+    for (int base = closest + 1; base < bound; base += 128) {
+      float4 t[4];
+      unsigned int bm[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = base + 32 * u + lane;
+        t[u] = (j < bound) ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      bool stop = false;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = base + 32 * u + lane;
+        const bool valid = j < bound;
+        const int r = int(t[u].w);
+        bm[u] = __ballot_sync(0xffffffffu, valid && (r > scan + 1.5));
+        const bool live = !stop && valid && (bm[u] == 0u || lane < (__ffs(bm[u]) - 1));
+        if (live) {
+          float d = sqd(t[u], sel);
+          if (d < 25) {
+            unsigned long long key = lg_pack_nbr(d, j);
+            if (is_c) {
+              if (r > scan) f2 = min(f2, key);
+            } else {
+              if (r <= scan) f2 = min(f2, key); else f3 = min(f3, key);
+            }
           }
         }
+        if (bm[u] != 0u) stop = true;
       }
-      if (bm != 0u) break;
+      if (stop) break;
     }
-    for (int base = closest - 1; base >= 0; base -= 32) {
-      const int j = base - lane;
-      const bool valid = j >= 0;
-      float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r = int(t.w);
-      const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r < scan - 1.5));
-      const bool live = valid && (bm == 0u || lane < (__ffs(bm) - 1));
-      if (live) {
-        float d = sqd(t, sel);
-        if (d < 25) {
-          unsigned long long key = lg_pack_nbr(d, 0x7fffffff - j);  // first met (largest j) wins ties
-          if (is_c) {
-            if (r < scan) b2 = min(b2, key);
-          } else {
-            if (r >= scan) b2 = min(b2, key); else b3 = min(b3, key);
+    for (int base = closest - 1; base >= 0; base -= 128) {
+      float4 t[4];
+      unsigned int bm[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = base - 32 * u - lane;
+        t[u] = (j >= 0) ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      bool stop = false;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = base - 32 * u - lane;
+        const bool valid = j >= 0;
+        const int r = int(t[u].w);
+        bm[u] = __ballot_sync(0xffffffffu, valid && (r < scan - 1.5));
+        const bool live = !stop && valid && (bm[u] == 0u || lane < (__ffs(bm[u]) - 1));
+        if (live) {
+          float d = sqd(t[u], sel);
+          if (d < 25) {
+            unsigned long long key = lg_pack_nbr(d, 0x7fffffff - j);  // first met (largest j) wins ties
+            if (is_c) {
+              if (r < scan) b2 = min(b2, key);
+            } else {
+              if (r >= scan) b2 = min(b2, key); else b3 = min(b3, key);
+            }
           }
         }
+        if (bm[u] != 0u) stop = true;
       }
-      if (bm != 0u) break;
+      if (stop) break;
     }
     f2 = warp_min_u64(f2); b2 = warp_min_u64(b2);
     if (f2 != NONE64 && (b2 == NONE64 || !(lg_nbr_d2(b2) < lg_nbr_d2(f2)))) r2 = lg_nbr_idx(f2);
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, i
 // memory, the cluster synchronises once and CTA 0 adds the eight partials straight out of its peers' shared memory
 // (DSMEM) in rank order before publishing to the host mailbox — no global partials, no ticket atomic, no second
 // pass.  Used whenever the features fit one cluster's grid-stride budget (any VLP-16-sized sweep).
-constexpr int CL_CTAS = 8, CL_NT = 512;
+constexpr int CL_CTAS = 8, CL_NT = 256;
 __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
     odom_iter_cluster_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
                              int n_flat, const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
