@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=1000, help="sweeps per sequence (configs[1]: 1000)")
     ap.add_argument("--cpu-sweeps", type=int, default=150, help="bounded CPU sample (first sweeps of the same sequence)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-segments", type=int, default=4, help="extra: independent segments sharing one GPU (0/1 = skip)")
     args = ap.parse_args()
 
     # exactly ONE line on stdout (the JSON): libraries that print banners to fd 1 (NCCL version line) go to stderr
@@ -339,6 +340,39 @@ def main():
            "roofline": roofline,
            "final_pose_odom": [round(float(x), 4) for x in last.odom.transform_sum],
            "results_identical_sync_vs_pipelined": list(last.odom.transform_sum) == list(last_sync.odom.transform_sum)}
+
+    # extra (not the headline): capacity of one GPU when several independent segments share it (cfg 4 with more segments
+    # than GPUs): SEG pipelined handles driven by SEG host threads over the first sweeps of the rank's sequence family
+    if world == 1 and args.multi_segments > 1:
+        import threading
+        SEG, NS = args.multi_segments, min(400, S)
+        seg_data = [(arr, offs)] + [make_sequence(NS, 100 + i, pinned=True)[1:] for i in range(1, SEG)]
+        seg_pipes = [pipe] + [LoamGpuPipeline(device=local_rank) for _ in range(1, SEG)]
+        seg_t = [0.0] * SEG
+
+        def seg_run(i):
+            a, o = seg_data[i]
+            p = seg_pipes[i]
+            for rep in range(2):
+                p.reset()
+                t0 = time.perf_counter()
+                for k in range(NS):
+                    p.submit(a[o[k]:o[k + 1]])
+                    if k >= DEPTH:
+                        p.wait()
+                while p.pending:
+                    p.wait()
+                seg_t[i] = time.perf_counter() - t0
+
+        ths = [threading.Thread(target=seg_run, args=(i,)) for i in range(SEG)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        out["multi_segment"] = {"segments_on_one_gpu": SEG, "sweeps_per_segment": NS, "value": SEG * NS / max(seg_t), "unit": UNIT,
+                                "note": "independent sequences sharing one B200 (host buffers, wall clock of the slowest segment, second pass)"}
+        for p in seg_pipes[1:]:
+            p.close()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(args.cpu_sweeps, S)

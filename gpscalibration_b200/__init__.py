@@ -6,5 +6,5 @@ Only what the hot path needs lives here: ``csrc/`` holds the hand-w
 generator used by tests and bench.  There is no CPU fallback: without libloamgpu.so or a CUDA device, calls fail.
 """
 from .capi import LoamGpu, LoamGpuPipeline, LoamError, load_library, library_path  # noqa: F401
-from .nodes import ScanRegistration, LaserOdometry, LaserMapping, LoamPipeline  # noqa: F401
+from .nodes import ScanRegistration, LaserOdometry, LaserMapping, TransformMaintenance, LoamPipeline  # noqa: F401
 from .synth import SweepGenerator  # noqa: F401

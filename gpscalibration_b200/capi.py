@@ -56,7 +56,7 @@ class SweepResult(C.Structure):
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
            "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_extract", "loam_extract_device", "loam_odometry_process",
-           "loam_mapping_odometry", "loam_mapping_process", "loam_process_sweep", "loam_process_sweep_device",
+           "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
@@ -101,6 +101,8 @@ def load_library():
     lib.loam_odometry_process.argtypes = [vp, C.POINTER(OdomResult)]
     lib.loam_mapping_odometry.argtypes = [vp, vp]
     lib.loam_mapping_process.argtypes = [vp, C.POINTER(MapResult)]
+    lib.loam_integrate_odometry.argtypes = [vp, vp, C.c_double, vp, vp]
+    lib.loam_integrate_mapping.argtypes = [vp, vp, vp]
     lib.loam_process_sweep.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
     lib.loam_process_sweep_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
     lib.loam_get_cloud.argtypes = [vp, C.c_int, vp, C.c_int, ip]
@@ -230,6 +232,17 @@ class LoamGpu:
         r = MapResult()
         self._check(self.lib.loam_mapping_process(self._h, C.byref(r)), "loam_mapping_process")
         return r
+
+    def integrate_odometry(self, transform_sum, stamp):
+        t = _f32(transform_sum)
+        out, track = np.zeros(6, np.float32), np.zeros(4, np.float64)
+        self._check(self.lib.loam_integrate_odometry(self._h, t.ctypes.data, float(stamp), out.ctypes.data, track.ctypes.data),
+                    "loam_integrate_odometry")
+        return out, track
+
+    def integrate_mapping(self, aft, bef):
+        a, b = _f32(aft), _f32(bef)
+        self._check(self.lib.loam_integrate_mapping(self._h, a.ctypes.data, b.ctypes.data), "loam_integrate_mapping")
 
     def process_sweep(self, xyz, stamp=0.0):
         xyz = _f32(xyz)

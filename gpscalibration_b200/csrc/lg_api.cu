@@ -98,6 +98,10 @@ struct loam_handle {
   int n_corner_last = 0, n_surf_last = 0, n_fullres3 = 0;
   int cornerLastNum = 0, surfLastNum = 0;  // LO:98-99 (gate values, lag one sweep behind after init)
 
+  // ---- transformMaintenance state (TM:77-81, 99-100)
+  float tmSum[6] = {0}, tmIncre[6] = {0}, tmMapped[6] = {0}, tmBef[6] = {0}, tmAft[6] = {0};
+  double tmPre[4] = {0, 0, 0, 0}, tmTmp[4] = {0, 0, 0, 0};
+
   // ---- laserMapping state
   bool lm_inited = false;  // systemInited LM:49
   int mapFrameCount = 4;   // LM:419
@@ -1020,6 +1024,38 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
     out->transform_bef_mapped[i] = h->Tbef[i];
     out->transform_tobe_mapped[i] = Tt[i];
   }
+  return LOAM_OK;
+}
+
+// ============================================================================================ transformMaintenance
+int loam_integrate_odometry(loam_handle* h, const float* Tsum, double stamp, float* out6, double* track4) {
+  if (!h || !Tsum || !out6 || !track4) return LOAM_EINVAL;
+  if (fabs((double)Tsum[3]) < 0.000001 && fabs((double)Tsum[4]) < 0.000001 && fabs((double)Tsum[5]) < 0.000001) {  // TM:264-275
+    h->tmPre[3] = 0;
+    for (int i = 0; i < 6; i++) h->tmSum[i] = h->tmIncre[i] = h->tmMapped[i] = h->tmBef[i] = h->tmAft[i] = 0;
+  }
+  for (int i = 0; i < 6; i++) h->tmSum[i] = Tsum[i];
+  lgh::transform_associate_to_map(h->tmSum, h->tmBef, h->tmAft, h->tmIncre, h->tmMapped);  // TM:175-260
+  for (int i = 0; i < 6; i++) out6[i] = h->tmMapped[i];
+  double px = h->tmMapped[3], py = h->tmMapped[4], pz = h->tmMapped[5];  // TM:116-157
+  double* pre = h->tmPre;
+  double* tmp = h->tmTmp;
+  if (pre[3] == 0) {
+    pre[0] = pz; pre[1] = px; pre[2] = py; pre[3] = stamp;
+    for (int i = 0; i < 4; i++) tmp[i] = pre[i];
+  } else {
+    double dX = pz - pre[0], dY = px - pre[1], dZ = py - pre[2];
+    double dX1 = dX * sqrt(pow(dX, 2) + pow(dY, 2) + pow(dZ, 2)) / sqrt(pow(dX, 2) + pow(dY, 2));
+    double dY1 = dY * sqrt(pow(dX, 2) + pow(dY, 2) + pow(dZ, 2)) / sqrt(pow(dX, 2) + pow(dY, 2));
+    tmp[0] += dX1; tmp[1] += dY1; tmp[2] = py; tmp[3] = stamp;
+    pre[0] = pz; pre[1] = px; pre[2] = py; pre[3] = stamp;
+  }
+  track4[0] = tmp[0]; track4[1] = tmp[1]; track4[2] = 10; track4[3] = tmp[3];
+  return LOAM_OK;
+}
+int loam_integrate_mapping(loam_handle* h, const float* aft, const float* bef) {
+  if (!h || !aft || !bef) return LOAM_EINVAL;
+  for (int i = 0; i < 6; i++) { h->tmAft[i] = aft[i]; h->tmBef[i] = bef[i]; }
   return LOAM_OK;
 }
 

@@ -94,6 +94,19 @@ class LaserMapping:
         return self.gpu.cloud("surround")
 
 
+class TransformMaintenance:
+    """/laser_odom_to_init + /aft_mapped_to_init -> /integrated_to_init, /true_odometry_to_init (TM:346-362)."""
+
+    def __init__(self, gpu: LoamGpu):
+        self.gpu = gpu
+
+    def laserOdometryHandler(self, transform_sum, stamp):  # TM:262-315
+        return self.gpu.integrate_odometry(transform_sum, stamp)
+
+    def odomAftMappedHandler(self, aft_mapped, bef_mapped):  # TM:317-338
+        self.gpu.integrate_mapping(aft_mapped, bef_mapped)
+
+
 class LoamPipeline:
     """The three nodes wired the way gpsCalibration.launch wires them (LA:14-26), one sweep per call."""
 

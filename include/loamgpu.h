@@ -150,6 +150,14 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out);
 int loam_mapping_odometry(loam_handle* h, const float transform_sum[6]);
 int loam_mapping_process(loam_handle* h, loam_map_result* out);
 
+/* ---- transformMaintenance: replaces laserOdometryHandler TM:262-315 and odomAftMappedHandler TM:317-338 --
+ * Host-only scalar code (no kernels): fuses every odometry pose with the latest mapping correction and builds the
+ * height-compensated planar track.  integrated6 = /integrated_to_init pose; track4 = /true_odometry_to_init
+ * {x, y, 10 (HEIGHT), stamp}.  Call loam_integrate_odometry for every published odometry pose and
+ * loam_integrate_mapping after every mapping run (transform_aft_mapped, transform_bef_mapped). */
+int loam_integrate_odometry(loam_handle* h, const float transform_sum[6], double stamp, float integrated6[6], double track4[4]);
+int loam_integrate_mapping(loam_handle* h, const float aft_mapped[6], const float bef_mapped[6]);
+
 /* ---- whole hot path for one sweep (SR -> LO -> LM with device-resident hand-over) -------------- */
 int loam_process_sweep(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, loam_sweep_result* out);
 int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, loam_sweep_result* out);

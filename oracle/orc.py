@@ -55,6 +55,10 @@ def lib():
         L.orc_transform_associate_to_map.argtypes = [vp, vp, vp, vp, vp]
         L.orc_map_iteration.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, ip]
         L.orc_map_iteration_sums28.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_tm_create.restype = vp
+        L.orc_tm_destroy.argtypes = [vp]
+        L.orc_tm_odometry.argtypes = [vp, vp, C.c_double, vp, vp]
+        L.orc_tm_aft_mapped.argtypes = [vp, vp, vp]
         L.orc_pipeline_create.restype = vp
         L.orc_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_pipeline_destroy.argtypes = [vp]
@@ -221,6 +225,29 @@ def map_iteration_sums28(corner_stack, surf_stack, corner_map, surf_map, T):
     lib().orc_map_iteration_sums28(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], c.ctypes.data, c.shape[0], d.ctypes.data,
                                    d.shape[0], T.ctypes.data, out.ctypes.data)
     return out
+
+
+class TransformMaintenance:
+    """Oracle restatement of transformMaintenance.cpp (TM:116-157, 262-338)."""
+
+    def __init__(self):
+        self._h = lib().orc_tm_create()
+
+    def __del__(self):
+        try:
+            lib().orc_tm_destroy(self._h)
+        except Exception:
+            pass
+
+    def odometry(self, Tsum, stamp):
+        T = _f32(Tsum)
+        out, track = np.zeros(6, np.float32), np.zeros(4, np.float64)
+        lib().orc_tm_odometry(self._h, T.ctypes.data, float(stamp), out.ctypes.data, track.ctypes.data)
+        return out, track
+
+    def aft_mapped(self, aft, bef):
+        a, b = _f32(aft), _f32(bef)
+        lib().orc_tm_aft_mapped(self._h, a.ctypes.data, b.ctypes.data)
 
 
 class Pipeline:

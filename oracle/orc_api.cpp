@@ -274,6 +274,12 @@ void* orc_lm_create(int brute) {
 }
 void orc_lm_destroy(void* h) { delete (LaserMapping*)h; }
 
+// ---------------------------------------------------------------- transformMaintenance (N2)
+void* orc_tm_create() { return new TransformMaintenance; }
+void orc_tm_destroy(void* h) { delete (TransformMaintenance*)h; }
+void orc_tm_odometry(void* h, const float* Tsum6, double stamp, float* out6, double* track4) { ((TransformMaintenance*)h)->odometry(Tsum6, stamp, out6, track4); }
+void orc_tm_aft_mapped(void* h, const float* aft6, const float* bef6) { ((TransformMaintenance*)h)->aft_mapped(aft6, bef6); }
+
 // ---------------------------------------------------------------- full pipeline SR -> LO -> LM (one process, no ROS)
 void* orc_pipeline_create(int n_scans, int ring_mode, float ang_min, float ang_step, int brute, int keep_clouds) {
   Pipeline* p = new Pipeline;

@@ -124,6 +124,41 @@ inline void odometry_ros_hop(const float* Tsum_in, float* Tsum_out) {
   Tsum_out[5] = (float)(double)Tsum_in[5];
 }
 
+// transformMaintenance.cpp (TM): fuses the per-sweep odometry pose with the latest mapping correction
+// (laserOdometryHandler TM:262-315, odomAftMappedHandler TM:317-338; its transformAssociateToMap TM:175-260 is the
+// same function as LM:120-205) and builds the "height compensated" planar track /true_odometry_to_init
+// (SaveTrailWithTimeTotxt TM:116-157).  SURVEY 8f row N2.
+struct TransformMaintenance {
+  float Tsum[6] = {0}, Tincre[6] = {0}, Tmapped[6] = {0}, Tbef[6] = {0}, Taft[6] = {0};
+  double preX = 0, preY = 0, preZ = 0, preT = 0, tmpX = 0, tmpY = 0, tmpZ = 0, tmpT = 0;
+  // out6 = /integrated_to_init pose (transformMapped); track4 = /true_odometry_to_init {x, y, HEIGHT = 10, stamp}
+  void odometry(const float* Tsum_in, double stamp, float* out6, double* track4) {
+    if (fabs((double)Tsum_in[3]) < 0.000001 && fabs((double)Tsum_in[4]) < 0.000001 && fabs((double)Tsum_in[5]) < 0.000001) {
+      preT = 0;
+      for (int i = 0; i < 6; i++) Tsum[i] = Tincre[i] = Tmapped[i] = Tbef[i] = Taft[i] = 0;
+    }
+    for (int i = 0; i < 6; i++) Tsum[i] = Tsum_in[i];
+    transform_associate_to_map(Tsum, Tbef, Taft, Tincre, Tmapped);
+    for (int i = 0; i < 6; i++) out6[i] = Tmapped[i];
+    // TM:116-157; laserOdometry2.pose.position = (transformMapped[3], [4], [5]) as doubles
+    double px = Tmapped[3], py = Tmapped[4], pz = Tmapped[5];
+    if (preT == 0) {
+      preX = pz; preY = px; preZ = py; preT = stamp;
+      tmpX = preX; tmpY = preY; tmpZ = preZ; tmpT = preT;
+    } else {
+      double dX = pz - preX, dY = px - preY, dZ = py - preZ;
+      double dX1 = dX * sqrt(pow(dX, 2) + pow(dY, 2) + pow(dZ, 2)) / sqrt(pow(dX, 2) + pow(dY, 2));
+      double dY1 = dY * sqrt(pow(dX, 2) + pow(dY, 2) + pow(dZ, 2)) / sqrt(pow(dX, 2) + pow(dY, 2));
+      tmpX += dX1; tmpY += dY1; tmpZ = py; tmpT = stamp;
+      preX = pz; preY = px; preZ = py; preT = stamp;
+    }
+    track4[0] = tmpX; track4[1] = tmpY; track4[2] = 10; track4[3] = tmpT;
+  }
+  void aft_mapped(const float* aft6, const float* bef6) {
+    for (int i = 0; i < 6; i++) { Taft[i] = aft6[i]; Tbef[i] = bef6[i]; }
+  }
+};
+
 struct MapCorr {  // 5 neighbour indices per stack point, -1 when the 5th neighbour is not within 1 m (diagnostic)
   std::vector<int> corner, surf;
 };

@@ -46,6 +46,50 @@ def _libs():
     return _LIBS
 
 
+_TM = None
+
+
+def pose7_from_T(T):
+    """The nav_msgs/Odometry pose the nodes publish for a pose vector T (LO:1066-1078, LM:1114-1124): position +
+    quaternion built from createQuaternionMsgFromRollPitchYaw(rz, -rx, -ry) with the axes permuted."""
+    T = np.asarray(T, np.float32)
+    roll, pitch, yaw = float(T[2]), float(-T[0]), float(-T[1])
+    hy, hp, hr = yaw * 0.5, pitch * 0.5, roll * 0.5
+    cy, sy, cp, sp, cr, sr = np.cos(hy), np.sin(hy), np.cos(hp), np.sin(hp), np.cos(hr), np.sin(hr)
+    gx = sr * cp * cy - cr * sp * sy
+    gy = cr * sp * cy + sr * cp * sy
+    gz = cr * cp * sy - sr * sp * cy
+    gw = cr * cp * cy + sr * sp * sy
+    return np.array([float(T[3]), float(T[4]), float(T[5]), -gy, -gz, gx, gw], np.float64)
+
+
+def tm():
+    """The reference's transformMaintenance node (oracle/_ref/libref_tm.so)."""
+    global _TM
+    if _TM is None:
+        vp = C.c_void_p
+        L = C.CDLL(os.path.join(_DIR, "libref_tm.so"))
+        L.ref_tm_odometry.argtypes = [vp, C.c_double, vp, vp]
+        L.ref_tm_aft_mapped.argtypes = [vp, vp, C.c_double]
+        L.ref_tm_start()
+        atexit.register(L.ref_tm_stop)
+        _TM = L
+    return _TM
+
+
+def tm_odometry(Tsum, stamp):
+    p = pose7_from_T(Tsum)
+    out, track = np.zeros(6, np.float32), np.zeros(4, np.float64)
+    tm().ref_tm_odometry(p.ctypes.data, float(stamp), out.ctypes.data, track.ctypes.data)
+    return out, track
+
+
+def tm_aft_mapped(aft, bef, stamp):
+    p = pose7_from_T(aft)
+    b = np.ascontiguousarray(bef, np.float32)
+    tm().ref_tm_aft_mapped(p.ctypes.data, b.ctypes.data, float(stamp))
+
+
 def shutdown():
     """Stops the two node loop threads (must run before the interpreter exits)."""
     global _LIBS

@@ -67,6 +67,7 @@ struct Loop {
   std::condition_variable cv;
   int state = 1;  // 1 = loop body running, 0 = parked in spinOnce waiting for the next message batch
   bool stop = false;
+  bool spin_blocks = false;  // ros::spin() parks until stop (nodes whose main() keeps state in locals, e.g. transformMaintenance)
   std::vector<std::function<void()>> inbox;
 };
 inline Loop& loop() {
@@ -78,7 +79,14 @@ inline Loop& loop() {
 namespace ros {
 inline void init(int, char**, const char*) {}
 inline bool ok() { return !refshim::loop().stop; }
-inline void spin() {}
+inline void spin() {
+  refshim::Loop& L = refshim::loop();
+  if (!L.spin_blocks) return;
+  std::unique_lock<std::mutex> l(L.m);
+  L.state = 0;
+  L.cv.notify_all();
+  L.cv.wait(l, [&] { return L.stop; });
+}
 inline void spinOnce() {
   refshim::Loop& L = refshim::loop();
   std::vector<std::function<void()>> batch;
