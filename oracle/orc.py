@@ -55,6 +55,10 @@ def lib():
         L.orc_transform_associate_to_map.argtypes = [vp, vp, vp, vp, vp]
         L.orc_map_iteration.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, ip]
         L.orc_map_iteration_sums28.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_lm_create.restype = vp
+        L.orc_lm_create.argtypes = [C.c_int]
+        L.orc_lm_destroy.argtypes = [vp]
+        L.orc_lm_step.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]
         L.orc_tm_create.restype = vp
         L.orc_tm_destroy.argtypes = [vp]
         L.orc_tm_odometry.argtypes = [vp, vp, C.c_double, vp, vp]
@@ -225,6 +229,31 @@ def map_iteration_sums28(corner_stack, surf_stack, corner_map, surf_map, T):
     lib().orc_map_iteration_sums28(a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], c.ctypes.data, c.shape[0], d.ctypes.data,
                                    d.shape[0], T.ctypes.data, out.ctypes.data)
     return out
+
+
+class LaserMapping:
+    """Oracle laserMapping node driven directly (odometry message + optional full message set)."""
+
+    def __init__(self, brute=False):
+        self._h = lib().orc_lm_create(int(brute))
+
+    def __del__(self):
+        try:
+            lib().orc_lm_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, Tsum, corner=None, surf=None, full=None):
+        T = _f32(Tsum)
+        out = np.zeros(25, np.float32)
+        if corner is None:
+            lib().orc_lm_step(self._h, T.ctypes.data, 0, None, 0, None, 0, None, 0, out.ctypes.data)
+            return None
+        c, s = _f32(corner), _f32(surf)
+        f = _f32(full) if full is not None else np.zeros((0, 4), np.float32)
+        lib().orc_lm_step(self._h, T.ctypes.data, 1, c.ctypes.data, c.shape[0], s.ctypes.data, s.shape[0], f.ctypes.data, f.shape[0],
+                          out.ctypes.data)
+        return out
 
 
 class TransformMaintenance:

@@ -273,6 +273,32 @@ void* orc_lm_create(int brute) {
   return h;
 }
 void orc_lm_destroy(void* h) { delete (LaserMapping*)h; }
+// One odometry message (LM:314-335) and, when `full_set`, one loop body LM:425-1139.  out: [0..6) aft, [6..12) bef,
+// [12..18) tobe, then iterations, n_corner_map, n_surf_map, n_corner_stack, n_surf_stack, total corner, total surf.
+int orc_lm_step(void* hv, const float* Tsum6, int full_set, const float* corner, int nc, const float* surf, int ns, const float* full, int nf,
+                float* out25) {
+  LaserMapping* lm = (LaserMapping*)hv;
+  lm->odometry_msg(Tsum6);
+  if (!full_set) return 0;
+  Cloud c, s, f;
+  to_cloud(corner, nc, c);
+  to_cloud(surf, ns, s);
+  to_cloud(full, nf, f);
+  MapOut mo;
+  lm->keepClouds = false;
+  lm->process(c, s, f, mo);
+  for (int i = 0; i < 6; i++) {
+    out25[i] = mo.transformAftMapped[i];
+    out25[6 + i] = mo.transformBefMapped[i];
+    out25[12 + i] = mo.transformTobeMapped[i];
+  }
+  size_t a = 0, b = 0;
+  for (auto& cl : lm->cornerArr) a += cl.size();
+  for (auto& cl : lm->surfArr) b += cl.size();
+  out25[18] = (float)mo.iterations; out25[19] = (float)mo.nCornerFromMap; out25[20] = (float)mo.nSurfFromMap;
+  out25[21] = (float)mo.nCornerStack; out25[22] = (float)mo.nSurfStack; out25[23] = (float)a; out25[24] = (float)b;
+  return 0;
+}
 
 // ---------------------------------------------------------------- transformMaintenance (N2)
 void* orc_tm_create() { return new TransformMaintenance; }

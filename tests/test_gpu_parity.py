@@ -328,3 +328,31 @@ def test_pipelined_mode_equals_fused(sweeps16):
                     assert (r.map.n_corner_map, r.map.n_surf_map, r.map.iterations) == (g.map.n_corner_map, g.map.n_surf_map, g.map.iterations)
         p.reset()
     p.close()
+
+
+def test_mapping_cube_grid_rolls_like_the_reference(orc, sweeps16):
+    """K11 / a14 / a18: drive laserMapping alone with odometry poses that travel hundreds of metres (and back), so the
+    21 x 11 x 21 cube grid re-centres in every direction (LM:497-657), cubes get cleared, points land in cubes outside
+    the voxel-gridded set and the arena compacts.  Geometry is meaningless here (the same two clouds every time); what
+    must hold is bit-equality with the oracle's cube bookkeeping, gather order and voxel grids."""
+    from gpscalibration_b200 import LoamGpu
+    f = orc.ScanRegistration().extract(sweeps16[0])
+    T0 = np.zeros(6, np.float32)
+    corner = orc.transform_to_end(f["less_sharp"], T0)
+    surf = orc.transform_to_end(f["less_flat"], T0)
+    gpu = LoamGpu()
+    lm = orc.LaserMapping()
+    gpu.odom_set_inputs(f["sharp"], f["flat"], corner, surf)  # fills corner_last / surf_last of the handle
+    path = [(0.0, 0.0, 0.0)]
+    for step in ((45.0, 0.0, 0.0),) * 10 + ((0.0, 0.0, 45.0),) * 9 + ((0.0, 40.0, 0.0),) * 5 + ((-45.0, -20.0, -45.0),) * 14:
+        path.append(tuple(a + b for a, b in zip(path[-1], step)))
+    for k, (x, y, z) in enumerate(path[1:]):
+        Tsum = np.array([0.001 * k, 0.02 * k, -0.0005 * k, x, y, z], np.float32)
+        ro = lm.step(Tsum, corner, surf)
+        gpu.mapping_odometry(Tsum)
+        r = gpu.mapping_process()
+        assert (r.n_corner_map, r.n_surf_map, r.n_corner_stack, r.n_surf_stack, r.iterations) == \
+            (int(ro[19]), int(ro[20]), int(ro[21]), int(ro[22]), int(ro[18])), (k, x, y, z)
+        assert np.array_equal(np.array(r.transform_aft_mapped, np.float32), ro[:6]), k
+        assert np.array_equal(np.array(r.transform_tobe_mapped, np.float32), ro[12:18]), k
+    gpu.close()
