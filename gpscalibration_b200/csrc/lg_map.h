@@ -28,6 +28,7 @@ struct GridD {  // voxel hash over one map cloud (cell = 1 m), open addressing o
   int* cursor;     // global allocation cursor into `sorted`
   int* slot_of;    // slot of every map point
   float4* sorted;  // cells with more than GRID_INLINE points: all their points, contiguous
+  const unsigned int* occ;  // one bit per slot (occupied), small enough to stay in L2: empty cells cost no DRAM access
   int bits;        // log2(slots)
   int n;
 };

@@ -11,8 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def synth_map(n_surf, n_corner, extent, seed=7):
-    """Planar 'city': ground plane + wall planes every 40 m (surf) and vertical edges (corner), ~0.4 / 0.2 m spacing jitter."""
+def synth_map_unfiltered(n_surf, n_corner, extent, seed=7):
+    """Worst case (--unfiltered-map): uniformly random points on the planes / edges, NOT voxel-filtered, so wall cells hold
+    ~11 and edge cells ~30 points (a real LM map never does: every cube is re-filtered at 0.2 / 0.4 m, LM:642-662)."""
     rng = np.random.default_rng(seed)
     ng = int(n_surf * 0.6)
     g = np.empty((ng, 4), np.float32)
@@ -26,7 +27,40 @@ def synth_map(n_surf, n_corner, extent, seed=7):
     c[:, 0] = rng.integers(-int(extent / 10), int(extent / 10) + 1, n_corner) * 10.0 + rng.normal(0, 0.01, n_corner)
     c[:, 2] = rng.integers(-6, 7, n_corner) * 40.0 + rng.normal(0, 0.01, n_corner)
     c[:, 1] = rng.uniform(-1.8, 10, n_corner); c[:, 3] = 0
-    return c, np.concatenate([g, w])
+    return c, np.concatenate([g, w]), extent
+
+
+def synth_map(n_surf, n_corner, seed=7):
+    """Planar 'city' as LM keeps it: every surface carries one point per 0.4 m voxel (surf) and every vertical edge one
+    point per 0.2 m voxel (corner), i.e. what the per-cube voxel filter (LM:642-662) leaves.  Ground plane 2E x E,
+    13 wall planes across it, edges on the walls; E follows from the requested point counts.  Returns (corner, surf, E)."""
+    rng = np.random.default_rng(seed)
+    n_g = int(n_surf * 0.8)
+    nz = int(np.sqrt(n_g / 2)); nx = 2 * nz
+    E = 0.4 * nz
+    gx, gz = np.meshgrid(np.arange(nx, dtype=np.float32), np.arange(nz, dtype=np.float32), indexing="ij")
+    g = np.empty((nx * nz, 4), np.float32)
+    g[:, 0] = (gx.ravel() + rng.uniform(0.1, 0.9, nx * nz)) * 0.4 - E
+    g[:, 2] = (gz.ravel() + rng.uniform(0.1, 0.9, nx * nz)) * 0.4 - E / 2
+    g[:, 1] = -1.8 + rng.normal(0, 0.01, nx * nz); g[:, 3] = 0
+    n_w = n_surf - nx * nz
+    ny = max(1, n_w // (13 * nx))
+    wx, wy, wk = np.meshgrid(np.arange(nx, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(13, dtype=np.float32), indexing="ij")
+    m = nx * ny * 13
+    w = np.empty((m, 4), np.float32)
+    w[:, 0] = (wx.ravel() + rng.uniform(0.1, 0.9, m)) * 0.4 - E
+    w[:, 1] = (wy.ravel() + rng.uniform(0.1, 0.9, m)) * 0.4 - 1.8
+    w[:, 2] = (wk.ravel() - 6) * (E / 13.0) + rng.normal(0, 0.01, m); w[:, 3] = 0
+    H = ny * 0.4
+    nyc = max(1, int(H / 0.2))
+    nl = max(1, n_corner // (13 * nyc))  # edges per wall
+    cx, cy, ck = np.meshgrid(np.arange(nl, dtype=np.float32), np.arange(nyc, dtype=np.float32), np.arange(13, dtype=np.float32), indexing="ij")
+    m = nl * nyc * 13
+    c = np.empty((m, 4), np.float32)
+    c[:, 0] = (cx.ravel() + 0.5) * (2 * E / nl) - E + rng.normal(0, 0.01, m)
+    c[:, 1] = (cy.ravel() + rng.uniform(0.1, 0.9, m)) * 0.2 - 1.8
+    c[:, 2] = (ck.ravel() - 6) * (E / 13.0) + rng.normal(0, 0.01, m); c[:, 3] = 0
+    return c, np.concatenate([g, w]), E
 
 
 def main():
@@ -34,7 +68,9 @@ def main():
     ap.add_argument("--map-points", type=int, default=10_000_000)
     ap.add_argument("--queries", type=int, default=1_000_000)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--extent", type=float, default=2000.0)
+    ap.add_argument("--extent", type=float, default=2000.0, help="half-length in x of the --unfiltered-map scene")
+    ap.add_argument("--unfiltered-map", action="store_true", help="worst case: map NOT voxel-filtered (crowded cells)")
+    ap.add_argument("--random-query-order", action="store_true", help="worst case: no spatial coherence between consecutive queries")
     args = ap.parse_args()
     import torch, torch.distributed as dist
     from gpscalibration_b200 import LoamGpu, capi, sharding
@@ -42,17 +78,28 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_corner, n_surf = args.map_points // 5, args.map_points - args.map_points // 5
-    corner_map, surf_map = synth_map(n_surf, n_corner, args.extent)
+    if args.unfiltered_map:
+        n_corner, n_surf = args.map_points // 5, args.map_points - args.map_points // 5
+        corner_map, surf_map, extent = synth_map_unfiltered(n_surf, n_corner, args.extent)
+    else:
+        n_corner, n_surf = args.map_points // 20, args.map_points - args.map_points // 20
+        corner_map, surf_map, extent = synth_map(n_surf, n_corner)
+    n_corner, n_surf = len(corner_map), len(surf_map)
     rng = np.random.default_rng(11)
     T_true = np.array([0.002, 0.01, -0.003, 0.05, -0.02, 0.08], np.float32)
-    qi_s = rng.choice(n_surf, args.queries * 4 // 5, replace=False); qi_c = rng.choice(n_corner, args.queries // 5, replace=False)
+    qi_c = rng.choice(n_corner, min(args.queries // 5, n_corner // 2), replace=False); qi_s = rng.choice(n_surf, args.queries - len(qi_c), replace=False)
     # queries = map points pushed through the INVERSE of T_true (approximately: small angles), so T converges towards T_true
     def inv(p):
         q = p.copy(); q[:, :3] -= T_true[3:]
         return q
     surf_stack, corner_stack = inv(surf_map[qi_s]), inv(corner_map[qi_c])
-    edges = sharding.slab_edges(-args.extent, args.extent, world)
+
+    def voxel_order(c, leaf):  # stack clouds are voxel-grid outputs: ascending (k, j, i) cell order (PCL's linear id)
+        ijk = np.floor(c[:, :3] / leaf).astype(np.int64)
+        return c[np.lexsort((ijk[:, 0], ijk[:, 1], ijk[:, 2]))]
+    if not args.random_query_order:
+        surf_stack, corner_stack = voxel_order(surf_stack, 0.4), voxel_order(corner_stack, 0.2)
+    edges = sharding.slab_edges(-extent, extent, world)
     T = np.zeros(6, np.float32)
     t0 = time.time()
     my_cm, my_sm = sharding.shard_map(corner_map, edges, rank), sharding.shard_map(surf_map, edges, rank)
@@ -89,7 +136,7 @@ def main():
     nq = my_cs.shape[0] + my_ss.shape[0]
     kern_ms = np.median(it_ms[2:]) - np.median(ar_us[2:]) / 1e3
     out = {"config": "cfg5 sharded map", "n_gpus": world, "map_points": args.map_points, "queries": args.queries, "rank0_map_points": int(my_cm.shape[0] + my_sm.shape[0]),
-           "rank0_queries": int(nq), "n_sel": int(n_sel), "iter_ms_max_over_ranks": float(t_it.item()), "iterations_per_s": 1e3 / float(t_it.item()),
+           "rank0_queries": int(nq), "query_order": "random" if args.random_query_order else "voxel-grid (ascending cell id)", "n_sel": int(n_sel), "iter_ms_max_over_ranks": float(t_it.item()), "iterations_per_s": 1e3 / float(t_it.item()),
            "allreduce_plus_d2h_us": float(np.median(ar_us[2:])), "index_build_ms": build_ms,
            "knn_fit_GBps_algorithmic": 96.0 * nq / (kern_ms * 1e-3) / 1e9, "index_build_GBps_algorithmic_incl_h2d": 36.0 * (my_cm.shape[0] + my_sm.shape[0]) / (build_ms * 1e-3) / 1e9,
            "kernel_ms_per_iter": {k: round(prof[k]["ms"] / args.iters, 4) for k in ("map_knn", "map_fit")},
