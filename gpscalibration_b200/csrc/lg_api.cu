@@ -609,20 +609,43 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
   h->T[4] -= imu[10] * scanPeriod;
   h->T[5] -= imu[11] * scanPeriod;
   if (h->cornerLastNum > 10 && h->surfLastNum > 100) {  // LO:572
-    for (int iter = 0; iter < 25; iter++) {
-      out->iterations = iter + 1;
-      float AtA[36], AtB[6], X[6];
-      int n_sel = 0;
-      int rc = odom_iter(h, iter, h->T, AtA, AtB, &n_sel);
+    static const bool host_loop = getenv("LOAM_HOST_GN_LOOP") != nullptr;  // diagnostic: every iteration through the host
+    for (int iter = 0; iter < 25;) {
+      if (iter == 0 || host_loop) {  // iteration 0 carries the eigen-decomposition / degeneracy test (LO:977-999): host
+        out->iterations = iter + 1;
+        float AtA[36], AtB[6], X[6];
+        int n_sel = 0;
+        int rc = odom_iter(h, iter, h->T, AtA, AtB, &n_sel);
+        if (rc) return rc;
+        iter++;
+        if (n_sel < 10) continue;  // LO:904-907
+        lg_gn_solve_step(AtA, AtB, iter - 1, 10.f, h->lo_gn, X);
+        for (int i = 0; i < 6; i++) h->T[i] += X[i];
+        for (int i = 0; i < 6; i++)
+          if (isnan(h->T[i])) h->T[i] = 0;
+        float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
+        float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
+        if (deltaR < 0.1 && deltaT < 0.1) break;
+        continue;
+      }
+      // iterations up to the next correspondence refresh run on the device without the host in between
+      OdomLoopArgs la;
+      for (int i = 0; i < 6; i++) la.T.t[i] = h->T[i];
+      la.sc = host_sincos3(h->T);
+      memcpy(la.matP, h->lo_gn.matP, sizeof(la.matP));
+      la.degenerate = h->lo_gn.degenerate ? 1 : 0;
+      la.it0 = iter;
+      la.it1 = std::min(25, (iter / 5 + 1) * 5);
+      int rc = lg_odom_loop_launch(h->od, la, h->cur_sharp, c.n_sharp, h->cur_flat, c.n_flat, h->corner_last.as<float4>(), h->n_corner_last,
+                                   h->surf_last.as<float4>(), h->n_surf_last, h->d_mail, ++h->mail_seq, h->st, &h->launches);
       if (rc) return rc;
-      if (n_sel < 10) continue;  // LO:904-907
-      lg_gn_solve_step(AtA, AtB, iter, 10.f, h->lo_gn, X);
-      for (int i = 0; i < 6; i++) h->T[i] += X[i];
-      for (int i = 0; i < 6; i++)
-        if (isnan(h->T[i])) h->T[i] = 0;
-      float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
-      float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
-      if (deltaR < 0.1 && deltaT < 0.1) break;
+      rc = mailbox_wait(h);
+      if (rc) return rc;
+      h->d2h_bytes += 8 * 8;
+      for (int i = 0; i < 6; i++) h->T[i] = (float)h->h_mail[i];
+      out->iterations = (int)h->h_mail[6] + 1;
+      if (h->h_mail[7] != 0.0) break;
+      iter = la.it1;
     }
   }
   ht.lap(&h->host_s[HT_ODOM_END]);

@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "lg_odom.h"
+#include "lg_linalg.cuh"
 #include "lg_reduce.cuh"
 
 namespace {
@@ -347,6 +348,115 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
 }
 
 
+// Iterations it0 .. it1-1 of the Gauss-Newton loop in ONE launch (see lg_odom.h).  Per iteration: rows -> 31-shuffle warp
+// reduction -> CTA partial in shared memory -> cluster barrier -> CTA 0 adds the partials of its peers out of their shared
+// memory (DSMEM, rank order) -> thread 0 solves (Householder QR, LO:975), projects when degenerate (LO:1000-1004),
+// updates the transform (LO:1006-1011 + the NaN guards LO:1013-1018), evaluates the convergence test (LO:1020-1031) and
+// the sin/cos of the new angles (bit-exact libm ports) -> cluster barrier -> every CTA picks the new transform up from
+// CTA 0's shared memory.  No global memory, no atomics and no host between iterations.
+constexpr int LP_NT = 256;
+struct OdomLoopShared {
+  float T[6];
+  float sc[6];  // srx crx sry cry srz crz
+  int done, last_iter;
+};
+__global__ void __launch_bounds__(LP_NT)
+    odom_loop_kernel(OdomLoopArgs A, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
+                     const float4* __restrict__ corner_last, const float4* __restrict__ surf_last, const int* __restrict__ c1,
+                     const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
+                     double* __restrict__ out, unsigned long long seq) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  __shared__ double s_part[LP_NT / 32][28];
+  __shared__ double s_cta[28];
+  __shared__ double s_tot[28];
+  __shared__ OdomLoopShared s_state;  // authoritative copy lives in CTA 0
+  __shared__ OdomLoopShared s_mine;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  OdomT T = A.T;
+  SinCos3 sc = A.sc;
+  int iter = A.it0;
+  if (rank == 0 && tid == 0) {
+    s_state.done = 0;
+    s_state.last_iter = A.it0 - 1;
+  }
+  while (true) {
+    Acc28 acc;
+    acc.clear();
+    for (int q = rank * LP_NT + tid; q < n_sharp + n_flat; q += nranks * LP_NT)
+      odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
+    const double r = lg_warp_reduce28(acc.v, lane);
+    if (lane < 28) s_part[w][lane] = r;
+    __syncthreads();
+    if (tid < 28) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < LP_NT / 32; k++) s += s_part[k][tid];
+      s_cta[tid] = s;
+    }
+    cluster.sync();
+    if (rank == 0) {
+      if (tid < 28) {
+        double s = 0.0;
+        for (unsigned int k = 0; k < nranks; k++) s += cluster.map_shared_rank(s_cta, k)[tid];
+        s_tot[tid] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float AtA[36], AtB[6], X[6];
+        int n_sel;
+        lg_unpack28(s_tot, AtA, AtB, &n_sel);
+        int done = 0;
+        if (n_sel >= 10) {  // LO:904-907
+          lg_qr_solve<6, 6>(AtA, AtB, X);
+          if (A.degenerate) {
+            float X2[6];
+            for (int i = 0; i < 6; i++) X2[i] = X[i];
+            lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
+          }
+          for (int i = 0; i < 6; i++) {
+            float v = T.t[i] + X[i];
+            if (isnan(v)) v = 0.f;
+            T.t[i] = v;
+          }
+          const double r0 = X[0] * 180.0 / M_PI, r1 = X[1] * 180.0 / M_PI, r2 = X[2] * 180.0 / M_PI;
+          const double t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+          const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+          const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+          if (deltaR < 0.1 && deltaT < 0.1) done = 1;
+        }
+        for (int i = 0; i < 6; i++) s_state.T[i] = T.t[i];
+        s_state.sc[0] = lgm_sinf(T.t[0]); s_state.sc[1] = lgm_cosf(T.t[0]);
+        s_state.sc[2] = lgm_sinf(T.t[1]); s_state.sc[3] = lgm_cosf(T.t[1]);
+        s_state.sc[4] = lgm_sinf(T.t[2]); s_state.sc[5] = lgm_cosf(T.t[2]);
+        s_state.done = done;
+        s_state.last_iter = iter;
+      }
+    }
+    cluster.sync();
+    if (tid < (int)(sizeof(OdomLoopShared) / 4))
+      reinterpret_cast<int*>(&s_mine)[tid] = reinterpret_cast<const int*>(cluster.map_shared_rank(&s_state, 0))[tid];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 6; i++) T.t[i] = s_mine.T[i];
+    sc.srx = s_mine.sc[0]; sc.crx = s_mine.sc[1]; sc.sry = s_mine.sc[2]; sc.cry = s_mine.sc[3]; sc.srz = s_mine.sc[4]; sc.crz = s_mine.sc[5];
+    const int done = s_mine.done;
+    iter++;
+    if (done || iter >= A.it1) break;
+    __syncthreads();  // s_mine is rewritten next round
+  }
+  if (rank == 0 && tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) out[i] = (double)s_mine.T[i];
+    out[6] = (double)s_mine.last_iter;
+    out[7] = (double)s_mine.done;
+    __threadfence_system();
+    *((volatile unsigned long long*)(out + 31)) = seq;
+  }
+  cluster.sync();  // CTA 0 must outlive its peers' last read of s_state
+}
+
 // LO:156-227.  sT = sin/cos of the full transform, imu sin/cos evaluated on the host.
 __global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
                                                            int n0, const float4* __restrict__ in1, float4* __restrict__ out1, int n1,
@@ -400,9 +510,7 @@ __global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, I
 
 }  // namespace
 
-int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
-                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, unsigned long long seq, cudaStream_t st,
-                        long long* launches) {
+static int odom_ensure(OdomWs& ws, int n_sharp, int n_flat, cudaStream_t st) {
   const int nq = n_sharp + n_flat;
   const int nb = std::max(1, lg_div_up(nq, IT_NT));
   LG_CHECK(ws.best.ensure((size_t)(nq + 1) * 8, st));
@@ -416,20 +524,39 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
     LG_CHECK(ws.ticket.ensure(4, st));
     LG_CHECK(cudaMemsetAsync(ws.ticket.p, 0, 4, st));
   }
-  if (iter % 5 == 0 && nq > 0) {
-    LG_CHECK(cudaMemsetAsync(ws.best.p, 0xff, (size_t)nq * 8, st));
-    const int tiles_c = lg_div_up(n_sharp, KNN_Q), tiles_s = lg_div_up(n_flat, KNN_Q);
-    const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
-    if (tiles_c + tiles_s > 0) {
-      dim3 grid(tiles_c + tiles_s, chunks);
-      LgProfScope prof_scope(LGK_ODOM_KNN, st, (double)nq);
-      odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
-                                              ws.best.as<unsigned long long>());
-      odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
-                                                                              ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
-                                                                              ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
-      (*launches) += 2;
-    }
+  return LOAM_OK;
+}
+
+// LO:603-677 / LO:758-844: nearest neighbour + ring scans for every feature (every 5th iteration)
+static int odom_refresh_corr(OdomWs& ws, const OdomT& T, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
+                             const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, cudaStream_t st, long long* launches) {
+  const int nq = n_sharp + n_flat;
+  if (nq <= 0) return LOAM_OK;
+  LG_CHECK(cudaMemsetAsync(ws.best.p, 0xff, (size_t)nq * 8, st));
+  const int tiles_c = lg_div_up(n_sharp, KNN_Q), tiles_s = lg_div_up(n_flat, KNN_Q);
+  const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
+  dim3 grid(tiles_c + tiles_s, chunks);
+  LgProfScope prof_scope(LGK_ODOM_KNN, st, (double)nq);
+  odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
+                                          ws.best.as<unsigned long long>());
+  odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
+                                                                          ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
+                                                                          ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
+  (*launches) += 2;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, unsigned long long seq, cudaStream_t st,
+                        long long* launches) {
+  const int nq = n_sharp + n_flat;
+  const int nb = std::max(1, lg_div_up(nq, IT_NT));
+  int rc = odom_ensure(ws, n_sharp, n_flat, st);
+  if (rc) return rc;
+  if (iter % 5 == 0) {
+    rc = odom_refresh_corr(ws, T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, st, launches);
+    if (rc) return rc;
   }
   LgProfScope prof_scope(LGK_ODOM_ITER, st, (double)nq);
   if (nq <= CL_CTAS * CL_NT * 3) {
@@ -442,6 +569,50 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
   }
   (*launches)++;
   LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_odom_loop_launch(OdomWs& ws, const OdomLoopArgs& args, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out, unsigned long long seq, cudaStream_t st,
+                        long long* launches) {
+  static int cluster_ctas = 0;  // 16 where the device schedules a 16-CTA cluster, else the portable 8
+  if (cluster_ctas == 0) {
+    cluster_ctas = 8;
+    if (cudaFuncSetAttribute(odom_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16);
+      cfg.blockDim = dim3(LP_NT);
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 16; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, odom_loop_kernel, &cfg) == cudaSuccess && n_clusters > 0) cluster_ctas = 16;
+    }
+    (void)cudaGetLastError();
+  }
+  int rc = odom_ensure(ws, n_sharp, n_flat, st);
+  if (rc) return rc;
+  if (args.it0 % 5 == 0) {
+    rc = odom_refresh_corr(ws, args.T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, st, launches);
+    if (rc) return rc;
+  }
+  const int nq = n_sharp + n_flat;
+  LgProfScope prof_scope(LGK_ODOM_ITER, st, (double)nq * (args.it1 - args.it0));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_ctas);
+  cfg.blockDim = dim3(LP_NT);
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = cluster_ctas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  LG_CHECK(cudaLaunchKernelEx(&cfg, odom_loop_kernel, args, sharp, n_sharp, flat, n_flat, corner_last, surf_last, (const int*)ws.c1.as<int>(),
+                              (const int*)ws.c2.as<int>(), (const int*)ws.s1.as<int>(), (const int*)ws.s2.as<int>(), (const int*)ws.s3.as<int>(), out,
+                              seq));
+  (*launches)++;
   return LOAM_OK;
 }
 

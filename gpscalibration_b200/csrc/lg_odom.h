@@ -27,5 +27,19 @@ struct OdomWs {
 int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
                         const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out28, unsigned long long seq, cudaStream_t st,
                         long long* launches);
+// Iterations it0 .. it1-1 of the Gauss-Newton loop (LO:579-1011) WITHOUT the host in between: one thread-block cluster
+// computes the rows, reduces them through distributed shared memory, solves the 6x6 system on one thread, updates the
+// transform and goes round again.  it0 >= 1 (iteration 0 holds the eigen-decomposition, which stays on the host);
+// correspondences are refreshed first when it0 % 5 == 0.  Publishes {T[6], last iteration, converged} to `out`.
+struct OdomLoopArgs {
+  OdomT T;
+  SinCos3 sc;
+  float matP[36];
+  int degenerate;
+  int it0, it1;
+};
+int lg_odom_loop_launch(OdomWs& ws, const OdomLoopArgs& args, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
+                        const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out, unsigned long long seq, cudaStream_t st,
+                        long long* launches);
 int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, const float4* in0, float4* out0, int n0, const float4* in1,
                           float4* out1, int n1, const float4* in2, float4* out2, int n2, cudaStream_t st, long long* launches);

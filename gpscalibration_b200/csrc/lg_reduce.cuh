@@ -26,6 +26,35 @@ struct Acc28 {
   }
 };
 
+// All 28 sums of a warp with 31 shuffles instead of 140: at every step the two halves of a lane pair swap one half of
+// their vector and add the other, so the vector halves as the lanes pair up; lane L (< 28) ends with the total of v[L].
+__device__ __forceinline__ double lg_warp_reduce28(const double (&v)[28], int lane) {
+  double a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const double lo = v[i], hi = (i + 16 < 28) ? v[i + 16] : 0.0;
+    const bool up = lane & 16;
+    a[i] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const bool up = lane & 8;
+    b[i] = (up ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + 8], 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const bool up = lane & 4;
+    c[i] = (up ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, up ? b[i] : b[i + 4], 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const bool up = lane & 2;
+    d[i] = (up ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, up ? c[i] : c[i + 2], 2);
+  }
+  const bool up = lane & 1;
+  return (up ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, up ? d[0] : d[1], 1);
+}
+
 // Warp shuffle -> shared memory -> per-CTA partial in global memory; the last CTA to arrive (ticket) adds the partials
 // in CTA order (deterministic) and writes the 28 results to out28 (device memory or mapped pinned host memory).
 template <int NT>
@@ -74,7 +103,10 @@ __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ par
 
 #endif  // __CUDACC__
 
-// host: 28 doubles -> AtA (6x6 row-major float), AtB (6 float), n_sel
+// 28 doubles -> AtA (6x6 row-major float), AtB (6 float), n_sel
+#ifdef __CUDACC__
+__host__ __device__
+#endif
 static inline void lg_unpack28(const double* r, float* AtA, float* AtB, int* n_sel) {
   int t = 0;
   for (int i = 0; i < 6; i++)
