@@ -318,11 +318,8 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (int q = blockIdx.x * CL_NT + tid; q < n_sharp + n_flat; q += CL_CTAS * CL_NT)
     odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
-#pragma unroll
-  for (int i = 0; i < 28; i++) {
-    double x = lg_warp_sum(acc.v[i]);
-    if (lane == 0) s_part[w][i] = x;
-  }
+  const double wsum = lg_warp_reduce28(acc.v, lane);
+  if (lane < 28) s_part[w][lane] = wsum;
   __syncthreads();
   if (tid < 28) {
     double s = 0.0;
@@ -403,35 +400,57 @@ __global__ void __launch_bounds__(LP_NT)
         s_tot[tid] = s;
       }
       __syncthreads();
-      if (tid == 0) {
-        float AtA[36], AtB[6], X[6];
-        int n_sel;
-        lg_unpack28(s_tot, AtA, AtB, &n_sel);
-        int done = 0;
-        if (n_sel >= 10) {  // LO:904-907
-          lg_qr_solve<6, 6>(AtA, AtB, X);
-          if (A.degenerate) {
-            float X2[6];
-            for (int i = 0; i < 6; i++) X2[i] = X[i];
-            lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
+      if (w == 0) {  // lane 0 solves; the six sin/cos and the two convergence norms then run on eight lanes side by side
+        float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int solved = 0;
+        if (lane == 0) {
+          float AtA[36], AtB[6];
+          int n_sel;
+          lg_unpack28(s_tot, AtA, AtB, &n_sel);
+          if (n_sel >= 10) {  // LO:904-907
+            lg_qr_solve<6, 6>(AtA, AtB, X);
+            if (A.degenerate) {
+              float X2[6];
+              for (int i = 0; i < 6; i++) X2[i] = X[i];
+              lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+              float v = T.t[i] + X[i];
+              if (isnan(v)) v = 0.f;
+              T.t[i] = v;
+            }
+            solved = 1;
           }
-          for (int i = 0; i < 6; i++) {
-            float v = T.t[i] + X[i];
-            if (isnan(v)) v = 0.f;
-            T.t[i] = v;
-          }
-          const double r0 = X[0] * 180.0 / M_PI, r1 = X[1] * 180.0 / M_PI, r2 = X[2] * 180.0 / M_PI;
-          const double t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
-          const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
-          const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
-          if (deltaR < 0.1 && deltaT < 0.1) done = 1;
         }
-        for (int i = 0; i < 6; i++) s_state.T[i] = T.t[i];
-        s_state.sc[0] = lgm_sinf(T.t[0]); s_state.sc[1] = lgm_cosf(T.t[0]);
-        s_state.sc[2] = lgm_sinf(T.t[1]); s_state.sc[3] = lgm_cosf(T.t[1]);
-        s_state.sc[4] = lgm_sinf(T.t[2]); s_state.sc[5] = lgm_cosf(T.t[2]);
-        s_state.done = done;
-        s_state.last_iter = iter;
+        solved = __shfl_sync(0xffffffffu, solved, 0);
+        float Tn[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          X[i] = __shfl_sync(0xffffffffu, X[i], 0);
+          Tn[i] = __shfl_sync(0xffffffffu, T.t[i], 0);
+        }
+        int small = 0;
+        if (lane < 6) {
+          const int k = lane >> 1;
+          const float ang = k == 0 ? Tn[0] : (k == 1 ? Tn[1] : Tn[2]);
+          s_state.sc[lane] = (lane & 1) ? lgm_cosf(ang) : lgm_sinf(ang);
+          float tv = Tn[0];
+#pragma unroll
+          for (int i = 1; i < 6; i++) tv = lane == i ? Tn[i] : tv;
+          s_state.T[lane] = tv;
+        } else if (lane == 6) {
+          const double r0 = X[0] * 180.0 / M_PI, r1 = X[1] * 180.0 / M_PI, r2 = X[2] * 180.0 / M_PI;
+          small = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2) < 0.1;
+        } else if (lane == 7) {
+          const double t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+          small = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2) < 0.1;
+        }
+        const unsigned int both = __ballot_sync(0xffffffffu, small) & 0xc0u;
+        if (lane == 0) {
+          s_state.done = (solved && both == 0xc0u) ? 1 : 0;
+          s_state.last_iter = iter;
+        }
       }
     }
     cluster.sync();

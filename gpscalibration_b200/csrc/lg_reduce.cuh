@@ -63,11 +63,8 @@ __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ par
   __shared__ double s_part[NT / 32][28];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-#pragma unroll
-  for (int i = 0; i < 28; i++) {
-    double x = lg_warp_sum(acc.v[i]);
-    if (lane == 0) s_part[w][i] = x;
-  }
+  const double wsum = lg_warp_reduce28(acc.v, lane);
+  if (lane < 28) s_part[w][lane] = wsum;
   __syncthreads();
   if (tid < 28) {
     double s = 0.0;
