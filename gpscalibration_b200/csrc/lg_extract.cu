@@ -306,32 +306,39 @@ constexpr int SEL_CAP = 2048;   // points per sector the shared-memory sort acce
 constexpr int RING_CAP = 8192;  // points per ring whose flags are staged in shared memory
 
 // SR:597-622 / 641-666: how far the suppression of a pick at `ind` reaches forwards / backwards (0..5 each), from the
-// gap flags alone — independent of the pick state, which is what lets a warp resolve 32 candidates at once.
+// gap flags alone — independent of the pick state, which is what lets a warp resolve 32 candidates at once.  Evaluated
+// once per ring point (all threads) and packed as nf | nb << 4.
 // FENCE (iv) (bounds) as in oracle/orc_sr.h suppress_neighbours.
-__device__ __forceinline__ void suppress_reach(const unsigned char* s_cond, int li, int len, int& nf, int& nb) {
-  nf = 0;
+__device__ __forceinline__ unsigned char suppress_reach(const unsigned char* s_cond, int li, int len) {
+  int nf = 0;
   for (int l = 1; l <= 5; l++) {
     if (li + l >= len) break;
     if (s_cond[li + l] & C_GAP) break;
     nf = l;
   }
-  nb = 0;
+  int nb = 0;
   for (int l = 1; l <= 5; l++) {
     if (li - l < 0) break;
     if (s_cond[li - l + 1] & C_GAP) break;
     nb = l;
   }
+  return (unsigned char)(nf | (nb << 4));
 }
 
-// One CTA per ring.  Per sector: bitonic sort of (curvature, index) keys by the whole CTA, then warp 0 replays the
-// reference's greedy walk 32 candidates at a time: every lane knows its candidate's suppression interval, and the
+constexpr int SEL_NT = 512;
+
+// One CTA per ring.  The six sectors' (curvature, index) keys are sorted TOGETHER (one shared-memory bitonic network
+// over six padded segments: the keys do not depend on the picks, and six independent compare-exchanges per thread and
+// step hide the shared-memory latency a single 300-key sort cannot), then warp 0 replays the reference's greedy walk
+// sector after sector, 32 candidates at a time: every lane knows its candidate's suppression interval, and the
 // sequential "picked earlier => suppress neighbours" dependency inside a batch is resolved with ballots.
-__global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
-                                                         const float* __restrict__ curv, const unsigned char* __restrict__ cond,
-                                                         unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
-                                                         signed char* __restrict__ label, int* __restrict__ picks) {
-  __shared__ unsigned long long skeys[SEL_CAP];
+__global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                            const float* __restrict__ curv, const unsigned char* __restrict__ cond,
+                                                            unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
+                                                            signed char* __restrict__ label, int* __restrict__ picks) {
+  extern __shared__ unsigned long long skeys[];  // [6][P]
   __shared__ unsigned char s_cond[RING_CAP];
+  __shared__ unsigned char s_reach[RING_CAP];
   __shared__ unsigned char s_picked[RING_CAP];
   __shared__ signed char s_label[RING_CAP];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -351,58 +358,79 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
     }
     return;
   }
-  for (int li = tid; li < len; li += blockDim.x) {
+  for (int li = tid; li < len; li += SEL_NT) {
     unsigned char m = mask_at(cond, a + li, n);
     s_cond[li] = cond[a + li];
     s_picked[li] = m;
     s_label[li] = 0;
     mask_diag[a + li] = m;
   }
-  int nsharp = 0, nless = 0, nflat = 0;
+  // sector bounds (SR:561-562); a sector that does not fit is skipped and flagged, as before
+  int sp6[6], m6[6];
+  int maxm = 2;
   bool too_big = false;
-  __syncthreads();
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     const int sp = (S * (6 - j) + E * j) / 6;
     const int ep = (S * (5 - j) + E * (j + 1)) / 6 - 1;
-    const int m = ep - sp + 1;
-    if (m <= 0) continue;
-    if (m > SEL_CAP || sp < a || ep >= b) {
+    int m = ep - sp + 1;
+    if (m > 0 && (m > SEL_CAP || sp < a || ep >= b)) {
       too_big = true;
-      continue;
+      m = 0;
     }
-    int P = 2;
-    while (P < m) P <<= 1;
-    for (int t = tid; t < P; t += blockDim.x)
-      skeys[t] = t < m ? (((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned int)(sp + t)) : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= P; k <<= 1)
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (int t = tid; t < (P >> 1); t += blockDim.x) {
-          int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-          int l = i | jj;
-          unsigned long long x = skeys[i], y = skeys[l];
-          bool asc = (i & k) == 0;
-          if ((x > y) == asc) {
-            skeys[i] = y;
-            skeys[l] = x;
-          }
+    sp6[j] = sp;
+    m6[j] = max(m, 0);
+    maxm = max(maxm, m6[j]);
+  }
+  int P = 2, lgP = 1;
+  while (P < maxm) P <<= 1, lgP++;
+#pragma unroll
+  for (int j = 0; j < 6; j++)
+    for (int t = tid; t < P; t += SEL_NT)
+      skeys[j * P + t] = t < m6[j] ? (((unsigned long long)__float_as_uint(curv[sp6[j] + t]) << 32) | (unsigned int)(sp6[j] + t)) : ~0ull;
+  __syncthreads();
+  for (int li = tid; li < len; li += SEL_NT) s_reach[li] = suppress_reach(s_cond, li, len);
+  const int half = P >> 1;
+  for (int k = 2; k <= P; k <<= 1)
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = tid; t < 6 * half; t += SEL_NT) {
+        const int seg = t >> (lgP - 1), tt = t & (half - 1);
+        const int i = ((tt & ~(jj - 1)) << 1) | (tt & (jj - 1));
+        const int l = i | jj;
+        unsigned long long* sk = skeys + seg * P;
+        const unsigned long long x = sk[i], y = sk[l];
+        const bool asc = (i & k) == 0;
+        if ((x > y) == asc) {
+          sk[i] = y;
+          sk[l] = x;
         }
-        __syncthreads();
       }
-    if (tid < 32) {
+      __syncthreads();
+    }
+  int nsharp = 0, nless = 0, nflat = 0;
+  if (tid < 32) {
+    for (int j = 0; j < 6; j++) {
+      const int m = m6[j];
+      if (m <= 0) continue;
+      const unsigned long long* sk = skeys + j * P;
       // ---- SR:578-624: walk down from the largest curvature
       int count = 0;
       bool done = false;
       for (int k = m - 1; k >= 0 && !done; k -= 32) {
         const int kk = k - lane;
         const bool have = kk >= 0;
-        const unsigned long long key = have ? skeys[kk] : 0ull;
+        const unsigned long long key = have ? sk[kk] : 0ull;
         const float cv = __uint_as_float((unsigned int)(key >> 32));
         const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
         const bool pass = have && (cv > 0.1);
         const unsigned int pm = __ballot_sync(0xffffffffu, pass);
         int nf = 0, nb = 0;
-        if (pass) suppress_reach(s_cond, li, len, nf, nb);
+        if (pass) {
+          const unsigned char rr = s_reach[li];
+          nf = rr & 15;
+          nb = rr >> 4;
+        }
+        const int span = (li - nb) | ((li + nf) << 16);
         const bool alive = pass && s_picked[li] == 0;
         unsigned int am = __ballot_sync(0xffffffffu, alive);
         int mynum = 0;
@@ -415,9 +443,8 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
             break;
           }
           if (lane == p) mynum = count;
-          const int pli = __shfl_sync(0xffffffffu, li, p);
-          const int plo = pli - __shfl_sync(0xffffffffu, nb, p), phi = pli + __shfl_sync(0xffffffffu, nf, p);
-          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
+          const int ps = __shfl_sync(0xffffffffu, span, p);
+          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= (ps & 0xffff) && li <= (ps >> 16));
         }
         if (mynum > 0) {
           const int ind = li + a;
@@ -442,13 +469,18 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
       for (int k = 0; k < m && !done; k += 32) {
         const int kk = k + lane;
         const bool have = kk < m;
-        const unsigned long long key = have ? skeys[kk] : 0ull;
+        const unsigned long long key = have ? sk[kk] : 0ull;
         const float cv = __uint_as_float((unsigned int)(key >> 32));
         const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
         const bool pass = have && (cv < 0.1);
         const unsigned int pm = __ballot_sync(0xffffffffu, pass);
         int nf = 0, nb = 0;
-        if (pass) suppress_reach(s_cond, li, len, nf, nb);
+        if (pass) {
+          const unsigned char rr = s_reach[li];
+          nf = rr & 15;
+          nb = rr >> 4;
+        }
+        const int span = (li - nb) | ((li + nf) << 16);
         const bool alive = pass && s_picked[li] == 0;
         unsigned int am = __ballot_sync(0xffffffffu, alive);
         int mynum = 0;
@@ -463,9 +495,8 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
             done = true;
             break;
           }
-          const int pli = __shfl_sync(0xffffffffu, li, p);
-          const int plo = pli - __shfl_sync(0xffffffffu, nb, p), phi = pli + __shfl_sync(0xffffffffu, nf, p);
-          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
+          const int ps = __shfl_sync(0xffffffffu, span, p);
+          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= (ps & 0xffff) && li <= (ps >> 16));
         }
         if (mynum > 0) {
           s_label[li] = -1;
@@ -478,9 +509,9 @@ __global__ void __launch_bounds__(256) sr_select_kernel(SrParams prm, const floa
       }
       nflat += count;
     }
-    __syncthreads();
   }
-  for (int li = tid; li < len; li += blockDim.x) label[a + li] = s_label[li];
+  __syncthreads();
+  for (int li = tid; li < len; li += SEL_NT) label[a + li] = s_label[li];
   if (tid == 0) {
     cnt[0] = nsharp;
     cnt[1] = nless;
@@ -598,7 +629,15 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
   }
   {
   LgProfScope prof_scope(LGK_SR_SELECT, st, (double)n);
-  sr_select_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
+  static bool sel_attr[64] = {};  // the opt-in is per device
+  constexpr int sel_smem = 6 * SEL_CAP * 8;
+  int dev = 0;
+  LG_CHECK(cudaGetDevice(&dev));
+  if (!sel_attr[dev & 63]) {
+    LG_CHECK(cudaFuncSetAttribute(sr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sel_smem));
+    sel_attr[dev & 63] = true;
+  }
+  sr_select_kernel<<<R, SEL_NT, sel_smem, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
                                       ws.picked.as<unsigned char>(), ws.mask_diag.as<unsigned char>(), ws.label.as<signed char>(),
                                       ws.picks.as<int>());
   }

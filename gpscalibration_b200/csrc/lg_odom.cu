@@ -594,7 +594,10 @@ int lg_odom_iter_launch(OdomWs& ws, const OdomT& T, const SinCos3& sc, int iter,
 int lg_odom_loop_launch(OdomWs& ws, const OdomLoopArgs& args, const float4* sharp, int n_sharp, const float4* flat, int n_flat,
                         const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, double* out, unsigned long long seq, cudaStream_t st,
                         long long* launches) {
-  static int cluster_ctas = 0;  // 16 where the device schedules a 16-CTA cluster, else the portable 8
+  static int cluster_ctas_dev[64] = {};  // 16 where the device schedules a 16-CTA cluster, else the portable 8
+  int dev = 0;
+  LG_CHECK(cudaGetDevice(&dev));
+  int& cluster_ctas = cluster_ctas_dev[dev & 63];
   if (cluster_ctas == 0) {
     cluster_ctas = 8;
     if (cudaFuncSetAttribute(odom_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
