@@ -802,9 +802,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (h->n_map_c > 10 && h->n_map_s > 100) {  // LM:749
     out->optimised = 1;
     ht.lap(&h->host_s[HT_MAP_GRID]);
-    rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), h->n_map_c, h->st, &h->launches);
-    if (rc) return rc;
-    rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), h->n_map_s, h->st, &h->launches);
+    rc = lg_grid_build2(h->grid_c, h->map_c.as<float4>(), h->n_map_c, h->grid_s, h->map_s.as<float4>(), h->n_map_s, h->st, &h->launches);
     if (rc) return rc;
     h->grids_valid = true;
     ht.lap(&h->host_s[HT_MAP_ITERS]);
@@ -1287,8 +1285,7 @@ int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, con
   if (!rc) rc = upload(h, h->map_s, surf_map, (size_t)n_sm * 16);
   if (rc) return rc;
   h->n_stack_c = n_cs; h->n_stack_s = n_ss; h->n_map_c = n_cm; h->n_map_s = n_sm;
-  rc = lg_grid_build(h->grid_c, h->map_c.as<float4>(), n_cm, h->st, &h->launches);
-  if (!rc) rc = lg_grid_build(h->grid_s, h->map_s.as<float4>(), n_sm, h->st, &h->launches);
+  rc = lg_grid_build2(h->grid_c, h->map_c.as<float4>(), n_cm, h->grid_s, h->map_s.as<float4>(), n_sm, h->st, &h->launches);
   if (rc) return rc;
   LG_SYNC(h);
   h->grids_valid = true;

@@ -76,48 +76,66 @@ __device__ __forceinline__ unsigned long long cell_key(int ix, int iy, int iz) {
 }
 __device__ __forceinline__ unsigned int cell_hash(unsigned long long k, int bits) { return (unsigned int)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
 
-// Bucket = one 128-byte line per occupied cell: key, count, start and the first GRID_INLINE points inline, so a query
-// lane resolves a cell with ONE memory round trip (two 16-byte loads of the first sector, the rest of the line only
-// when the cell holds more than one point); cells with more points continue in the cell-sorted array.
-__global__ void grid_init_kernel(GridD g) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= (1 << g.bits)) return;
-  g.buckets[s].key = EMPTY;
-  g.buckets[s].count = 0;
-  g.buckets[s].start = 0;
+// The corner grid and the surf grid are always built together: every build kernel serves both (CTAs below `split` work
+// on grid 0, the rest on grid 1), so a map refresh costs four launches instead of ten.
+struct GridJob {
+  GridD g[2];
+  const float4* pts[2];
+  int n[2];
+};
+__global__ void grid_init_kernel(GridJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const GridD& g = J.g[w];
+  const int s = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;  // the slot count is a multiple of the block size
+  uint4* raw = reinterpret_cast<uint4*>(&g.slots[s]);
+  raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0xffffffffu);  // key = EMPTY, count = 0, line = -1
+  raw[1] = make_uint4(0u, 0u, 0u, 0u);
   g.fill[s] = 0;
+  if (s == 0) g.cursor[0] = g.cursor[1] = 0;
 }
-__global__ void grid_count_kernel(GridD g, const float4* __restrict__ pts, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = pts[i];
+__global__ void grid_count_kernel(GridJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const GridD& g = J.g[w];
+  const int i = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;
+  if (i >= J.n[w]) return;
+  float4 p = J.pts[w][i];
   unsigned long long key = cell_key((int)floorf(p.x), (int)floorf(p.y), (int)floorf(p.z));
   unsigned int h = cell_hash(key, g.bits);
   const unsigned int mask = (1u << g.bits) - 1u;
   while (true) {
-    unsigned long long prev = atomicCAS(&g.buckets[h].key, EMPTY, key);
+    unsigned long long prev = atomicCAS(&g.slots[h].key, EMPTY, key);
     if (prev == EMPTY || prev == key) break;
     h = (h + 1) & mask;
   }
-  atomicAdd(&g.buckets[h].count, 1);
+  atomicAdd(&g.slots[h].count, 1);
   g.slot_of[i] = (int)h;
 }
-__global__ void grid_alloc_kernel(GridD g) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;  // the slot count is a multiple of the block size
-  int c = g.buckets[s].count;
-  if (c > GRID_INLINE) g.buckets[s].start = atomicAdd(g.cursor, c);
+__global__ void grid_alloc_kernel(GridJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const GridD& g = J.g[w];
+  const int s = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;
+  const int c = g.slots[s].count;
+  if (c > 1) {
+    const int line = atomicAdd(&g.cursor[1], 1);
+    g.slots[s].line = line;
+    if (c > GRID_INLINE) g.ovf_start[line] = atomicAdd(&g.cursor[0], c);
+  }
   const unsigned int b = __ballot_sync(0xffffffffu, c > 0);
   if ((threadIdx.x & 31) == 0) const_cast<unsigned int*>(g.occ)[s >> 5] = b;
 }
-__global__ void grid_fill_kernel(GridD g, const float4* __restrict__ pts, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__global__ void grid_fill_kernel(GridJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const GridD& g = J.g[w];
+  const int i = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;
+  if (i >= J.n[w]) return;
   int s = g.slot_of[i];
   int pos = atomicAdd(&g.fill[s], 1);
-  float4 p = pts[i];
+  float4 p = J.pts[w][i];
   float4 e = make_float4(p.x, p.y, p.z, __int_as_float(i));
-  if (pos < GRID_INLINE) g.buckets[s].pts[pos] = e;
-  if (g.buckets[s].count > GRID_INLINE) g.sorted[g.buckets[s].start + pos] = e;
+  const int cnt = g.slots[s].count, line = g.slots[s].line;
+  if (pos == 0) g.slots[s].p0 = e;
+  else if (pos < GRID_INLINE) g.lines[line].pts[pos - 1] = e;
+  if (cnt > GRID_INLINE) g.sorted[g.ovf_start[line] + pos] = e;
 }
 
 // ---------------------------------------------------------------------------------------------- exact 5-NN
@@ -201,33 +219,37 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
       float4 p0;
       unsigned long long kk;
       while (true) {
-        hd = __ldg(reinterpret_cast<const uint4*>(&g.buckets[h]));
-        p0 = __ldg(&g.buckets[h].pts[0]);
+        // one 32-byte sector: {key, count, line} + point 0, two independent 16-byte loads
+        hd = __ldg(reinterpret_cast<const uint4*>(&g.slots[h]));
+        p0 = __ldg(&g.slots[h].p0);
         kk = ((unsigned long long)hd.y << 32) | hd.x;
         if (kk == key || kk == EMPTY) break;
         h = (h + 1) & mask;
       }
       if (kk != key) continue;
-      const int cnt = (int)hd.z, start = (int)hd.w;
-      if (cnt > 0) offer(p0);
+      const int cnt = (int)hd.z;
+      offer(p0);
       if (cnt > 1) {
-        const float4* line = g.buckets[h].pts;
-        const int ninl = min(cnt, GRID_INLINE);
-        float4 rest[GRID_INLINE - 1];
+        const float4* line = g.lines[(int)hd.w].pts;
+        const int ninl = min(cnt - 1, GRID_LINE);
+        float4 pt[GRID_LINE];
 #pragma unroll
-        for (int i = 1; i < GRID_INLINE; i++)
-          if (i < ninl) rest[i - 1] = __ldg(&line[i]);
+        for (int i = 0; i < GRID_LINE; i++)
+          if (i < ninl) pt[i] = __ldg(&line[i]);  // issued back to back: one more round trip for the whole line
 #pragma unroll
-        for (int i = 1; i < GRID_INLINE; i++)
-          if (i < ninl) offer(rest[i - 1]);
-        for (int i = GRID_INLINE; i < cnt; i += 4) {
-          float4 o[4];
+        for (int i = 0; i < GRID_LINE; i++)
+          if (i < ninl) offer(pt[i]);
+        if (cnt > GRID_INLINE) {  // overflow of a crowded cell, four loads in flight
+          const int start = __ldg(&g.ovf_start[(int)hd.w]);
+          for (int i = GRID_INLINE; i < cnt; i += 4) {
+            float4 o[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (i + u < cnt) o[u] = __ldg(&g.sorted[start + i + u]);
+            for (int u = 0; u < 4; u++)
+              if (i + u < cnt) o[u] = __ldg(&g.sorted[start + i + u]);
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (i + u < cnt) offer(o[u]);
+            for (int u = 0; u < 4; u++)
+              if (i + u < cnt) offer(o[u]);
+          }
         }
       }
     }
@@ -414,16 +436,20 @@ int lg_map_register_launch(const MapT& T, const float4* in, float4* out, int n, 
   return LOAM_OK;
 }
 
-int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long long* launches) {
+static int grid_prepare(GridWs& ws, int n, cudaStream_t st, size_t* slots_out) {
   int bits = 10;
   while ((1 << bits) < 2 * n) bits++;
   const size_t slots = (size_t)1 << bits;
-  LG_CHECK(ws.keys.ensure(slots * sizeof(GridBucket), st));
+  LG_CHECK(ws.keys.ensure(slots * sizeof(GridSlot), st));
+  LG_CHECK(ws.lines.ensure((size_t)(n + 1) * sizeof(GridLine), st));
+  LG_CHECK(ws.ovf.ensure((size_t)(n + 1) * 4, st));
   LG_CHECK(ws.ints.ensure((slots + 8 + slots / 32) * 4, st));
   LG_CHECK(ws.slot_of.ensure((size_t)(n + 1) * 4, st));
   LG_CHECK(ws.sorted.ensure((size_t)(n + 1) * 16, st));
   GridD& g = ws.d;
-  g.buckets = ws.keys.as<GridBucket>();
+  g.slots = ws.keys.as<GridSlot>();
+  g.lines = ws.lines.as<GridLine>();
+  g.ovf_start = ws.ovf.as<int>();
   g.fill = ws.ints.as<int>();
   g.cursor = g.fill + slots;
   g.occ = reinterpret_cast<const unsigned int*>(g.cursor + 8);
@@ -431,14 +457,29 @@ int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long lo
   g.sorted = ws.sorted.as<float4>();
   g.bits = bits;
   g.n = n;
-  LgProfScope prof_scope(LGK_GRID, st, (double)n);
-  grid_init_kernel<<<lg_div_up((int)slots, 256), 256, 0, st>>>(g);
-  LG_CHECK(cudaMemsetAsync(g.cursor, 0, 16, st));
+  *slots_out = slots;
+  return LOAM_OK;
+}
+
+int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches) {
+  size_t slots0 = 0, slots1 = 0;
+  int rc = grid_prepare(ws0, n0, st, &slots0);
+  if (rc) return rc;
+  rc = grid_prepare(ws1, n1, st, &slots1);
+  if (rc) return rc;
+  GridJob J;
+  J.g[0] = ws0.d; J.g[1] = ws1.d;
+  J.pts[0] = pts0; J.pts[1] = pts1;
+  J.n[0] = n0; J.n[1] = n1;
+  LgProfScope prof_scope(LGK_GRID, st, (double)(n0 + n1));
+  const int sb0 = (int)(slots0 / 256), sb1 = (int)(slots1 / 256);
+  const int pb0 = lg_div_up(n0, 256), pb1 = lg_div_up(n1, 256);
+  grid_init_kernel<<<sb0 + sb1, 256, 0, st>>>(J, sb0);
   (*launches)++;
-  if (n > 0) {
-    grid_count_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(g, pts, n);
-    grid_alloc_kernel<<<lg_div_up((int)slots, 256), 256, 0, st>>>(g);
-    grid_fill_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(g, pts, n);
+  if (pb0 + pb1 > 0) {
+    grid_count_kernel<<<pb0 + pb1, 256, 0, st>>>(J, pb0);
+    grid_alloc_kernel<<<sb0 + sb1, 256, 0, st>>>(J, sb0);
+    grid_fill_kernel<<<pb0 + pb1, 256, 0, st>>>(J, pb0);
     (*launches) += 3;
   }
   LG_CHECK(cudaGetLastError());

@@ -13,30 +13,40 @@ struct CubeGeom {  // LM:69-75
   int W, H, D, cenW, cenH, cenD;
 };
 
-constexpr int GRID_INLINE = 7;  // points stored inside a bucket
+constexpr int GRID_LINE = 8;                // points in a cell's line
+constexpr int GRID_INLINE = 1 + GRID_LINE;  // points reachable without touching `sorted`
 
-struct alignas(128) GridBucket {  // one 128-byte line per occupied 1 m cell
-  unsigned long long key;        // cell key, ~0 = empty
-  int count;                     // points in the cell
-  int start;                     // first position in `sorted` (only when count > GRID_INLINE)
-  float4 pts[GRID_INLINE];       // {x, y, z, original index as int bits}
+// Voxel hash over one map cloud (cell = 1 m).  Two levels: a 32-byte slot per hash position (open addressing, 2x
+// over-provisioned) holding the cell key, its point count and its FIRST point -- one 32-byte sector answers "is the
+// cell there, and if it holds a single point, which" -- and one 128-byte line of eight more points per cell that has
+// more than one; cells with more than nine continue in `sorted`.  For a 5^3-cube local map both levels stay in L2.
+struct alignas(32) GridSlot {
+  unsigned long long key;  // cell key, ~0 = empty
+  int count;               // points in the cell
+  int line;                // index of the cell's line (count > 1)
+  float4 p0;               // {x, y, z, original index as int bits}
+};
+struct alignas(128) GridLine {
+  float4 pts[GRID_LINE];
 };
 
-struct GridD {  // voxel hash over one map cloud (cell = 1 m), open addressing over 128-byte buckets
-  GridBucket* buckets;
+struct GridD {
+  GridSlot* slots;
+  GridLine* lines;
   int* fill;       // build-time scatter cursor per slot
-  int* cursor;     // global allocation cursor into `sorted`
+  int* cursor;     // [0] allocation cursor into `sorted`, [1] next free line
   int* slot_of;    // slot of every map point
+  int* ovf_start;  // per line: first position in `sorted` (only when count > GRID_INLINE)
   float4* sorted;  // cells with more than GRID_INLINE points: all their points, contiguous
-  const unsigned int* occ;  // one bit per slot (occupied), small enough to stay in L2: empty cells cost no DRAM access
+  const unsigned int* occ;  // one bit per slot (occupied): most of the 27 cells a query probes are empty and stop here
   int bits;        // log2(slots)
   int n;
 };
 
 struct GridWs {
-  DevBuf keys, ints, slot_of, sorted;
+  DevBuf keys, lines, ints, slot_of, sorted, ovf;
   GridD d;
-  void release() { keys.release(); ints.release(); slot_of.release(); sorted.release(); }
+  void release() { keys.release(); lines.release(); ints.release(); slot_of.release(); sorted.release(); ovf.release(); }
 };
 
 struct MapIterWs {
@@ -47,7 +57,8 @@ struct MapIterWs {
 int lg_map_stack_launch(const MapT& T, const float4* in0, float4* out0, int n0, const float4* in1, float4* out1, int n1, cudaStream_t st,
                         long long* launches);
 int lg_map_register_launch(const MapT& T, const float4* in, float4* out, int n, cudaStream_t st, long long* launches);
-int lg_grid_build(GridWs& ws, const float4* pts, int n, cudaStream_t st, long long* launches);
+// Builds the corner grid and the surf grid together (four launches).
+int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches);
 int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
                        const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
                        long long* launches);
