@@ -366,6 +366,97 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const unsigned long l
   }
 }
 
+// Whole stable LSD radix sort of up to 16384 (key, value) pairs in ONE CTA: the map stage sorts ~10 k new points twice
+// per run (by cube, then by voxel), and at that size the three-kernels-per-digit path above is pure launch latency
+// (~23 us per digit).  The keys stay put in shared memory; what moves is a 16-bit permutation.  Warp w owns positions
+// [w*R*32, (w+1)*R*32) of the current order; a digit pass ranks every element inside its warp chunk with
+// __match_any_sync (stable: row, then lane), scans the 256 x 32 (digit, warp) counters once, and scatters the permutation.
+constexpr int RSS_CAP = 16384, RSS_NT = 1024, RSS_ROWS = RSS_CAP / RSS_NT;
+constexpr int RSS_SMEM = RSS_CAP * 8 + 2 * RSS_CAP * 2 + 256 * 32 * 2;
+struct RsShifts {
+  int s[8];
+  int n;
+};
+__global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long long* __restrict__ kin, const unsigned int* __restrict__ vin,
+                                                           unsigned long long* __restrict__ kout, unsigned int* __restrict__ vout, int n,
+                                                           RsShifts sh) {
+  extern __shared__ unsigned long long rss_smem[];
+  unsigned long long* s_key = rss_smem;
+  unsigned short* s_idx0 = reinterpret_cast<unsigned short*>(s_key + RSS_CAP);
+  unsigned short* s_idx1 = s_idx0 + RSS_CAP;
+  unsigned short* s_cnt = s_idx1 + RSS_CAP;  // [256][32]
+  __shared__ int s_scan[34];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int R = (n + RSS_NT - 1) / RSS_NT;  // rows per warp
+  for (int i = tid; i < n; i += RSS_NT) {
+    s_key[i] = kin[i];
+    s_idx0[i] = (unsigned short)i;
+  }
+  unsigned short* in = s_idx0;
+  unsigned short* out = s_idx1;
+  __syncthreads();
+  for (int pass = 0; pass < sh.n; pass++) {
+    const int shift = sh.s[pass];
+    for (int i = tid; i < 256 * 32; i += RSS_NT) s_cnt[i] = 0;
+    __syncthreads();
+    unsigned short e[RSS_ROWS], rk[RSS_ROWS];
+#pragma unroll
+    for (int r = 0; r < RSS_ROWS; r++) {
+      if (r < R) {
+        const int p = (w * R + r) * 32 + lane;
+        const bool valid = p < n;
+        const unsigned int ei = valid ? in[p] : 0u;
+        const unsigned int d = valid ? ((unsigned int)(s_key[ei] >> shift) & 255u) : (256u + lane);
+        const unsigned int m = __match_any_sync(0xffffffffu, d);
+        const unsigned int rank = __popc(m & ((1u << lane) - 1u));
+        unsigned int before = 0;
+        if (valid) before = s_cnt[d * 32 + w];
+        __syncwarp();
+        if (valid && rank == 0) s_cnt[d * 32 + w] = (unsigned short)(before + __popc(m));
+        __syncwarp();
+        e[r] = (unsigned short)ei;
+        rk[r] = (unsigned short)(before + rank);
+      }
+    }
+    __syncthreads();
+    {  // exclusive scan of the 8192 counters in (digit, warp) order
+      int v[8], local = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        v[k] = s_cnt[tid * 8 + k];
+        local += v[k];
+      }
+      int tot;
+      int run = block_excl_scan<RSS_NT>(local, &tot, s_scan);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        s_cnt[tid * 8 + k] = (unsigned short)run;
+        run += v[k];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RSS_ROWS; r++) {
+      if (r < R) {
+        const int p = (w * R + r) * 32 + lane;
+        if (p < n) {
+          const unsigned int d = (unsigned int)(s_key[e[r]] >> shift) & 255u;
+          out[(unsigned int)s_cnt[d * 32 + w] + rk[r]] = e[r];
+        }
+      }
+    }
+    __syncthreads();
+    unsigned short* tmp = in;
+    in = out;
+    out = tmp;
+  }
+  for (int i = tid; i < n; i += RSS_NT) {
+    const unsigned int ei = in[i];
+    kout[i] = s_key[ei];
+    vout[i] = vin[ei];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ big path
 __device__ __forceinline__ int find_seg(const int* __restrict__ seg_off, int nseg, int i) {
   int lo = 0, hi = nseg;  // largest s with seg_off[s] <= i
@@ -596,8 +687,32 @@ int lg_vox_split(DevBuf& staging, DevBuf& counts, const VoxSegD* d_segs, int nse
   return LOAM_OK;
 }
 
+static int rs_small_launch(RadixWs& ws, int n, const int* shifts, int nshifts, cudaStream_t st, long long* launches, int* result_in_b) {
+  static bool attr[64] = {};
+  int dev = 0;
+  LG_CHECK(cudaGetDevice(&dev));
+  if (!attr[dev & 63]) {
+    LG_CHECK(cudaFuncSetAttribute(rs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RSS_SMEM));
+    attr[dev & 63] = true;
+  }
+  RsShifts sh;
+  sh.n = nshifts;
+  for (int i = 0; i < 8; i++) sh.s[i] = i < nshifts ? shifts[i] : 0;
+  rs_small_kernel<<<1, RSS_NT, RSS_SMEM, st>>>(ws.keysA.as<unsigned long long>(), ws.valsA.as<unsigned int>(), ws.keysB.as<unsigned long long>(),
+                                               ws.valsB.as<unsigned int>(), n, sh);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  *result_in_b = 1;
+  return LOAM_OK;
+}
+
 int lg_radix_sort(RadixWs& ws, int n, int bits, cudaStream_t st, long long* launches, int* result_in_b) {
   // keys/vals in ws.keysA/valsA; sorted result ends in A or B (result_in_b)
+  if (n <= RSS_CAP && bits <= 64) {
+    int shifts[8], ns = 0;
+    for (int shift = 0; shift < bits; shift += 8) shifts[ns++] = shift;
+    return rs_small_launch(ws, n, shifts, ns, st, launches, result_in_b);
+  }
   int nblocks = lg_div_up(n, RS_TILE);
   LG_CHECK(ws.hist.ensure((size_t)256 * nblocks * sizeof(unsigned int), st));
   unsigned long long* ka = ws.keysA.as<unsigned long long>();
@@ -662,6 +777,7 @@ int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const flo
 
 
 int lg_radix_sort_shifts(RadixWs& ws, int n, const int* shifts, int nshifts, cudaStream_t st, long long* launches, int* result_in_b) {
+  if (n <= RSS_CAP && nshifts <= 8) return rs_small_launch(ws, n, shifts, nshifts, st, launches, result_in_b);
   int nblocks = lg_div_up(n, RS_TILE);
   LG_CHECK(ws.hist.ensure((size_t)256 * nblocks * sizeof(unsigned int), st));
   unsigned long long* ka = ws.keysA.as<unsigned long long>();
