@@ -160,13 +160,14 @@ constexpr int KNN_SUB = 8;                       // lanes per query
 constexpr int KNN_QPW = 32 / KNN_SUB;            // queries per warp
 constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;     // queries per CTA
 
-// Exact 5-NN, EIGHT lanes per query (four queries per warp).  Every lane walks 3-4 of the 27 neighbour cells: one L2-
-// resident occupancy bit decides whether the cell exists at all (most of the 27 do not, and an absent cell then costs
-// no DRAM access), one 32-byte sector {key, count, start, point 0} resolves it, the rest of the 128-byte line follows
-// only for cells with more than one point.  Each lane keeps a sorted top-5 of (d2, index) keys in registers; the eight
-// lanes are merged with masked hardware warp reductions.  Variants measured and dropped on a 20 M-point map: a full warp
-// per query (same time, 3x the instructions), all probes of a lane issued up front (more registers, slower), a
-// block-local hash layout (slower build, no gain).
+// Exact 5-NN, EIGHT lanes per query (four queries per warp), two phases.  Probe: every lane resolves 3-4 of the 27
+// neighbour cells -- one L2-resident occupancy bit decides whether the cell exists at all (most do not), one 32-byte
+// sector {key, count, line, point 0} resolves it.  Scan: the cells that hold more than one point are then walked by
+// the whole group TOGETHER, lane i taking point i of the cell's 128-byte line (one coalesced read, and every lane sees
+// the same number of candidates whatever the occupancy of "its" cells).  Each lane keeps a sorted top-5 of (d2, index)
+// keys in registers (branch-free min/max insertion); the eight lanes are merged with masked warp reductions.
+// Variants measured and dropped on a 20 M-point map: a full warp per query (same time, 3x the instructions), all
+// probes of a lane issued up front (more registers, slower), a block-local hash layout (slower build, no gain).
 __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const float4* __restrict__ corner_stack, int n_cs,
                                                                   const float4* __restrict__ surf_stack, int n_ss, GridD gc, GridD gs,
                                                                   int* __restrict__ nbr /* [n_cs + n_ss][5] */) {
@@ -180,38 +181,27 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
   if (active) sel = assoc_to_map(T, is_c ? corner_stack[q] : surf_stack[q - n_cs]);
   unsigned long long k0 = EMPTY, k1 = EMPTY, k2 = EMPTY, k3 = EMPTY, k4 = EMPTY;
   auto offer = [&](float4 p) {
-    float d2 = lg_sqdist(p.x, p.y, p.z, sel.x, sel.y, sel.z);
+    const float d2 = lg_sqdist(p.x, p.y, p.z, sel.x, sel.y, sel.z);
     if (d2 < 1.0f) {
-      unsigned long long c = lg_pack_nbr(d2, __float_as_int(p.w));
-      if (c < k4) {  // insert into the sorted local top-5
-        if (c < k3) {
-          k4 = k3;
-          if (c < k2) {
-            k3 = k2;
-            if (c < k1) {
-              k2 = k1;
-              if (c < k0) {
-                k1 = k0;
-                k0 = c;
-              } else {
-                k1 = c;
-              }
-            } else {
-              k2 = c;
-            }
-          } else {
-            k3 = c;
-          }
-        } else {
-          k4 = c;
-        }
+      const unsigned long long c = lg_pack_nbr(d2, __float_as_int(p.w));
+      if (c < k4) {  // sorted insertion without branches: new_i = min(max(c, k_{i-1}), k_i)
+        const unsigned long long n4 = min(max(c, k3), k4), n3 = min(max(c, k2), k3), n2 = min(max(c, k1), k2), n1 = min(max(c, k0), k1);
+        k0 = min(c, k0);
+        k1 = n1; k2 = n2; k3 = n3; k4 = n4;
       }
     }
   };
-  if (active) {
+  constexpr int CPL = (27 + KNN_SUB - 1) / KNN_SUB;  // cells per lane
+  int ccnt[CPL], cline[CPL];
+  {
     const int bx = (int)floorf(sel.x), by = (int)floorf(sel.y), bz = (int)floorf(sel.z);
     const unsigned int mask = (1u << g.bits) - 1u;
-    for (int c = sub; c < 27; c += KNN_SUB) {
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+      const int c = sub + j * KNN_SUB;
+      ccnt[j] = 0;
+      cline[j] = -1;
+      if (!active || c >= 27) continue;
       const unsigned long long key = cell_key(bx + (c % 3) - 1, by + ((c / 3) % 3) - 1, bz + (c / 9) - 1);
       unsigned int h = cell_hash(key, g.bits);
       if (!((__ldg(&g.occ[h >> 5]) >> (h & 31)) & 1u)) continue;  // home slot empty => cell absent (linear probing)
@@ -227,30 +217,23 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
         h = (h + 1) & mask;
       }
       if (kk != key) continue;
-      const int cnt = (int)hd.z;
       offer(p0);
-      if (cnt > 1) {
-        const float4* line = g.lines[(int)hd.w].pts;
-        const int ninl = min(cnt - 1, GRID_LINE);
-        float4 pt[GRID_LINE];
+      ccnt[j] = (int)hd.z;
+      cline[j] = (int)hd.w;
+    }
+  }
 #pragma unroll
-        for (int i = 0; i < GRID_LINE; i++)
-          if (i < ninl) pt[i] = __ldg(&line[i]);  // issued back to back: one more round trip for the whole line
-#pragma unroll
-        for (int i = 0; i < GRID_LINE; i++)
-          if (i < ninl) offer(pt[i]);
-        if (cnt > GRID_INLINE) {  // overflow of a crowded cell, four loads in flight
-          const int start = __ldg(&g.ovf_start[(int)hd.w]);
-          for (int i = GRID_INLINE; i < cnt; i += 4) {
-            float4 o[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-              if (i + u < cnt) o[u] = __ldg(&g.sorted[start + i + u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-              if (i + u < cnt) offer(o[u]);
-          }
-        }
+  for (int j = 0; j < CPL; j++) {
+    unsigned int todo = (__ballot_sync(0xffffffffu, ccnt[j] > 1) >> (grp * KNN_SUB)) & ((1u << KNN_SUB) - 1u);
+    while (todo) {  // uniform inside the 8-lane group
+      const int src = grp * KNN_SUB + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int cnt = __shfl_sync(gmask, ccnt[j], src);
+      const int line = __shfl_sync(gmask, cline[j], src);
+      if (sub < min(cnt - 1, GRID_LINE)) offer(__ldg(&g.lines[line].pts[sub]));
+      if (cnt > GRID_INLINE) {  // crowded cell: the rest comes from the cell-sorted array, eight points per step
+        const int start = __ldg(&g.ovf_start[line]);
+        for (int i = GRID_INLINE + sub; i < cnt; i += KNN_SUB) offer(__ldg(&g.sorted[start + i]));
       }
     }
   }

@@ -72,12 +72,22 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
   }
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
   int cnt = 0;
-  for (int i = tid; i < n; i += NT) {
-    if (sg.valid && !sg.valid[i]) continue;
-    float4 p = sg.in[i];
-    mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
-    mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
-    cnt++;
+  for (int i0 = tid; i0 < n; i0 += 4 * NT) {  // four loads in flight per thread
+    float4 p[4];
+    bool take[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * NT;
+      take[u] = i < n && (!sg.valid || sg.valid[i]);
+      if (i < n) p[u] = sg.in[i];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (take[u]) {
+        mn0 = fminf(mn0, p[u].x); mn1 = fminf(mn1, p[u].y); mn2 = fminf(mn2, p[u].z);
+        mx0 = fmaxf(mx0, p[u].x); mx1 = fmaxf(mx1, p[u].y); mx2 = fmaxf(mx2, p[u].z);
+        cnt++;
+      }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -111,6 +121,7 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
   const bool ok = vox_grid_setup(s_bb[0], s_bb[1], s_bb[2], s_bb[3], s_bb[4], s_bb[5], sg.leaf, g);
   int P = 2;
   while (P < n) P <<= 1;
+#pragma unroll 4
   for (int i = tid; i < P; i += NT) {
     unsigned long long key = ~0ull;
     if (i < n && (!sg.valid || sg.valid[i])) {
@@ -183,10 +194,17 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
     return;
   }
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
-  for (int i = tid; i < n; i += VS_NT) {
-    float4 p = sg.in[i];
-    mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
-    mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
+  for (int i0 = tid; i0 < n; i0 += 4 * VS_NT) {  // four loads in flight per thread: every CTA streams the whole segment
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * VS_NT < n) p[u] = sg.in[i0 + u * VS_NT];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * VS_NT < n) {
+        mn0 = fminf(mn0, p[u].x); mn1 = fminf(mn1, p[u].y); mn2 = fminf(mn2, p[u].z);
+        mx0 = fmaxf(mx0, p[u].x); mx1 = fmaxf(mx1, p[u].y); mx2 = fmaxf(mx2, p[u].z);
+      }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -221,11 +239,21 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
   const long long total = (long long)g.divxy * (maxb2 - g.minb2 + 1);
   const long long wdt = (total + C - 1) / C;
   const long long lo = wdt * c, hi = lo + wdt;
-  for (int i = tid; i < n; i += VS_NT) {
-    int cell = vox_cell(g, sg.in[i]);
-    if (cell >= lo && cell < hi) {
-      int pos = atomicAdd(&s_n, 1);
-      if (pos < VS_CAP) skeys[pos] = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
+  for (int i0 = tid; i0 < n; i0 += 4 * VS_NT) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * VS_NT < n) p[u] = sg.in[i0 + u * VS_NT];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * VS_NT;
+      if (i < n) {
+        int cell = vox_cell(g, p[u]);
+        if (cell >= lo && cell < hi) {
+          int pos = atomicAdd(&s_n, 1);  // slot order is irrelevant: the keys embed the point index and are sorted next
+          if (pos < VS_CAP) skeys[pos] = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
+        }
+      }
     }
   }
   __syncthreads();
@@ -298,6 +326,19 @@ __global__ void __launch_bounds__(256) vox_split_concat_kernel(const VoxSegD* __
 }
 
 // ------------------------------------------------------------------------------------------------ radix sort
+// Lanes of the warp holding the same 8-bit digit, from eight ballots (MATCH.ANY resolves one distinct value per
+// iteration and made a digit pass over 10 k keys cost ~13 us).  Invalid lanes get an unspecified mask.
+__device__ __forceinline__ unsigned int lg_match8(unsigned int d, bool valid) {
+  unsigned int m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
 constexpr int RS_NT = 256, RS_ITEMS = 8, RS_TILE = RS_NT * RS_ITEMS;
 
 __global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const unsigned long long* __restrict__ keys, int n, int shift,
@@ -347,7 +388,7 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const unsigned long l
     bool valid = i < n;
     unsigned long long key = valid ? kin[i] : 0ull;
     unsigned int d = (unsigned int)(key >> shift) & 255u;
-    unsigned int m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+    unsigned int m = lg_match8(d, valid);
     unsigned int rank = __popc(m & ((1u << lane) - 1u));
     if (valid && rank == 0) s_wcnt[w][d] = __popc(m);
     __syncthreads();
@@ -372,7 +413,8 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const unsigned long l
 // [w*R*32, (w+1)*R*32) of the current order; a digit pass ranks every element inside its warp chunk with
 // __match_any_sync (stable: row, then lane), scans the 256 x 32 (digit, warp) counters once, and scatters the permutation.
 constexpr int RSS_CAP = 16384, RSS_NT = 1024, RSS_ROWS = RSS_CAP / RSS_NT;
-constexpr int RSS_SMEM = RSS_CAP * 8 + 2 * RSS_CAP * 2 + 256 * 32 * 2;
+constexpr int RSS_CW = 258;  // counter row pitch (warp-major, padded: the 32 lanes of a warp hit 32 different digits)
+constexpr int RSS_SMEM = RSS_CAP * 8 + 2 * RSS_CAP * 2 + 32 * RSS_CW * 2;
 struct RsShifts {
   int s[8];
   int n;
@@ -384,7 +426,7 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
   unsigned long long* s_key = rss_smem;
   unsigned short* s_idx0 = reinterpret_cast<unsigned short*>(s_key + RSS_CAP);
   unsigned short* s_idx1 = s_idx0 + RSS_CAP;
-  unsigned short* s_cnt = s_idx1 + RSS_CAP;  // [256][32]
+  unsigned short* s_cnt = s_idx1 + RSS_CAP;  // [32 warps][RSS_CW]
   __shared__ int s_scan[34];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int R = (n + RSS_NT - 1) / RSS_NT;  // rows per warp
@@ -397,7 +439,7 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
   __syncthreads();
   for (int pass = 0; pass < sh.n; pass++) {
     const int shift = sh.s[pass];
-    for (int i = tid; i < 256 * 32; i += RSS_NT) s_cnt[i] = 0;
+    for (int i = tid; i < 32 * RSS_CW; i += RSS_NT) s_cnt[i] = 0;
     __syncthreads();
     unsigned short e[RSS_ROWS], rk[RSS_ROWS];
 #pragma unroll
@@ -406,31 +448,32 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
         const int p = (w * R + r) * 32 + lane;
         const bool valid = p < n;
         const unsigned int ei = valid ? in[p] : 0u;
-        const unsigned int d = valid ? ((unsigned int)(s_key[ei] >> shift) & 255u) : (256u + lane);
-        const unsigned int m = __match_any_sync(0xffffffffu, d);
+        const unsigned int d = valid ? ((unsigned int)(s_key[ei] >> shift) & 255u) : 0u;
+        const unsigned int m = lg_match8(d, valid);
         const unsigned int rank = __popc(m & ((1u << lane) - 1u));
         unsigned int before = 0;
-        if (valid) before = s_cnt[d * 32 + w];
+        if (valid) before = s_cnt[w * RSS_CW + d];
         __syncwarp();
-        if (valid && rank == 0) s_cnt[d * 32 + w] = (unsigned short)(before + __popc(m));
+        if (valid && rank == 0) s_cnt[w * RSS_CW + d] = (unsigned short)(before + __popc(m));
         __syncwarp();
         e[r] = (unsigned short)ei;
         rk[r] = (unsigned short)(before + rank);
       }
     }
     __syncthreads();
-    {  // exclusive scan of the 8192 counters in (digit, warp) order
+    {  // exclusive scan of the 8192 counters in (digit, warp) order: thread t owns digit t / 4, warps (t % 4) * 8 .. + 7
+      const int dd = tid >> 2, w0 = (tid & 3) * 8;
       int v[8], local = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        v[k] = s_cnt[tid * 8 + k];
+        v[k] = s_cnt[(w0 + k) * RSS_CW + dd];
         local += v[k];
       }
       int tot;
       int run = block_excl_scan<RSS_NT>(local, &tot, s_scan);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        s_cnt[tid * 8 + k] = (unsigned short)run;
+        s_cnt[(w0 + k) * RSS_CW + dd] = (unsigned short)run;
         run += v[k];
       }
     }
@@ -441,7 +484,7 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
         const int p = (w * R + r) * 32 + lane;
         if (p < n) {
           const unsigned int d = (unsigned int)(s_key[e[r]] >> shift) & 255u;
-          out[(unsigned int)s_cnt[d * 32 + w] + rk[r]] = e[r];
+          out[(unsigned int)s_cnt[w * RSS_CW + d] + rk[r]] = e[r];
         }
       }
     }
