@@ -49,7 +49,8 @@ ALGO_BYTES = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
 # (r1_ncu_full_<kernel>.csv, first 60 sweeps of the same sequence); None where no capture exists
-NCU_TRAFFIC = {"sr_select": 154880, "odom_iter": 328448, "map_knn": 3706880, "voxel": None, "extract": None, "odom_knn": None}
+NCU_TRAFFIC = {"sr_select": 154880, "odom_iter": 328448, "map_knn": 1962000, "voxel": None, "extract": None,
+               "odom_knn": 372000 + 385000}  # odom_knn_kernel + odom_corr_kernel of one refresh (profiles/r1_ncu_full_final.csv)
 
 
 def log(*a):
