@@ -8,6 +8,7 @@
 //   small: one CTA per segment, keys (cell << 32 | index) bitonic-sorted in shared memory (<= 16384 points);
 //   big  : global LSD radix sort of (segment << 32 | cell, index), 8 bits per pass, any size.
 // HBM roofline: algorithmic bytes 16 (M + V) per call.
+#include <cooperative_groups.h>
 #include <float.h>
 
 #include "lg_voxel.h"
@@ -407,47 +408,54 @@ __global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const unsigned long l
   }
 }
 
-// Whole stable LSD radix sort of up to 16384 (key, value) pairs in ONE CTA: the map stage sorts ~10 k new points twice
-// per run (by cube, then by voxel), and at that size the three-kernels-per-digit path above is pure launch latency
-// (~23 us per digit).  The keys stay put in shared memory; what moves is a 16-bit permutation.  Warp w owns positions
-// [w*R*32, (w+1)*R*32) of the current order; a digit pass ranks every element inside its warp chunk with
-// __match_any_sync (stable: row, then lane), scans the 256 x 32 (digit, warp) counters once, and scatters the permutation.
-constexpr int RSS_CAP = 16384, RSS_NT = 1024, RSS_ROWS = RSS_CAP / RSS_NT;
+// Whole stable LSD radix sort of up to 16384 (key, value) pairs in ONE launch of ONE 8-CTA cluster: the map stage sorts
+// ~10 k new points twice per run (by cube, then by voxel), and at that size the three-kernels-per-digit path above is
+// pure launch latency (~23 us per digit) while a single CTA is bound by one SM's issue rate (~10 us per digit).
+// Every CTA keeps ALL keys in shared memory (they never move) and owns one eighth of the positions of the current
+// order; what moves is a 16-bit permutation in global memory.  A digit pass: rank every element inside its warp's
+// rows with ballots (stable: row, then lane) -> per-CTA (digit, warp) prefix + digit totals -> cluster barrier ->
+// every CTA reads its peers' digit totals out of their shared memory (DSMEM) and derives its global bases ->
+// scatter the permutation -> cluster barrier.
+constexpr int RSS_CAP = 16384, RSS_NT = 1024, RSC_CTAS = 8;
+constexpr int RSS_ROWS = RSS_CAP / RSC_CTAS / RSS_NT;  // rows per warp (2)
 constexpr int RSS_CW = 258;  // counter row pitch (warp-major, padded: the 32 lanes of a warp hit 32 different digits)
-constexpr int RSS_SMEM = RSS_CAP * 8 + 2 * RSS_CAP * 2 + 32 * RSS_CW * 2;
+constexpr int RSS_SMEM = RSS_CAP * 8 + 32 * RSS_CW * 2;
 struct RsShifts {
   int s[8];
   int n;
 };
-__global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long long* __restrict__ kin, const unsigned int* __restrict__ vin,
-                                                           unsigned long long* __restrict__ kout, unsigned int* __restrict__ vout, int n,
-                                                           RsShifts sh) {
+__global__ void __cluster_dims__(RSC_CTAS, 1, 1) __launch_bounds__(RSS_NT)
+    rs_cluster_kernel(const unsigned long long* __restrict__ kin, const unsigned int* __restrict__ vin, unsigned long long* __restrict__ kout,
+                      unsigned int* __restrict__ vout, int n, RsShifts sh, unsigned short* perm /* [2][RSS_CAP] */) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ unsigned long long rss_smem[];
   unsigned long long* s_key = rss_smem;
-  unsigned short* s_idx0 = reinterpret_cast<unsigned short*>(s_key + RSS_CAP);
-  unsigned short* s_idx1 = s_idx0 + RSS_CAP;
-  unsigned short* s_cnt = s_idx1 + RSS_CAP;  // [32 warps][RSS_CW]
+  unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_key + RSS_CAP);  // [32 warps][RSS_CW]
+  __shared__ unsigned int s_tot[256], s_base[256];
   __shared__ int s_scan[34];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int R = (n + RSS_NT - 1) / RSS_NT;  // rows per warp
-  for (int i = tid; i < n; i += RSS_NT) {
-    s_key[i] = kin[i];
-    s_idx0[i] = (unsigned short)i;
-  }
-  unsigned short* in = s_idx0;
-  unsigned short* out = s_idx1;
+  const int c = (int)cluster.block_rank();
+  const int chunk = ((n + RSC_CTAS * 32 - 1) / (RSC_CTAS * 32)) * 32;  // positions per CTA
+  const int p0 = c * chunk, p1 = min(n, p0 + chunk);
+  const int R = (chunk / 32 + 31) / 32;  // rows per warp
+  unsigned short* in = perm;
+  unsigned short* out = perm + RSS_CAP;
+  for (int i = tid; i < n; i += RSS_NT) s_key[i] = kin[i];
+  for (int p = p0 + tid; p < p1; p += RSS_NT) in[p] = (unsigned short)p;
   __syncthreads();
   for (int pass = 0; pass < sh.n; pass++) {
     const int shift = sh.s[pass];
     for (int i = tid; i < 32 * RSS_CW; i += RSS_NT) s_cnt[i] = 0;
     __syncthreads();
-    unsigned short e[RSS_ROWS], rk[RSS_ROWS];
+    unsigned int e[RSS_ROWS], rk[RSS_ROWS];
 #pragma unroll
     for (int r = 0; r < RSS_ROWS; r++) {
+      e[r] = rk[r] = 0;
       if (r < R) {
-        const int p = (w * R + r) * 32 + lane;
-        const bool valid = p < n;
-        const unsigned int ei = valid ? in[p] : 0u;
+        const int p = p0 + (w * R + r) * 32 + lane;
+        const bool valid = p < p1;
+        const unsigned int ei = valid ? __ldcg(&in[p]) : 0u;  // written by other SMs in the previous pass: bypass L1
         const unsigned int d = valid ? ((unsigned int)(s_key[ei] >> shift) & 255u) : 0u;
         const unsigned int m = lg_match8(d, valid);
         const unsigned int rank = __popc(m & ((1u << lane) - 1u));
@@ -456,12 +464,12 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
         __syncwarp();
         if (valid && rank == 0) s_cnt[w * RSS_CW + d] = (unsigned short)(before + __popc(m));
         __syncwarp();
-        e[r] = (unsigned short)ei;
-        rk[r] = (unsigned short)(before + rank);
+        e[r] = ei;
+        rk[r] = before + rank;
       }
     }
     __syncthreads();
-    {  // exclusive scan of the 8192 counters in (digit, warp) order: thread t owns digit t / 4, warps (t % 4) * 8 .. + 7
+    {  // (digit, warp) exclusive prefix inside the CTA: thread t owns digit t / 4, warps (t % 4) * 8 .. + 7
       const int dd = tid >> 2, w0 = (tid & 3) * 8;
       int v[8], local = 0;
 #pragma unroll
@@ -469,34 +477,55 @@ __global__ void __launch_bounds__(RSS_NT) rs_small_kernel(const unsigned long lo
         v[k] = s_cnt[(w0 + k) * RSS_CW + dd];
         local += v[k];
       }
-      int tot;
-      int run = block_excl_scan<RSS_NT>(local, &tot, s_scan);
+      int incl = local;
+      int t1 = __shfl_up_sync(0xffffffffu, incl, 1, 4);
+      if ((lane & 3) >= 1) incl += t1;
+      int t2 = __shfl_up_sync(0xffffffffu, incl, 2, 4);
+      if ((lane & 3) >= 2) incl += t2;
+      const int total = __shfl_sync(0xffffffffu, incl, 3, 4);
+      int run = incl - local;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         s_cnt[(w0 + k) * RSS_CW + dd] = (unsigned short)run;
         run += v[k];
       }
+      if ((tid & 3) == 0) s_tot[dd] = (unsigned int)total;
+    }
+    cluster.sync();
+    {  // global base of (digit, this CTA): all smaller digits everywhere + the same digit in lower-ranked CTAs
+      unsigned int before = 0, all = 0;
+      if (tid < 256) {
+#pragma unroll
+        for (int cc = 0; cc < RSC_CTAS; cc++) {
+          const unsigned int t = cluster.map_shared_rank(s_tot, cc)[tid];
+          if (cc < c) before += t;
+          all += t;
+        }
+      }
+      int tot;
+      const int ex = block_excl_scan<RSS_NT>((int)all, &tot, s_scan);
+      if (tid < 256) s_base[tid] = (unsigned int)ex + before;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RSS_ROWS; r++) {
       if (r < R) {
-        const int p = (w * R + r) * 32 + lane;
-        if (p < n) {
+        const int p = p0 + (w * R + r) * 32 + lane;
+        if (p < p1) {
           const unsigned int d = (unsigned int)(s_key[e[r]] >> shift) & 255u;
-          out[(unsigned int)s_cnt[w * RSS_CW + d] + rk[r]] = e[r];
+          out[s_base[d] + s_cnt[w * RSS_CW + d] + rk[r]] = (unsigned short)e[r];
         }
       }
     }
-    __syncthreads();
+    cluster.sync();  // the new order is complete (and nobody still reads this pass's totals) before the next pass
     unsigned short* tmp = in;
     in = out;
     out = tmp;
   }
-  for (int i = tid; i < n; i += RSS_NT) {
-    const unsigned int ei = in[i];
-    kout[i] = s_key[ei];
-    vout[i] = vin[ei];
+  for (int p = p0 + tid; p < p1; p += RSS_NT) {
+    const unsigned int ei = __ldcg(&in[p]);
+    kout[p] = s_key[ei];
+    vout[p] = vin[ei];
   }
 }
 
@@ -735,14 +764,16 @@ static int rs_small_launch(RadixWs& ws, int n, const int* shifts, int nshifts, c
   int dev = 0;
   LG_CHECK(cudaGetDevice(&dev));
   if (!attr[dev & 63]) {
-    LG_CHECK(cudaFuncSetAttribute(rs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RSS_SMEM));
+    LG_CHECK(cudaFuncSetAttribute(rs_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RSS_SMEM));
     attr[dev & 63] = true;
   }
   RsShifts sh;
   sh.n = nshifts;
   for (int i = 0; i < 8; i++) sh.s[i] = i < nshifts ? shifts[i] : 0;
-  rs_small_kernel<<<1, RSS_NT, RSS_SMEM, st>>>(ws.keysA.as<unsigned long long>(), ws.valsA.as<unsigned int>(), ws.keysB.as<unsigned long long>(),
-                                               ws.valsB.as<unsigned int>(), n, sh);
+  LG_CHECK(ws.perm.ensure((size_t)2 * RSS_CAP * sizeof(unsigned short), st));
+  rs_cluster_kernel<<<RSC_CTAS, RSS_NT, RSS_SMEM, st>>>(ws.keysA.as<unsigned long long>(), ws.valsA.as<unsigned int>(),
+                                                        ws.keysB.as<unsigned long long>(), ws.valsB.as<unsigned int>(), n, sh,
+                                                        ws.perm.as<unsigned short>());
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   *result_in_b = 1;

@@ -20,8 +20,8 @@ struct CopyEnt {  // table-driven gather: dst[dst_off + i] = src[i], i < n
 };
 
 struct RadixWs {
-  DevBuf keysA, keysB, valsA, valsB, hist;
-  void release() { keysA.release(); keysB.release(); valsA.release(); valsB.release(); hist.release(); }
+  DevBuf keysA, keysB, valsA, valsB, hist, perm;
+  void release() { keysA.release(); keysB.release(); valsA.release(); valsB.release(); hist.release(); perm.release(); }
 };
 struct VoxBigWs {
   RadixWs rs;

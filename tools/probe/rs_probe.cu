@@ -35,8 +35,11 @@ int main(int argc, char** argv) {
     if (rep == 19) {
       std::vector<unsigned long long> out(n);
       cudaMemcpy(out.data(), in_b ? ws.keysB.p : ws.keysA.p, n * 8, cudaMemcpyDeviceToHost);
+      std::vector<unsigned int> outv(n);
+      cudaMemcpy(outv.data(), in_b ? ws.valsB.p : ws.valsA.p, n * 4, cudaMemcpyDeviceToHost);
       bool ok = true;
-      for (int i = 1; i < n; i++) ok = ok && out[i - 1] <= out[i];
+      for (int i = 1; i < n; i++) ok = ok && (out[i - 1] < out[i] || (out[i - 1] == out[i] && outv[i - 1] < outv[i]));
+      for (int i = 0; i < n; i++) ok = ok && out[i] == k[outv[i]];
       printf("n=%d bits=%d best %.1f us sorted=%d err=%s\n", n, bits, best * 1e3f, (int)ok, cudaGetErrorString(cudaGetLastError()));
     }
   }
