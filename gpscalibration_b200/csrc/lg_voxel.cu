@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
 // equal sub-ranges, one CTA each.  Every CTA scans the whole segment (L2-resident), keeps the points of its
 // sub-range, sorts them in shared memory and writes their centroids to its staging slice; a second kernel
 // concatenates the slices in range order, which is ascending cell id.  Same results as vox_small_kernel.
-constexpr int VS_CAP = 4096, VS_NT = 256;
+constexpr int VS_CAP = 4096, VS_NT = 256, VS_MLP = 8;  // VS_MLP loads in flight per thread: every CTA streams the whole segment
 __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restrict__ segs, float4* __restrict__ staging,
                                                            int* __restrict__ range_counts, int* __restrict__ overflow) {
   __shared__ unsigned long long skeys[VS_CAP];
@@ -195,13 +195,13 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
     return;
   }
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
-  for (int i0 = tid; i0 < n; i0 += 4 * VS_NT) {  // four loads in flight per thread: every CTA streams the whole segment
-    float4 p[4];
+  for (int i0 = tid; i0 < n; i0 += VS_MLP * VS_NT) {
+    float4 p[VS_MLP];
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < VS_MLP; u++)
       if (i0 + u * VS_NT < n) p[u] = sg.in[i0 + u * VS_NT];
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < VS_MLP; u++)
       if (i0 + u * VS_NT < n) {
         mn0 = fminf(mn0, p[u].x); mn1 = fminf(mn1, p[u].y); mn2 = fminf(mn2, p[u].z);
         mx0 = fmaxf(mx0, p[u].x); mx1 = fmaxf(mx1, p[u].y); mx2 = fmaxf(mx2, p[u].z);
@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
   const long long total = (long long)g.divxy * (maxb2 - g.minb2 + 1);
   const long long wdt = (total + C - 1) / C;
   const long long lo = wdt * c, hi = lo + wdt;
-  for (int i0 = tid; i0 < n; i0 += 4 * VS_NT) {
-    float4 p[4];
+  for (int i0 = tid; i0 < n; i0 += VS_MLP * VS_NT) {
+    float4 p[VS_MLP];
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < VS_MLP; u++)
       if (i0 + u * VS_NT < n) p[u] = sg.in[i0 + u * VS_NT];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < VS_MLP; u++) {
       const int i = i0 + u * VS_NT;
       if (i < n) {
         int cell = vox_cell(g, p[u]);
