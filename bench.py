@@ -49,8 +49,11 @@ ALGO_BYTES = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
 # (r1_ncu_full_<kernel>.csv, first 60 sweeps of the same sequence); None where no capture exists
-NCU_TRAFFIC = {"sr_select": 154880, "odom_iter": 328448, "map_knn": 1962000, "voxel": None, "extract": None,
-               "odom_knn": 372000 + 385000}  # odom_knn_kernel + odom_corr_kernel of one refresh (profiles/r1_ncu_full_final.csv)
+# DRAM bytes (read + write) per launch group of each class from the final `ncu --set full` capture
+# (profiles/r1_ncu_full_final.csv; ncu flushes caches between replays, so these are cold-cache upper bounds).
+NCU_TRAFFIC = {"odom_knn": 370432 + 381952,  # odom_knn_kernel + odom_corr_kernel of one refresh
+               "odom_iter": 358144,           # odom_loop_kernel (one launch = up to five iterations)
+               "sr_select": 172288, "map_knn": 2148608, "map_fit": 915200, "voxel": None, "extract": None}
 
 
 def log(*a):
