@@ -57,7 +57,7 @@ class SweepResult(C.Structure):
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
            "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_extract", "loam_extract_device", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
-           "loam_get_cloud", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
+           "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
@@ -106,6 +106,7 @@ def load_library():
     lib.loam_process_sweep.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
     lib.loam_process_sweep_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.POINTER(SweepResult)]
     lib.loam_get_cloud.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    lib.loam_get_cloud_wire.argtypes = [vp, C.c_int, vp, C.c_int, ip]
     lib.loam_get_diag.argtypes = [vp, C.c_int, vp, C.c_int, ip]
     lib.loam_voxel_grid.argtypes = [vp, vp, C.c_int, C.c_float, vp, C.c_int, ip]
     lib.loam_odom_set_inputs.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int]
@@ -266,6 +267,28 @@ class LoamGpu:
         if n.value:
             self._check(self.lib.loam_get_cloud(self._h, w, out.ctypes.data, n.value, C.byref(n)), "loam_get_cloud")
         return out
+
+    # field table of the payload returned by cloud_wire (what pcl::toROSMsg emits for PointXYZI)
+    WIRE_POINT_STEP = 32
+    WIRE_FIELDS = (("x", 0), ("y", 4), ("z", 8), ("intensity", 16))
+
+    def cloud_wire(self, which):
+        """PointCloud2 payload of cloud `which`: uint8 array (n, 32)."""
+        n = C.c_int()
+        w = CLOUD[which] if isinstance(which, str) else which
+        self._check(self.lib.loam_get_cloud_wire(self._h, w, None, 0, C.byref(n)), "loam_get_cloud_wire")
+        out = np.empty((n.value, 32), np.uint8)
+        if n.value:
+            self._check(self.lib.loam_get_cloud_wire(self._h, w, out.ctypes.data, n.value, C.byref(n)), "loam_get_cloud_wire")
+        return out
+
+    def extract_wire(self, payload, point_step, x_offset=0, stamp=0.0):
+        """loam_extract straight from a PointCloud2 payload (bytes / uint8 array), x y z contiguous at x_offset."""
+        buf = np.ascontiguousarray(np.frombuffer(payload, np.uint8) if not isinstance(payload, np.ndarray) else payload.reshape(-1).view(np.uint8))
+        n = buf.size // point_step
+        c = Counts()
+        self._check(self.lib.loam_extract(self._h, buf.ctypes.data + x_offset, n, point_step, stamp, None, C.byref(c)), "loam_extract")
+        return c
 
     def diag(self, which):
         w, dt = DIAG[which]

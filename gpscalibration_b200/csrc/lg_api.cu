@@ -6,6 +6,7 @@
 // the reset protocol LO:411-415,519-563 / LM:316-319,434-461.
 // There is NO CPU fallback: every compute step below is a kernel launch; without a CUDA device loam_create fails.
 #include <math.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <immintrin.h>
@@ -94,6 +95,7 @@ struct loam_handle {
   int frameCount = 1;              // LO:495 (= skipFrameNum)
   float T[6] = {0}, Tsum[6] = {0};  // transformation / transformationSum LO:111-112
   LgGNState lo_gn;                 // matP / isDegenerate LO:489-492
+  DevBuf xyz_packed, wire;
   DevBuf corner_last, surf_last, corner_new, surf_new, fullres3;
   int n_corner_last = 0, n_surf_last = 0, n_fullres3 = 0;
   int cornerLastNum = 0, surfLastNum = 0;  // LO:98-99 (gate values, lag one sweep behind after init)
@@ -326,9 +328,38 @@ int read_sr_counts(loam_handle* h, loam_counts* out) {
   return LOAM_OK;
 }
 
+// sensor_msgs/PointCloud2 payloads whose point_step is not a multiple of four (the Velodyne driver's 22-byte
+// PointXYZIR: x y z @0, intensity @16, ring @20) cannot be read with aligned 4-byte loads: repack x y z first.
+__global__ void unpack_xyz_kernel(const unsigned char* __restrict__ src, int n, int step, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = src + (size_t)i * step;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    unsigned int v = (unsigned int)p[4 * k] | ((unsigned int)p[4 * k + 1] << 8) | ((unsigned int)p[4 * k + 2] << 16) | ((unsigned int)p[4 * k + 3] << 24);
+    dst[3 * i + k] = __uint_as_float(v);
+  }
+}
+// pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZI>): point_step 32, x @0, y @4, z @8, padding 1.0f @12, intensity @16, zeros.
+__global__ void pack_pcl32_kernel(const float4* __restrict__ src, int n, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = src[i];
+  dst[2 * i] = make_float4(p.x, p.y, p.z, 1.0f);
+  dst[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
 int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out) {
   HostTimer ht(&h->host_s[HT_EXTRACT]);
-  if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return LOAM_EINVAL;
+  if (n < 0 || stride_bytes < 12) return LOAM_EINVAL;
+  if (n > 0 && ((stride_bytes & 3) || ((uintptr_t)d_xyz & 3))) {  // unaligned wire layout: repack to 12-byte points
+    LG_CHECK(h->xyz_packed.ensure((size_t)n * 12 + 16, h->st));
+    unpack_xyz_kernel<<<lg_div_up(n, 256), 256, 0, h->st>>>((const unsigned char*)d_xyz, n, stride_bytes, h->xyz_packed.as<float>());
+    h->launches++;
+    LG_CHECK(cudaGetLastError());
+    d_xyz = h->xyz_packed.as<float>();
+    stride_bytes = 12;
+  }
   for (int i = 0; i < 12; i++) h->imu[i] = imu_trans ? imu_trans[i] : 0.f;
   int rc = lg_extract_launch(h->sr, h->srp, d_xyz, n, stride_bytes, h->st, &h->launches);
   if (rc) return rc;
@@ -505,7 +536,7 @@ int loam_destroy(loam_handle* h) {
   h->prof.resolve(h->st);
   h->prof.release();
   h->sr.release(); h->od.release(); h->grid_c.release(); h->grid_s.release(); h->mi.release(); h->vb.release();
-  DevBuf* all[] = {&h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
+  DevBuf* all[] = {&h->xyz_packed, &h->wire, &h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
                    &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts};
@@ -1112,34 +1143,62 @@ int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int s
 }
 
 // ============================================================================================ data access
+static int select_cloud(loam_handle* h, int which, const void** src, int* cnt) {
+  switch (which) {
+    case LOAM_CLOUD_FULL: *src = h->cur_full; *cnt = h->counts.n_full; break;
+    case LOAM_CLOUD_SHARP: *src = h->cur_sharp; *cnt = h->counts.n_sharp; break;
+    case LOAM_CLOUD_LESS_SHARP: *src = h->cur_less_sharp; *cnt = h->counts.n_less_sharp; break;
+    case LOAM_CLOUD_FLAT: *src = h->cur_flat; *cnt = h->counts.n_flat; break;
+    case LOAM_CLOUD_LESS_FLAT: *src = h->cur_less_flat; *cnt = h->counts.n_less_flat; break;
+    case LOAM_CLOUD_CORNER_LAST: *src = h->corner_last.p; *cnt = h->n_corner_last; break;
+    case LOAM_CLOUD_SURF_LAST: *src = h->surf_last.p; *cnt = h->n_surf_last; break;
+    case LOAM_CLOUD_FULL_RES3: *src = h->fullres3.p; *cnt = h->n_fullres3; break;
+    case LOAM_CLOUD_CORNER_STACK: *src = h->stack_c.p; *cnt = h->n_stack_c; break;
+    case LOAM_CLOUD_SURF_STACK: *src = h->stack_s.p; *cnt = h->n_stack_s; break;
+    case LOAM_CLOUD_CORNER_MAP: *src = h->map_c.p; *cnt = h->n_map_c; break;
+    case LOAM_CLOUD_SURF_MAP: *src = h->map_s.p; *cnt = h->n_map_s; break;
+    case LOAM_CLOUD_SURROUND: *src = h->surround.p; *cnt = h->n_surround; break;
+    case LOAM_CLOUD_REGISTERED: *src = h->registered.p; *cnt = h->n_registered; break;
+    default: return LOAM_EINVAL;
+  }
+  return LOAM_OK;
+}
+
 int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n) {
   if (!h || !n) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   const void* src = nullptr;
   int cnt = 0;
-  switch (which) {
-    case LOAM_CLOUD_FULL: src = h->cur_full; cnt = h->counts.n_full; break;
-    case LOAM_CLOUD_SHARP: src = h->cur_sharp; cnt = h->counts.n_sharp; break;
-    case LOAM_CLOUD_LESS_SHARP: src = h->cur_less_sharp; cnt = h->counts.n_less_sharp; break;
-    case LOAM_CLOUD_FLAT: src = h->cur_flat; cnt = h->counts.n_flat; break;
-    case LOAM_CLOUD_LESS_FLAT: src = h->cur_less_flat; cnt = h->counts.n_less_flat; break;
-    case LOAM_CLOUD_CORNER_LAST: src = h->corner_last.p; cnt = h->n_corner_last; break;
-    case LOAM_CLOUD_SURF_LAST: src = h->surf_last.p; cnt = h->n_surf_last; break;
-    case LOAM_CLOUD_FULL_RES3: src = h->fullres3.p; cnt = h->n_fullres3; break;
-    case LOAM_CLOUD_CORNER_STACK: src = h->stack_c.p; cnt = h->n_stack_c; break;
-    case LOAM_CLOUD_SURF_STACK: src = h->stack_s.p; cnt = h->n_stack_s; break;
-    case LOAM_CLOUD_CORNER_MAP: src = h->map_c.p; cnt = h->n_map_c; break;
-    case LOAM_CLOUD_SURF_MAP: src = h->map_s.p; cnt = h->n_map_s; break;
-    case LOAM_CLOUD_SURROUND: src = h->surround.p; cnt = h->n_surround; break;
-    case LOAM_CLOUD_REGISTERED: src = h->registered.p; cnt = h->n_registered; break;
-    default: return LOAM_EINVAL;
-  }
+  int rc = select_cloud(h, which, &src, &cnt);
+  if (rc) return rc;
   *n = cnt;
   if (!host_buf) return LOAM_OK;
   if (cap < cnt) return LOAM_ENOSPC;
   if (cnt > 0) {
     LG_D2H(h, host_buf, src, (size_t)cnt * 16);
+    LG_SYNC(h);
+  }
+  return LOAM_OK;
+}
+
+int loam_get_cloud_wire(loam_handle* h, int which, void* host_buf, int cap_points, int* n_points) {
+  if (!h || !n_points) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+  const void* src = nullptr;
+  int cnt = 0;
+  int rc = select_cloud(h, which, &src, &cnt);
+  if (rc) return rc;
+  *n_points = cnt;
+  if (!host_buf) return LOAM_OK;
+  if (cap_points < cnt) return LOAM_ENOSPC;
+  if (cnt > 0) {
+    LG_CHECK(h->wire.ensure((size_t)cnt * 32 + 16, h->st));
+    pack_pcl32_kernel<<<lg_div_up(cnt, 256), 256, 0, h->st>>>((const float4*)src, cnt, h->wire.as<float4>());
+    h->launches++;
+    LG_CHECK(cudaGetLastError());
+    LG_D2H(h, host_buf, h->wire.p, (size_t)cnt * 32);
     LG_SYNC(h);
   }
   return LOAM_OK;

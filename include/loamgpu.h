@@ -134,7 +134,10 @@ int loam_profile(loam_handle* h, int enable);
 int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n);
 
 /* ---- scanRegistration: replaces the body of laserCloudHandler, SR:238-752 ------------------------------------
- * xyz: n points in the SENSOR frame (x fwd, y left, z up), `stride_bytes` apart (12 for packed xyz, 16 for PointXYZ).
+ * xyz: n points in the SENSOR frame (x fwd, y left, z up), `stride_bytes` apart: 12 for packed xyz, 16 for PointXYZ,
+ * or the point_step of a sensor_msgs/PointCloud2 payload whose x y z fields are contiguous (pass data + offset of x;
+ * 32 for PCL's PointXYZI wire layout, 22 for the Velodyne driver's PointXYZIR: any step >= 12 and any byte alignment is
+ * accepted -- this replaces pcl::fromROSMsg at SR:260-261).
  * imu_trans: the 12 floats of /imu_trans (SR:730-745), NULL = zeros (IMU branch dormant in the shipped pipeline).
  * Results stay device-resident for loam_odometry_process; counts are returned; clouds via loam_get_cloud. */
 int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
@@ -166,6 +169,10 @@ int loam_process_sweep_device(loam_handle* h, const float* xyz_dev, int n, int s
 /* Copies cloud `which` (float4 per point) into host_buf (capacity `cap` points); *n = point count.  LOAM_ENOSPC when
  * cap is too small (*n still set).  host_buf may be NULL to query the size. */
 int loam_get_cloud(loam_handle* h, int which, float* host_buf, int cap, int* n);
+/* The same cloud as the payload pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZI>) would put on the wire (SR:689-726,
+ * LO:1129-1145, LM:1096-1112): point_step 32, x @0, y @4, z @8, 1.0f @12, intensity @16, zero padding @20..31.
+ * host_buf holds cap_points * 32 bytes; may be NULL to query the size. */
+int loam_get_cloud_wire(loam_handle* h, int which, void* host_buf, int cap_points, int* n_points);
 int loam_get_diag(loam_handle* h, int which, void* host_buf, int cap_bytes, int* n_items);
 
 /* ---- stage-level entry points (what the node-level calls are made of; used by the parity tests) --------------- */

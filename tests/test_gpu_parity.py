@@ -356,3 +356,38 @@ def test_mapping_cube_grid_rolls_like_the_reference(orc, sweeps16):
         assert np.array_equal(np.array(r.transform_aft_mapped, np.float32), ro[:6]), k
         assert np.array_equal(np.array(r.transform_tobe_mapped, np.float32), ro[12:18]), k
     gpu.close()
+
+
+# ------------------------------------------------------------------------------------------------ PointCloud2 wire (N3)
+@pytest.mark.gpu
+def test_pointcloud2_wire_in_and_out(gpu, sweeps16):
+    """the library reads sensor_msgs/PointCloud2 payloads directly (any point_step, any alignment) and
+    emits the payload pcl::toROSMsg would (SR:260-261, 689-726)."""
+    xyz = sweeps16[2]
+    n = xyz.shape[0]
+    ref_counts = gpu.extract(xyz)
+    ref = {nm: gpu.cloud(nm) for nm in ("full", "sharp", "less_sharp", "flat", "less_flat")}
+    # Velodyne driver layout (PointXYZIR, point_step 22) behind a 3-byte header offset: nothing is 4-byte aligned
+    rec = np.zeros((n, 22), np.uint8)
+    rec[:, 0:12] = xyz.view(np.uint8).reshape(n, 12)
+    rec[:, 16:20] = np.full(n, 7.0, np.float32).view(np.uint8).reshape(n, 4)
+    rec[:, 20:22] = (np.arange(n) % 16).astype(np.uint16).view(np.uint8).reshape(n, 2)
+    blob = np.concatenate([np.zeros(3, np.uint8), rec.reshape(-1)])
+    c = gpu.extract_wire(blob[3:], 22)
+    assert [c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat] == \
+        [ref_counts.n_full, ref_counts.n_sharp, ref_counts.n_less_sharp, ref_counts.n_flat, ref_counts.n_less_flat]
+    for nm, want in ref.items():
+        assert np.array_equal(gpu.cloud(nm), want), nm
+    # PCL PointXYZI layout (point_step 32)
+    rec32 = np.zeros((n, 8), np.float32)
+    rec32[:, 0:3] = xyz
+    rec32[:, 3] = 1.0
+    c = gpu.extract_wire(rec32.view(np.uint8), 32)
+    assert c.n_full == ref_counts.n_full and np.array_equal(gpu.cloud("less_flat"), ref["less_flat"])
+    # and out again
+    for nm, want in ref.items():
+        wire = gpu.cloud_wire(nm)
+        assert wire.shape == (want.shape[0], 32)
+        f = wire.view(np.float32).reshape(-1, 8)
+        assert np.array_equal(f[:, 0:3], want[:, 0:3]) and np.array_equal(f[:, 4], want[:, 3])
+        assert np.all(f[:, 3] == 1.0) and not f[:, 5:].any()
