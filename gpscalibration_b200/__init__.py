@@ -8,3 +8,4 @@ generator used by tests and bench.  There is no CPU fallback: without libloamgpu
 from .capi import LoamGpu, LoamGpuPipeline, LoamError, load_library, library_path  # noqa: F401
 from .nodes import ScanRegistration, LaserOdometry, LaserMapping, TransformMaintenance, LoamPipeline  # noqa: F401
 from .synth import SweepGenerator  # noqa: F401
+from .scheduler import SegmentScheduler, GpuSlam, replay_segments  # noqa: F401

@@ -62,7 +62,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
-           "loam_pipeline_stats"]
+           "loam_pipeline_stats", "loam_replay_segments"]
 
 
 def library_path():

@@ -222,6 +222,29 @@ int loam_pipeline_pending(loam_pipeline* p);
 void* loam_pipeline_stream(loam_pipeline* p, int which);
 int loam_pipeline_stats(loam_pipeline* p, long long out4[4]);
 
+/* ---- N1: segment scheduler, replaces the replay loop of input_data.cpp (IN:244-446) -----------------
+ * Decides which messages of a bag list are (re)published to the SLAM pipeline, when the pipeline is reset
+ * (IMControl{systemInited=false}, IN:281-285, 348-353) and which tracks go out on /slam_track (IN:355-364, 428-441).
+ * Pass 0 cuts tracks of `long_distance` metres without overlap, pass 1 tracks of `short_distance` overlapping by
+ * `overlap_distance` (IN:257-262; requires long > short > overlap > 0); distances are measured on the odometry the
+ * pipeline returns (IN:78-116).  Host-only.  [first_pass, last_pass] = [0, 1] is the reference's run.  A caller may
+ * instead run [0, 0] and [1, 1] on two pipelines / GPUs at once; pass 1 started alone lacks the reference's artefact
+ * of a one-pose track at its start (the last pose of pass 0 leaks into it through preOdometry, IN:362). */
+typedef struct {
+  /* publish message `msg_index` (0-based) of bag `bag_index` to the pipeline; report its stamp and, if the pipeline
+   * produced /true_odometry_to_init for it, that pose as {x, y, z, stamp} with *odometry_arrived = 1 */
+  void (*publish)(void* user, int bag_index, int msg_index, double* stamp, double odometry_xyzt[4], int* odometry_arrived);
+  void (*control)(void* user);                                                         /* reset the pipeline */
+  void (*slam_track)(void* user, int track_flag, const double* xyzt, int n_points);    /* one IMTrack message */
+  void* user;
+} loam_replay_callbacks;
+typedef struct {
+  long long published, lost, resets, tracks;
+} loam_replay_stats;
+int loam_replay_segments(const int* messages_per_bag, int n_bags, double long_distance, double short_distance,
+                         double overlap_distance, int first_pass, int last_pass, const loam_replay_callbacks* cb,
+                         loam_replay_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

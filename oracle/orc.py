@@ -67,6 +67,7 @@ def lib():
         L.orc_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_pipeline_destroy.argtypes = [vp]
         L.orc_pipeline_reset.argtypes = [vp]
+        L.orc_pipeline_bef_mapped.argtypes = [vp, vp]
         L.orc_pipeline_set_ros_hop.argtypes = [vp, C.c_int]
         L.orc_odometry_ros_hop.argtypes = [vp, vp]
         L.orc_pipeline_process.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(PipelineResult)]
@@ -303,6 +304,11 @@ class Pipeline:
         r = PipelineResult()
         lib().orc_pipeline_process(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] // 4, C.byref(r))
         return r
+
+    def bef_mapped(self):
+        out = np.zeros(6, np.float32)
+        lib().orc_pipeline_bef_mapped(self._h, out.ctypes.data)
+        return out
 
     def run_threaded(self, xyz_all, offsets):
         """Three stage threads (SR | LO | LM) over a whole sequence; returns the per-sweep PipelineResult array."""

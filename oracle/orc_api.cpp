@@ -359,6 +359,12 @@ int orc_pipeline_process(void* hv, const float* xyz, int n, int stride_floats, P
   r->t_extract = t1 - t0; r->t_odom = t2 - t1; r->t_map = t3 - t2;
   return 0;
 }
+// transformBefMapped as /aft_mapped_to_init carries it in the twist fields (LM:1125-1130): transformMaintenance needs it
+int orc_pipeline_bef_mapped(void* hv, float* out6) {
+  Pipeline* p = (Pipeline*)hv;
+  for (int i = 0; i < 6; i++) out6[i] = p->lm.Tbef[i];
+  return 0;
+}
 // which: 0..4 SR clouds (as orc_sr_cloud), 5 cornerLast, 6 surfLast, 7 fullRes (odometry outputs, valid when published),
 // 8 surround, 9 fullResRegistered (mapping outputs)
 int orc_pipeline_cloud(void* hv, int which, float* buf, int cap) {
