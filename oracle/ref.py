@@ -214,3 +214,64 @@ def run_sequence(arr, offs, t0=100.0):
     for t in ts:
         t.join()
     return res
+
+
+# ---------------------------------------------------------------------------------------------- input_data.cpp (N1)
+_PUBLISH = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))
+_CONTROL = C.CFUNCTYPE(None, C.c_void_p)
+_TRACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int)
+
+
+class _ReplayCallbacks(C.Structure):
+    _fields_ = [("publish", _PUBLISH), ("control", _CONTROL), ("slam_track", _TRACK), ("user", C.c_void_p)]
+
+
+def input_data_available():
+    return os.path.exists(os.path.join(_DIR, "libref_in.so"))
+
+
+def input_replay(messages_per_bag, stamps, long_distance, short_distance, overlap_distance, publish, control, slam_track):
+    """Runs the reference's own input_data.cpp main() once over in-memory bags.  publish(bag, msg) -> (stamp, odometry
+    or None); control(); slam_track(flag, ndarray (n, 4)).  The node keeps its state in file-scope globals, so every
+    run loads a private copy of the shared object."""
+    import shutil
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="ref_in_")
+    try:
+        so = os.path.join(tmp, "libref_in_run.so")
+        shutil.copy(os.path.join(_DIR, "libref_in.so"), so)
+        L = C.CDLL(so)
+        L.ref_in_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(_ReplayCallbacks), C.c_char_p]
+        errors = []
+
+        def _pub(user, bag, msg, stamp, odo, arrived):
+            try:
+                s, o = publish(bag, msg)
+                stamp[0] = s
+                arrived[0] = 0 if o is None else 1
+                if o is not None:
+                    for i in range(4):
+                        odo[i] = o[i]
+            except BaseException as e:
+                errors.append(e)
+                arrived[0] = 0
+
+        def _ctl(user):
+            try:
+                control()
+            except BaseException as e:
+                errors.append(e)
+
+        def _trk(user, flag, xyzt, n):
+            slam_track(flag, np.ctypeslib.as_array(xyzt, shape=(n, 4)).copy() if n else np.zeros((0, 4)))
+
+        cb = _ReplayCallbacks(_PUBLISH(_pub), _CONTROL(_ctl), _TRACK(_trk), None)
+        counts = np.ascontiguousarray(messages_per_bag, np.int32)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float64) for s in stamps]) if len(stamps) else np.zeros(0))
+        rc = L.ref_in_run(counts.ctypes.data, flat.ctypes.data, len(messages_per_bag), long_distance, short_distance, overlap_distance,
+                          C.byref(cb), os.path.join(tmp, "baglist.txt").encode())
+        if errors:
+            raise errors[0]
+        return rc
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

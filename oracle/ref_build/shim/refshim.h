@@ -51,6 +51,10 @@ namespace refshim {
 struct Capture {
   std::map<std::string, std::shared_ptr<void>> last;
   std::map<std::string, int> count;
+  // optional hooks for nodes that are driven synchronously (input_data): called on every publish / instead of the
+  // thread handshake in spinOnce
+  std::function<void(const std::string&, const std::shared_ptr<void>&)> on_publish;
+  std::function<void()> on_spin_once;
 };
 inline Capture& capture() {
   static Capture c;
@@ -88,6 +92,10 @@ inline void spin() {
   L.cv.wait(l, [&] { return L.stop; });
 }
 inline void spinOnce() {
+  if (refshim::capture().on_spin_once) {
+    refshim::capture().on_spin_once();
+    return;
+  }
   refshim::Loop& L = refshim::loop();
   std::vector<std::function<void()>> batch;
   {
@@ -109,6 +117,7 @@ struct Publisher {
   void publish(const M& m) const {
     refshim::capture().last[topic] = std::make_shared<M>(m);
     refshim::capture().count[topic]++;
+    if (refshim::capture().on_publish) refshim::capture().on_publish(topic, refshim::capture().last[topic]);
   }
 };
 struct Subscriber {};
@@ -200,6 +209,45 @@ struct IMControl {
   typedef boost::shared_ptr<IMControl const> ConstPtr;
 };
 }  // namespace gpsCalibration
+
+// ------------------------------------------------------------------------------------------------ rosbag (input_data)
+// A "bag file" is an in-memory list of PointCloud2 messages registered under its path before the node runs.
+#define BOOST_FOREACH(decl, range) for (decl : range)
+namespace rosbag {
+struct BagIOException {};
+namespace bagmode {
+enum BagMode { Read = 1 };
+}
+struct MessageInstance {
+  boost::shared_ptr<sensor_msgs::PointCloud2 const> msg;
+  template <class M>
+  boost::shared_ptr<M const> instantiate() const {
+    return msg;
+  }
+};
+inline std::map<std::string, std::vector<MessageInstance>>& registry() {
+  static std::map<std::string, std::vector<MessageInstance>> r;
+  return r;
+}
+struct Bag {
+  const std::vector<MessageInstance>* cur = nullptr;
+  void open(const std::string& path, int = bagmode::Read) {
+    auto it = registry().find(path);
+    if (it == registry().end()) throw BagIOException();
+    cur = &it->second;
+  }
+  void close() { cur = nullptr; }
+};
+struct TopicQuery {
+  explicit TopicQuery(const std::vector<std::string>&) {}
+};
+struct View {
+  const std::vector<MessageInstance>* v;
+  View(const Bag& b, const TopicQuery&) : v(b.cur) {}
+  std::vector<MessageInstance>::const_iterator begin() const { return v->begin(); }
+  std::vector<MessageInstance>::const_iterator end() const { return v->end(); }
+};
+}  // namespace rosbag
 
 // ------------------------------------------------------------------------------------------------ PCL
 namespace pcl {
