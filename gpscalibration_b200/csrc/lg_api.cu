@@ -516,6 +516,13 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
       if (e == cudaSuccess) e = h->arena.ensure(mm * 4 * 16, h->st);
       if (e == cudaSuccess) e = h->arena2.ensure(mm * 4 * 16, h->st);
       if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
+      // voxel-hash index of the local map (a quarter of the capacity per cloud) and the merge-path key arrays
+      if (e == cudaSuccess && lg_grid_reserve(h->grid_c, (int)(mm / 4), h->st) != LOAM_OK) e = cudaErrorMemoryAllocation;
+      if (e == cudaSuccess && lg_grid_reserve(h->grid_s, (int)(mm / 4), h->st) != LOAM_OK) e = cudaErrorMemoryAllocation;
+      DevBuf* key_bufs[] = {&h->vb.keys_old, &h->vb.keys_m};
+      DevBuf* val_bufs[] = {&h->vb.vals_old, &h->vb.vals_m};
+      for (DevBuf* b : key_bufs) e = e == cudaSuccess ? b->ensure(mm * 8, h->st) : e;
+      for (DevBuf* b : val_bufs) e = e == cudaSuccess ? b->ensure(mm * 4, h->st) : e;
     }
     if (e != cudaSuccess) {
       lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);

@@ -1,6 +1,8 @@
 // Shared device/host helpers for libloamgpu (sm_100a).  The whole library is compiled with -fmad=false so that every
 // fp32 expression keeps the reference's evaluation order without FMA contraction.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -29,6 +31,8 @@ struct DevBuf {
   cudaError_t ensure(size_t bytes, cudaStream_t st, bool keep = false) {
     if (bytes <= cap) return cudaSuccess;
     size_t ncap = 2 * bytes + (1u << 20);  // grow rarely: cudaMalloc / cudaFree cost milliseconds and stall the stream
+    static const bool trace = getenv("LOAM_TRACE_ALLOC") != nullptr;
+    if (trace) fprintf(stderr, "[loamgpu] DevBuf %p grows %zu -> %zu bytes\n", (void*)this, cap, ncap);
     void* np = nullptr;
     cudaError_t e = cudaMalloc(&np, ncap);
     if (e != cudaSuccess) return e;

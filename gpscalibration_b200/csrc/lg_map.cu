@@ -444,6 +444,11 @@ static int grid_prepare(GridWs& ws, int n, cudaStream_t st, size_t* slots_out) {
   return LOAM_OK;
 }
 
+int lg_grid_reserve(GridWs& ws, int n, cudaStream_t st) {
+  size_t slots = 0;
+  return grid_prepare(ws, n, st, &slots);
+}
+
 int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches) {
   size_t slots0 = 0, slots1 = 0;
   int rc = grid_prepare(ws0, n0, st, &slots0);

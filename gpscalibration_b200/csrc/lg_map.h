@@ -57,6 +57,8 @@ struct MapIterWs {
 int lg_map_stack_launch(const MapT& T, const float4* in0, float4* out0, int n0, const float4* in1, float4* out1, int n1, cudaStream_t st,
                         long long* launches);
 int lg_map_register_launch(const MapT& T, const float4* in, float4* out, int n, cudaStream_t st, long long* launches);
+// Allocates the index buffers for a cloud of n points up front (reallocation on the steady-state path costs milliseconds).
+int lg_grid_reserve(GridWs& ws, int n, cudaStream_t st);
 // Builds the corner grid and the surf grid together (four launches).
 int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches);
 int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
