@@ -261,6 +261,35 @@ def test_pipeline_parity_vlp16(gpu, orc, sweeps16):
     print("pipeline worst pose diff", worst)
 
 
+def test_pipeline_parity_hdl64(orc):
+    """cfg 3 shape: 64 rings, ~120 k points, ~18 k features per sweep.  Exercises what the VLP-16 sequence does not: several
+    rows per thread in the device Gauss-Newton loop, the multi-pass radix sort (> 16 k pairs), the split / big voxel paths.
+    Poses, iteration counts and cloud sizes equal to the oracle, bit for bit."""
+    from gpscalibration_b200 import LoamGpu, SweepGenerator
+    g = SweepGenerator(sensor=2, scene=1, seed=0xC0FFEE)
+    step = 26.8 / 63.0
+    gpu = LoamGpu(n_scans=64, ring_mode=1, ring_ang_min=-24.8, ring_ang_step=step)
+    pipe = orc.Pipeline(64, 1, -24.8, step)
+    seen_map = 0
+    for k in range(7):
+        xyz = g.sweep(k)[0]
+        r, o = gpu.process_sweep(xyz), pipe.process(xyz)
+        assert (r.counts.n_full, r.counts.n_sharp, r.counts.n_less_sharp, r.counts.n_flat, r.counts.n_less_flat) == \
+            (o.n_full, o.n_sharp, o.n_less_sharp, o.n_flat, o.n_less_flat), k
+        assert r.odom.odom_published == o.odom_published and r.mapping_ran == o.mapping_ran, k
+        assert np.array_equal(np.array(r.odom.transform_sum, np.float32), np.array(o.odom, np.float32)), k
+        if o.odom_published:
+            assert r.odom.iterations == o.odom_iters, (k, r.odom.iterations, o.odom_iters)
+        if r.mapping_ran:
+            seen_map += 1
+            assert (r.map.n_corner_stack, r.map.n_surf_stack, r.map.n_corner_map, r.map.n_surf_map) == \
+                (o.n_corner_stack, o.n_surf_stack, o.n_corner_map, o.n_surf_map), k
+            assert np.array_equal(np.array(r.map.transform_aft_mapped, np.float32), np.array(o.mapped, np.float32)), k
+            assert r.map.iterations == o.map_iters, k
+    assert r.counts.n_sharp + r.counts.n_flat > 8192 and seen_map >= 2
+    gpu.close()
+
+
 def test_pipeline_reset_protocol(gpu, orc, sweeps16):
     """IMControl{false}: odometry re-initialises, mapping resets on the zero pose."""
     pipe = orc.Pipeline()
