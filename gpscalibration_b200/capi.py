@@ -59,7 +59,8 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
-           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_pipeline_create", "loam_pipeline_destroy",
+           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect",
+           "loam_map_iter_allreduce", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_replay_segments"]
@@ -119,6 +120,9 @@ def load_library():
     lib.loam_gn_solve.argtypes = [vp, vp, C.c_int, C.c_float, vp, vp]
     lib.loam_map_iter_partial.argtypes = [vp, C.c_int, vp, vp]
     lib.loam_map_finish_reduced.argtypes = [vp, vp, vp, ip]
+    lib.loam_shard_export.argtypes = [vp, vp]
+    lib.loam_shard_connect.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.loam_map_iter_allreduce.argtypes = [vp, C.c_int, vp, vp, vp, ip]
     lib.loam_pipeline_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
     lib.loam_pipeline_destroy.argtypes = [vp]
     lib.loam_pipeline_reset.argtypes = [vp]
@@ -289,6 +293,25 @@ class LoamGpu:
         c = Counts()
         self._check(self.lib.loam_extract(self._h, buf.ctypes.data + x_offset, n, point_step, stamp, None, C.byref(c)), "loam_extract")
         return c
+
+    # ---- sharded map with the all-reduce fused into the reduction kernel (NVLink peer memory, CUDA IPC)
+    def shard_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.loam_shard_export(self._h, buf), "loam_shard_export")
+        return bytes(buf)
+
+    def shard_connect(self, handles, rank):
+        """handles: list of the 64-byte blobs of all ranks in rank order."""
+        blob = b"".join(handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.loam_shard_connect(self._h, arr, len(handles), rank), "loam_shard_connect")
+
+    def map_iter_allreduce(self, it, T):
+        T = _f32(T)
+        AtA, AtB, n = np.zeros((6, 6), np.float32), np.zeros(6, np.float32), C.c_int()
+        self._check(self.lib.loam_map_iter_allreduce(self._h, it, T.ctypes.data, AtA.ctypes.data, AtB.ctypes.data, C.byref(n)),
+                    "loam_map_iter_allreduce")
+        return AtA, AtB, n.value
 
     def diag(self, which):
         w, dt = DIAG[which]

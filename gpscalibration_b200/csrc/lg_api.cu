@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "lg_extract.h"
@@ -26,6 +28,10 @@
 
 static thread_local char g_cuda_err[512] = "";
 thread_local LgProf* g_lg_prof = nullptr;
+// Exchange buffers (loam_shard_export) of THIS process: a CUDA IPC handle cannot be opened by its exporter, so ranks
+// that live in one process (several handles driven by host threads) are connected by pointer.
+static std::mutex g_xchg_mutex;
+static std::map<std::string, double*> g_xchg_local;
 void lg_set_error(const char* msg, const char* file, int line) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s:%d)", msg, file, line); }
 
 #define LG_SYNC(h) do { (h)->syncs++; LG_CHECK(cudaStreamSynchronize((h)->st)); } while (0)
@@ -96,6 +102,11 @@ struct loam_handle {
   float T[6] = {0}, Tsum[6] = {0};  // transformation / transformationSum LO:111-112
   LgGNState lo_gn;                 // matP / isDegenerate LO:489-492
   DevBuf xyz_packed, wire;
+  // sharded map with the fused all-reduce (loam_shard_*): exchange buffer, peers' mappings, iteration counter
+  double* xchg = nullptr;
+  PeerXchg px{};
+  bool px_connected = false;
+  bool px_local[LG_MAX_PEERS] = {};
   DevBuf corner_last, surf_last, corner_new, surf_new, fullres3;
   int n_corner_last = 0, n_surf_last = 0, n_fullres3 = 0;
   int cornerLastNum = 0, surfLastNum = 0;  // LO:98-99 (gate values, lag one sweep behind after init)
@@ -414,13 +425,13 @@ int odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, 
   return LOAM_OK;
 }
 
-int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, float* AtB, int* n_sel) {
+int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, float* AtB, int* n_sel, const PeerXchg* px = nullptr) {
   MapT mt;
   for (int i = 0; i < 6; i++) mt.t[i] = T[i];
   mt.sc = host_sincos3(T);
   int rc = lg_map_iter_launch(h->mi, mt, h->stack_c.as<float4>(), h->n_stack_c, h->stack_s.as<float4>(), h->n_stack_s, h->grid_c.d, h->grid_s.d,
                               h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail,
-                              out28_dev ? 0ull : ++h->mail_seq, h->st, &h->launches);
+                              out28_dev ? 0ull : ++h->mail_seq, h->st, &h->launches, px);
   if (rc) return rc;
   if (out28_dev) return LOAM_OK;
   rc = mailbox_wait(h);
@@ -548,6 +559,14 @@ int loam_destroy(loam_handle* h) {
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
                    &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts};
   for (DevBuf* b : all) b->release();
+  if (h->px_connected)
+    for (int r = 0; r < h->px.world; r++)
+      if (r != h->px.rank && h->px.buf[r] && !h->px_local[r]) cudaIpcCloseMemHandle(h->px.buf[r]);
+  if (h->xchg) {
+    std::lock_guard<std::mutex> lock(g_xchg_mutex);
+    for (auto it = g_xchg_local.begin(); it != g_xchg_local.end();) it = (it->second == h->xchg) ? g_xchg_local.erase(it) : std::next(it);
+    cudaFree(h->xchg);
+  }
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_ints) cudaFreeHost(h->h_ints);
   if (h->st) cudaStreamDestroy(h->st);
@@ -1404,6 +1423,77 @@ int loam_map_iter_partial(loam_handle* h, int iter, const float* T, double* part
   int rc = map_iter(h, T, partial_dev28, nullptr, nullptr, nullptr);
   if (rc) return rc;
   LG_SYNC(h);
+  return LOAM_OK;
+}
+
+// ---- sharded map, fused all-reduce over NVLink peer memory (SURVEY 8e "optimised") -------------------------------------
+int loam_shard_export(loam_handle* h, unsigned char* handle64) {
+  if (!h || !handle64) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  if (!h->xchg) {
+    LG_CHECK(cudaMalloc((void**)&h->xchg, LG_XCHG_BYTES));
+    LG_CHECK(cudaMemset(h->xchg, 0, LG_XCHG_BYTES));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  LG_CHECK(cudaIpcGetMemHandle(&hd, h->xchg));
+  memcpy(handle64, &hd, 64);
+  {
+    std::lock_guard<std::mutex> lock(g_xchg_mutex);
+    g_xchg_local[std::string((const char*)handle64, 64)] = h->xchg;
+  }
+  return LOAM_OK;
+}
+
+int loam_shard_connect(loam_handle* h, const unsigned char* handles, int world, int rank) {
+  if (!h || !handles || world < 1 || world > LG_MAX_PEERS || rank < 0 || rank >= world) return LOAM_EINVAL;
+  if (!h->xchg || h->px_connected) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  memset(&h->px, 0, sizeof(h->px));
+  h->px.world = world;
+  h->px.rank = rank;
+  h->h_mail[28] = 0.0;
+  h->px.timeout = (int*)(h->d_mail + 28);  // travels with the sums through the mapped mailbox
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      h->px.buf[r] = h->xchg;
+      continue;
+    }
+    {
+      std::lock_guard<std::mutex> lock(g_xchg_mutex);
+      auto it = g_xchg_local.find(std::string((const char*)handles + (size_t)r * 64, 64));
+      if (it != g_xchg_local.end()) {
+        h->px.buf[r] = it->second;
+        h->px_local[r] = true;
+        continue;
+      }
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    LG_CHECK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->px.buf[r] = (double*)p;
+  }
+  h->px_connected = true;
+  return LOAM_OK;
+}
+
+int loam_map_iter_allreduce(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel) {
+  if (!h || !T || !AtA || !AtB || !n_sel || iter < 0) return LOAM_EINVAL;
+  if (!h->grids_valid || !h->px_connected) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+  h->px.xseq++;
+  int rc = map_iter(h, T, nullptr, AtA, AtB, n_sel, &h->px);
+  if (rc) return rc;
+  if (*n_sel < 50) {  // LM:929-932 on the global count
+    memset(AtA, 0, 36 * sizeof(float));
+    memset(AtB, 0, 6 * sizeof(float));
+  }
+  if (*(volatile int*)(h->h_mail + 28)) {  // written by the kernel next to the sums (mapped mailbox)
+    lg_set_error("a peer rank never reached the all-reduce", __FILE__, __LINE__);
+    return LOAM_ECUDA;
+  }
   return LOAM_OK;
 }
 

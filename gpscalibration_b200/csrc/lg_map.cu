@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* _
                                                           const float4* __restrict__ surf_stack, int n_ss, const float4* __restrict__ corner_map,
                                                           const float4* __restrict__ surf_map, const int* __restrict__ nbr,
                                                           double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out28,
-                                                          unsigned long long seq) {
+                                                          unsigned long long seq, PeerXchg px) {
   Acc28 acc;
   acc.clear();
   // grid-stride over the queries: the grid is capped (a few CTAs per SM) so the last-CTA reduction stays short
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(FIT_NT) map_fit_kernel(MapT T, const float4* _
     acc.add_row(a, -c.w);
   }
   }
-  lg_reduce28<FIT_NT>(acc, partials, ticket, out28, seq);
+  lg_reduce28<FIT_NT>(acc, partials, ticket, out28, seq, &px);
 }
 
 // LM:1023-1059: map-frame point and cube index; key 0xFFFFFFFF.. sorts dropped points to the end.
@@ -476,7 +476,7 @@ int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const f
 
 int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
                        const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
-                       long long* launches) {
+                       long long* launches, const PeerXchg* px) {
   const int nq = n_cs + n_ss;
   const int nb = std::max(1, std::min(lg_div_up(nq, FIT_NT), 148 * 8));
   LG_CHECK(ws.nbr.ensure((size_t)(nq + 1) * 5 * 4, st));
@@ -491,8 +491,10 @@ int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack,
     (*launches)++;
   }
   LgProfScope prof_scope(LGK_MAP_FIT, st, (double)nq);
+  PeerXchg none;
+  memset(&none, 0, sizeof(none));
   map_fit_kernel<<<nb, FIT_NT, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, corner_map, surf_map, ws.nbr.as<int>(), ws.partials.as<double>(),
-                                        ws.ticket.as<unsigned int>(), out28, seq);
+                                        ws.ticket.as<unsigned int>(), out28, seq, px ? *px : none);
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;

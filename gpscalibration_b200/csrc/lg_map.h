@@ -63,7 +63,7 @@ int lg_grid_reserve(GridWs& ws, int n, cudaStream_t st);
 int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches);
 int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
                        const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
-                       long long* launches);
+                       long long* launches, const struct PeerXchg* px = nullptr);
 int lg_map_insert_launch(const MapT& T, const CubeGeom& cg, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss,
                          float4* sel_out, unsigned long long* keys, unsigned int* vals, cudaStream_t st, long long* launches);
 int lg_map_runs_launch(const unsigned long long* keys, const unsigned int* vals, const float4* sel, int n, float4* sorted_sel, int* n_runs,

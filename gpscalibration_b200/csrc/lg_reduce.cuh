@@ -6,6 +6,18 @@
 #pragma once
 #include "lg_common.cuh"
 
+// One-shot all-reduce of the 28 sums over NVLink peer memory (sharded map): every rank owns an exchange buffer
+// {slots[2 parities][LG_MAX_PEERS][32 doubles], flags[LG_MAX_PEERS]} that its peers map through CUDA IPC.
+constexpr int LG_MAX_PEERS = 8;
+constexpr int LG_XCHG_FLAG_OFFSET = 2 * LG_MAX_PEERS * 32;  // in doubles
+constexpr int LG_XCHG_BYTES = (LG_XCHG_FLAG_OFFSET + LG_MAX_PEERS) * 8;
+struct PeerXchg {
+  double* buf[LG_MAX_PEERS];  // buf[r] = rank r's exchange buffer as seen from this GPU (buf[rank] is local)
+  int world, rank;
+  unsigned long long xseq;  // same on every rank: the iteration number since connect
+  int* timeout;             // set when a peer never showed up
+};
+
 #ifdef __CUDACC__
 
 struct Acc28 {
@@ -59,7 +71,7 @@ __device__ __forceinline__ double lg_warp_reduce28(const double (&v)[28], int la
 // in CTA order (deterministic) and writes the 28 results to out28 (device memory or mapped pinned host memory).
 template <int NT>
 __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                            double* __restrict__ out28, unsigned long long seq = 0ull) {
+                                            double* __restrict__ out28, unsigned long long seq = 0ull, const PeerXchg* px = nullptr) {
   __shared__ double s_part[NT / 32][28];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -81,12 +93,41 @@ __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ par
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (tid < 28) {
-      double s = 0.0;
+    double s = 0.0;
+    if (tid < 28)
       for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * 28 + tid]);
-      out28[tid] = s;
-    }
     if (tid == 0) *ticket = 0u;
+    if (px != nullptr && px->world > 1) {
+      // Fused all-reduce: the last CTA stores this rank's 28 sums straight into every peer's exchange buffer (NVLink
+      // P2P stores), raises its flag there, waits for the peers' flags in its own buffer and adds the partials in rank
+      // order -- every rank ends with bit-identical totals, one NVLink round trip after the slowest rank's reduction.
+      // Slots alternate with the iteration parity: a rank one iteration ahead never overwrites sums still being read.
+      const int W = px->world, me = px->rank;
+      const size_t slot = ((size_t)(px->xseq & 1ull) * LG_MAX_PEERS + me) * 32;
+      if (tid < 28)
+        for (int r = 0; r < W; r++) px->buf[r][slot + tid] = s;
+      __threadfence_system();
+      __syncthreads();
+      if (tid < W) *((volatile unsigned long long*)(px->buf[tid] + LG_XCHG_FLAG_OFFSET) + me) = px->xseq;
+      if (tid < W) {
+        volatile unsigned long long* f = (volatile unsigned long long*)(px->buf[me] + LG_XCHG_FLAG_OFFSET) + tid;
+        const long long t0 = clock64();
+        while (*f < px->xseq) {
+          if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer died or never called; the host turns this into an error
+            *px->timeout = 1;
+            break;
+          }
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < 28) {
+        s = 0.0;
+        const volatile double* mine = px->buf[me] + (size_t)(px->xseq & 1ull) * LG_MAX_PEERS * 32;
+        for (int r = 0; r < W; r++) s += mine[(size_t)r * 32 + tid];
+      }
+    }
+    if (tid < 28) out28[tid] = s;
     if (seq != 0ull) {  // host mailbox: publish the sequence number after the 28 values are visible system-wide
       __threadfence_system();
       __syncthreads();

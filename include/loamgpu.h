@@ -204,6 +204,16 @@ int loam_gn_solve(const float AtA[36], const float AtB[6], int iter, float eig_t
  * all-reduce by the caller; loam_map_finish_reduced turns the reduced sums into AtA/AtB. */
 int loam_map_iter_partial(loam_handle* h, int iter, const float T[6], double* partial_dev28);
 int loam_map_finish_reduced(const double reduced28_host[28], float AtA[36], float AtB[6], int* n_sel);
+/* The same exchange fused into the reduction kernel (one process per GPU, NVLink peer memory through CUDA IPC): the last
+ * CTA of every rank stores its 28 sums into every peer's exchange buffer, raises a flag, waits for the peers' flags and
+ * adds the partials in rank order, so every rank's host mailbox receives bit-identical global sums one NVLink round
+ * trip after the slowest rank's reduction -- no NCCL launch, no separate read-back.
+ *   loam_shard_export   allocate this rank's exchange buffer, return its 64-byte cudaIpcMemHandle_t
+ *   loam_shard_connect  handles = world x 64 bytes gathered from all ranks (any transport), in rank order
+ *   loam_map_iter_allreduce  loam_map_iter over the union of all ranks' queries; every rank must call it (<= 8 ranks) */
+int loam_shard_export(loam_handle* h, unsigned char handle64[64]);
+int loam_shard_connect(loam_handle* h, const unsigned char* handles, int world, int rank);
+int loam_map_iter_allreduce(loam_handle* h, int iter, const float T[6], float AtA[36], float AtB[6], int* n_sel);
 
 /* ---- pipelined mode: the reference's three-process layout (SR | LO | LM connected by queues) on one GPU ----------
  * Three stage threads inside the library, one handle (state + stream) per stage, device-resident hand-over.  Results

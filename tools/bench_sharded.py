@@ -69,6 +69,7 @@ def main():
     ap.add_argument("--queries", type=int, default=1_000_000)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--extent", type=float, default=2000.0, help="half-length in x of the --unfiltered-map scene")
+    ap.add_argument("--fused-allreduce", action="store_true", help="also run loam_map_iter_allreduce (P2P one-shot all-reduce in the kernel)")
     ap.add_argument("--unfiltered-map", action="store_true", help="worst case: map NOT voxel-filtered (crowded cells)")
     ap.add_argument("--random-query-order", action="store_true", help="worst case: no spatial coherence between consecutive queries")
     args = ap.parse_args()
@@ -130,6 +131,33 @@ def main():
         it_ms.append(1e3 * (w2 - w0)); ar_us.append(1e6 * (w2 - w1))
     prof = gpu.profile_read()
     gpu.profile(False)
+    # ---- the same iterations with the all-reduce fused into the reduction kernel (NVLink peer stores, CUDA IPC)
+    fused = None
+    if args.fused_allreduce:
+        hd = gpu.shard_export()
+        if world > 1:
+            mine = torch.frombuffer(bytearray(hd), dtype=torch.uint8).cuda()
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            handles = [bytes(g.cpu().numpy().tobytes()) for g in gathered]
+        else:
+            handles = [hd]
+        gpu.shard_connect(handles, rank)
+        T2, state2, f_ms = np.zeros(6, np.float32), np.zeros(37, np.float32), []
+        for it in range(args.iters):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(); w0 = time.perf_counter()
+            AtA, AtB, n2 = gpu.map_iter_allreduce(it, T2)
+            w1 = time.perf_counter()
+            X = capi.gn_solve(AtA, AtB, it, 100.0, state2)
+            T2 = (T2 + X).astype(np.float32)
+            f_ms.append(1e3 * (w1 - w0))
+        tf = torch.tensor([np.median(f_ms[2:])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fused = {"iter_ms_max_over_ranks": float(tf.item()), "n_sel": int(n2), "T_final_equals_nccl_path": bool(np.array_equal(T2, T)),
+                 "T_final": [float(x) for x in T2]}
     t_it = torch.tensor([np.median(it_ms[2:])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_it, op=dist.ReduceOp.MAX)
@@ -142,6 +170,8 @@ def main():
            "kernel_ms_per_iter": {k: round(prof[k]["ms"] / args.iters, 4) for k in ("map_knn", "map_fit")},
            "knn_fit_GBps_kernel_only": 96.0 * nq / ((prof["map_knn"]["ms"] + prof["map_fit"]["ms"]) / args.iters * 1e-3) / 1e9,
            "T_final": [round(float(x), 5) for x in T], "T_true": [float(x) for x in T_true]}
+    if fused is not None:
+        out["fused_allreduce"] = fused
     if rank == 0:
         print(json.dumps(out))
     gpu.close()
