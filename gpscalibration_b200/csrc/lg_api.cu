@@ -651,6 +651,7 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
     if (c.n_less_flat) LG_CHECK(cudaMemcpyAsync(h->surf_last.p, h->cur_less_flat, (size_t)c.n_less_flat * 16, cudaMemcpyDeviceToDevice, h->st));
     h->n_corner_last = c.n_less_sharp;
     h->n_surf_last = c.n_less_flat;
+    h->od.bounds_valid = false;
     for (int i = 0; i < 6; i++) h->T[i] = h->Tsum[i] = 0.f;
     h->Tsum[0] += imu[0];  // imuPitchStart
     h->Tsum[2] += imu[2];  // imuRollStart
@@ -738,6 +739,7 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
   if (rc) return rc;
   std::swap(h->corner_last, h->corner_new);
   std::swap(h->surf_last, h->surf_new);
+  h->od.bounds_valid = false;
   h->n_corner_last = c.n_less_sharp;
   h->n_surf_last = c.n_less_flat;
   h->cornerLastNum = h->n_corner_last;
@@ -1302,6 +1304,7 @@ int loam_odom_set_inputs(loam_handle* h, const float* sharp, int n_sharp, const 
   h->counts.n_sharp = n_sharp;
   h->counts.n_flat = n_flat;
   h->n_corner_last = n_corner_last;
+  h->od.bounds_valid = false;
   h->n_surf_last = n_surf_last;
   return LOAM_OK;
 }

@@ -1,7 +1,10 @@
 // K6 / K8 / K9 — scan-to-scan odometry kernels, the B200 replacement for the hot loops of laserOdometry.cpp:
-//   odom_knn_kernel     LO:603,758   exact nearest neighbour of every de-skewed feature in the previous sweep's
-//                                    corner / surf cloud (replaces KdTreeFLANN::nearestKSearch(k = 1)); brute force over
-//                                    shared-memory target tiles, (d2, index) packed into one 64-bit atomicMin key
+//   odom_knn_pruned_kernel LO:603,758 exact nearest neighbour of every de-skewed feature in the previous sweep's
+//                                    corner / surf cloud (replaces KdTreeFLANN::nearestKSearch(k = 1)): the clouds are
+//                                    ring-ordered, so every 32 consecutive points share a tight box; a warp bounds all
+//                                    boxes and visits only those that can still hold the answer
+//   odom_knn_kernel     (same)       brute force over shared-memory target tiles, (d2, index) packed into one 64-bit
+//                                    atomicMin key -- the cross-check (LOAM_ODOM_BRUTE_FORCE=1)
 //   odom_corr_kernel    LO:604-677,760-844  the +-1-ring scans for the 2nd / 3rd point, one warp per feature
 //   odom_iter_kernel    LO:595,680-971  TransformToStart, point-to-line / point-to-plane coefficients, Jacobian row,
 //                                    and the 21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
@@ -71,6 +74,153 @@ __global__ void __launch_bounds__(KNN_Q) odom_knn_kernel(OdomT T, const float4* 
     }
   }
   if (bi >= 0) atomicMin(&best[(is_c ? 0 : n_sharp) + qi], lg_pack_nbr(bd, bi));
+}
+
+// ---- exact nearest neighbour with box pruning -------------------------------------------------------------------------
+// Two levels of axis-aligned boxes over a ring-ordered cloud: a BOX bounds 32 consecutive points, a SUPER-BOX bounds 32
+// consecutive boxes (1024 points).  box[2c] / box[2c + 1] = component-wise minimum / maximum (.w of the pair = smallest /
+// largest ring id); super[2s], super[2s + 1] likewise.  One CTA of 1024 threads per super-box builds both.
+__global__ void __launch_bounds__(1024) odom_bounds_kernel(const float4* __restrict__ corner_last, int n_cl, const float4* __restrict__ surf_last,
+                                                            int n_sl, float4* __restrict__ box_c, float4* __restrict__ sup_c,
+                                                            float4* __restrict__ box_s, float4* __restrict__ sup_s) {
+  __shared__ float s_red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nsup_c = (n_cl + 1023) >> 10;
+  const bool is_c = (int)blockIdx.x < nsup_c;
+  const int s = is_c ? blockIdx.x : blockIdx.x - nsup_c;
+  const float4* pts = is_c ? corner_last : surf_last;
+  const int n = is_c ? n_cl : n_sl;
+  float4* box = is_c ? box_c : box_s;
+  float4* sup = is_c ? sup_c : sup_s;
+  const int c = s * 32 + w, j = c * 32 + lane;
+  const float inf = __int_as_float(0x7f800000);
+  float v[8] = {inf, inf, inf, inf, -inf, -inf, -inf, -inf};  // lo x y z ring, hi x y z ring
+  if (j < n) {
+    const float4 p = pts[j];
+    const float ring = (float)int(p.w);
+    v[0] = v[4] = p.x; v[1] = v[5] = p.y; v[2] = v[6] = p.z; v[3] = v[7] = ring;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float x = __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[k] = k < 4 ? fminf(v[k], x) : fmaxf(v[k], x);
+    }
+  if (lane == 0) {
+    if (c * 32 < n) {
+      box[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+      box[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s_red[k][w] = v[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = s_red[k][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float x = __shfl_xor_sync(0xffffffffu, r[k], o);
+        r[k] = k < 4 ? fminf(r[k], x) : fmaxf(r[k], x);
+      }
+    if (lane == 0) {
+      sup[2 * s] = make_float4(r[0], r[1], r[2], r[3]);
+      sup[2 * s + 1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
+// squared distance from s to the box [lo, hi] (0 inside)
+__device__ __forceinline__ float box_d2(float4 s, float4 lo, float4 hi) {
+  const float dx = fmaxf(fmaxf(lo.x - s.x, s.x - hi.x), 0.f);
+  const float dy = fmaxf(fmaxf(lo.y - s.y, s.y - hi.y), 0.f);
+  const float dz = fmaxf(fmaxf(lo.z - s.z, s.z - hi.z), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// One WARP per feature.  Lower-bound the super-boxes, descend into the most promising one first, then into every other
+// super-box / box whose bound (shrunk by 1e-5 relative, far more than the rounding of either distance) does not exceed the
+// best distance so far.  Everything skipped holds only points that are strictly farther, so the result -- the minimum of
+// the same packed (fp32 d2, index) key as the brute-force kernel -- is identical, ties included.
+constexpr int KP_WARPS = 8;
+__global__ void __launch_bounds__(KP_WARPS * 32) odom_knn_pruned_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
+                                                                         const float4* __restrict__ flat, int n_flat,
+                                                                         const float4* __restrict__ corner_last, int n_cl,
+                                                                         const float4* __restrict__ surf_last, int n_sl,
+                                                                         const float4* __restrict__ box_c, const float4* __restrict__ sup_c,
+                                                                         const float4* __restrict__ box_s, const float4* __restrict__ sup_s,
+                                                                         unsigned long long* __restrict__ best) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * KP_WARPS + (threadIdx.x >> 5);
+  if (q >= n_sharp + n_flat) return;
+  const bool is_c = q < n_sharp;
+  const float4* pts = is_c ? corner_last : surf_last;
+  const float4* box = is_c ? box_c : box_s;
+  const float4* sup = is_c ? sup_c : sup_s;
+  const int nt = is_c ? n_cl : n_sl;
+  const int nbox = (nt + 31) >> 5, nsup = (nt + 1023) >> 10;
+  const float4 sel = transform_to_start(T, is_c ? sharp[q] : flat[q - n_sharp]);
+  const float inf = __int_as_float(0x7f800000);
+  unsigned long long bestkey = ~0ull;
+  auto warp_min_key = [&](unsigned long long k) {
+    const unsigned int hi = (unsigned int)(k >> 32);
+    const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int lo = (hi == mhi) ? (unsigned int)k : 0xffffffffu;
+    const unsigned int mlo = __reduce_min_sync(0xffffffffu, lo);
+    return ((unsigned long long)mhi << 32) | mlo;
+  };
+  auto open_box = [&](int c) {
+    const int j = c * 32 + lane;
+    unsigned long long k = ~0ull;
+    if (j < nt) {
+      const float4 t = pts[j];
+      k = lg_pack_nbr(lg_sqdist(t.x, t.y, t.z, sel.x, sel.y, sel.z), j);
+    }
+    bestkey = min(bestkey, warp_min_key(k));
+  };
+  // all boxes of super-box s that can still matter, the closest-looking one first
+  auto open_super = [&](int s) {
+    const int c = s * 32 + lane;
+    float lb = inf;
+    if (c < nbox) lb = box_d2(sel, box[2 * c], box[2 * c + 1]) * 0.99999f;
+    const unsigned int mlb = __reduce_min_sync(0xffffffffu, __float_as_uint(lb));  // non-negative floats order like their bits
+    unsigned int m = __ballot_sync(0xffffffffu, lb <= lg_nbr_d2(bestkey) || bestkey == ~0ull);
+    const unsigned int mfirst = __ballot_sync(0xffffffffu, __float_as_uint(lb) == mlb);
+    if (mfirst & m) {
+      const int p = __ffs(mfirst & m) - 1;
+      m &= ~(1u << p);
+      open_box(s * 32 + p);
+    }
+    while (m) {
+      const int p = __ffs(m) - 1;
+      m &= m - 1;
+      if (__shfl_sync(0xffffffffu, lb, p) <= lg_nbr_d2(bestkey)) open_box(s * 32 + p);  // the best may have improved meanwhile
+    }
+  };
+  // the most promising super-box first
+  unsigned long long mine = ~0ull;
+  for (int s = lane; s < nsup; s += 32) {
+    const float lb = box_d2(sel, sup[2 * s], sup[2 * s + 1]);
+    mine = min(mine, ((unsigned long long)__float_as_uint(lb) << 32) | (unsigned int)s);
+  }
+  const int first = nsup > 0 ? (int)(unsigned int)warp_min_key(mine) : -1;
+  if (first >= 0) open_super(first);
+  for (int base = 0; base < nsup; base += 32) {
+    const int s = base + lane;
+    float lb = inf;
+    if (s < nsup && s != first) lb = box_d2(sel, sup[2 * s], sup[2 * s + 1]) * 0.99999f;
+    unsigned int m = __ballot_sync(0xffffffffu, lb <= lg_nbr_d2(bestkey));
+    while (m) {
+      const int p = __ffs(m) - 1;
+      m &= m - 1;
+      if (__shfl_sync(0xffffffffu, lb, p) <= lg_nbr_d2(bestkey)) open_super(base + p);
+    }
+  }
+  if (lane == 0) best[q] = bestkey;
 }
 
 __device__ __forceinline__ float sqd(float4 a, float4 sel) {
@@ -551,13 +701,35 @@ static int odom_refresh_corr(OdomWs& ws, const OdomT& T, const float4* sharp, in
                              const float4* corner_last, int n_cl, const float4* surf_last, int n_sl, cudaStream_t st, long long* launches) {
   const int nq = n_sharp + n_flat;
   if (nq <= 0) return LOAM_OK;
-  LG_CHECK(cudaMemsetAsync(ws.best.p, 0xff, (size_t)nq * 8, st));
-  const int tiles_c = lg_div_up(n_sharp, KNN_Q), tiles_s = lg_div_up(n_flat, KNN_Q);
-  const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
-  dim3 grid(tiles_c + tiles_s, chunks);
+  static const bool brute = getenv("LOAM_ODOM_BRUTE_FORCE") != nullptr;  // cross-check path
+  if (!brute && !ws.bounds_valid) {  // once per sweep: the previous sweep's clouds do not change between refreshes
+    const int nsup_c = lg_div_up(n_cl, 1024), nsup_s = lg_div_up(n_sl, 1024);
+    // per cloud: [2 * 32 * nsup boxes | 2 * nsup super-boxes] float4
+    LG_CHECK(ws.bounds_c.ensure((size_t)(nsup_c + 1) * 66 * 16, st));
+    LG_CHECK(ws.bounds_s.ensure((size_t)(nsup_s + 1) * 66 * 16, st));
+    if (nsup_c + nsup_s > 0) {
+      LgProfScope prof_scope(LGK_ODOM_KNN, st, 0.0);
+      odom_bounds_kernel<<<nsup_c + nsup_s, 1024, 0, st>>>(corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(),
+                                                           ws.bounds_c.as<float4>() + (size_t)nsup_c * 64, ws.bounds_s.as<float4>(),
+                                                           ws.bounds_s.as<float4>() + (size_t)nsup_s * 64);
+      (*launches)++;
+    }
+    ws.bounds_valid = true;
+  }
   LgProfScope prof_scope(LGK_ODOM_KNN, st, (double)nq);
-  odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
-                                          ws.best.as<unsigned long long>());
+  if (brute) {
+    LG_CHECK(cudaMemsetAsync(ws.best.p, 0xff, (size_t)nq * 8, st));
+    const int tiles_c = lg_div_up(n_sharp, KNN_Q), tiles_s = lg_div_up(n_flat, KNN_Q);
+    const int chunks = std::max(1, lg_div_up(std::max(n_cl, n_sl), KNN_T));
+    dim3 grid(tiles_c + tiles_s, chunks);
+    odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
+                                            ws.best.as<unsigned long long>());
+  } else {
+    const int nsup_c = lg_div_up(n_cl, 1024), nsup_s = lg_div_up(n_sl, 1024);
+    odom_knn_pruned_kernel<<<lg_div_up(nq, KP_WARPS), KP_WARPS * 32, 0, st>>>(
+        T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_c.as<float4>() + (size_t)nsup_c * 64,
+        ws.bounds_s.as<float4>(), ws.bounds_s.as<float4>() + (size_t)nsup_s * 64, ws.best.as<unsigned long long>());
+  }
   odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
                                                                           ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
                                                                           ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());

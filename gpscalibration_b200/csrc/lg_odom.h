@@ -18,8 +18,10 @@ struct OdomWs {
   DevBuf best;                // packed (d2, idx) per query, refreshed every 5th iteration
   DevBuf c1, c2, s1, s2, s3;  // pointSearchCornerInd1/2, pointSearchSurfInd1/2/3 (LO:102-109) as int32
   DevBuf partials, ticket;
+  DevBuf bounds_c, bounds_s;   // axis-aligned boxes of every 32 consecutive points of the previous sweep's clouds
+  bool bounds_valid = false;   // cleared by whoever rewrites those clouds
   void release() {
-    DevBuf* all[] = {&best, &c1, &c2, &s1, &s2, &s3, &partials, &ticket};
+    DevBuf* all[] = {&best, &c1, &c2, &s1, &s2, &s3, &partials, &ticket, &bounds_c, &bounds_s};
     for (DevBuf* b : all) b->release();
   }
 };
