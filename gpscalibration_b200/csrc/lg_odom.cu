@@ -367,6 +367,166 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_kernel(OdomT T, con
   }
 }
 
+// The same ring scans with box pruning.  The scan windows are index ranges of the ring-ordered cloud, so they are walked
+// box by box (32 boxes bounded per step, one per lane): a box is opened only if it may hold a candidate that beats the
+// current best of its category (or is the one in which the reference's `break` fires, recognised by its ring range);
+// everything else holds only points at 5 m or more, or strictly farther than the best so far.  Inside an opened box the
+// literal rules of odom_corr_kernel apply, so the result is identical (tests compare both against the oracle).
+__global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_pruned_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
+                                                                            const float4* __restrict__ flat, int n_flat,
+                                                                            const float4* __restrict__ corner_last, int n_cl,
+                                                                            const float4* __restrict__ surf_last, int n_sl,
+                                                                            const float4* __restrict__ box_c, const float4* __restrict__ box_s,
+                                                                            const unsigned long long* __restrict__ best, int* __restrict__ c1,
+                                                                            int* __restrict__ c2, int* __restrict__ s1, int* __restrict__ s2,
+                                                                            int* __restrict__ s3) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * CORR_WARPS + (threadIdx.x >> 5);
+  if (q >= n_sharp + n_flat) return;
+  const bool is_c = q < n_sharp;
+  const int f = is_c ? q : q - n_sharp;
+  const float4* pts = is_c ? corner_last : surf_last;
+  const float4* box = is_c ? box_c : box_s;
+  const int nlast = is_c ? n_cl : n_sl;
+  const int bound = min(is_c ? n_sharp : n_flat, nlast);  // FENCE (i): LO:620 / LO:776 bound by the CURRENT feature count
+  const float4 sel = transform_to_start(T, is_c ? sharp[f] : flat[f]);
+  const unsigned long long b = best[q];
+  const float inf = __int_as_float(0x7f800000);
+  int closest = -1, r2 = -1, r3 = -1;
+  if (b != NONE64 && lg_nbr_d2(b) < 25) {
+    closest = lg_nbr_idx(b);
+    const int scan = int(pts[closest].w);
+    const float fscan = (float)scan;
+    unsigned long long f2 = NONE64, f3 = NONE64, b2 = NONE64, b3 = NONE64;
+    auto dist_of = [&](unsigned long long k) {  // warp-wide best distance of a category (inf while it is empty)
+      const unsigned int hi = (unsigned int)(k >> 32);
+      const unsigned int mhi = __reduce_min_sync(0xffffffffu, hi);
+      return mhi == 0xffffffffu ? inf : __uint_as_float(mhi);
+    };
+    // ---- forward: j = closest + 1 .. , stops at the first j whose ring exceeds scan + 1.5 or at `bound`
+    {
+      float F2 = inf, F3 = inf;
+      bool stop = false;
+      for (int cbase = (closest + 1) >> 5; !stop && cbase * 32 < bound; cbase += 32) {
+        const int cb = cbase + lane;
+        const bool inr = cb * 32 < bound;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (inr) {
+          lo = box[2 * cb];
+          hi = box[2 * cb + 1];
+        }
+        const unsigned int brkm = __ballot_sync(0xffffffffu, inr && hi.w > fscan + 1.5f);
+        const int last = brkm ? __ffs(brkm) - 1 : 31;  // boxes behind the one in which the scan breaks are never reached
+        const float lbm = inr ? box_d2(sel, lo, hi) * 0.99999f : inf;
+        bool need = lbm < 25.f;
+        if (is_c) need = need && hi.w > fscan && lbm <= F2;
+        else need = need && ((lo.w <= fscan && lbm <= F2) || (hi.w > fscan && lbm <= F3));
+        // the box in which the scan may break is always opened: only the points themselves tell whether it does
+        need = inr && lane <= last && (need || ((brkm >> lane) & 1u));
+        unsigned int m = __ballot_sync(0xffffffffu, need);
+        bool broke = false;
+        while (m) {
+          const int p = __ffs(m) - 1;
+          m &= m - 1;
+          const bool flagged = (brkm >> p) & 1u;
+          if (!flagged && __shfl_sync(0xffffffffu, lbm, p) > fmaxf(F2, is_c ? F2 : F3)) continue;  // pruned by an improvement meanwhile
+          const int j = (cbase + p) * 32 + lane;
+          const bool valid = j > closest && j < bound;
+          const float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int r = int(t.w);
+          const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r > scan + 1.5));
+          const bool live = valid && (bm == 0u || lane < (__ffs(bm) - 1));
+          if (live) {
+            const float d = sqd(t, sel);
+            if (d < 25) {
+              const unsigned long long key = lg_pack_nbr(d, j);
+              if (is_c) {
+                if (r > scan) f2 = min(f2, key);
+              } else {
+                if (r <= scan) f2 = min(f2, key); else f3 = min(f3, key);
+              }
+            }
+          }
+          F2 = dist_of(f2);
+          if (!is_c) F3 = dist_of(f3);
+          if (bm != 0u) broke = true;
+        }
+        if (broke) stop = true;
+        else if (brkm) cbase += last + 1 - 32;  // the flagged box did not break after all (rings out of order): go on behind it
+      }
+    }
+    // ---- backward: j = closest - 1 .. 0, stops at the first j whose ring falls below scan - 1.5
+    {
+      float B2 = inf, B3 = inf;
+      bool stop = false;
+      for (int ctop = (closest - 1) >> 5; !stop && ctop >= 0 && closest >= 1; ctop -= 32) {
+        const int cb = ctop - lane;
+        const bool inr = cb >= 0;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (inr) {
+          lo = box[2 * cb];
+          hi = box[2 * cb + 1];
+        }
+        const unsigned int brkm = __ballot_sync(0xffffffffu, inr && lo.w < fscan - 1.5f);
+        const int last = brkm ? __ffs(brkm) - 1 : 31;
+        const float lbm = inr ? box_d2(sel, lo, hi) * 0.99999f : inf;
+        bool need = lbm < 25.f;
+        if (is_c) need = need && lo.w < fscan && lbm <= B2;
+        else need = need && ((hi.w >= fscan && lbm <= B2) || (lo.w < fscan && lbm <= B3));
+        need = inr && lane <= last && (need || ((brkm >> lane) & 1u));
+        unsigned int m = __ballot_sync(0xffffffffu, need);
+        bool broke = false;
+        while (m) {
+          const int p = __ffs(m) - 1;
+          m &= m - 1;
+          const bool flagged = (brkm >> p) & 1u;
+          if (!flagged && __shfl_sync(0xffffffffu, lbm, p) > fmaxf(B2, is_c ? B2 : B3)) continue;
+          const int j = (ctop - p) * 32 + lane;
+          const bool valid = j < closest && j >= 0;
+          const float4 t = valid ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int r = int(t.w);
+          const unsigned int bm = __ballot_sync(0xffffffffu, valid && (r < scan - 1.5));
+          const bool live = valid && (bm == 0u || lane > (31 - __clz(bm)));  // descending j: the highest violating lane breaks
+          if (live) {
+            const float d = sqd(t, sel);
+            if (d < 25) {
+              const unsigned long long key = lg_pack_nbr(d, 0x7fffffff - j);  // first met (largest j) wins ties
+              if (is_c) {
+                if (r < scan) b2 = min(b2, key);
+              } else {
+                if (r >= scan) b2 = min(b2, key); else b3 = min(b3, key);
+              }
+            }
+          }
+          B2 = dist_of(b2);
+          if (!is_c) B3 = dist_of(b3);
+          if (bm != 0u) broke = true;
+        }
+        if (broke) stop = true;
+        else if (brkm) ctop -= last + 1 - 32;
+      }
+    }
+    f2 = warp_min_u64(f2); b2 = warp_min_u64(b2);
+    if (f2 != NONE64 && (b2 == NONE64 || !(lg_nbr_d2(b2) < lg_nbr_d2(f2)))) r2 = lg_nbr_idx(f2);
+    else if (b2 != NONE64) r2 = 0x7fffffff - lg_nbr_idx(b2);
+    if (!is_c) {
+      f3 = warp_min_u64(f3); b3 = warp_min_u64(b3);
+      if (f3 != NONE64 && (b3 == NONE64 || !(lg_nbr_d2(b3) < lg_nbr_d2(f3)))) r3 = lg_nbr_idx(f3);
+      else if (b3 != NONE64) r3 = 0x7fffffff - lg_nbr_idx(b3);
+    }
+  }
+  if (lane == 0) {
+    if (is_c) {
+      c1[f] = closest;
+      c2[f] = r2;
+    } else {
+      s1[f] = closest;
+      s2[f] = r2;
+      s3[f] = r3;
+    }
+  }
+}
+
 constexpr int IT_NT = 128;
 
 // One feature's contribution to the normal equations: TransformToStart, coefficients (LO:680-746 / LO:847-901), Jacobian
@@ -730,9 +890,14 @@ static int odom_refresh_corr(OdomWs& ws, const OdomT& T, const float4* sharp, in
         T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_c.as<float4>() + (size_t)nsup_c * 64,
         ws.bounds_s.as<float4>(), ws.bounds_s.as<float4>() + (size_t)nsup_s * 64, ws.best.as<unsigned long long>());
   }
-  odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
-                                                                          ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
-                                                                          ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
+  if (brute)
+    odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
+                                                                            ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
+                                                                            ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
+  else
+    odom_corr_pruned_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(
+        T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_s.as<float4>(),
+        ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
   (*launches) += 2;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;
