@@ -51,7 +51,7 @@ ALGO_BYTES = {
 # (r1_ncu_full_<kernel>.csv, first 60 sweeps of the same sequence); None where no capture exists
 # DRAM bytes (read + write) per launch group of each class from the final `ncu --set full` capture
 # (profiles/r1_ncu_full_final.csv; ncu flushes caches between replays, so these are cold-cache upper bounds).
-NCU_TRAFFIC = {"odom_knn": 370432 + 381952,  # odom_knn_kernel + odom_corr_kernel of one refresh
+NCU_TRAFFIC = {"odom_knn": 351000 + 381000,  # odom_knn_pruned_kernel + odom_corr_pruned_kernel of one refresh
                "odom_iter": 358144,           # odom_loop_kernel (one launch = up to five iterations)
                "sr_select": 172288, "map_knn": 2148608, "map_fit": 915200, "voxel": None, "extract": None}
 
