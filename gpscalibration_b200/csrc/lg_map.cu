@@ -156,9 +156,6 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 constexpr int KNN_WARPS = 8;
-constexpr int KNN_SUB = 8;                       // lanes per query
-constexpr int KNN_QPW = 32 / KNN_SUB;            // queries per warp
-constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;     // queries per CTA
 
 // Exact 5-NN, EIGHT lanes per query (four queries per warp), two phases.  Probe: every lane resolves 3-4 of the 27
 // neighbour cells -- one L2-resident occupancy bit decides whether the cell exists at all (most do not), one 32-byte
@@ -168,12 +165,15 @@ constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;     // queries per CTA
 // keys in registers (branch-free min/max insertion); the eight lanes are merged with masked warp reductions.
 // Variants measured and dropped on a 20 M-point map: a full warp per query (same time, 3x the instructions), all
 // probes of a lane issued up front (more registers, slower), a block-local hash layout (slower build, no gain).
+template <int KNN_SUB>  // lanes per query: 8 (four queries per warp) for large batches, 16 when the batch cannot fill the GPU
 __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const float4* __restrict__ corner_stack, int n_cs,
                                                                   const float4* __restrict__ surf_stack, int n_ss, GridD gc, GridD gs,
                                                                   int* __restrict__ nbr /* [n_cs + n_ss][5] */) {
+  constexpr int KNN_QPW = 32 / KNN_SUB;  // queries per warp
+  constexpr unsigned int SUBMASK = KNN_SUB == 32 ? 0xffffffffu : ((1u << (KNN_SUB & 31)) - 1u);
   const int lane = threadIdx.x & 31, sub = lane & (KNN_SUB - 1), grp = lane / KNN_SUB;
   const int q = (blockIdx.x * KNN_WARPS + (threadIdx.x >> 5)) * KNN_QPW + grp;
-  const unsigned int gmask = ((1u << KNN_SUB) - 1u) << (grp * KNN_SUB);
+  const unsigned int gmask = SUBMASK << (grp * (KNN_SUB & 31));
   const bool active = q < n_cs + n_ss;
   const bool is_c = q < n_cs;
   const GridD& g = is_c ? gc : gs;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) map_knn_kernel(MapT T, const f
   }
 #pragma unroll
   for (int j = 0; j < CPL; j++) {
-    unsigned int todo = (__ballot_sync(0xffffffffu, ccnt[j] > 1) >> (grp * KNN_SUB)) & ((1u << KNN_SUB) - 1u);
+    unsigned int todo = (__ballot_sync(0xffffffffu, ccnt[j] > 1) >> (grp * (KNN_SUB & 31))) & SUBMASK;
     while (todo) {  // uniform inside the 8-lane group
       const int src = grp * KNN_SUB + __ffs(todo) - 1;
       todo &= todo - 1;
@@ -487,7 +487,10 @@ int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack,
   }
   if (nq > 0) {
     LgProfScope prof_scope(LGK_MAP_KNN, st, (double)nq);
-    map_knn_kernel<<<lg_div_up(nq, KNN_QPB), KNN_WARPS * 32, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, gc, gs, ws.nbr.as<int>());
+    if (nq <= 148 * 128)  // fewer than ~four resident warps per scheduler at 8 lanes per query: spread every query wider
+      map_knn_kernel<16><<<lg_div_up(nq, KNN_WARPS * 2), KNN_WARPS * 32, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, gc, gs, ws.nbr.as<int>());
+    else
+      map_knn_kernel<8><<<lg_div_up(nq, KNN_WARPS * 4), KNN_WARPS * 32, 0, st>>>(T, corner_stack, n_cs, surf_stack, n_ss, gc, gs, ws.nbr.as<int>());
     (*launches)++;
   }
   LgProfScope prof_scope(LGK_MAP_FIT, st, (double)nq);
