@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
 // equal sub-ranges, one CTA each.  Every CTA scans the whole segment (L2-resident), keeps the points of its
 // sub-range, sorts them in shared memory and writes their centroids to its staging slice; a second kernel
 // concatenates the slices in range order, which is ascending cell id.  Same results as vox_small_kernel.
-constexpr int VS_CAP = 4096, VS_NT = 256, VS_MLP = 8;  // VS_MLP loads in flight per thread: every CTA streams the whole segment
+constexpr int VS_CAP = 4096, VS_NT = 1024, VS_MLP = 4, VS_BINS = 1024;  // VS_MLP loads in flight per thread: every CTA streams the whole segment
 __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restrict__ segs, float4* __restrict__ staging,
                                                            int* __restrict__ range_counts, int* __restrict__ overflow) {
   __shared__ unsigned long long skeys[VS_CAP];
@@ -184,7 +184,11 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
   __shared__ int s_scan[VS_NT / 32 + 2];
   __shared__ float s_bb[6];
   __shared__ int s_n;
+  __shared__ int s_hist[VS_BINS];
   const VoxSegD sg = segs[blockIdx.y];
+#ifdef VS_DEBUG
+  const long long dbg_t0 = clock64();
+#endif
   const int C = gridDim.x, c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int* my_count = range_counts + blockIdx.y * C + c;
@@ -238,8 +242,55 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
   }
   const int maxb2 = (int)floorf(s_bb[5] * g.inv);
   const long long total = (long long)g.divxy * (maxb2 - g.minb2 + 1);
-  const long long wdt = (total + C - 1) / C;
-  const long long lo = wdt * c, hi = lo + wdt;
+  // Split the cell-id range so that every CTA gets about n / C POINTS (an even split of the id range gave a few CTAs
+  // most of the cloud and 4096-key sorts while the rest idled): coarse histogram over VS_BINS id bins, built by every
+  // CTA for itself (integer counts: identical everywhere), CTA c takes the bins between the c-th and (c+1)-th
+  // quantile.  Bin edges are cell-id multiples, so no voxel is ever split and the concatenation stays in id order.
+  int bin_shift = 0;  // power-of-two bin width: cell >> bin_shift < VS_BINS
+  while (((total - 1) >> bin_shift) >= VS_BINS) bin_shift++;
+  const long long binw = 1ll << bin_shift;
+  for (int b = tid; b < VS_BINS; b += VS_NT) s_hist[b] = 0;
+  __syncthreads();
+  for (int i0 = tid; i0 < n; i0 += VS_MLP * VS_NT) {
+    float4 p[VS_MLP];
+#pragma unroll
+    for (int u = 0; u < VS_MLP; u++)
+      if (i0 + u * VS_NT < n) p[u] = sg.in[i0 + u * VS_NT];
+#pragma unroll
+    for (int u = 0; u < VS_MLP; u++)
+      if (i0 + u * VS_NT < n) atomicAdd(&s_hist[vox_cell(g, p[u]) >> bin_shift], 1);
+  }
+  __syncthreads();
+  {  // inclusive prefix over the bins (VS_BINS / VS_NT consecutive bins per thread)
+    constexpr int PER = VS_BINS / VS_NT;
+    int v[PER], local = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      v[k] = s_hist[tid * PER + k];
+      local += v[k];
+    }
+    int tot;
+    int run = block_excl_scan<VS_NT>(local, &tot, s_scan);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      run += v[k];
+      s_hist[tid * PER + k] = run;
+    }
+  }
+  __syncthreads();
+  // first bin whose inclusive prefix exceeds the quantile target = start of CTA c's range (monotone in c)
+  auto first_bin = [&](int cc) {
+    if (cc <= 0) return 0;
+    if (cc >= C) return VS_BINS;
+    const long long target = (long long)n * cc / C;
+    int lo_b = 0, hi_b = VS_BINS;
+    while (lo_b < hi_b) {
+      const int mid = (lo_b + hi_b) >> 1;
+      if ((long long)s_hist[mid] > target) hi_b = mid; else lo_b = mid + 1;
+    }
+    return lo_b;
+  };
+  const long long lo = (long long)first_bin(c) * binw, hi = (c + 1 >= C) ? total + binw : (long long)first_bin(c + 1) * binw;
   for (int i0 = tid; i0 < n; i0 += VS_MLP * VS_NT) {
     float4 p[VS_MLP];
 #pragma unroll
@@ -309,6 +360,9 @@ __global__ void __launch_bounds__(VS_NT) vox_split_kernel(const VoxSegD* __restr
     }
   }
   if (tid == 0) *my_count = V;
+#ifdef VS_DEBUG
+  if (tid == 0) printf("vs seg %d cta %d n %d m %d P %d V %d cycles %lld\n", (int)blockIdx.y, c, n, m, P, V, clock64() - dbg_t0);
+#endif
 }
 
 __global__ void __launch_bounds__(256) vox_split_concat_kernel(const VoxSegD* __restrict__ segs, const float4* __restrict__ staging,
