@@ -529,33 +529,35 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_pruned_kernel(OdomT
 
 constexpr int IT_NT = 128;
 
-// One feature's contribution to the normal equations: TransformToStart, coefficients (LO:680-746 / LO:847-901), Jacobian
-// row (LO:915-971) accumulated into `acc`.
-__device__ __forceinline__ void odom_row(int q, const OdomT& T, const SinCos3& sc, int iter, const float4* __restrict__ sharp, int n_sharp,
-                                         const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
-                                         const float4* __restrict__ surf_last, const int* __restrict__ c1, const int* __restrict__ c2,
-                                         const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3, Acc28& acc) {
-  float4 ori, coef;
-  bool keep = false;
+// One feature's contribution to the normal equations, in two parts.  odom_row_load: everything that does not depend on
+// the transform -- the feature point, its correspondence points (line, LO:680-687) or the normalised plane through them
+// (LO:847-866); odom_row_eval: TransformToStart, point-to-line / point-to-plane distance and weight (LO:688-746 /
+// LO:867-901), Jacobian row (LO:915-971), accumulated into `acc`.  A kernel that iterates (odom_loop_kernel) loads once.
+struct OdomRowIn {
+  float4 ori;   // the feature point
+  float4 a, b;  // line: the two correspondence points; plane: a = {pa, pb, pc, pd}
+  int kind;     // 0 = no correspondence, 1 = line, 2 = plane
+};
+__device__ __forceinline__ OdomRowIn odom_row_load(int q, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
+                                                   const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
+                                                   const int* __restrict__ c1, const int* __restrict__ c2, const int* __restrict__ s1,
+                                                   const int* __restrict__ s2, const int* __restrict__ s3) {
+  OdomRowIn in;
+  in.kind = 0;
+  in.ori = in.a = in.b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (q < n_sharp) {
-    ori = sharp[q];
-    const float4 sel = transform_to_start(T, ori);
+    in.ori = sharp[q];
     const int i2 = c2[q];
-    if (i2 >= 0) {  // LO:680-746
-      float4 t1 = corner_last[c1[q]], t2 = corner_last[i2];
-      float la, lb, lc, ld2;
-      line_coeff(sel.x, sel.y, sel.z, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z, la, lb, lc, ld2);
-      float s = 1;
-      if (iter >= 5) s = (float)(1 - 1.8 * fabsf(ld2));
-      coef = make_float4(s * la, s * lb, s * lc, s * ld2);
-      keep = (s > 0.1 && ld2 != 0);
+    if (i2 >= 0) {
+      in.a = corner_last[c1[q]];
+      in.b = corner_last[i2];
+      in.kind = 1;
     }
   } else if (q < n_sharp + n_flat) {
     const int f = q - n_sharp;
-    ori = flat[f];
-    const float4 sel = transform_to_start(T, ori);
+    in.ori = flat[f];
     const int i2 = s2[f], i3 = s3[f];
-    if (i2 >= 0 && i3 >= 0) {  // LO:847-901
+    if (i2 >= 0 && i3 >= 0) {  // LO:847-866
       float4 t1 = surf_last[s1[f]], t2 = surf_last[i2], t3 = surf_last[i3];
       float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
       float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
@@ -563,12 +565,33 @@ __device__ __forceinline__ void odom_row(int q, const OdomT& T, const SinCos3& s
       float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
       float ps = sqrtf(pa * pa + pb * pb + pc * pc);
       pa /= ps; pb /= ps; pc /= ps; pd /= ps;
-      float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
-      float s = 1;
-      if (iter >= 5) s = (float)(1 - 1.8 * fabsf(pd2) / sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
-      coef = make_float4(s * pa, s * pb, s * pc, s * pd2);
-      keep = (s > 0.1 && pd2 != 0);
+      in.a = make_float4(pa, pb, pc, pd);
+      in.kind = 2;
     }
+  }
+  return in;
+}
+
+__device__ __forceinline__ void odom_row_eval(const OdomRowIn& in, const OdomT& T, const SinCos3& sc, int iter, Acc28& acc) {
+  if (in.kind == 0) return;
+  const float4 ori = in.ori;
+  const float4 sel = transform_to_start(T, ori);
+  float4 coef;
+  bool keep;
+  if (in.kind == 1) {  // LO:688-746
+    float la, lb, lc, ld2;
+    line_coeff(sel.x, sel.y, sel.z, in.a.x, in.a.y, in.a.z, in.b.x, in.b.y, in.b.z, la, lb, lc, ld2);
+    float s = 1;
+    if (iter >= 5) s = (float)(1 - 1.8 * fabsf(ld2));
+    coef = make_float4(s * la, s * lb, s * lc, s * ld2);
+    keep = (s > 0.1 && ld2 != 0);
+  } else {  // LO:867-901
+    const float pa = in.a.x, pb = in.a.y, pc = in.a.z, pd = in.a.w;
+    float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+    float s = 1;
+    if (iter >= 5) s = (float)(1 - 1.8 * fabsf(pd2) / sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
+    coef = make_float4(s * pa, s * pb, s * pc, s * pd2);
+    keep = (s > 0.1 && pd2 != 0);
   }
   if (keep) {  // LO:915-971 with s = 1 folded away (x * 1.0f is exact)
     const float srx = sc.srx, crx = sc.crx, sry = sc.sry, cry = sc.cry, srz = sc.srz, crz = sc.crz;
@@ -593,6 +616,14 @@ __device__ __forceinline__ void odom_row(int q, const OdomT& T, const SinCos3& s
     float b = (float)(-0.05 * c.w);
     acc.add_row(a, b);
   }
+}
+
+__device__ __forceinline__ void odom_row(int q, const OdomT& T, const SinCos3& sc, int iter, const float4* __restrict__ sharp, int n_sharp,
+                                         const float4* __restrict__ flat, int n_flat, const float4* __restrict__ corner_last,
+                                         const float4* __restrict__ surf_last, const int* __restrict__ c1, const int* __restrict__ c2,
+                                         const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3, Acc28& acc) {
+  const OdomRowIn in = odom_row_load(q, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3);
+  odom_row_eval(in, T, sc, iter, acc);
 }
 
 __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp,
@@ -688,11 +719,20 @@ __global__ void __launch_bounds__(LP_NT)
     s_state.done = 0;
     s_state.last_iter = A.it0 - 1;
   }
+  // one row per thread (every VLP-16-sized sweep): its inputs stay in registers for all iterations of this launch
+  const bool one_row = n_sharp + n_flat <= (int)(nranks * LP_NT);
+  OdomRowIn mine;
+  mine.kind = 0;
+  if (one_row) mine = odom_row_load(rank * LP_NT + tid, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3);
   while (true) {
     Acc28 acc;
     acc.clear();
-    for (int q = rank * LP_NT + tid; q < n_sharp + n_flat; q += nranks * LP_NT)
-      odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
+    if (one_row) {
+      odom_row_eval(mine, T, sc, iter, acc);
+    } else {
+      for (int q = rank * LP_NT + tid; q < n_sharp + n_flat; q += nranks * LP_NT)
+        odom_row(q, T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, acc);
+    }
     const double r = lg_warp_reduce28(acc.v, lane);
     if (lane < 28) s_part[w][lane] = r;
     __syncthreads();
