@@ -93,9 +93,27 @@ __device__ __forceinline__ void lg_reduce28(Acc28& acc, double* __restrict__ par
   __syncthreads();
   if (s_last) {
     __threadfence();
+    // the per-CTA partials, added by all warps: warp w takes CTAs w, w + NT/32, ... (four loads in flight), the warps'
+    // sums are then added in warp order -- a fixed order, so the result does not depend on which CTA came last
     double s = 0.0;
-    if (tid < 28)
-      for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * 28 + tid]);
+    if (lane < 28) {
+      constexpr unsigned int W = NT / 32;
+      for (unsigned int b = w; b < gridDim.x; b += 4 * W) {
+        double v[4];
+#pragma unroll
+        for (unsigned int u = 0; u < 4; u++) v[u] = b + u * W < gridDim.x ? __ldcg(&partials[(size_t)(b + u * W) * 28 + lane]) : 0.0;
+#pragma unroll
+        for (unsigned int u = 0; u < 4; u++) s += v[u];
+      }
+    }
+    __syncthreads();  // s_part is free again: every warp has passed the barrier after its first use
+    if (lane < 28) s_part[w][lane] = s;
+    __syncthreads();
+    s = 0.0;
+    if (tid < 28) {
+#pragma unroll
+      for (int k = 0; k < NT / 32; k++) s += s_part[k][tid];
+    }
     if (tid == 0) *ticket = 0u;
     if (px != nullptr && px->world > 1) {
       // Fused all-reduce: the last CTA stores this rank's 28 sums straight into every peer's exchange buffer (NVLink
