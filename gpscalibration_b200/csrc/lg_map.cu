@@ -139,22 +139,6 @@ __global__ void grid_fill_kernel(GridJob J, int split) {
 }
 
 // ---------------------------------------------------------------------------------------------- exact 5-NN
-__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
-  unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)v, src);
-  unsigned int hi = __shfl_sync(0xffffffffu, (unsigned int)(v >> 32), src);
-  return ((unsigned long long)hi << 32) | lo;
-}
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)v, o);
-    unsigned int hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(v >> 32), o);
-    unsigned long long t = ((unsigned long long)hi << 32) | lo;
-    v = t < v ? t : v;
-  }
-  return v;
-}
-
 constexpr int KNN_WARPS = 8;
 
 // Exact 5-NN, EIGHT lanes per query (four queries per warp), two phases.  Probe: every lane resolves 3-4 of the 27
