@@ -194,8 +194,11 @@ class LoamGpu:
     PROFILE_CLASSES = ("extract", "odom_knn", "odom_iter", "to_end", "map_stack", "voxel", "gather", "grid", "map_knn",
                        "map_fit", "insert", "sr_select")
 
+    # host wall-clock sections of the blocking calls (loam_host_times); the names t9..t15 are kept as aliases in tools/
     HOST_SECTIONS = ("extract", "odom_iters", "odom_end", "map_prep", "map_grid", "map_iters", "map_insert", "map_cube_ds", "map_rest",
                      "t9", "t10", "t11", "t12", "t13", "t14", "t15")
+    HOST_SECTION_MEANING = {"t9": "cube bookkeeping / grid roll", "t10": "gather of the local map", "t11": "stack voxel grid incl. count read-back",
+                            "t12": "arena reserve", "t13": "cube tables + uploads", "t14": "cube merge launches", "t15": "cube merge wait + read-back"}
 
     def host_times(self, clear=True):
         out = np.zeros(16)
