@@ -79,6 +79,78 @@ LG_UNROLL
   return true;
 }
 
+#ifdef __CUDACC__
+// lg_qr_solve<6, 6> spread over seven lanes of a warp: lane c < 6 owns column c of A, lane 6 owns b.  Per reflection the
+// owner of the pivot column forms the Householder vector and broadcasts it, the lanes to its right apply it to their
+// own column.  Every element goes through exactly the operations of the one-thread version in the same order, so the
+// result is bit-identical; the six serial column updates per reflection collapse into one.  All 32 lanes must call;
+// all lanes return the solution.
+__device__ __forceinline__ bool lg_qr_solve6_warp(const float* A0 /* 6x6 row-major */, const float* b0, int lane, float* x) {
+  float col[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float v = b0[i];
+#pragma unroll
+    for (int c = 0; c < 6; c++) v = lane == c ? A0[i * 6 + c] : v;
+    col[i] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    float v[6], vn2 = 0.f, nrm = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[i] = 0.f;
+    if (lane == k) {
+      float nrm2 = 0.f;
+#pragma unroll
+      for (int i = k; i < 6; i++) nrm2 = nrm2 + col[i] * col[i];
+      nrm = sqrtf(nrm2);
+      const float alpha = (col[k] > 0.f) ? -nrm : nrm;
+      v[k] = col[k] - alpha;
+#pragma unroll
+      for (int i = k + 1; i < 6; i++) v[i] = col[i];
+#pragma unroll
+      for (int i = k; i < 6; i++) vn2 = vn2 + v[i] * v[i];
+      col[k] = alpha;
+#pragma unroll
+      for (int i = k + 1; i < 6; i++) col[i] = 0.f;
+    }
+    nrm = __shfl_sync(0xffffffffu, nrm, k);
+    if (nrm == 0.f) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) x[i] = 0.f;
+      return false;
+    }
+    vn2 = __shfl_sync(0xffffffffu, vn2, k);
+#pragma unroll
+    for (int i = k; i < 6; i++) v[i] = __shfl_sync(0xffffffffu, v[i], k);
+    if (lane > k && lane <= 6) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = k; i < 6; i++) s = s + v[i] * col[i];
+      const float f = (2.f * s) / vn2;
+#pragma unroll
+      for (int i = k; i < 6; i++) col[i] = col[i] - f * v[i];
+    }
+  }
+  // back-substitution: every lane gathers the triangle and the right-hand side and solves for itself
+  float r[6][6], rb[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    rb[i] = __shfl_sync(0xffffffffu, col[i], 6);
+#pragma unroll
+    for (int j = i; j < 6; j++) r[i][j] = __shfl_sync(0xffffffffu, col[i], j);
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = rb[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) s = s - r[i][j] * x[j];
+    x[i] = s / r[i][i];
+  }
+  return true;
+}
+#endif
+
 // Symmetric eigen-decomposition.  W descending, eigenvectors are the ROWS of V.  Pivot = first largest |a_kl| of the
 // upper triangle (row-major scan); stops at |pivot| <= FLT_EPSILON or after 30 N^2 rotations.
 template <int N>

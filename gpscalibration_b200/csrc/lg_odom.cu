@@ -750,36 +750,29 @@ __global__ void __launch_bounds__(LP_NT)
         s_tot[tid] = s;
       }
       __syncthreads();
-      if (w == 0) {  // lane 0 solves; the six sin/cos and the two convergence norms then run on eight lanes side by side
+      if (w == 0) {  // the QR runs on seven lanes, the six sin/cos and the two convergence norms on eight, side by side
         float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int solved = 0;
-        if (lane == 0) {
-          float AtA[36], AtB[6];
-          int n_sel;
-          lg_unpack28(s_tot, AtA, AtB, &n_sel);
-          if (n_sel >= 10) {  // LO:904-907
-            lg_qr_solve<6, 6>(AtA, AtB, X);
-            if (A.degenerate) {
-              float X2[6];
-              for (int i = 0; i < 6; i++) X2[i] = X[i];
-              lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
-            }
+        float AtA[36], AtB[6];
+        int n_sel;
+        lg_unpack28(s_tot, AtA, AtB, &n_sel);  // every lane for itself: 28 shared-memory reads
+        const int solved = n_sel >= 10;        // LO:904-907
+        if (solved) {
+          lg_qr_solve6_warp(AtA, AtB, lane, X);
+          if (A.degenerate) {
+            float X2[6];
+            for (int i = 0; i < 6; i++) X2[i] = X[i];
+            lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
+          }
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-              float v = T.t[i] + X[i];
-              if (isnan(v)) v = 0.f;
-              T.t[i] = v;
-            }
-            solved = 1;
+          for (int i = 0; i < 6; i++) {
+            float v = T.t[i] + X[i];
+            if (isnan(v)) v = 0.f;
+            T.t[i] = v;
           }
         }
-        solved = __shfl_sync(0xffffffffu, solved, 0);
         float Tn[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          X[i] = __shfl_sync(0xffffffffu, X[i], 0);
-          Tn[i] = __shfl_sync(0xffffffffu, T.t[i], 0);
-        }
+        for (int i = 0; i < 6; i++) Tn[i] = T.t[i];
         int small = 0;
         if (lane < 6) {
           const int k = lane >> 1;
