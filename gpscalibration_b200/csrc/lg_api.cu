@@ -387,7 +387,8 @@ int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, 
 
 // Waits until the reduction kernel has published sequence number h->mail_seq next to the 28 sums in the mapped pinned
 // mailbox.  Spinning on host memory the GPU writes over PCIe costs ~2 us; cudaStreamSynchronize costs 10-20 us, and
-// there is one such hand-over per Gauss-Newton iteration (the 6x6 solve stays on the host).
+// there is one such hand-over per host-visited Gauss-Newton iteration (every mapping iteration, the first odometry
+// iteration of a sweep and once per device loop launch).
 int mailbox_wait(loam_handle* h) {
   volatile unsigned long long* flag = (volatile unsigned long long*)(h->h_mail + 31);
   h->syncs++;

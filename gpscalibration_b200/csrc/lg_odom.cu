@@ -9,7 +9,9 @@
 //   odom_iter_kernel    LO:595,680-971  TransformToStart, point-to-line / point-to-plane coefficients, Jacobian row,
 //                                    and the 21 + 6 term reduction (warp shuffle -> CTA -> last-CTA) into a 28-double mailbox
 //   odom_to_end_kernel  LO:1087-1106 TransformToEnd over less-sharp, less-flat and (every 2nd sweep) the full cloud
-// The 6x6 solve, degeneracy projection, convergence test and pose accumulation stay on the host (lg_api.cu).
+//   odom_loop_kernel    LO:579-1031  iterations 1..4, 5..9, ... of a registration in one launch (solve, convergence test and
+//                                    sin/cos of the new angles on the device)
+// Iteration 0 (eigen-decomposition, degeneracy projection) and the pose accumulation stay on the host (lg_api.cu).
 #include <cooperative_groups.h>
 
 #include "lg_odom.h"
