@@ -153,7 +153,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-worker"])
+    ap.add_argument("--worker-rank", type=int, default=0, help="(reference-worker) which rank's sequence to run")
     ap.add_argument("--sweeps", type=int, default=1000, help="sweeps per sequence (configs[1]: 1000)")
     ap.add_argument("--cpu-sweeps", type=int, default=150, help="bounded CPU sample (first sweeps of the same sequence)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -176,21 +177,41 @@ def main():
               "l2": "inputs larger than L2 (%d MB of sweeps per step, each touched once)" % (args.sweeps * 28800 * 12 // 1000000)}
 
     # ------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference-worker":  # one reference pipeline (three stage threads) on sequence `--worker-rank`
+        n = min(args.cpu_sweeps, args.sweeps)
+        _, arr, offs = make_sequence(n, args.worker_rank, pinned=False)
+        times = []
+        kind = None
+        for s in range(args.warmup + args.steps):
+            dt, kind, _, _ = run_cpu(arr, offs, n)
+            if s >= args.warmup:
+                times.append(dt)
+            log(f"[reference worker {args.worker_rank}] step {s}: {n / dt:.2f} sweeps/s")
+        emit({"times": times, "kind": kind})
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
         n = min(args.cpu_sweeps, args.sweeps)
-        _, arr, offs = make_sequence(n, 0, pinned=False)
-        times = []
-        kind = cores = None
-        for s in range(args.warmup + args.steps):
-            dt, kind, cores, _ = run_cpu(arr, offs, n)
-            if s >= args.warmup:
-                times.append(dt)
-            log(f"[reference] step {s}: {n / dt:.2f} sweeps/s")
-        total = sum(times)
-        val = n * args.steps / total
-        sample = f"first {n} sweeps of the rank-0 sequence per step, three stage threads (SR | LO | LM) like the reference's three ROS processes"
+        # --gpus N: N reference pipelines side by side (N x 3 stage threads, distinct sequences: the ones the N GPU ranks
+        # get), SURVEY 8d(ii) -- the reference's nodes keep their state in file-scope globals, so one process per pipeline
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference-worker", "--worker-rank", str(i),
+                                   "--steps", str(args.steps), "--warmup", str(args.warmup), "--sweeps", str(args.sweeps),
+                                   "--cpu-sweeps", str(args.cpu_sweeps)], stdout=subprocess.PIPE, env=env, text=True)
+                 for i in range(max(1, args.gpus))]
+        outs = [json.loads(pr.communicate()[0].strip().splitlines()[-1]) for pr in procs]
+        for pr in procs:
+            if pr.returncode:
+                raise RuntimeError("reference worker failed")
+        kind = outs[0]["kind"]
+        npipe = len(outs)
+        total = max(sum(o["times"]) for o in outs)  # the slowest pipeline bounds the job, like max-over-ranks on the GPU arm
+        val = npipe * n * args.steps / total
+        cores = 3 * npipe
+        sample = (f"first {n} sweeps per step of each of {npipe} independent sequence(s) (the ranks' own), one reference pipeline per "
+                  f"sequence running concurrently, three stage threads (SR | LO | LM) each like the reference's three ROS processes; "
+                  f"{os.cpu_count()} host cores present")
         emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -227,8 +248,10 @@ def main():
 
     from gpscalibration_b200 import LoamGpuPipeline
     dev_t = torch.device("cuda", local_rank)
-    gpu = LoamGpu(device=local_rank)          # synchronous per-sweep call (loam_process_sweep)
-    pipe = LoamGpuPipeline(device=local_rank)  # pipelined mode (loam_pipeline_*): the reference's SR | LO | LM layout
+    # want_registered / want_surround: the timed arm produces /velodyne_cloud_registered (LM:1103-1112) and
+    # /laser_cloud_surround (LM:1081-1101) like the reference arm always does
+    gpu = LoamGpu(device=local_rank, want_registered=True, want_surround=True)          # synchronous per-sweep call (loam_process_sweep)
+    pipe = LoamGpuPipeline(device=local_rank, want_registered=True, want_surround=True)  # pipelined mode: the reference's SR | LO | LM layout
     sync_stream = torch.cuda.ExternalStream(gpu.stream, device=dev_t)
     stage_streams = [torch.cuda.ExternalStream(pipe.stream(i), device=dev_t) for i in range(3)]
     join_stream = torch.cuda.Stream(device=dev_t)
@@ -351,7 +374,7 @@ def main():
         import threading
         SEG, NS = args.multi_segments, min(400, S)
         seg_data = [(arr, offs)] + [make_sequence(NS, 100 + i, pinned=True)[1:] for i in range(1, SEG)]
-        seg_pipes = [pipe] + [LoamGpuPipeline(device=local_rank) for _ in range(1, SEG)]
+        seg_pipes = [pipe] + [LoamGpuPipeline(device=local_rank, want_registered=True, want_surround=True) for _ in range(1, SEG)]
         seg_t = [0.0] * SEG
 
         def seg_run(i):
@@ -380,9 +403,26 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(args.cpu_sweeps, S)
-        dt, kind, cores, _ = run_cpu(arr, offs, n)
+        dt, kind, cores, cpu_res = run_cpu(arr, offs, n)
         out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": f"first {n} sweeps of the same sequence, three stage threads (SR | LO | LM), {os.cpu_count()} host cores present"}
+        # trajectory parity (SURVEY 8d cfg 2): the CUDA path's poses over the same sweeps against the CPU arm's, bit for bit
+        gpu.reset()
+        worst_o = worst_m = 0.0
+        n_map = 0
+        for k in range(n):
+            r = gpu.process_sweep(arr[offs[k]:offs[k + 1]])
+            if kind == "reference":
+                co, cm = cpu_res[k]
+            else:
+                co, cm = np.array(cpu_res[k].odom), (np.array(cpu_res[k].mapped) if cpu_res[k].mapping_ran else None)
+            worst_o = max(worst_o, float(np.abs(np.array(r.odom.transform_sum, np.float32) - np.asarray(co, np.float32)).max()))
+            assert bool(r.mapping_ran) == (cm is not None), k
+            if cm is not None:
+                n_map += 1
+                worst_m = max(worst_m, float(np.abs(np.array(r.map.transform_aft_mapped, np.float32) - np.asarray(cm, np.float32)).max()))
+        out["parity"] = {"sweeps": n, "mapping_runs": n_map, "against": kind, "max_abs_pose_diff_odometry": worst_o,
+                         "max_abs_pose_diff_mapping": worst_m}
     if rank == 0:
         emit(out)
     gpu.close()

@@ -61,7 +61,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect",
            "loam_map_iter_allreduce", "loam_pipeline_create", "loam_pipeline_destroy",
-           "loam_pipeline_reset", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_replay_segments"]
 
@@ -126,6 +126,8 @@ def load_library():
     lib.loam_pipeline_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
     lib.loam_pipeline_destroy.argtypes = [vp]
     lib.loam_pipeline_reset.argtypes = [vp]
+    lib.loam_pipeline_last_error.restype = C.c_char_p
+    lib.loam_pipeline_last_error.argtypes = [vp]
     lib.loam_pipeline_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
@@ -145,13 +147,17 @@ class LoamGpu:
     """One handle = one GPU + one stream + the state of the three LOAM stages (thin wrapper, no logic)."""
 
     def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
-                 want_registered=False, want_surround=False):
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
         p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
         p.skip_frame_num = skip_frame_num
         p.want_registered, p.want_surround = int(want_registered), int(want_surround)
+        if max_points:
+            p.max_points = int(max_points)
+        if max_map_points:
+            p.max_map_points = int(max_map_points)
         self.params = p
         self._h = C.c_void_p()
         self._check(self.lib.loam_create(C.byref(p), device, C.byref(self._h)), "loam_create")
@@ -386,12 +392,18 @@ class LoamGpu:
 class LoamGpuPipeline:
     """Pipelined mode (loam_pipeline_*): submit sweeps, collect results in order; same results as LoamGpu.process_sweep."""
 
-    def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1):
+    def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
         p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
         p.skip_frame_num = skip_frame_num
+        p.want_registered, p.want_surround = int(want_registered), int(want_surround)
+        if max_points:
+            p.max_points = int(max_points)
+        if max_map_points:
+            p.max_map_points = int(max_map_points)
         self._h = C.c_void_p()
         rc = self.lib.loam_pipeline_create(C.byref(p), device, C.byref(self._h))
         if rc:
@@ -399,7 +411,10 @@ class LoamGpuPipeline:
 
     def _check(self, rc, where):
         if rc != 0:
-            raise LoamError(rc, where, self.lib.loam_strerror(rc).decode())
+            detail = self.lib.loam_strerror(rc).decode()
+            if rc == LOAM_ECUDA:
+                detail += ": " + self.lib.loam_pipeline_last_error(self._h).decode()
+            raise LoamError(rc, where, detail)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

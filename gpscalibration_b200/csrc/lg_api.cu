@@ -12,6 +12,7 @@
 #include <immintrin.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -77,7 +78,7 @@ struct loam_handle {
   long long h2d_bytes = 0, d2h_bytes = 0, syncs = 0;
   unsigned long long mail_seq = 0;  // sequence number the reduction kernels publish into the mapped mailbox
   LgProf prof;
-  double host_s[16] = {0};  // host wall-clock per section (diagnostics, loam_host_times)
+  double host_s[LOAM_HOST_SECTIONS] = {0};  // host wall-clock per section (diagnostics, loam_host_times)
   // pinned host staging
   double* h_mail = nullptr;  // mapped: 28 doubles written by the reduction kernels
   double* d_mail = nullptr;
@@ -393,7 +394,10 @@ int mailbox_wait(loam_handle* h) {
   volatile unsigned long long* flag = (volatile unsigned long long*)(h->h_mail + 31);
   h->syncs++;
   for (long spin = 0;; spin++) {
-    if (*flag == h->mail_seq) return LOAM_OK;
+    if (*flag == h->mail_seq) {
+      std::atomic_thread_fence(std::memory_order_acquire);  // the 28 payload doubles are read after the flag
+      return LOAM_OK;
+    }
     _mm_pause();
     if ((spin & 0xffff) == 0xffff) {  // every ~65k polls make sure the stream has not died
       cudaError_t e = cudaStreamQuery(h->st);
@@ -402,7 +406,10 @@ int mailbox_wait(loam_handle* h) {
         return LOAM_ECUDA;
       }
       if (e == cudaSuccess && *flag != h->mail_seq) {  // stream drained but no flag: should not happen
-        if (*flag == h->mail_seq) return LOAM_OK;
+        if (*flag == h->mail_seq) {
+          std::atomic_thread_fence(std::memory_order_acquire);
+          return LOAM_OK;
+        }
         lg_set_error("mailbox sequence never arrived", __FILE__, __LINE__);
         return LOAM_ECUDA;
       }
@@ -515,6 +522,7 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
     delete h;
     return LOAM_ECUDA;
   }
+  memset(h->h_mail, 0, 64 * sizeof(double));  // the sequence word must not start at a recycled page's stale value
   // reserve the steady-state working set up front (HBM is plentiful; reallocation stalls are not)
   {
     const size_t mp = (size_t)std::max(prm.max_points, 1024), mm = (size_t)std::max(prm.max_map_points, 1024);
@@ -589,10 +597,10 @@ int loam_stats(const loam_handle* h, long long out4[4]) {
   out4[3] = h->syncs;
   return LOAM_OK;
 }
-int loam_host_times(loam_handle* h, double* out9, int clear) {
-  if (!h || !out9) return LOAM_EINVAL;
-  for (int i = 0; i < 16; i++) {
-    out9[i] = h->host_s[i];
+int loam_host_times(loam_handle* h, double* out16, int clear) {
+  if (!h || !out16) return LOAM_EINVAL;
+  for (int i = 0; i < LOAM_HOST_SECTIONS; i++) {
+    out16[i] = h->host_s[i];
     if (clear) h->host_s[i] = 0.0;
   }
   return LOAM_OK;
@@ -1568,6 +1576,7 @@ struct Job {
   int n, stride;
   int odom_published, full;
   float Tsum[6];
+  long long epoch;    // number of loam_pipeline_reset calls before this job: an error only poisons its own epoch
 };
 constexpr int PNS = 4;  // slots per ring
 
@@ -1595,17 +1604,30 @@ struct loam_pipeline {
   std::condition_variable rcv;
   std::map<long long, loam_sweep_result> partial, done;
   long long next_submit = 0, next_wait = 0, in_count = 0, feat_count = 0, map_count = 0;
+  // first error of the current epoch (an epoch ends at loam_pipeline_reset): sweeps of that epoch are skipped and
+  // loam_pipeline_wait reports the code for them; sweeps submitted after the reset run normally again
   std::atomic<int> error{0};
+  std::atomic<long long> error_epoch{-1};
+  long long epoch = 0;
+  std::map<long long, long long> epoch_of;  // sweep -> epoch (for loam_pipeline_wait)
+  char err_text[512] = "";
   std::thread tA, tB, tC;
 };
 
 namespace {
 
-void pipe_fail(loam_pipeline* p, int rc) {
-  int expected = 0;
-  p->error.compare_exchange_strong(expected, rc);
+void pipe_fail(loam_pipeline* p, int rc, long long epoch) {
+  {
+    std::lock_guard<std::mutex> l(p->rm);
+    if (p->error_epoch.load() != epoch) {  // first error of this epoch (a stale one from an earlier epoch is replaced)
+      snprintf(p->err_text, sizeof(p->err_text), "%s", g_cuda_err);  // the stage thread's text, visible to the caller
+      p->error.store(rc);
+      p->error_epoch.store(epoch);
+    }
+  }
   p->rcv.notify_all();
 }
+int pipe_error(loam_pipeline* p, long long epoch) { return p->error_epoch.load() == epoch ? p->error.load() : 0; }
 
 void stage_a(loam_pipeline* p) {
   cudaSetDevice(p->device);
@@ -1618,7 +1640,8 @@ void stage_a(loam_pipeline* p) {
       continue;
     }
     loam_counts c = {0, 0, 0, 0, 0};
-    int rc = p->error.load();
+    int rc = pipe_error(p, j.epoch);
+    const bool skip_a = rc != 0;
     if (!rc) {
       if (j.slot >= 0) cudaStreamWaitEvent(h->st, p->in_copied[j.slot], 0);
       g_lg_prof = h->prof.on ? &h->prof : nullptr;
@@ -1639,7 +1662,7 @@ void stage_a(loam_pipeline* p) {
       }
       cudaEventRecord(f.ready, h->st);
     }
-    if (rc) pipe_fail(p, rc);
+    if (rc && !skip_a) pipe_fail(p, rc, j.epoch);
     {
       std::lock_guard<std::mutex> l(p->rm);
       p->partial[j.k].counts = c;
@@ -1663,7 +1686,8 @@ void stage_b(loam_pipeline* p) {
     loam_pipeline::Feat& f = p->feat[j.slot];
     loam_odom_result o;
     memset(&o, 0, sizeof(o));
-    int rc = p->error.load();
+    int rc = pipe_error(p, j.epoch);
+    const bool skip_b = rc != 0;
     int ms = -1;
     if (!rc) {
       cudaStreamWaitEvent(h->st, f.ready, 0);
@@ -1695,7 +1719,7 @@ void stage_b(loam_pipeline* p) {
         cudaEventRecord(m.ready, h->st);
       }
     }
-    if (rc) pipe_fail(p, rc);
+    if (rc && !skip_b) pipe_fail(p, rc, j.epoch);
     {
       std::lock_guard<std::mutex> l(p->rm);
       p->partial[j.k].odom = o;
@@ -1717,7 +1741,8 @@ void stage_c(loam_pipeline* p) {
     if (j.kind != JOB_SWEEP) continue;
     loam_map_result mr;
     memset(&mr, 0, sizeof(mr));
-    int rc = p->error.load();
+    int rc = pipe_error(p, j.epoch);
+    const bool skip_c = rc != 0;
     int ran = 0;
     if (!rc && j.odom_published) rc = loam_mapping_odometry(h, j.Tsum);
     if (j.full) {
@@ -1737,7 +1762,7 @@ void stage_c(loam_pipeline* p) {
       }
       p->map_free.release();
     }
-    if (rc) pipe_fail(p, rc);
+    if (rc && !skip_c) pipe_fail(p, rc, j.epoch);
     {
       std::lock_guard<std::mutex> l(p->rm);
       loam_sweep_result r = p->partial[j.k];
@@ -1816,13 +1841,30 @@ int loam_pipeline_reset(loam_pipeline* p) {
   Job j;
   memset(&j, 0, sizeof(j));
   j.kind = JOB_RESET;
+  {
+    std::lock_guard<std::mutex> l(p->rm);
+    p->epoch++;  // an error of the epoch that ends here no longer blocks submit / stages
+  }
   p->qA.push(j);
   return LOAM_OK;
 }
+const char* loam_pipeline_last_error(loam_pipeline* p) {
+  static thread_local char buf[512];
+  if (!p) return "";
+  std::lock_guard<std::mutex> l(p->rm);
+  memcpy(buf, p->err_text, sizeof(buf));
+  return buf;
+}
 
 static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride_bytes, bool host) {
-  if (!p || n < 0 || (!xyz && n > 0) || stride_bytes < 12 || (stride_bytes & 3)) return LOAM_EINVAL;
-  if (int e = p->error.load()) return e;
+  // any point_step >= 12 and any alignment is accepted, like loam_extract: extract_common repacks unaligned layouts
+  if (!p || n < 0 || (!xyz && n > 0) || stride_bytes < 12) return LOAM_EINVAL;
+  long long epoch;
+  {
+    std::lock_guard<std::mutex> l(p->rm);
+    epoch = p->epoch;
+  }
+  if (int e = pipe_error(p, epoch)) return e;
   LG_CHECK(cudaSetDevice(p->device));
   Job j;
   memset(&j, 0, sizeof(j));
@@ -1831,13 +1873,24 @@ static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride
   j.stride = stride_bytes;
   j.slot = -1;
   j.xyz = xyz;
+  j.epoch = epoch;
   if (host) {
     p->in_free.acquire();
-    const int s = (int)(p->in_count++ % PNS);
-    LG_CHECK(p->in_xyz[s].ensure((size_t)n * stride_bytes + 64, p->copy_st));
-    if (n) LG_CHECK(cudaMemcpyAsync(p->in_xyz[s].p, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, p->copy_st));
-    LG_CHECK(cudaEventRecord(p->in_copied[s], p->copy_st));
-    LG_CHECK(cudaEventSynchronize(p->in_copied[s]));  // the caller may reuse its buffer as soon as we return
+    const int s = (int)(p->in_count % PNS);  // the slot is only taken once the copy has succeeded
+    cudaError_t e = p->in_xyz[s].ensure((size_t)n * stride_bytes + 64, p->copy_st);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(p->in_xyz[s].p, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, p->copy_st);
+    if (e == cudaSuccess) e = cudaEventRecord(p->in_copied[s], p->copy_st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(p->in_copied[s]);  // the caller may reuse its buffer as soon as we return
+    if (e != cudaSuccess) {
+      lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      {
+        std::lock_guard<std::mutex> l(p->rm);
+        snprintf(p->err_text, sizeof(p->err_text), "%s", g_cuda_err);
+      }
+      p->in_free.release();
+      return LOAM_ECUDA;
+    }
+    p->in_count++;
     p->hA->h2d_bytes += (long long)n * stride_bytes;
     j.slot = s;
     j.xyz = p->in_xyz[s].as<float>();
@@ -1846,6 +1899,7 @@ static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride
     std::lock_guard<std::mutex> l(p->rm);
     j.k = p->next_submit++;
     memset(&p->partial[j.k], 0, sizeof(loam_sweep_result));
+    p->epoch_of[j.k] = epoch;
   }
   p->qA.push(j);
   return LOAM_OK;
@@ -1866,7 +1920,9 @@ int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out) {
   *out = p->done[k];
   p->done.erase(k);
   p->next_wait++;
-  return p->error.load();
+  const long long ep = p->epoch_of[k];
+  p->epoch_of.erase(k);
+  return p->error_epoch.load() == ep ? p->error.load() : LOAM_OK;  // an error is reported for the sweeps of its epoch only
 }
 
 void* loam_pipeline_stream(loam_pipeline* p, int which) {

@@ -126,10 +126,13 @@ int loam_stats(const loam_handle* h, long long out4[4]);
  * 6 gather, 7 grid build, 8 map_knn, 9 map_fit, 10 insert, 11 sr_select (not counted in 0).  loam_profile(h, 1) clears
  * the counters. */
 #define LOAM_PROFILE_CLASSES 12
-/* Host wall-clock seconds per section of the node-level calls (incl. waits on the GPU): 0 extract, 1 odometry
- * iterations, 2 odometry end, 3 mapping prepare (stack, gather, voxel), 4 grid build, 5 mapping iterations, 6 insert,
- * 7 cube voxel grids, 8 rest.  Diagnostics only. */
-int loam_host_times(loam_handle* h, double* out9, int clear);
+/* Host wall-clock seconds per section of the node-level calls (incl. waits on the GPU); out16 receives
+ * LOAM_HOST_SECTIONS = 16 doubles: 0 extract, 1 odometry iterations, 2 odometry end, 3 mapping prepare (stack transform),
+ * 4 grid build, 5 mapping iterations, 6 insert, 7 cube voxel grids, 8 rest, and the finer split of the mapping run:
+ * 9 cube bookkeeping / grid roll, 10 gather of the local map, 11 stack voxel grid, 12 arena reserve, 13 cube tables +
+ * uploads, 14 cube merge launches, 15 cube merge wait.  Diagnostics only. */
+#define LOAM_HOST_SECTIONS 16
+int loam_host_times(loam_handle* h, double* out16, int clear);
 int loam_profile(loam_handle* h, int enable);
 int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n);
 
@@ -222,7 +225,11 @@ int loam_map_iter_allreduce(loam_handle* h, int iter, const float T[6], float At
 typedef struct loam_pipeline loam_pipeline;
 int loam_pipeline_create(const loam_params* p, int device, loam_pipeline** out);
 int loam_pipeline_destroy(loam_pipeline* p);
-int loam_pipeline_reset(loam_pipeline* p); /* IMControl{false}, ordered with the submitted sweeps */
+/* IMControl{false}, ordered with the submitted sweeps.  Also ends the current error epoch: a failed sweep makes the
+ * remaining sweeps of ITS epoch return that error from loam_pipeline_wait; sweeps submitted after the reset run again. */
+int loam_pipeline_reset(loam_pipeline* p);
+/* text of the last CUDA error raised inside the pipeline (stage threads or submit); "" if none */
+const char* loam_pipeline_last_error(loam_pipeline* p);
 int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double stamp);
 /* device-resident sweep: the buffer must stay valid until the sweep's result has been returned */
 int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp);
