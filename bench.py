@@ -407,11 +407,12 @@ def main():
         out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": f"first {n} sweeps of the same sequence, three stage threads (SR | LO | LM), {os.cpu_count()} host cores present"}
         # trajectory parity (SURVEY 8d cfg 2): the CUDA path's poses over the same sweeps against the CPU arm's, bit for bit
-        gpu.reset()
+        # (a fresh handle: the publish cadence LO:1099-1106 depends on frameCount, which survives a reset -- the CPU arm starts fresh too)
+        g2 = LoamGpu(device=local_rank, want_registered=True, want_surround=True)
         worst_o = worst_m = 0.0
         n_map = 0
         for k in range(n):
-            r = gpu.process_sweep(arr[offs[k]:offs[k + 1]])
+            r = g2.process_sweep(arr[offs[k]:offs[k + 1]])
             if kind == "reference":
                 co, cm = cpu_res[k]
             else:
@@ -421,6 +422,7 @@ def main():
             if cm is not None:
                 n_map += 1
                 worst_m = max(worst_m, float(np.abs(np.array(r.map.transform_aft_mapped, np.float32) - np.asarray(cm, np.float32)).max()))
+        g2.close()
         out["parity"] = {"sweeps": n, "mapping_runs": n_map, "against": kind, "max_abs_pose_diff_odometry": worst_o,
                          "max_abs_pose_diff_mapping": worst_m}
     if rank == 0:

@@ -326,9 +326,50 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
 }
 
 int read_sr_counts(loam_handle* h, loam_counts* out) {
-  LG_D2H(h, h->h_ints, h->sr.meta.p, 9 * 4);
+  LG_D2H(h, h->h_ints, h->sr.meta.p, SRM_HEAD * 4);
   LG_SYNC(h);
-  if (h->h_ints[SRM_EMPTY_RING]) return LOAM_EUNSUPPORTED;
+  if (h->h_ints[SRM_VIRTUAL]) {
+    // A ring whose scanStartInd was never written (empty rings: true VLP-16 angles leave rings 6 / 8 / 10 of the
+    // reference's table empty): it spans [0, scanEndInd) and is replayed after the rings before it, serially (SR:480-490).
+    const int R = h->prm.n_scans, n = h->h_ints[SRM_N_FULL];
+    LG_D2H(h, h->h_ints, h->sr.meta.p, SRM_SIZE * 4);
+    LG_SYNC(h);
+    std::vector<int> vr, vE;
+    size_t stage = 0;
+    for (int r = 1; r < R; r++) {
+      const int S = h->h_ints[SRM_SCAN_START + r], E = (r == R - 1) ? n - 5 : h->h_ints[SRM_SCAN_END + r];
+      if (S == 0 && E > 0) {
+        vr.push_back(r);
+        vE.push_back(E);
+        stage += (size_t)E;
+      }
+    }
+    int rc = lg_extract_virtual_launch(h->sr, h->srp, n, stage, h->st, &h->launches);
+    if (rc) return rc;
+    LG_D2H(h, h->h_ints, h->sr.lf_meta.p, (size_t)2 * R * 4);
+    LG_SYNC(h);
+    std::vector<VoxSegD> segs(vr.size());
+    std::vector<int> offs(vr.size());
+    for (size_t i = 0; i < vr.size(); i++) {
+      offs[i] = h->h_ints[2 * vr[i]];
+      segs[i] = VoxSegD{h->sr.lf_stage.as<float4>() + offs[i], nullptr, h->sr.lf_vout.as<float4>() + offs[i], nullptr, h->h_ints[2 * vr[i] + 1], 0.2f};
+    }
+    std::vector<int> cnt;
+    rc = voxel_segments(h, segs, cnt);  // SR:677-683, one VoxelGrid per ring
+    if (rc) return rc;
+    for (size_t i = 0; i < vr.size(); i++) {  // patch the ring's voxel job: concat reads segs[r].out and meta[SRM_LF_CNT + r]
+      VoxSegD sg = segs[i];
+      sg.out_count = h->sr.meta.as<int>() + SRM_LF_CNT + vr[i];
+      h->h2d_bytes += sizeof(VoxSegD) + 4;
+      LG_CHECK(cudaMemcpyAsync(h->sr.segs.as<VoxSegD>() + vr[i], &sg, sizeof(VoxSegD), cudaMemcpyHostToDevice, h->st));
+      LG_CHECK(cudaMemcpyAsync(h->sr.meta.as<int>() + SRM_LF_CNT + vr[i], &cnt[i], 4, cudaMemcpyHostToDevice, h->st));
+    }
+    LG_CHECK(cudaStreamSynchronize(h->st));  // sg / cnt are stack and vector storage
+    rc = lg_extract_finish_launch(h->sr, h->srp, h->st, &h->launches);
+    if (rc) return rc;
+    LG_D2H(h, h->h_ints, h->sr.meta.p, SRM_HEAD * 4);
+    LG_SYNC(h);
+  }
   if (h->h_ints[SRM_ERR]) return LOAM_ENOSPC;
   if (h->h_ints[SRM_VOX_OVERFLOW]) return LOAM_ENOSPC;
   h->counts.n_full = h->h_ints[SRM_N_FULL];
@@ -473,7 +514,7 @@ const char* loam_strerror(int code) {
     case LOAM_ECUDA: return "CUDA error";
     case LOAM_ENOSPC: return "buffer or capacity too small";
     case LOAM_ESTATE: return "call order violated";
-    case LOAM_EUNSUPPORTED: return "unsupported input: a ring of the sweep is empty";
+    case LOAM_EUNSUPPORTED: return "unsupported input";
   }
   return "unknown error";
 }

@@ -167,10 +167,11 @@ __global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned in
     meta[SRM_N_FULL] = tot;
     meta[SRM_VOX_OVERFLOW] = 0;
     meta[SRM_ERR] = 0;
+    meta[SRM_VIRTUAL] = 0;
     int empty = 0;
     for (int r = 0; r < prm.n_scans; r++)
       if (hist[r * nblocks] == ((r + 1 < prm.n_scans) ? hist[(r + 1) * nblocks] : (unsigned int)tot)) empty = 1;
-    meta[SRM_EMPTY_RING] = (tot >= 11) ? empty : 0;  // below 11 points the reference selects nothing at all (SR:454 loop is empty)
+    meta[SRM_EMPTY_RING] = empty;
   }
 }
 
@@ -335,7 +336,8 @@ constexpr int SEL_NT = 512;
 __global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                             const float* __restrict__ curv, const unsigned char* __restrict__ cond,
                                                             unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
-                                                            signed char* __restrict__ label, int* __restrict__ picks) {
+                                                            signed char* __restrict__ label, int* __restrict__ picks,
+                                                            int* __restrict__ sort_ind, unsigned char* __restrict__ stale) {
   extern __shared__ unsigned long long skeys[];  // [6][P]
   __shared__ unsigned char s_cond[RING_CAP];
   __shared__ unsigned char s_reach[RING_CAP];
@@ -348,10 +350,36 @@ __global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const f
   const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];  // SR:490
   int* my_picks = picks + r * SR_PICKS_PER_RING;
   int* cnt = meta + SRM_PICK_CNT + r * 3;
+  // SR:480-490 with empty rings: scanStartInd[r] is only written when the loop SEES ring r begin, scanEndInd[r] only when it
+  // sees ring r+1 begin.  A ring whose start was never written keeps 0 and -- if its end was -- spans [0, E): a VIRTUAL
+  // ring that overlaps every earlier ring (true VLP-16 angles: rings 6, 8, 10 of the reference's table).  Those depend on
+  // the picks of the rings before them and are replayed in ring order by sr_virtual_kernel afterwards; here every CTA
+  // only leaves the state that kernel needs (pick flags, sort order) in global memory when the sweep has one.
+  int vflag = 0;
+  if (tid > 0 && tid < R) {
+    const int e_t = (tid == R - 1) ? n - 5 : meta[SRM_SCAN_END + tid];
+    vflag = meta[SRM_SCAN_START + tid] == 0 && e_t > 0;
+  }
+  const bool any_virtual = __syncthreads_or(vflag) != 0;
+  const bool is_virtual = r > 0 && S == 0 && E > 0;
+  if (any_virtual) {  // this ring's own points: state as SR:454-549 leaves it
+    const int p0 = meta[SRM_RING_START + r], p1 = meta[SRM_RING_START + r + 1];
+    for (int i = p0 + tid; i < p1; i += SEL_NT) {
+      const unsigned char m = mask_at(cond, i, n);
+      picked[i] = m;
+      mask_diag[i] = m;
+      sort_ind[i] = i;
+    }
+    if (r == 0 && tid == 0) atomicExch(&meta[SRM_VIRTUAL], 1);
+  }
   // this ring's points: [S - 5, E + 5)
   const int a = max(S - 5, 0), b = min(E + 5, n);
   const int len = b - a;
-  if (len > RING_CAP || meta[SRM_EMPTY_RING]) {
+  if (is_virtual || len <= 0) {  // virtual: replayed later; empty range (end never written): the reference's loops do not run
+    if (tid == 0) cnt[0] = cnt[1] = cnt[2] = 0;
+    return;
+  }
+  if (len > RING_CAP) {
     if (tid == 0) {
       cnt[0] = cnt[1] = cnt[2] = 0;
       atomicExch(&meta[SRM_ERR], 1);
@@ -512,6 +540,14 @@ __global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const f
   }
   __syncthreads();
   for (int li = tid; li < len; li += SEL_NT) label[a + li] = s_label[li];
+  if (any_virtual) {  // what a later, overlapping ring of the reference would find: pick flags and the sorted index order
+    for (int li = tid; li < len; li += SEL_NT) picked[a + li] = s_picked[li];
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      for (int t = tid; t < m6[j]; t += SEL_NT) sort_ind[sp6[j] + t] = (int)(unsigned int)(skeys[j * P + t] & 0xffffffffull);
+  }
+  // cloudNeighborPicked[0..4] is never re-initialised by the reference (SR:454 starts at 5): marks persist between sweeps
+  if (a + tid < 5 && tid < len && s_picked[tid]) stale[a + tid] = 1;
   if (tid == 0) {
     cnt[0] = nsharp;
     cnt[1] = nless;
@@ -520,11 +556,234 @@ __global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const f
   }
 }
 
+// Suppression reach with whole-cloud bounds (FENCE (iv) as in oracle/orc_sr.h suppress_neighbours).
+__device__ __forceinline__ unsigned char suppress_reach_g(const unsigned char* __restrict__ cond, int i, int n) {
+  int nf = 0;
+  for (int l = 1; l <= 5; l++) {
+    if (i + l >= n) break;
+    if (cond[i + l] & C_GAP) break;
+    nf = l;
+  }
+  int nb = 0;
+  for (int l = 1; l <= 5; l++) {
+    if (i - l < 0) break;
+    if (cond[i - l + 1] & C_GAP) break;
+    nb = l;
+  }
+  return (unsigned char)(nf | (nb << 4));
+}
+
+constexpr int VIRT_NT = 1024;
+constexpr int VIRT_SMEM_KEYS = 16384;  // sectors up to this many points sort in shared memory, longer ones in global scratch
+constexpr int VIRT_MAX_KEYS = 32768;
+
+// SR:559-684 for the VIRTUAL rings of a sweep (see sr_select_kernel), replayed with the reference's serial semantics: one
+// CTA walks them in ring order on the global state the per-ring CTAs left behind -- cloudSortInd (its current permutation
+// decides ties of the stable sort, SR:568-576), cloudNeighborPicked, cloudLabel -- including the five leading entries
+// the reference never re-initialises (static arrays SR:68-74: curvature 0, sort index 0, pick flag / label from earlier
+// sweeps; `stale`).  Per ring it leaves the picks and the less-flat candidates (label <= 0 at that moment, SR:670-674),
+// compacted in index order, for the per-ring voxel grid.
+__global__ void __launch_bounds__(VIRT_NT) sr_virtual_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                              const float* __restrict__ curv, const unsigned char* __restrict__ cond,
+                                                              unsigned char* picked_g, signed char* label, int* sort_ind,
+                                                              unsigned char* __restrict__ reach, unsigned char* stale, int* __restrict__ picks,
+                                                              float4* __restrict__ lf_stage, int* __restrict__ lf_meta,
+                                                              unsigned long long* gkeys) {
+  extern __shared__ unsigned long long vkeys[];
+  __shared__ int s_scan[VIRT_NT / 32 + 2];
+  volatile unsigned char* picked = picked_g;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = meta[SRM_N_FULL];
+  const int R = prm.n_scans;
+  for (int i = tid; i < n; i += VIRT_NT) reach[i] = suppress_reach_g(cond, i, n);
+  if (tid < 5 && tid < n) {
+    if (stale[tid]) picked[tid] = 1;
+    label[tid] = (signed char)stale[8 + tid];
+    sort_ind[tid] = 0;
+  }
+  __syncthreads();
+  int lf_off = 0;
+  for (int r = 1; r < R; r++) {
+    const int S = meta[SRM_SCAN_START + r];
+    const int E = (r == R - 1) ? n - 5 : meta[SRM_SCAN_END + r];
+    if (tid == 0) lf_meta[2 * r] = lf_meta[2 * r + 1] = 0;
+    if (!(S == 0 && E > 0)) continue;
+    int* my_picks = picks + r * SR_PICKS_PER_RING;
+    int nsharp = 0, nless = 0, nflat = 0;
+    for (int j = 0; j < 6; j++) {
+      const int sp = (int)(((long long)E * j) / 6);
+      const int ep = (int)(((long long)E * (j + 1)) / 6) - 1;
+      const int m = ep - sp + 1;
+      if (m <= 0) continue;
+      if (m > VIRT_MAX_KEYS) {
+        if (tid == 0) atomicExch(&meta[SRM_ERR], 1);
+        continue;
+      }
+      int P = 2;
+      while (P < m) P <<= 1;
+      unsigned long long* sk = P <= VIRT_SMEM_KEYS ? vkeys : gkeys;
+      for (int t = tid; t < P; t += VIRT_NT)
+        sk[t] = t < m ? (((unsigned long long)__float_as_uint(curv[sort_ind[sp + t]]) << 32) | (unsigned int)t) : ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          for (int t = tid; t < (P >> 1); t += VIRT_NT) {
+            const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+            const int l = i | jj;
+            const unsigned long long x = sk[i], y = sk[l];
+            const bool asc = (i & k) == 0;
+            if ((x > y) == asc) {
+              sk[i] = y;
+              sk[l] = x;
+            }
+          }
+          __syncthreads();
+        }
+      {  // position in the previous order -> point index; the sorted order becomes the new cloudSortInd
+        int tmp[VIRT_MAX_KEYS / VIRT_NT];
+        int q = 0;
+        for (int t = tid; t < m; t += VIRT_NT, q++) tmp[q] = sort_ind[sp + (int)(unsigned int)(sk[t] & 0xffffffffull)];
+        __syncthreads();
+        q = 0;
+        for (int t = tid; t < m; t += VIRT_NT, q++) {
+          sort_ind[sp + t] = tmp[q];
+          sk[t] = (sk[t] & 0xffffffff00000000ull) | (unsigned int)tmp[q];
+        }
+        __syncthreads();
+      }
+      if (tid < 32) {
+        // ---- SR:578-624: walk down from the largest curvature
+        int count = 0;
+        bool done = false;
+        for (int k = m - 1; k >= 0 && !done; k -= 32) {
+          const int kk = k - lane;
+          const bool have = kk >= 0;
+          const unsigned long long key = have ? sk[kk] : 0ull;
+          const float cv = __uint_as_float((unsigned int)(key >> 32));
+          const int li = (int)(unsigned int)(key & 0xffffffffull);
+          const bool pass = have && (cv > 0.1);
+          const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+          int nf = 0, nb = 0;
+          if (pass) {
+            const unsigned char rr = reach[li];
+            nf = rr & 15;
+            nb = rr >> 4;
+          }
+          const int lo = li - nb, hi = li + nf;
+          const bool alive = pass && picked[li] == 0;
+          unsigned int am = __ballot_sync(0xffffffffu, alive);
+          int mynum = 0;
+          while (am) {
+            const int p = __ffs(am) - 1;
+            am &= ~(1u << p);
+            count++;
+            if (count > 20) {  // SR:592-594: the 21st candidate only ends the walk
+              done = true;
+              break;
+            }
+            if (lane == p) mynum = count;
+            const int plo = __shfl_sync(0xffffffffu, lo, p), phi = __shfl_sync(0xffffffffu, hi, p);
+            am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
+          }
+          if (mynum > 0) {
+            if (mynum <= 16) {
+              label[li] = 2;
+              my_picks[SR_PICK_SHARP + nsharp + mynum - 1] = li;
+            } else {
+              label[li] = 1;
+            }
+            my_picks[SR_PICK_LESS + nless + mynum - 1] = li;
+            for (int l = -nb; l <= nf; l++) picked[li + l] = 1;
+          }
+          __syncwarp();
+          if (pm != 0xffffffffu) done = true;  // sorted: nothing below the first c <= 0.1 can pass
+        }
+        const int npick = min(count, 20);
+        nsharp += min(npick, 16);
+        nless += npick;
+        // ---- SR:626-668: walk up from the smallest curvature
+        count = 0;
+        done = false;
+        for (int k = 0; k < m && !done; k += 32) {
+          const int kk = k + lane;
+          const bool have = kk < m;
+          const unsigned long long key = have ? sk[kk] : 0ull;
+          const float cv = __uint_as_float((unsigned int)(key >> 32));
+          const int li = (int)(unsigned int)(key & 0xffffffffull);
+          const bool pass = have && (cv < 0.1);
+          const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+          int nf = 0, nb = 0;
+          if (pass) {
+            const unsigned char rr = reach[li];
+            nf = rr & 15;
+            nb = rr >> 4;
+          }
+          const int lo = li - nb, hi = li + nf;
+          const bool alive = pass && picked[li] == 0;
+          unsigned int am = __ballot_sync(0xffffffffu, alive);
+          int mynum = 0;
+          bool last32 = false;
+          while (am) {
+            const int p = __ffs(am) - 1;
+            am &= ~(1u << p);
+            count++;
+            if (lane == p) mynum = count;
+            if (count >= 32) {  // SR:635-638: the 32nd flat point is kept but neither marked nor suppressing
+              if (lane == p) last32 = true;
+              done = true;
+              break;
+            }
+            const int plo = __shfl_sync(0xffffffffu, lo, p), phi = __shfl_sync(0xffffffffu, hi, p);
+            am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= plo && li <= phi);
+          }
+          if (mynum > 0) {
+            label[li] = -1;
+            my_picks[SR_PICK_FLAT + nflat + mynum - 1] = li;
+            if (!last32)
+              for (int l = -nb; l <= nf; l++) picked[li + l] = 1;
+          }
+          __syncwarp();
+          if (pm != 0xffffffffu) done = true;
+        }
+        nflat += count;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int* cnt = meta + SRM_PICK_CNT + r * 3;
+      cnt[0] = nsharp;
+      cnt[1] = nless;
+      cnt[2] = nflat;
+    }
+    // SR:670-674 less-flat candidates of this ring: every k in [0, E) whose label is <= 0 NOW, in index order
+    int base = lf_off;
+    for (int k0 = 0; k0 < E; k0 += VIRT_NT) {
+      const int k = k0 + tid;
+      const int flag = (k < E && label[k] <= 0) ? 1 : 0;
+      int tot;
+      const int ex = block_excl_scan<VIRT_NT>(flag, &tot, s_scan);
+      if (flag) lf_stage[base + ex] = c[k];
+      base += tot;
+    }
+    if (tid == 0) {
+      lf_meta[2 * r] = lf_off;
+      lf_meta[2 * r + 1] = base - lf_off;
+    }
+    lf_off = base;
+    __syncthreads();
+  }
+  if (tid < 5 && tid < n) {
+    stale[tid] = picked[tid];
+    stale[8 + tid] = (unsigned char)label[tid];
+  }
+}
+
 // Compacts picks to feature clouds, derives the less-flat mask (SR:670-674) and the per-ring voxel jobs (SR:677-683).
 __global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                           const signed char* __restrict__ label, const int* __restrict__ picks,
                                                           float4* __restrict__ sharp, float4* __restrict__ less_sharp, float4* __restrict__ flat,
-                                                          unsigned char* __restrict__ lf_valid, float4* __restrict__ lf_tmp, VoxSegD* __restrict__ segs) {
+                                                          unsigned char* __restrict__ lf_valid, float4* __restrict__ lf_tmp, VoxSegD* __restrict__ segs,
+                                                          int features_only) {
   const int r = blockIdx.x, tid = threadIdx.x;
   const int n = meta[SRM_N_FULL];
   const int R = prm.n_scans;
@@ -542,7 +801,16 @@ __global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const flo
   for (int i = tid; i < cnt[0]; i += blockDim.x) sharp[off[0] + i] = c[my[SR_PICK_SHARP + i]];
   for (int i = tid; i < cnt[1]; i += blockDim.x) less_sharp[off[1] + i] = c[my[SR_PICK_LESS + i]];
   for (int i = tid; i < cnt[2]; i += blockDim.x) flat[off[2] + i] = c[my[SR_PICK_FLAT + i]];
-  const int a = max(S - 5, 0), b = min(E + 5, n);
+  if (features_only) {  // second pass after sr_virtual_kernel: the voxel jobs of the first pass stand
+    if (tid == 0 && r == 0) {
+      meta[SRM_N_SHARP] = tot[0];
+      meta[SRM_N_LESS_SHARP] = tot[1];
+      meta[SRM_N_FLAT] = tot[2];
+    }
+    return;
+  }
+  const bool is_virtual = r > 0 && S == 0 && E > 0;  // handled by sr_virtual_kernel (empty job here)
+  const int a = is_virtual ? 0 : max(S - 5, 0), b = is_virtual ? 0 : min(E + 5, n);
   for (int i = a + tid; i < b; i += blockDim.x) lf_valid[i] = (i >= S && i < E && label[i] <= 0) ? 1 : 0;
   if (tid == 0) {
     VoxSegD sg;
@@ -605,6 +873,11 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
   LG_CHECK(ws.less_sharp.ensure((size_t)R * 120 * 16, st));
   LG_CHECK(ws.flat.ensure((size_t)R * 192 * 16, st));
   LG_CHECK(ws.segs.ensure((size_t)R * sizeof(VoxSegD), st));
+  LG_CHECK(ws.sort_ind.ensure((size_t)(n + 16) * 4, st));
+  if (!ws.stale.p) {
+    LG_CHECK(ws.stale.ensure(16, st));
+    LG_CHECK(cudaMemsetAsync(ws.stale.p, 0, 16, st));
+  }
   if (!ws.meta.p) {
     LG_CHECK(ws.meta.ensure(SRM_SIZE * 4, st));
     LG_CHECK(cudaMemsetAsync(ws.meta.p, 0, SRM_SIZE * 4, st));
@@ -639,17 +912,56 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
   }
   sr_select_kernel<<<R, SEL_NT, sel_smem, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
                                       ws.picked.as<unsigned char>(), ws.mask_diag.as<unsigned char>(), ws.label.as<signed char>(),
-                                      ws.picks.as<int>());
+                                      ws.picks.as<int>(), ws.sort_ind.as<int>(), ws.stale.as<unsigned char>());
   }
   LgProfScope prof_scope(LGK_EXTRACT, st, 0.0);
   sr_collect_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.label.as<signed char>(), ws.picks.as<int>(),
                                        ws.sharp.as<float4>(), ws.less_sharp.as<float4>(), ws.flat.as<float4>(),
-                                       ws.lf_valid.as<unsigned char>(), ws.lf_tmp.as<float4>(), ws.segs.as<VoxSegD>());
+                                       ws.lf_valid.as<unsigned char>(), ws.lf_tmp.as<float4>(), ws.segs.as<VoxSegD>(), 0);
   (*launches) += 6;
   int rc = lg_vox_small(ws.segs.as<VoxSegD>(), R, (n / R) * 2 + 64 <= 4096 ? 4096 : 16384, meta + SRM_VOX_OVERFLOW, st, launches);
   if (rc) return rc;
   sr_concat_kernel<<<R, 256, 0, st>>>(prm, meta, ws.segs.as<VoxSegD>(), ws.less_flat.as<float4>());
   (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_extract_virtual_launch(SrWs& ws, const SrParams& prm, int n, size_t stage_points, cudaStream_t st, long long* launches) {
+  const int R = prm.n_scans;
+  LG_CHECK(ws.reach.ensure((size_t)n + 16, st));
+  LG_CHECK(ws.lf_stage.ensure((stage_points + 16) * 16, st));
+  LG_CHECK(ws.lf_vout.ensure((stage_points + 16) * 16, st));
+  LG_CHECK(ws.lf_meta.ensure((size_t)2 * MAXR * 4, st));
+  LG_CHECK(ws.gkeys.ensure((size_t)VIRT_MAX_KEYS * 8, st));
+  LG_CHECK(ws.less_flat.ensure(((size_t)n + stage_points + 16) * 16, st));  // virtual rings contribute the rings before them AGAIN
+  static bool virt_attr[64] = {};
+  constexpr int virt_smem = VIRT_SMEM_KEYS * 8;
+  int dev = 0;
+  LG_CHECK(cudaGetDevice(&dev));
+  if (!virt_attr[dev & 63]) {
+    LG_CHECK(cudaFuncSetAttribute(sr_virtual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, virt_smem));
+    virt_attr[dev & 63] = true;
+  }
+  LgProfScope prof_scope(LGK_SR_SELECT, st, 0.0);
+  sr_virtual_kernel<<<1, VIRT_NT, virt_smem, st>>>(prm, ws.full.as<float4>(), ws.meta.as<int>(), ws.curv.as<float>(), ws.cond.as<unsigned char>(),
+                                                   ws.picked.as<unsigned char>(), ws.label.as<signed char>(), ws.sort_ind.as<int>(),
+                                                   ws.reach.as<unsigned char>(), ws.stale.as<unsigned char>(), ws.picks.as<int>(),
+                                                   ws.lf_stage.as<float4>(), ws.lf_meta.as<int>(), ws.gkeys.as<unsigned long long>());
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  (void)R;
+  return LOAM_OK;
+}
+
+int lg_extract_finish_launch(SrWs& ws, const SrParams& prm, cudaStream_t st, long long* launches) {
+  const int R = prm.n_scans;
+  LgProfScope prof_scope(LGK_EXTRACT, st, 0.0);
+  sr_collect_kernel<<<R, 256, 0, st>>>(prm, ws.full.as<float4>(), ws.meta.as<int>(), ws.label.as<signed char>(), ws.picks.as<int>(),
+                                       ws.sharp.as<float4>(), ws.less_sharp.as<float4>(), ws.flat.as<float4>(),
+                                       ws.lf_valid.as<unsigned char>(), ws.lf_tmp.as<float4>(), ws.segs.as<VoxSegD>(), 1);
+  sr_concat_kernel<<<R, 256, 0, st>>>(prm, ws.meta.as<int>(), ws.segs.as<VoxSegD>(), ws.less_flat.as<float4>());
+  (*launches) += 2;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;
 }

@@ -20,7 +20,10 @@ enum {
   SRM_N_LESS_FLAT = 5,
   SRM_VOX_OVERFLOW = 6,  // a ring exceeded the shared-memory voxel capacity
   SRM_ERR = 7,           // a sector exceeded the shared-memory sort capacity
-  SRM_EMPTY_RING = 8,    // some ring received no point: scanStartInd/EndInd overlap in the reference (SR:480-490)
+  SRM_EMPTY_RING = 8,    // some ring received no point (information only)
+  SRM_VIRTUAL = 9,       // some ring's scanStartInd was never written: it spans [0, scanEndInd) and overlaps the rings before
+                         // it (SR:480-490) -> the host runs lg_extract_virtual_* after the first pass
+  SRM_HEAD = 10,         // ints the host reads back after every sweep
   SRM_RING_START = 16,   // [n_scans + 1] first index of every ring in the ring-major cloud
   SRM_SCAN_START = 96,   // [n_scans] scanStartInd (SR:484,489)
   SRM_SCAN_END = 160,    // [n_scans] scanEndInd   (SR:485,490)
@@ -35,12 +38,22 @@ struct SrWs {
   DevBuf full, curv, cond, picked, mask_diag, label;
   DevBuf picks, sharp, less_sharp, flat;
   DevBuf lf_valid, lf_tmp, less_flat, segs;
+  DevBuf sort_ind, stale;                          // cloudSortInd; pick flags / labels of the five never re-initialised entries
+  DevBuf reach, lf_stage, lf_vout, lf_meta, gkeys;  // virtual-ring pass only
   void release() {
     DevBuf* all[] = {&ring8, &ori_raw, &hist, &meta, &full, &curv, &cond, &picked, &mask_diag, &label,
-                     &picks, &sharp, &less_sharp, &flat, &lf_valid, &lf_tmp, &less_flat, &segs};
+                     &picks, &sharp, &less_sharp, &flat, &lf_valid, &lf_tmp, &less_flat, &segs,
+                     &sort_ind, &stale, &reach, &lf_stage, &lf_vout, &lf_meta, &gkeys};
     for (DevBuf* b : all) b->release();
   }
 };
 
 // Enqueues the whole extraction of one sweep on `st`; results and counts (meta) stay on the device.
 int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches);
+// Sweeps with virtual rings (SRM_VIRTUAL set after the first pass).  lg_extract_virtual_launch replays those rings in the
+// reference's serial order; `stage_points` = sum of their scanEndInd (capacity of the less-flat staging).  It leaves
+// {offset, count} per ring in ws.lf_meta; the caller voxel-grids ws.lf_stage[offset .. +count) into ws.lf_vout + offset,
+// writes the output sizes to meta[SRM_LF_CNT + r] and segs[r].out, and calls lg_extract_finish_launch (feature clouds +
+// concatenation, again).
+int lg_extract_virtual_launch(SrWs& ws, const SrParams& prm, int n, size_t stage_points, cudaStream_t st, long long* launches);
+int lg_extract_finish_launch(SrWs& ws, const SrParams& prm, cudaStream_t st, long long* launches);

@@ -1,0 +1,720 @@
+// K7 / K10 — the scan-to-map Gauss-Newton loop of laserMapping.cpp (LM:749-1020) as ONE persistent kernel over a
+// cell-sorted (CSR) grid of the local map:
+//
+//   csr_*_kernel     LM:750-751  replaces KdTreeFLANN::setInputCloud.  The corner map and the surf map are bucketed into
+//                                1 m cells of a dense grid over their bounding boxes (x fastest, then y, then z): a
+//                                histogram, one exclusive scan over BOTH tables, a scatter.  Output: the points in cell
+//                                order (float4 {x, y, z, original index}) and, per cell, the END of its run.  The 27 cells
+//                                around a query are then nine contiguous x-runs, each found with two loads of the table
+//                                (E[row + cx] and E[row + cx + 3]) -- no hashing, no probing, no per-cell indirection, and
+//                                queries that are neighbours in space read neighbouring table entries and runs.
+//                                Index build traffic 36 T bytes (16 T read, 4 T cell ids, 16 T reordered write).
+//   map_gn_kernel    LM:753-1017 every iteration: pointAssociateToMap of the stack points (LM:756, 865), exact 5-NN
+//                                (LM:760, 867) with eight lanes per query scanning the nine runs together, line / plane
+//                                fit (LM:763-919) and Jacobian row (LM:940-964) one query per thread on the neighbours
+//                                staged in shared memory, the 21 + 6 + 1 sums (LM:965-967) warp -> CTA -> grid, then -- on
+//                                the device, by the last CTA to arrive -- the 6x6 solve, degeneracy projection, pose
+//                                update and convergence test (LM:968-1017), the six sin / cos of the new pose, and a grid
+//                                barrier into the next iteration.  The host sees one mailbox write per mapping run.
+//                                With the map sharded over several GPUs every rank keeps the whole stack,
+//                                evaluates the queries whose map-frame x falls into its slab (re-routed every iteration
+//                                with the same arithmetic), and the last CTA exchanges the 28 sums with its peers through
+//                                NVLink peer memory before the solve: reduction + collective + solve in one kernel.
+//
+// Exactness: neighbours are ordered by (d2 ascending, original index ascending), d2 = ((dx*dx)+(dy*dy))+(dz*dz) in fp32
+// without contraction; only neighbours with d2 < 1 m^2 can take part in an accepted correspondence (LM:762, 869), so the
+// 27-cell search is exact for everything the reference uses.  The fit, the rows and the solve are the operations of the
+// host code in the same order (lg_linalg.cuh, lg_libm.cuh); the sums are exact float products added in double in a fixed
+// order and rounded once.
+#include <cooperative_groups.h>
+
+#include "lg_linalg.cuh"
+#include "lg_map.h"
+#include "lg_reduce.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ CSR grid build
+struct CsrJob {
+  CsrGridD g[2];
+  const float4* pts[2];
+  int n[2];
+  unsigned int* tab;  // both tables, back to back: [guard, cells of grid 0 ..., guard, cells of grid 1 ...]
+  int off[2];         // first entry (the guard) of each grid's table inside `tab`
+  float4* sorted;     // both grids' points in cell order, grid 0 first
+};
+
+__device__ __forceinline__ int csr_axis(float v, float origin, int n) {
+  // cell coordinate clamped into the box: clamping is monotone and 1-Lipschitz, so two points less than 1 m apart along
+  // an axis still land in the same or in adjacent cells -- a point outside the box is found from outside the box
+  return (int)fminf(fmaxf(floorf(v) - origin, 0.f), (float)(n - 1));
+}
+__device__ __forceinline__ int csr_cell(const CsrGridD& g, float4 p) {
+  const int cx = csr_axis(p.x, g.x0, g.nx), cy = csr_axis(p.y, g.y0, g.ny), cz = csr_axis(p.z, g.z0, g.nz);
+  // entry 0 of a table is the guard in front, entry 1 + padded index belongs to the cell; a row is padded by one empty
+  // cell on either side, so the real cell cx has padded index row + cx + 1
+  return (cz * g.ny + cy) * g.nxp + cx + 2;
+}
+
+// min / max cell coordinates of a cloud (stage-level API only: the mapping node knows its cubes' box)
+__global__ void csr_bbox_kernel(const float4* __restrict__ p0, int n0, const float4* __restrict__ p1, int n1, int* __restrict__ bb /* [2][6] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = i >= n0;
+  const int k = w ? i - n0 : i;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  if (k < (w ? n1 : n0)) {
+    const float4 p = w ? p1[k] : p0[k];
+    const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int v = (int)fminf(fmaxf(floorf(c[a]), -1.0e6f), 1.0e6f);  // NaN -> lower bound, wild values clamped
+      lo[a] = hi[a] = v;
+    }
+  }
+  // a warp holds points of one cloud except at the seam; reduce per cloud with a match mask
+  const unsigned int m = __match_any_sync(0xffffffffu, w);
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    lo[a] = __reduce_min_sync(m, lo[a]);
+    hi[a] = __reduce_max_sync(m, hi[a]);
+  }
+  if ((threadIdx.x & 31) == __ffs(m) - 1 && lo[0] != INT_MAX) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      atomicMin(&bb[w * 6 + a], lo[a]);
+      atomicMax(&bb[w * 6 + 3 + a], hi[a]);
+    }
+  }
+}
+
+__global__ void csr_count_kernel(CsrJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const int i = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;
+  if (i >= J.n[w]) return;
+  atomicAdd(&J.tab[J.off[w] + csr_cell(J.g[w], J.pts[w][i])], 1u);
+}
+__global__ void csr_fill_kernel(CsrJob J, int split) {
+  const int w = (int)blockIdx.x >= split;
+  const int i = ((int)blockIdx.x - (w ? split : 0)) * blockDim.x + threadIdx.x;
+  if (i >= J.n[w]) return;
+  const float4 p = J.pts[w][i];
+  const unsigned int pos = atomicAdd(&J.tab[J.off[w] + csr_cell(J.g[w], p)], 1u);
+  J.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+// Exclusive scan of an unsigned array in place: tile sums, scan of the tile sums by one CTA, tile scan + offset.
+constexpr int SCAN_NT = 1024, SCAN_ITEMS = 8, SCAN_TILE = SCAN_NT * SCAN_ITEMS;
+__global__ void __launch_bounds__(SCAN_NT) scan_sums_kernel(const unsigned int* __restrict__ a, size_t len, unsigned int* __restrict__ sums) {
+  __shared__ int s_w[SCAN_NT / 32 + 2];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  unsigned int s = 0;
+  if (base + SCAN_ITEMS <= len) {
+    const uint4 u = *reinterpret_cast<const uint4*>(a + base), v = *reinterpret_cast<const uint4*>(a + base + 4);
+    s = u.x + u.y + u.z + u.w + v.x + v.y + v.z + v.w;
+  } else {
+    for (int k = 0; k < SCAN_ITEMS; k++)
+      if (base + k < len) s += a[base + k];
+  }
+  int tot;
+  block_excl_scan<SCAN_NT>((int)s, &tot, s_w);
+  if (threadIdx.x == 0) sums[blockIdx.x] = (unsigned int)tot;
+}
+__global__ void __launch_bounds__(SCAN_NT) scan_top_kernel(unsigned int* __restrict__ sums, int nb) {
+  __shared__ int s_w[SCAN_NT / 32 + 2];
+  unsigned int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += SCAN_NT) {
+    const int b = b0 + threadIdx.x;
+    const unsigned int v = b < nb ? sums[b] : 0u;
+    int tot;
+    const int ex = block_excl_scan<SCAN_NT>((int)v, &tot, s_w);
+    if (b < nb) sums[b] = carry + (unsigned int)ex;
+    carry += (unsigned int)tot;
+  }
+}
+__global__ void __launch_bounds__(SCAN_NT) scan_apply_kernel(unsigned int* __restrict__ a, size_t len, const unsigned int* __restrict__ sums) {
+  __shared__ int s_w[SCAN_NT / 32 + 2];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  unsigned int v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= len) {
+    const uint4 u = *reinterpret_cast<const uint4*>(a + base), w = *reinterpret_cast<const uint4*>(a + base + 4);
+    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = base + k < len ? a[base + k] : 0u;
+  }
+  unsigned int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+  int tot;
+  unsigned int run = sums[blockIdx.x] + (unsigned int)block_excl_scan<SCAN_NT>((int)s, &tot, s_w);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const unsigned int t = v[k];
+    v[k] = run;
+    run += t;
+  }
+  if (base + SCAN_ITEMS <= len) {
+    *reinterpret_cast<uint4*>(a + base) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(a + base + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+      if (base + k < len) a[base + k] = v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the iteration
+// LM:244-262 with the six sin/cos values of the pose (libm-exact: host sinf/cosf or their device ports).
+__device__ __forceinline__ float4 gn_assoc_to_map(const float* t, const float* sc, float4 pi) {
+  const float srx = sc[0], crx = sc[1], sry = sc[2], cry = sc[3], srz = sc[4], crz = sc[5];
+  float x1 = crz * pi.x - srz * pi.y;
+  float y1 = srz * pi.x + crz * pi.y;
+  float z1 = pi.z;
+  float x2 = x1;
+  float y2 = crx * y1 - srx * z1;
+  float z2 = srx * y1 + crx * z1;
+  float4 po;
+  po.x = cry * x2 + sry * z2 + t[3];
+  po.y = y2 + t[4];
+  po.z = -sry * x2 + cry * z2 + t[5];
+  po.w = pi.w;
+  return po;
+}
+
+__device__ __forceinline__ void gn_line_coeff(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2, float& la,
+                                              float& lb, float& lc, float& ld2) {
+  float cxy = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+  float cxz = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+  float cyz = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+  float a012 = sqrtf(cxy * cxy + cxz * cxz + cyz * cyz);
+  float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+  la = ((y1 - y2) * cxy + (z1 - z2) * cxz) / a012 / l12;
+  lb = -((x1 - x2) * cxy - (z1 - z2) * cyz) / a012 / l12;
+  lc = -((x1 - x2) * cxz + (y1 - y2) * cyz) / a012 / l12;
+  ld2 = a012 / l12;
+}
+
+// LM:763-964 for one stack point and its five neighbours: the row of A and b, or nothing.
+__device__ __forceinline__ bool gn_fit_row(const float* sc, bool is_c, float4 ori, float4 sel, const float* px, const float* py, const float* pz,
+                                           float* a, float* b) {
+  float4 coef;
+  bool keep = false;
+  if (is_c) {  // LM:763-861
+    float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      cx += px[j]; cy += py[j]; cz += pz[j];
+    }
+    cx /= 5; cy /= 5; cz /= 5;
+    float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      float ax = px[j] - cx, ay = py[j] - cy, az = pz[j] - cz;
+      a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+      a22 += ay * ay; a23 += ay * az; a33 += az * az;
+    }
+    a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+    float A1[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+    float D1[3], V1[9];
+    lg_jacobi_eigen<3>(A1, D1, V1);
+    if (D1[0] > 3 * D1[1]) {
+      float x1 = (float)(cx + 0.1 * V1[0]), y1 = (float)(cy + 0.1 * V1[1]), z1 = (float)(cz + 0.1 * V1[2]);
+      float x2 = (float)(cx - 0.1 * V1[0]), y2 = (float)(cy - 0.1 * V1[1]), z2 = (float)(cz - 0.1 * V1[2]);
+      float la, lb, lc, ld2;
+      gn_line_coeff(sel.x, sel.y, sel.z, x1, y1, z1, x2, y2, z2, la, lb, lc, ld2);
+      float s = (float)(1 - 0.9 * fabsf(ld2));
+      coef = make_float4(s * la, s * lb, s * lc, s * ld2);
+      keep = s > 0.1;
+    }
+  } else {  // LM:870-919
+    float A0[15], B0[5] = {-1, -1, -1, -1, -1}, X0[3];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      A0[j * 3 + 0] = px[j]; A0[j * 3 + 1] = py[j]; A0[j * 3 + 2] = pz[j];
+    }
+    lg_qr_solve<5, 3>(A0, B0, X0);
+    float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
+    float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+    bool planeValid = true;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+      if (fabsf(pa * px[j] + pb * py[j] + pc * pz[j] + pd) > 0.2) planeValid = false;
+    if (planeValid) {
+      float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+      float s = (float)(1 - 0.9 * fabsf(pd2) / sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
+      coef = make_float4(s * pa, s * pb, s * pc, s * pd2);
+      keep = s > 0.1;
+    }
+  }
+  if (!keep) return false;
+  // LM:940-964
+  const float srx = sc[0], crx = sc[1], sry = sc[2], cry = sc[3], srz = sc[4], crz = sc[5];
+  const float4 p = ori, c = coef;
+  a[0] = (crx * sry * srz * p.x + crx * crz * sry * p.y - srx * sry * p.z) * c.x + (-srx * srz * p.x - crz * srx * p.y - crx * p.z) * c.y +
+         (crx * cry * srz * p.x + crx * cry * crz * p.y - cry * srx * p.z) * c.z;
+  a[1] = ((cry * srx * srz - crz * sry) * p.x + (sry * srz + cry * crz * srx) * p.y + crx * cry * p.z) * c.x +
+         ((-cry * crz - srx * sry * srz) * p.x + (cry * srz - crz * srx * sry) * p.y - crx * sry * p.z) * c.z;
+  a[2] = ((crz * srx * sry - cry * srz) * p.x + (-cry * crz - srx * sry * srz) * p.y) * c.x + (crx * crz * p.x - crx * srz * p.y) * c.y +
+         ((sry * srz + cry * crz * srx) * p.x + (crz * sry - cry * srx * srz) * p.y) * c.z;
+  a[3] = c.x;
+  a[4] = c.y;
+  a[5] = c.z;
+  *b = -c.w;
+  return true;
+}
+
+constexpr int GN_NT = 256;           // threads per CTA
+constexpr int GN_TILE = 256;         // stack points per CTA step (one per thread in the fit phase)
+constexpr int GN_SUB = 8;            // lanes per query in the search phase
+constexpr int GN_GROUPS = GN_NT / GN_SUB;
+constexpr unsigned long long GN_EMPTY = ~0ull;
+
+// Sorted insertion of (key, payload) into an ascending 5-list held in registers, without branches on the position.
+#define GN_INSERT(c, pc)                                                                         \
+  do {                                                                                           \
+    const bool l3 = (c) < k3, l2 = (c) < k2, l1 = (c) < k1, l0 = (c) < k0;                        \
+    k4 = l3 ? k3 : (c); p4 = l3 ? p3 : (pc);                                                      \
+    k3 = l2 ? k2 : (l3 ? (c) : k3); p3 = l2 ? p2 : (l3 ? (pc) : p3);                              \
+    k2 = l1 ? k1 : (l2 ? (c) : k2); p2 = l1 ? p1 : (l2 ? (pc) : p2);                              \
+    k1 = l0 ? k0 : (l1 ? (c) : k1); p1 = l0 ? p0 : (l1 ? (pc) : p1);                              \
+    k0 = l0 ? (c) : k0; p0 = l0 ? (pc) : p0;                                                      \
+  } while (0)
+
+struct GnShared {
+  float4 ori[GN_TILE];        // stack point (sensor frame)
+  float4 sel[GN_TILE];        // the same in the map frame under the current pose (LM:756, 865)
+  float nb[GN_TILE][5][3];    // its five neighbours
+  unsigned short list[GN_TILE];  // queries of the tile this rank evaluates (owner rule), in order
+  unsigned char ok[GN_TILE];  // five neighbours within 1 m found
+  int wcount[GN_NT / 32];
+  int n_own;
+  double acc[GN_NT / 32][28];  // per-warp sums of the rows of this CTA
+  double tot[28];
+  float T[6], sc[6];
+  int done, stop;
+  bool last;
+};
+
+__global__ void __launch_bounds__(GN_NT) map_gn_kernel(MapGnArgs A) {
+  __shared__ GnShared S;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int sub = lane & (GN_SUB - 1), grp = lane / GN_SUB;
+  const unsigned int gmask = 0xffu << (grp * GN_SUB);
+  const int nq = A.n_cs + A.n_ss;
+  const int ntiles = (nq + GN_TILE - 1) / GN_TILE;
+  if (tid < 6) {
+    S.T[tid] = A.T[tid];
+    S.sc[tid] = A.sc[tid];
+  }
+  unsigned int gen = 0;  // grid-barrier generations this launch has passed
+  // generation counter at launch: read before this CTA's first ticket, i.e. before the first iteration can complete
+  const unsigned int gen0 = tid == 0 ? *((volatile unsigned int*)A.gen) : 0u;
+  __syncthreads();
+  for (int iter = A.it0; iter < A.it1; iter++) {
+    float T[6], sc[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      T[i] = S.T[i];
+      sc[i] = S.sc[i];
+    }
+    if (lane < 28) S.acc[w][lane] = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      // ---- phase 0: transform, owner rule, ordered compaction of the owned queries
+      const int q = tile * GN_TILE + tid;
+      bool own = false;
+      if (q < nq) {
+        const float4 ori = q < A.n_cs ? A.cstack[q] : A.sstack[q - A.n_cs];
+        const float4 sel = gn_assoc_to_map(T, sc, ori);
+        S.ori[tid] = ori;
+        S.sel[tid] = sel;
+        own = sel.x >= A.slab_lo && sel.x < A.slab_hi;
+      }
+      S.ok[tid] = 0;
+      const unsigned int bal = __ballot_sync(0xffffffffu, own);
+      if (lane == 0) S.wcount[w] = __popc(bal);
+      __syncthreads();
+      {
+        int base = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < GN_NT / 32; k++) {
+          const int c = S.wcount[k];
+          base += k < w ? c : 0;
+          total += c;
+        }
+        if (own) S.list[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)tid;
+        if (tid == 0) S.n_own = total;
+      }
+      __syncthreads();
+      // ---- phase 1: exact 5-NN, eight lanes per query
+      const int n_own = S.n_own;
+      for (int e0 = w * (32 / GN_SUB); e0 < n_own; e0 += GN_GROUPS) {  // warp-uniform trip count: the four groups stay together
+        const int e = e0 + grp;
+        const bool active = e < n_own;
+        const int lq = active ? (int)S.list[e] : 0;
+        const float4 sel = S.sel[lq];
+        const bool is_c = tile * GN_TILE + lq < A.n_cs;
+        const CsrGridD& g = is_c ? A.gc : A.gs;
+        const float4* __restrict__ pts = g.sorted;
+        const unsigned int* __restrict__ E = g.E;
+        const int cx = csr_axis(sel.x, g.x0, g.nx), cy = csr_axis(sel.y, g.y0, g.ny), cz = csr_axis(sel.z, g.z0, g.nz);
+        // the nine x-runs: lane `sub` looks up row `sub`, lane 0 also row 8
+        unsigned int lo = 0, hi = 0, lo8 = 0, hi8 = 0;
+        if (active) {
+          {
+            const int ry = cy + (sub % 3) - 1, rz = cz + (sub / 3) - 1;
+            if (ry >= 0 && ry < g.ny && rz >= 0 && rz < g.nz) {
+              const unsigned int* r = E + (size_t)(rz * g.ny + ry) * g.nxp + cx;
+              lo = __ldg(r);
+              hi = __ldg(r + 3);
+            }
+          }
+          if (sub == 0) {
+            const int ry = cy + 1, rz = cz + 1;
+            if (ry < g.ny && rz < g.nz) {
+              const unsigned int* r = E + (size_t)(rz * g.ny + ry) * g.nxp + cx;
+              lo8 = __ldg(r);
+              hi8 = __ldg(r + 3);
+            }
+          }
+        }
+        unsigned long long k0 = GN_EMPTY, k1 = GN_EMPTY, k2 = GN_EMPTY, k3 = GN_EMPTY, k4 = GN_EMPTY;
+        unsigned int p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+          const unsigned int rlo = j < 8 ? __shfl_sync(gmask, lo, grp * GN_SUB + j) : __shfl_sync(gmask, lo8, grp * GN_SUB);
+          const unsigned int rhi = j < 8 ? __shfl_sync(gmask, hi, grp * GN_SUB + j) : __shfl_sync(gmask, hi8, grp * GN_SUB);
+          for (unsigned int i = rlo + sub; i < rhi; i += GN_SUB) {
+            const float4 p = __ldg(&pts[i]);
+            const float d2 = lg_sqdist(p.x, p.y, p.z, sel.x, sel.y, sel.z);
+            if (d2 < 1.0f) {
+              const unsigned long long c = lg_pack_nbr(d2, __float_as_int(p.w));
+              if (c < k4) GN_INSERT(c, i);
+            }
+          }
+        }
+        // merge inside the group: five rounds of "minimum of the lanes' heads"; keys are unique (they embed the index)
+        unsigned long long res4 = GN_EMPTY;
+        unsigned int mypos = 0;  // lane r < 5 of the group ends with the position of neighbour r
+        int nbr_idx = -1;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const unsigned int hi32 = (unsigned int)(k0 >> 32);
+          const unsigned int mhi = __reduce_min_sync(gmask, hi32);
+          const unsigned int lo32 = (hi32 == mhi) ? (unsigned int)k0 : 0xffffffffu;
+          const unsigned int mlo = __reduce_min_sync(gmask, lo32);
+          const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+          const bool mine = k0 == m && m != GN_EMPTY;
+          const unsigned int pos = __reduce_max_sync(gmask, mine ? p0 : 0u);
+          if (sub == r) {
+            mypos = pos;
+            nbr_idx = (int)mlo;
+          }
+          if (r == 4) res4 = m;
+          if (mine) {
+            k0 = k1; k1 = k2; k2 = k3; k3 = k4; k4 = GN_EMPTY;
+            p0 = p1; p1 = p2; p2 = p3; p3 = p4;
+          }
+        }
+        const bool found = active && res4 != GN_EMPTY;
+        if (sub < 5 && found) {
+          const float4 p = __ldg(&pts[mypos]);
+          S.nb[lq][sub][0] = p.x;
+          S.nb[lq][sub][1] = p.y;
+          S.nb[lq][sub][2] = p.z;
+        }
+        if (sub == 0 && found) S.ok[lq] = 1;
+        if (A.nbr != nullptr && sub < 5 && active) A.nbr[(size_t)(tile * GN_TILE + lq) * 5 + sub] = found ? nbr_idx : -1;
+      }
+      __syncthreads();
+      // ---- phase 2: fit + Jacobian row, one query per thread; the warp's 28 sums go to its shared accumulator
+      {
+        Acc28 acc;
+        acc.clear();
+        if (S.ok[tid]) {
+          float px[5], py[5], pz[5], a[6], b;
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            px[j] = S.nb[tid][j][0];
+            py[j] = S.nb[tid][j][1];
+            pz[j] = S.nb[tid][j][2];
+          }
+          if (gn_fit_row(sc, q < A.n_cs, S.ori[tid], S.sel[tid], px, py, pz, a, &b)) acc.add_row(a, b);
+        }
+        if (__any_sync(0xffffffffu, S.ok[tid])) {
+          const double r = lg_warp_reduce28(acc.v, lane);
+          if (lane < 28) S.acc[w][lane] += r;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- grid reduction: CTA partial -> global, last CTA adds them in CTA order
+    __syncthreads();
+    if (tid < 28) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < GN_NT / 32; k++) s += S.acc[k][tid];
+      A.partials[(size_t)blockIdx.x * 28 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(A.ticket, 1u);
+      S.last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (S.last) {
+      __threadfence();
+      double s = 0.0;
+      if (lane < 28) {
+        constexpr unsigned int W = GN_NT / 32;
+        for (unsigned int b = w; b < gridDim.x; b += 4 * W) {
+          double v[4];
+#pragma unroll
+          for (unsigned int u = 0; u < 4; u++) v[u] = b + u * W < gridDim.x ? __ldcg(&A.partials[(size_t)(b + u * W) * 28 + lane]) : 0.0;
+#pragma unroll
+          for (unsigned int u = 0; u < 4; u++) s += v[u];
+        }
+        S.acc[w][lane] = s;
+      }
+      __syncthreads();
+      if (tid < 28) {
+        s = 0.0;
+#pragma unroll
+        for (int k = 0; k < GN_NT / 32; k++) s += S.acc[k][tid];
+      }
+      if (tid == 0) *A.ticket = 0u;
+      if (A.px.world > 1) {
+        // One-shot all-reduce over NVLink peer memory (see lg_reduce.cuh): store this rank's sums into every peer's
+        // exchange buffer, raise the flag there, wait for the peers' flags here, add the partials in rank order.
+        const int W = A.px.world, me = A.px.rank;
+        const unsigned long long xs = A.px.xseq + (unsigned long long)(iter - A.it0);
+        const size_t slot = ((size_t)(xs & 1ull) * LG_MAX_PEERS + me) * 32;
+        if (tid < 28)
+          for (int r = 0; r < W; r++) A.px.buf[r][slot + tid] = s;
+        __threadfence_system();
+        __syncthreads();
+        if (tid < W) *((volatile unsigned long long*)(A.px.buf[tid] + LG_XCHG_FLAG_OFFSET) + me) = xs;
+        if (tid < W) {
+          volatile unsigned long long* f = (volatile unsigned long long*)(A.px.buf[me] + LG_XCHG_FLAG_OFFSET) + tid;
+          const long long t0 = clock64();
+          while (*f < xs) {
+            if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer died or never called; the host turns this into an error
+              *A.px.timeout = 1;
+              break;
+            }
+          }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < 28) {
+          s = 0.0;
+          const volatile double* mine = A.px.buf[me] + (size_t)(xs & 1ull) * LG_MAX_PEERS * 32;
+          for (int r = 0; r < W; r++) s += mine[(size_t)r * 32 + tid];
+        }
+      }
+      if (tid < 28) S.tot[tid] = s;
+      __syncthreads();
+      if (!A.solve) {
+        if (tid < 28) A.out[tid] = S.tot[tid];
+      } else if (w == 0) {
+        // ---- LM:929-932, 968-1017 on the device, same operations in the same order as the host code
+        float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float AtA[36], AtB[6];
+        int n_sel;
+        lg_unpack28(S.tot, AtA, AtB, &n_sel);
+        const int solved = n_sel >= 50;
+        float Tn[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Tn[i] = T[i];
+        if (solved) {
+          lg_qr_solve6_warp(AtA, AtB, lane, X);
+          // iteration 0: the eigen-decomposition / degeneracy test (LM:970-997) is checked by the host afterwards on the
+          // sums published here; the device goes on as if it said "not degenerate" (the host re-runs the rare other case)
+          int degenerate = A.degenerate;
+          if (iter == 0) {
+            degenerate = 0;
+            if (lane < 28) A.out[lane] = S.tot[lane];
+            if (lane == 0) A.out[40] = 1.0;
+          }
+          if (degenerate) {
+            float X2[6];
+            for (int i = 0; i < 6; i++) X2[i] = X[i];
+            lg_gemm_dacc(A.matP, X2, X, 6, 6, 1);
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) Tn[i] = T[i] + X[i];
+        }
+        int small = 0;
+        if (lane < 6) {
+          const int k = lane >> 1;
+          const float ang = k == 0 ? Tn[0] : (k == 1 ? Tn[1] : Tn[2]);
+          S.sc[lane] = (lane & 1) ? lgm_cosf(ang) : lgm_sinf(ang);
+          float tv = Tn[0];
+#pragma unroll
+          for (int i = 1; i < 6; i++) tv = lane == i ? Tn[i] : tv;
+          S.T[lane] = tv;
+        } else if (lane == 6) {
+          const double r0 = X[0] * 180.0 / M_PI, r1 = X[1] * 180.0 / M_PI, r2 = X[2] * 180.0 / M_PI;
+          small = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2) < 0.05;
+        } else if (lane == 7) {
+          const double t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+          small = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2) < 0.05;
+        }
+        const unsigned int both = __ballot_sync(0xffffffffu, small) & 0xc0u;
+        __syncwarp();
+        if (lane == 0) S.done = (solved && both == 0xc0u) ? 1 : 0;
+        __syncwarp();
+        // publish pose, sin / cos and the verdict for every CTA (and, at the end, for the host)
+        if (lane < 6) {
+          A.state[lane] = S.T[lane];
+          A.state[6 + lane] = S.sc[lane];
+        }
+        if (lane == 0) {
+          A.state[12] = __int_as_float(S.done);
+          A.state[13] = __int_as_float(iter);
+        }
+      }
+      __syncthreads();
+      const bool stop = !A.solve || S.done || iter + 1 >= A.it1;
+      if (stop) {  // host mailbox: results first, then the sequence word
+        if (A.solve && tid < 6) A.out[32 + tid] = (double)S.T[tid];
+        if (A.solve && tid == 6) A.out[38] = (double)iter;
+        if (A.solve && tid == 7) A.out[39] = (double)S.done;
+        if (A.seq != 0ull) {
+          __threadfence_system();
+          __syncthreads();
+          if (tid == 0) {
+            *((volatile unsigned long long*)(A.out + 31)) = A.seq;
+            __threadfence_system();
+          }
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(A.gen, 1u);  // release the grid barrier
+    }
+    if (!A.solve) return;
+    // ---- grid barrier: wait for the last CTA's verdict, pick up the new pose
+    gen++;
+    if (tid == 0) {
+      while (*((volatile unsigned int*)A.gen) - gen0 < gen) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid < 6) {
+      S.T[tid] = __ldcg(&A.state[tid]);
+      S.sc[tid] = __ldcg(&A.state[6 + tid]);
+    }
+    if (tid == 0) S.done = __float_as_int(__ldcg(&A.state[12]));
+    __syncthreads();
+    if (S.done) break;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------ host side
+int lg_csr_reserve(CsrWs& ws, size_t table_entries, int n_points, cudaStream_t st) {
+  LG_CHECK(ws.tab.ensure((table_entries + 16) * 4, st));
+  LG_CHECK(ws.sorted.ensure(((size_t)n_points + 16) * 16, st));
+  LG_CHECK(ws.sums.ensure((table_entries / SCAN_TILE + 16) * 4, st));
+  return LOAM_OK;
+}
+
+static size_t csr_set_box(CsrGridD& g, const int lo[3], const int hi[3]) {
+  g.x0 = (float)lo[0]; g.y0 = (float)lo[1]; g.z0 = (float)lo[2];
+  g.nx = std::max(1, hi[0] - lo[0] + 1);
+  g.ny = std::max(1, hi[1] - lo[1] + 1);
+  g.nz = std::max(1, hi[2] - lo[2] + 1);
+  g.nxp = g.nx + 2;
+  return (size_t)g.nz * g.ny * g.nxp + 1;  // + the guard entry in front
+}
+
+int lg_csr_build2(CsrWs& ws, const float4* pts0, int n0, const int lo0[3], const int hi0[3], const float4* pts1, int n1, const int lo1[3],
+                  const int hi1[3], cudaStream_t st, long long* launches) {
+  CsrJob J;
+  const size_t len0 = csr_set_box(J.g[0], lo0, hi0), len1 = csr_set_box(J.g[1], lo1, hi1);
+  const size_t len = len0 + len1;
+  if (len > (size_t)0x7fffffff) return LOAM_ENOSPC;
+  int rc = lg_csr_reserve(ws, len, n0 + n1, st);
+  if (rc) return rc;
+  J.pts[0] = pts0; J.pts[1] = pts1;
+  J.n[0] = n0; J.n[1] = n1;
+  J.tab = ws.tab.as<unsigned int>();
+  J.off[0] = 0; J.off[1] = (int)len0;
+  J.sorted = ws.sorted.as<float4>();
+  for (int w = 0; w < 2; w++) {
+    J.g[w].sorted = J.sorted;
+    J.g[w].E = J.tab + J.off[w];
+    J.g[w].n = J.n[w];
+  }
+  ws.d[0] = J.g[0];
+  ws.d[1] = J.g[1];
+  LgProfScope prof_scope(LGK_GRID, st, (double)(n0 + n1));
+  LG_CHECK(cudaMemsetAsync(J.tab, 0, len * 4, st));
+  const int pb0 = lg_div_up(n0, 256), pb1 = lg_div_up(n1, 256);
+  const int nb = (int)((len + SCAN_TILE - 1) / SCAN_TILE);
+  if (pb0 + pb1 > 0) {
+    csr_count_kernel<<<pb0 + pb1, 256, 0, st>>>(J, pb0);
+    (*launches)++;
+  }
+  // the guard entries hold 0, every cell entry its count: after the exclusive scan a cell entry holds the START of its run
+  // in the concatenated sorted array (grid 1 continues after grid 0), the scatter turns it into the END
+  scan_sums_kernel<<<nb, SCAN_NT, 0, st>>>(J.tab, len, ws.sums.as<unsigned int>());
+  scan_top_kernel<<<1, SCAN_NT, 0, st>>>(ws.sums.as<unsigned int>(), nb);
+  scan_apply_kernel<<<nb, SCAN_NT, 0, st>>>(J.tab, len, ws.sums.as<unsigned int>());
+  (*launches) += 3;
+  if (pb0 + pb1 > 0) {
+    csr_fill_kernel<<<pb0 + pb1, 256, 0, st>>>(J, pb0);
+    (*launches)++;
+  }
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_csr_bbox_launch(const float4* pts0, int n0, const float4* pts1, int n1, int* d_bb12, cudaStream_t st, long long* launches) {
+  const int init[12] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  LG_CHECK(cudaMemcpyAsync(d_bb12, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  LG_CHECK(cudaStreamSynchronize(st));  // `init` is on the stack
+  if (n0 + n1 > 0) {
+    csr_bbox_kernel<<<lg_div_up(n0 + n1, 256), 256, 0, st>>>(pts0, n0, pts1, n1, d_bb12);
+    (*launches)++;
+  }
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_map_gn_grid(int nq, int device) {
+  static int per_sm[64] = {0}, sms[64] = {0};
+  const int d = device & 63;
+  if (!per_sm[d]) {
+    int occ = 0, n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_gn_kernel, GN_NT, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n < 1) n = 1;
+    per_sm[d] = occ;
+    sms[d] = n;
+  }
+  const int ntiles = std::max(1, (nq + GN_TILE - 1) / GN_TILE);
+  return std::min(ntiles, per_sm[d] * sms[d]);
+}
+
+int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, long long* launches) {
+  const int nq = A.n_cs + A.n_ss;
+  const int grid = lg_map_gn_grid(nq, device);
+  LG_CHECK(ws.partials.ensure((size_t)grid * 28 * 8 + 64, st));
+  if (!ws.sync.p) {
+    LG_CHECK(ws.sync.ensure(64 * 4, st));
+    LG_CHECK(cudaMemsetAsync(ws.sync.p, 0, 64 * 4, st));
+  }
+  A.partials = ws.partials.as<double>();
+  A.ticket = ws.sync.as<unsigned int>();
+  A.gen = ws.sync.as<unsigned int>() + 1;
+  A.state = ws.sync.as<float>() + 16;
+  LgProfScope prof_scope(LGK_MAP_KNN, st, (double)nq);
+  void* args[] = {(void*)&A};
+  LG_CHECK(cudaLaunchCooperativeKernel((const void*)map_gn_kernel, dim3(grid), dim3(GN_NT), args, 0, st));
+  (*launches)++;
+  return LOAM_OK;
+}

@@ -29,7 +29,7 @@ extern "C" {
 #define LOAM_ECUDA (-2)  /* CUDA runtime error (loam_last_cuda_error has the text) */
 #define LOAM_ENOSPC (-3) /* caller buffer or internal capacity too small */
 #define LOAM_ESTATE (-4) /* call order violated (e.g. odometry before any extract) */
-#define LOAM_EUNSUPPORTED (-5) /* input the CUDA path does not handle: a sweep with an EMPTY ring (fence iii) */
+#define LOAM_EUNSUPPORTED (-5) /* reserved (sweeps with empty rings are handled like the reference does, SR:480-490) */
 
 typedef struct loam_handle loam_handle;
 

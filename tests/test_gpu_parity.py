@@ -119,18 +119,84 @@ def test_extract_empty_and_tiny(gpu, orc):
     ref = orc.ScanRegistration().extract(xyz)
     c = gpu.extract(xyz)
     assert c.n_full == ref["full"].shape[0] and c.n_sharp == 0 and c.n_flat == 0
+    # 6..10 points: the curvature loop is empty but the last ring spans [0, n - 5) (SR:489-490) over never-initialised entries
+    from gpscalibration_b200 import LoamGpu
+    g2 = LoamGpu()
+    sr = orc.ScanRegistration()
+    for m in (8, 10, 11, 13):
+        xyz = np.stack([np.full(m, 6.0), np.linspace(-0.5, 0.5, m), np.zeros(m)], 1).astype(np.float32)
+        ref = sr.extract(xyz)
+        c = g2.extract(xyz)
+        assert (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat) == tuple(ref[k].shape[0] for k in sr.CLOUDS), m
+        for k in ("flat", "less_flat"):
+            assert np.array_equal(g2.cloud(k), ref[k]), (m, k)
+    g2.close()
 
 
-def test_extract_empty_ring_fails_loudly(gpu):
-    """Fence (iii): true VLP-16 angles leave rings 6/8/10 of the reference's table empty; the reference then indexes with
-    overlapping, partly uninitialised ranges (SR:480-490).  The CUDA path refuses such a sweep instead of guessing."""
-    from gpscalibration_b200 import SweepGenerator, LoamError, capi
-    xyz = SweepGenerator(sensor=1).sweep(0)[0]
-    with pytest.raises(LoamError) as e:
-        gpu.extract(xyz)
-    assert e.value.code == capi.LOAM_EUNSUPPORTED
-    c = gpu.extract(SweepGenerator(sensor=0).sweep(0)[0])  # the handle stays usable
-    assert c.n_full == 28800
+def test_extract_true_vlp16_angles_empty_rings(gpu, orc):
+    """True VLP-16 angles leave rings 6 / 8 / 10 of the reference's table empty and drop the +11/+13/+15 degree beams: the
+    reference's scanStartInd / scanEndInd then overlap (SR:480-490): rings 5 / 7 / 9 are skipped and rings 6 / 8 / 10 span
+    the cloud from index 0, re-sorting and re-picking over the rings before them, including the five leading entries of the
+    static arrays that are never re-initialised (state carried from sweep to sweep).  Bit-exact, sweep after sweep."""
+    from gpscalibration_b200 import SweepGenerator
+    g = SweepGenerator(sensor=1, scene=0, seed=0xC0FFEE)
+    sr = orc.ScanRegistration()
+    for k in range(4):
+        ref = _check_extract(gpu, sr, g.sweep(k)[0])
+        assert np.array_equal(sr.ints("scan_start")[[6, 8, 10]], [0, 0, 0]) and (sr.ints("scan_end")[[5, 7, 9]] == 0).all()
+        assert ref["less_flat"].shape[0] > ref["full"].shape[0] // 4  # the virtual rings contribute the earlier rings again
+
+
+def test_extract_top_rings_missing(gpu, orc, sweeps16):
+    """A sweep whose top three rings return nothing (sky): the last ring keeps scanStartInd 0 and spans the whole cloud."""
+    sr = orc.ScanRegistration()
+    for k in (3, 4):
+        xyz = sweeps16[k]
+        elev = np.degrees(np.arctan2(xyz[:, 2], np.hypot(xyz[:, 0], xyz[:, 1])))
+        cut = xyz[elev < 4.0]
+        assert cut.shape[0] < xyz.shape[0]
+        _check_extract(gpu, sr, cut)
+        assert sr.ints("scan_start")[15] == 0 and sr.ints("scan_end")[12] == 0
+    _check_extract(gpu, sr, sweeps16[5])  # a fully populated sweep afterwards (the five stale entries keep their marks)
+
+
+def test_extract_one_occluded_ring_mid_sequence(gpu, orc, sweeps16):
+    sr = orc.ScanRegistration()
+    _check_extract(gpu, sr, sweeps16[0])
+    xyz = sweeps16[1]
+    elev = np.degrees(np.arctan2(xyz[:, 2], np.hypot(xyz[:, 0], xyz[:, 1])))
+    _check_extract(gpu, sr, xyz[np.abs(elev + 2.0) > 0.5])  # ring 8 (-2 degrees) occluded
+    _check_extract(gpu, sr, xyz[elev > -14.0])               # ring 0 gone: every later ring keeps its own range
+    _check_extract(gpu, sr, sweeps16[2])
+
+
+def test_pipeline_parity_true_vlp16(orc):
+    """extract -> odometry -> mapping on true VLP-16 angles (empty rings every sweep): poses, iteration counts and cloud
+    sizes equal to the oracle bit for bit; the pipelined mode gives the same."""
+    from gpscalibration_b200 import LoamGpu, LoamGpuPipeline, SweepGenerator
+    g = SweepGenerator(sensor=1, scene=0, seed=0xC0FFEE)
+    sw = [g.sweep(k)[0].copy() for k in range(10)]
+    gpu, pipe = LoamGpu(), orc.Pipeline()
+    res = []
+    for k, xyz in enumerate(sw):
+        r, o = gpu.process_sweep(xyz), pipe.process(xyz)
+        res.append(r)
+        assert (r.counts.n_full, r.counts.n_sharp, r.counts.n_less_sharp, r.counts.n_flat, r.counts.n_less_flat) == \
+            (o.n_full, o.n_sharp, o.n_less_sharp, o.n_flat, o.n_less_flat), k
+        assert np.array_equal(np.array(r.odom.transform_sum, np.float32), np.array(o.odom, np.float32)), k
+        assert r.mapping_ran == o.mapping_ran
+        if r.mapping_ran:
+            assert np.array_equal(np.array(r.map.transform_aft_mapped, np.float32), np.array(o.mapped, np.float32)), k
+            assert r.map.iterations == o.map_iters
+    gpu.close()
+    p = LoamGpuPipeline()
+    for xyz in sw:
+        p.submit(xyz)
+    for k in range(len(sw)):
+        r = p.wait()
+        assert list(r.odom.transform_sum) == list(res[k].odom.transform_sum), k
+        assert list(r.map.transform_aft_mapped) == list(res[k].map.transform_aft_mapped), k
+    p.close()
 
 
 # ------------------------------------------------------------------------------------------------ odometry (a6-a12)
