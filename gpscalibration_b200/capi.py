@@ -59,8 +59,8 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
-           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect",
-           "loam_map_iter_allreduce", "loam_pipeline_create", "loam_pipeline_destroy",
+           "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect", "loam_shard_set_slab", "loam_shard_inject",
+           "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_replay_segments"]
@@ -123,6 +123,9 @@ def load_library():
     lib.loam_shard_export.argtypes = [vp, vp]
     lib.loam_shard_connect.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.loam_map_iter_allreduce.argtypes = [vp, C.c_int, vp, vp, vp, ip]
+    lib.loam_map_optimize.argtypes = [vp, vp, C.c_int, ip]
+    lib.loam_shard_set_slab.argtypes = [vp, C.c_float, C.c_float]
+    lib.loam_shard_inject.argtypes = [vp, C.c_int, vp]
     lib.loam_pipeline_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
     lib.loam_pipeline_destroy.argtypes = [vp]
     lib.loam_pipeline_reset.argtypes = [vp]
@@ -314,6 +317,20 @@ class LoamGpu:
         blob = b"".join(handles)
         arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(self.lib.loam_shard_connect(self._h, arr, len(handles), rank), "loam_shard_connect")
+
+    def shard_set_slab(self, x_lo, x_hi):
+        self._check(self.lib.loam_shard_set_slab(self._h, float(x_lo), float(x_hi)), "loam_shard_set_slab")
+
+    def shard_inject(self, from_rank, sums28):
+        s = np.ascontiguousarray(sums28, np.float64)
+        self._check(self.lib.loam_shard_inject(self._h, int(from_rank), s.ctypes.data), "loam_shard_inject")
+
+    def map_optimize(self, T, max_iters=10):
+        """Whole Gauss-Newton loop on the device (LM:753-1017); returns (T_new, iterations)."""
+        T = _f32(T).copy()
+        n = C.c_int()
+        self._check(self.lib.loam_map_optimize(self._h, T.ctypes.data, int(max_iters), C.byref(n)), "loam_map_optimize")
+        return T, n.value
 
     def map_iter_allreduce(self, it, T):
         T = _f32(T)

@@ -129,9 +129,10 @@ struct loam_handle {
   size_t bump = 0;  // in points
   DevBuf stack2_c, stack2_s, stack_c, stack_s, map_c, map_s;
   int n_stack_c = 0, n_stack_s = 0, n_map_c = 0, n_map_s = 0;
-  GridWs grid_c, grid_s;
+  CsrWs csr;     // cell-sorted grids over the gathered corner / surf map (replace the kd-trees, LM:750-751)
+  MapGnWs gn;    // workspace of the fused Gauss-Newton kernel
   bool grids_valid = false;
-  MapIterWs mi;
+  float slab_lo = -INFINITY, slab_hi = INFINITY;  // sharded map: this rank evaluates queries whose map-frame x is in [lo, hi)
   DevBuf d_ents, d_segs, d_ints, d_seg_off, d_seg_leaf, d_out_se;
   VoxBigWs vb;
   DevBuf ds_in, ins_sel, ins_sorted, d_runs;
@@ -474,20 +475,121 @@ int odom_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, 
   return LOAM_OK;
 }
 
-int map_iter(loam_handle* h, const float* T, double* out28_dev, float* AtA, float* AtB, int* n_sel, const PeerXchg* px = nullptr) {
-  MapT mt;
-  for (int i = 0; i < 6; i++) mt.t[i] = T[i];
-  mt.sc = host_sincos3(T);
-  int rc = lg_map_iter_launch(h->mi, mt, h->stack_c.as<float4>(), h->n_stack_c, h->stack_s.as<float4>(), h->n_stack_s, h->grid_c.d, h->grid_s.d,
-                              h->map_c.as<float4>(), h->map_s.as<float4>(), out28_dev ? out28_dev : h->d_mail,
-                              out28_dev ? 0ull : ++h->mail_seq, h->st, &h->launches, px);
+// Enqueues iterations [it0, it1) of the scan-to-map Gauss-Newton loop (lg_mapgn.cu).  solve = 0: one pass, the 28 sums go
+// to out_dev (device memory, no sequence word) or to the host mailbox; solve = 1: the loop runs on the device, the mailbox
+// receives the pose, the iteration count and the sums of iteration 0.
+int map_gn_enqueue(loam_handle* h, const float* T, int it0, int it1, int solve, double* out_dev, bool use_px) {
+  MapGnArgs A;
+  memset(&A, 0, sizeof(A));
+  const SinCos3 sc = host_sincos3(T);
+  const float scv[6] = {sc.srx, sc.crx, sc.sry, sc.cry, sc.srz, sc.crz};
+  for (int i = 0; i < 6; i++) {
+    A.T[i] = T[i];
+    A.sc[i] = scv[i];
+  }
+  memcpy(A.matP, h->lm_gn.matP, sizeof(A.matP));
+  A.degenerate = h->lm_gn.degenerate ? 1 : 0;
+  A.it0 = it0;
+  A.it1 = it1;
+  A.solve = solve;
+  A.cstack = h->stack_c.as<float4>();
+  A.n_cs = h->n_stack_c;
+  A.sstack = h->stack_s.as<float4>();
+  A.n_ss = h->n_stack_s;
+  A.gc = h->csr.d[0];
+  A.gs = h->csr.d[1];
+  A.slab_lo = h->slab_lo;
+  A.slab_hi = h->slab_hi;
+  LG_CHECK(h->gn.nbr.ensure((size_t)(A.n_cs + A.n_ss + 1) * 5 * 4, h->st));
+  A.nbr = h->gn.nbr.as<int>();
+  A.out = out_dev ? out_dev : h->d_mail;
+  A.seq = out_dev ? 0ull : ++h->mail_seq;
+  if (!out_dev) h->h_mail[40] = 0.0;
+  if (use_px) {
+    A.px = h->px;
+    A.px.xseq = h->px.xseq + 1;  // sequence number of this launch's first iteration
+  }
+  return lg_map_gn_launch(h->gn, A, h->device, h->st, &h->launches);
+}
+
+// One iteration body without the solve (LM:754-967), sums through the mailbox.
+int map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* AtB, int* n_sel, bool use_px = false) {
+  int rc = map_gn_enqueue(h, T, iter, iter + 1, 0, nullptr, use_px);
   if (rc) return rc;
-  if (out28_dev) return LOAM_OK;
   rc = mailbox_wait(h);
   if (rc) return rc;
+  if (use_px) h->px.xseq++;
   h->d2h_bytes += 28 * 8;
   lg_unpack28(h->h_mail, AtA, AtB, n_sel);
   return LOAM_OK;
+}
+
+// LM:753-1017: the whole Gauss-Newton loop of one mapping run.  Default: on the device in one launch; the host then checks
+// the eigen-decomposition of iteration 0 (LM:970-997) on the sums the kernel published, and only if that says "degenerate"
+// (the kernel went on as if it did not) replays the run through the host, iteration by iteration.  LOAM_HOST_GN_LOOP=1
+// forces the host path (bit-identical cross-check).
+int map_optimize(loam_handle* h, float* Tt, int max_iters, int* iterations, bool use_px) {
+  static const bool host_loop_env = getenv("LOAM_HOST_GN_LOOP") != nullptr;
+  *iterations = 0;
+  if (max_iters <= 0) return LOAM_OK;
+  if (!host_loop_env) {
+    int rc = map_gn_enqueue(h, Tt, 0, max_iters, 1, nullptr, use_px);
+    if (rc) return rc;
+    rc = mailbox_wait(h);
+    if (rc) return rc;
+    h->d2h_bytes += 41 * 8;
+    const int last = (int)h->h_mail[38];
+    if (use_px) h->px.xseq += (unsigned long long)(last + 1);
+    bool speculation_held = true;
+    if (h->h_mail[40] != 0.0) {  // iteration 0 had >= 50 rows: its eigen-decomposition decides matP / isDegenerate
+      float AtA[36], AtB[6], X[6];
+      int n_sel = 0;
+      lg_unpack28(h->h_mail, AtA, AtB, &n_sel);
+      const LgGNState saved = h->lm_gn;
+      lg_gn_solve_step(AtA, AtB, 0, 100.f, h->lm_gn, X);
+      if (h->lm_gn.degenerate) {
+        h->lm_gn = saved;
+        speculation_held = false;
+      }
+    }
+    if (speculation_held) {
+      for (int i = 0; i < 6; i++) Tt[i] = (float)h->h_mail[32 + i];
+      *iterations = last + 1;
+      return LOAM_OK;
+    }
+  }
+  for (int iter = 0; iter < max_iters; iter++) {
+    *iterations = iter + 1;
+    float AtA[36], AtB[6], X[6];
+    int n_sel = 0;
+    int rc = map_iter(h, iter, Tt, AtA, AtB, &n_sel, use_px);
+    if (rc) return rc;
+    if (n_sel < 50) continue;  // LM:929-932
+    lg_gn_solve_step(AtA, AtB, iter, 100.f, h->lm_gn, X);
+    for (int i = 0; i < 6; i++) Tt[i] += X[i];
+    float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
+    float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
+    if (deltaR < 0.05 && deltaT < 0.05) break;
+  }
+  return LOAM_OK;
+}
+
+// Box (in 1 m cells, inclusive) of the non-empty cubes among `cubes_idx`: a cube holds the points with
+// int((p + 25) / 50) + cen == index (LM:1026-1032), i.e. floor(p) in [50 (index - cen) - 25, 50 (index - cen) + 24].
+void cube_box(const loam_handle* h, const std::vector<std::vector<Chunk>>& cubes, const std::vector<int>& cubes_idx, int lo[3], int hi[3]) {
+  for (int a = 0; a < 3; a++) lo[a] = INT32_MAX, hi[a] = INT32_MIN;
+  for (int ind : cubes_idx) {
+    long long n = 0;
+    for (auto& c : cubes[ind]) n += c.n;
+    if (!n) continue;
+    const int c3[3] = {ind % CW - h->cenW, (ind / CW) % CH - h->cenH, ind / (CW * CH) - h->cenD};
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], 50 * c3[a] - 25);
+      hi[a] = std::max(hi[a], 50 * c3[a] + 24);
+    }
+  }
+  if (lo[0] == INT32_MAX)
+    for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0;
 }
 
 ImuSC imu_sc(const float* v) {
@@ -577,9 +679,8 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
       if (e == cudaSuccess) e = h->arena.ensure(mm * 4 * 16, h->st);
       if (e == cudaSuccess) e = h->arena2.ensure(mm * 4 * 16, h->st);
       if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
-      // voxel-hash index of the local map (a quarter of the capacity per cloud) and the merge-path key arrays
-      if (e == cudaSuccess && lg_grid_reserve(h->grid_c, (int)(mm / 4), h->st) != LOAM_OK) e = cudaErrorMemoryAllocation;
-      if (e == cudaSuccess && lg_grid_reserve(h->grid_s, (int)(mm / 4), h->st) != LOAM_OK) e = cudaErrorMemoryAllocation;
+      // cell-sorted index of the local map (tables for a 250 x 100 x 250 m box twice) and the merge-path key arrays
+      if (e == cudaSuccess && lg_csr_reserve(h->csr, (size_t)16 << 20, (int)mm, h->st) != LOAM_OK) e = cudaErrorMemoryAllocation;
       DevBuf* key_bufs[] = {&h->vb.keys_old, &h->vb.keys_m};
       DevBuf* val_bufs[] = {&h->vb.vals_old, &h->vb.vals_m};
       for (DevBuf* b : key_bufs) e = e == cudaSuccess ? b->ensure(mm * 8, h->st) : e;
@@ -603,7 +704,7 @@ int loam_destroy(loam_handle* h) {
   cudaStreamSynchronize(h->st);
   h->prof.resolve(h->st);
   h->prof.release();
-  h->sr.release(); h->od.release(); h->grid_c.release(); h->grid_s.release(); h->mi.release(); h->vb.release();
+  h->sr.release(); h->od.release(); h->csr.release(); h->gn.release(); h->vb.release();
   DevBuf* all[] = {&h->xyz_packed, &h->wire, &h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
@@ -911,23 +1012,17 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (h->n_map_c > 10 && h->n_map_s > 100) {  // LM:749
     out->optimised = 1;
     ht.lap(&h->host_s[HT_MAP_GRID]);
-    rc = lg_grid_build2(h->grid_c, h->map_c.as<float4>(), h->n_map_c, h->grid_s, h->map_s.as<float4>(), h->n_map_s, h->st, &h->launches);
-    if (rc) return rc;
+    {
+      int loc[3], hic[3], los[3], his[3];
+      cube_box(h, h->cubeC, validInd, loc, hic);
+      cube_box(h, h->cubeS, validInd, los, his);
+      rc = lg_csr_build2(h->csr, h->map_c.as<float4>(), h->n_map_c, loc, hic, h->map_s.as<float4>(), h->n_map_s, los, his, h->st, &h->launches);
+      if (rc) return rc;
+    }
     h->grids_valid = true;
     ht.lap(&h->host_s[HT_MAP_ITERS]);
-    for (int iter = 0; iter < 10; iter++) {
-      out->iterations = iter + 1;
-      float AtA[36], AtB[6], X[6];
-      int n_sel = 0;
-      rc = map_iter(h, Tt, nullptr, AtA, AtB, &n_sel);
-      if (rc) return rc;
-      if (n_sel < 50) continue;  // LM:929-932
-      lg_gn_solve_step(AtA, AtB, iter, 100.f, h->lm_gn, X);
-      for (int i = 0; i < 6; i++) Tt[i] += X[i];
-      float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
-      float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
-      if (deltaR < 0.05 && deltaT < 0.05) break;
-    }
+    rc = map_optimize(h, Tt, 10, &out->iterations, false);
+    if (rc) return rc;
     for (int i = 0; i < 6; i++) {  // transformUpdate LM:238-241
       h->Tbef[i] = h->mTsum[i];
       h->Taft[i] = Tt[i];
@@ -1423,7 +1518,21 @@ int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, con
   if (!rc) rc = upload(h, h->map_s, surf_map, (size_t)n_sm * 16);
   if (rc) return rc;
   h->n_stack_c = n_cs; h->n_stack_s = n_ss; h->n_map_c = n_cm; h->n_map_s = n_sm;
-  rc = lg_grid_build2(h->grid_c, h->map_c.as<float4>(), n_cm, h->grid_s, h->map_s.as<float4>(), n_sm, h->st, &h->launches);
+  h->lm_gn = LgGNState();  // a new explicit problem starts with the reference's initial matP / isDegenerate (LM:399-400)
+  // explicit clouds: their boxes come from the data (the mapping node knows them from its cubes)
+  LG_CHECK(h->csr.bb.ensure(64, h->st));
+  rc = lg_csr_bbox_launch(h->map_c.as<float4>(), n_cm, h->map_s.as<float4>(), n_sm, h->csr.bb.as<int>(), h->st, &h->launches);
+  if (rc) return rc;
+  LG_D2H(h, h->h_ints, h->csr.bb.p, 12 * 4);
+  LG_SYNC(h);
+  int lo[2][3], hi[2][3];
+  for (int g = 0; g < 2; g++)
+    for (int a = 0; a < 3; a++) {
+      lo[g][a] = h->h_ints[g * 6 + a];
+      hi[g][a] = h->h_ints[g * 6 + 3 + a];
+      if (lo[g][a] > hi[g][a]) lo[g][a] = hi[g][a] = 0;  // empty cloud
+    }
+  rc = lg_csr_build2(h->csr, h->map_c.as<float4>(), n_cm, lo[0], hi[0], h->map_s.as<float4>(), n_sm, lo[1], hi[1], h->st, &h->launches);
   if (rc) return rc;
   LG_SYNC(h);
   h->grids_valid = true;
@@ -1435,7 +1544,7 @@ int loam_map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* A
   if (!h->grids_valid) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
-  int rc = map_iter(h, T, nullptr, AtA, AtB, n_sel);
+  int rc = map_iter(h, iter, T, AtA, AtB, n_sel);
   if (rc) return rc;
   if (*n_sel < 50) {
     memset(AtA, 0, 36 * sizeof(float));
@@ -1447,12 +1556,12 @@ int loam_map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* A
 int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int cap_s) {
   if (!h) return LOAM_EINVAL;
   if (cap_c < h->n_stack_c || cap_s < h->n_stack_s) return LOAM_ENOSPC;
-  if (!h->mi.nbr.p) return LOAM_ESTATE;
+  if (!h->gn.nbr.p) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
-  if (h->n_stack_c) LG_D2H(h, corner5, h->mi.nbr.p, (size_t)h->n_stack_c * 20);
+  if (h->n_stack_c) LG_D2H(h, corner5, h->gn.nbr.p, (size_t)h->n_stack_c * 20);
   if (h->n_stack_s)
-    LG_D2H(h, surf5, h->mi.nbr.as<int>() + (size_t)h->n_stack_c * 5, (size_t)h->n_stack_s * 20);
+    LG_D2H(h, surf5, h->gn.nbr.as<int>() + (size_t)h->n_stack_c * 5, (size_t)h->n_stack_s * 20);
   LG_SYNC(h);
   return LOAM_OK;
 }
@@ -1473,7 +1582,7 @@ int loam_map_iter_partial(loam_handle* h, int iter, const float* T, double* part
   if (!h->grids_valid) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
-  int rc = map_iter(h, T, partial_dev28, nullptr, nullptr, nullptr);
+  int rc = map_gn_enqueue(h, T, iter, iter + 1, 0, partial_dev28, false);
   if (rc) return rc;
   LG_SYNC(h);
   return LOAM_OK;
@@ -1536,14 +1645,46 @@ int loam_map_iter_allreduce(loam_handle* h, int iter, const float* T, float* AtA
   if (!h->grids_valid || !h->px_connected) return LOAM_ESTATE;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
-  h->px.xseq++;
-  int rc = map_iter(h, T, nullptr, AtA, AtB, n_sel, &h->px);
+  int rc = map_iter(h, iter, T, AtA, AtB, n_sel, true);
   if (rc) return rc;
   if (*n_sel < 50) {  // LM:929-932 on the global count
     memset(AtA, 0, 36 * sizeof(float));
     memset(AtB, 0, 6 * sizeof(float));
   }
   if (*(volatile int*)(h->h_mail + 28)) {  // written by the kernel next to the sums (mapped mailbox)
+    lg_set_error("a peer rank never reached the all-reduce", __FILE__, __LINE__);
+    return LOAM_ECUDA;
+  }
+  return LOAM_OK;
+}
+
+int loam_shard_inject(loam_handle* h, int from_rank, const double* sums28_host) {
+  if (!h || !sums28_host || from_rank < 0 || from_rank >= LG_MAX_PEERS) return LOAM_EINVAL;
+  if (!h->px_connected || from_rank == h->px.rank || from_rank >= h->px.world) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  const unsigned long long xs = h->px.xseq + 1;  // the next iteration's sequence number
+  const size_t slot = ((size_t)(xs & 1ull) * LG_MAX_PEERS + from_rank) * 32;
+  LG_CHECK(cudaMemcpy(h->xchg + slot, sums28_host, 28 * 8, cudaMemcpyHostToDevice));
+  LG_CHECK(cudaMemcpy((unsigned long long*)(h->xchg + LG_XCHG_FLAG_OFFSET) + from_rank, &xs, 8, cudaMemcpyHostToDevice));
+  return LOAM_OK;
+}
+
+int loam_shard_set_slab(loam_handle* h, float x_lo, float x_hi) {
+  if (!h || !(x_lo < x_hi)) return LOAM_EINVAL;
+  h->slab_lo = x_lo;
+  h->slab_hi = x_hi;
+  return LOAM_OK;
+}
+
+int loam_map_optimize(loam_handle* h, float* T, int max_iters, int* iterations) {
+  if (!h || !T || !iterations || max_iters < 0 || max_iters > 1000) return LOAM_EINVAL;
+  if (!h->grids_valid) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+  int rc = map_optimize(h, T, max_iters, iterations, h->px_connected);
+  if (rc) return rc;
+  if (h->px_connected && *(volatile int*)(h->h_mail + 28)) {
     lg_set_error("a peer rank never reached the all-reduce", __FILE__, __LINE__);
     return LOAM_ECUDA;
   }

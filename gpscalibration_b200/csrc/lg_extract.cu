@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(VIRT_NT) sr_virtual_kernel(SrParams prm, const
     if (!(S == 0 && E > 0)) continue;
     int* my_picks = picks + r * SR_PICKS_PER_RING;
     int nsharp = 0, nless = 0, nflat = 0;
+    int base = lf_off;
     for (int j = 0; j < 6; j++) {
       const int sp = (int)(((long long)E * j) / 6);
       const int ep = (int)(((long long)E * (j + 1)) / 6) - 1;
@@ -748,22 +749,23 @@ __global__ void __launch_bounds__(VIRT_NT) sr_virtual_kernel(SrParams prm, const
         nflat += count;
       }
       __syncthreads();
+      // SR:670-674 runs per SECTOR, right after its picks: the less-flat candidates of [sp, ep] are the points whose label
+      // is <= 0 NOW (a later sector of this ring may still label a point in here: its sort indices were permuted by the
+      // earlier, differently cut rings)
+      for (int k0 = sp; k0 <= ep; k0 += VIRT_NT) {
+        const int k = k0 + tid;
+        const int flag = (k <= ep && label[k] <= 0) ? 1 : 0;
+        int tot;
+        const int ex = block_excl_scan<VIRT_NT>(flag, &tot, s_scan);
+        if (flag) lf_stage[base + ex] = c[k];
+        base += tot;
+      }
     }
     if (tid == 0) {
       int* cnt = meta + SRM_PICK_CNT + r * 3;
       cnt[0] = nsharp;
       cnt[1] = nless;
       cnt[2] = nflat;
-    }
-    // SR:670-674 less-flat candidates of this ring: every k in [0, E) whose label is <= 0 NOW, in index order
-    int base = lf_off;
-    for (int k0 = 0; k0 < E; k0 += VIRT_NT) {
-      const int k = k0 + tid;
-      const int flag = (k < E && label[k] <= 0) ? 1 : 0;
-      int tot;
-      const int ex = block_excl_scan<VIRT_NT>(flag, &tot, s_scan);
-      if (flag) lf_stage[base + ex] = c[k];
-      base += tot;
     }
     if (tid == 0) {
       lf_meta[2 * r] = lf_off;

@@ -14,57 +14,9 @@ struct CubeGeom {  // LM:69-75
   int W, H, D, cenW, cenH, cenD;
 };
 
-constexpr int GRID_LINE = 8;                // points in a cell's line
-constexpr int GRID_INLINE = 1 + GRID_LINE;  // points reachable without touching `sorted`
-
-// Voxel hash over one map cloud (cell = 1 m).  Two levels: a 32-byte slot per hash position (open addressing, 2x
-// over-provisioned) holding the cell key, its point count and its FIRST point -- one 32-byte sector answers "is the
-// cell there, and if it holds a single point, which" -- and one 128-byte line of eight more points per cell that has
-// more than one; cells with more than nine continue in `sorted`.  For a 5^3-cube local map both levels stay in L2.
-struct alignas(32) GridSlot {
-  unsigned long long key;  // cell key, ~0 = empty
-  int count;               // points in the cell
-  int line;                // index of the cell's line (count > 1)
-  float4 p0;               // {x, y, z, original index as int bits}
-};
-struct alignas(128) GridLine {
-  float4 pts[GRID_LINE];
-};
-
-struct GridD {
-  GridSlot* slots;
-  GridLine* lines;
-  int* fill;       // build-time scatter cursor per slot
-  int* cursor;     // [0] allocation cursor into `sorted`, [1] next free line
-  int* slot_of;    // slot of every map point
-  int* ovf_start;  // per line: first position in `sorted` (only when count > GRID_INLINE)
-  float4* sorted;  // cells with more than GRID_INLINE points: all their points, contiguous
-  const unsigned int* occ;  // one bit per slot (occupied): most of the 27 cells a query probes are empty and stop here
-  int bits;        // log2(slots)
-  int n;
-};
-
-struct GridWs {
-  DevBuf keys, lines, ints, slot_of, sorted, ovf;
-  GridD d;
-  void release() { keys.release(); lines.release(); ints.release(); slot_of.release(); sorted.release(); ovf.release(); }
-};
-
-struct MapIterWs {
-  DevBuf nbr, partials, ticket;
-  void release() { nbr.release(); partials.release(); ticket.release(); }
-};
-
 int lg_map_stack_launch(const MapT& T, const float4* in0, float4* out0, int n0, const float4* in1, float4* out1, int n1, cudaStream_t st,
                         long long* launches);
 int lg_map_register_launch(const MapT& T, const float4* in, float4* out, int n, cudaStream_t st, long long* launches);
-// Allocates the index buffers for a cloud of n points up front (reallocation on the steady-state path costs milliseconds).
-int lg_grid_reserve(GridWs& ws, int n, cudaStream_t st);
-// Builds the corner grid and the surf grid together (four launches).
-int lg_grid_build2(GridWs& ws0, const float4* pts0, int n0, GridWs& ws1, const float4* pts1, int n1, cudaStream_t st, long long* launches);
-int lg_map_iter_launch(MapIterWs& ws, const MapT& T, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss, const GridD& gc,
-                       const GridD& gs, const float4* corner_map, const float4* surf_map, double* out28, unsigned long long seq, cudaStream_t st,
-                       long long* launches, const struct PeerXchg* px = nullptr);
 int lg_map_insert_launch(const MapT& T, const CubeGeom& cg, const float4* corner_stack, int n_cs, const float4* surf_stack, int n_ss,
                          float4* sel_out, unsigned long long* keys, unsigned int* vals, cudaStream_t st, long long* launches);
 int lg_map_runs_launch(const unsigned long long* keys, const unsigned int* vals, const float4* sel, int n, float4* sorted_sel, int* n_runs,
@@ -108,6 +60,7 @@ struct MapGnArgs {
   unsigned long long seq;
   PeerXchg px;             // world <= 1: no exchange; xseq = sequence number of this launch's FIRST iteration
   // filled by lg_map_gn_launch
+  int tile;                // stack points per CTA step (32 .. 256)
   double* partials;
   unsigned int* ticket;
   unsigned int* gen;

@@ -265,9 +265,7 @@ __device__ __forceinline__ bool gn_fit_row(const float* sc, bool is_c, float4 or
 }
 
 constexpr int GN_NT = 256;           // threads per CTA
-constexpr int GN_TILE = 256;         // stack points per CTA step (one per thread in the fit phase)
-constexpr int GN_SUB = 8;            // lanes per query in the search phase
-constexpr int GN_GROUPS = GN_NT / GN_SUB;
+constexpr int GN_TILE = 256;         // largest number of stack points per CTA step (one per thread in the fit phase)
 constexpr unsigned long long GN_EMPTY = ~0ull;
 
 // Sorted insertion of (key, payload) into an ascending 5-list held in registers, without branches on the position.
@@ -285,6 +283,7 @@ struct GnShared {
   float4 ori[GN_TILE];        // stack point (sensor frame)
   float4 sel[GN_TILE];        // the same in the map frame under the current pose (LM:756, 865)
   float nb[GN_TILE][5][3];    // its five neighbours
+  float row[GN_TILE][8];      // its row of A (6), b, and 1 / 0 = kept (LM:940-967)
   unsigned short list[GN_TILE];  // queries of the tile this rank evaluates (owner rule), in order
   unsigned char ok[GN_TILE];  // five neighbours within 1 m found
   int wcount[GN_NT / 32];
@@ -296,13 +295,14 @@ struct GnShared {
   bool last;
 };
 
-__global__ void __launch_bounds__(GN_NT) map_gn_kernel(MapGnArgs A) {
+template <int SUB>  // lanes per query in the search phase: 8 or 4
+__global__ void __launch_bounds__(GN_NT, 2) map_gn_kernel(MapGnArgs A) {
   __shared__ GnShared S;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int sub = lane & (GN_SUB - 1), grp = lane / GN_SUB;
-  const unsigned int gmask = 0xffu << (grp * GN_SUB);
+  const int sub = lane & (SUB - 1), grp = lane / SUB;
   const int nq = A.n_cs + A.n_ss;
-  const int ntiles = (nq + GN_TILE - 1) / GN_TILE;
+  const int tq = A.tile;  // stack points per CTA step: 256 when there is work for every SM, down to 32 (one search step) otherwise
+  const int ntiles = (nq + tq - 1) / tq;
   if (tid < 6) {
     S.T[tid] = A.T[tid];
     S.sc[tid] = A.sc[tid];
@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(GN_NT) map_gn_kernel(MapGnArgs A) {
     if (lane < 28) S.acc[w][lane] = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       // ---- phase 0: transform, owner rule, ordered compaction of the owned queries
-      const int q = tile * GN_TILE + tid;
+      const int q = tile * tq + tid;
       bool own = false;
-      if (q < nq) {
+      if (tid < tq && q < nq) {
         const float4 ori = q < A.n_cs ? A.cstack[q] : A.sstack[q - A.n_cs];
         const float4 sel = gn_assoc_to_map(T, sc, ori);
         S.ori[tid] = ori;
@@ -346,104 +346,182 @@ __global__ void __launch_bounds__(GN_NT) map_gn_kernel(MapGnArgs A) {
         if (tid == 0) S.n_own = total;
       }
       __syncthreads();
-      // ---- phase 1: exact 5-NN, eight lanes per query
+      // ---- phase 1: exact 5-NN, SUB lanes per query (32 / SUB queries per warp and step)
       const int n_own = S.n_own;
-      for (int e0 = w * (32 / GN_SUB); e0 < n_own; e0 += GN_GROUPS) {  // warp-uniform trip count: the four groups stay together
+      constexpr int QPW = 32 / SUB;            // queries per warp and step
+      constexpr int RPL = (9 + SUB - 1) / SUB;  // rows a lane looks up
+      const int gbase = grp * SUB;
+      // row look-ups of a step: lane `sub` takes rows sub, sub + SUB, ... of its query; they are issued one step AHEAD of
+      // the scan that needs them, so their latency hides behind the previous step's point loads
+      unsigned int lo[RPL], hi[RPL];
+      float4 sel_n = make_float4(0.f, 0.f, 0.f, 0.f);
+      int lq_n = 0;
+      bool active_n = false;
+      const float4* pts_n = nullptr;
+      auto lookup = [&](int e0) {
         const int e = e0 + grp;
-        const bool active = e < n_own;
-        const int lq = active ? (int)S.list[e] : 0;
-        const float4 sel = S.sel[lq];
-        const bool is_c = tile * GN_TILE + lq < A.n_cs;
-        const CsrGridD& g = is_c ? A.gc : A.gs;
-        const float4* __restrict__ pts = g.sorted;
-        const unsigned int* __restrict__ E = g.E;
-        const int cx = csr_axis(sel.x, g.x0, g.nx), cy = csr_axis(sel.y, g.y0, g.ny), cz = csr_axis(sel.z, g.z0, g.nz);
-        // the nine x-runs: lane `sub` looks up row `sub`, lane 0 also row 8
-        unsigned int lo = 0, hi = 0, lo8 = 0, hi8 = 0;
-        if (active) {
-          {
-            const int ry = cy + (sub % 3) - 1, rz = cz + (sub / 3) - 1;
-            if (ry >= 0 && ry < g.ny && rz >= 0 && rz < g.nz) {
-              const unsigned int* r = E + (size_t)(rz * g.ny + ry) * g.nxp + cx;
-              lo = __ldg(r);
-              hi = __ldg(r + 3);
-            }
-          }
-          if (sub == 0) {
-            const int ry = cy + 1, rz = cz + 1;
-            if (ry < g.ny && rz < g.nz) {
-              const unsigned int* r = E + (size_t)(rz * g.ny + ry) * g.nxp + cx;
-              lo8 = __ldg(r);
-              hi8 = __ldg(r + 3);
-            }
+        active_n = e < n_own;
+        lq_n = active_n ? (int)S.list[e] : 0;
+        sel_n = S.sel[lq_n];
+        const CsrGridD& g = (tile * tq + lq_n < A.n_cs) ? A.gc : A.gs;
+        pts_n = g.sorted;
+        const int cx = csr_axis(sel_n.x, g.x0, g.nx), cy = csr_axis(sel_n.y, g.y0, g.ny), cz = csr_axis(sel_n.z, g.z0, g.nz);
+#pragma unroll
+        for (int t = 0; t < RPL; t++) {
+          const int row = sub + t * SUB;
+          const int ry = cy + (row % 3) - 1, rz = cz + (row / 3) - 1;
+          lo[t] = hi[t] = 0u;
+          if (active_n && row < 9 && ry >= 0 && ry < g.ny && rz >= 0 && rz < g.nz) {
+            const unsigned int* r = g.E + (size_t)(rz * g.ny + ry) * g.nxp + cx;
+            lo[t] = __ldg(r);
+            hi[t] = __ldg(r + 3);
           }
         }
+      };
+      if (w * QPW < n_own) lookup(w * QPW);
+      for (int e0 = w * QPW; e0 < n_own; e0 += QPW * (GN_NT / 32)) {  // warp-uniform trip count: the groups of a warp stay together
+        const bool active = active_n;
+        const int lq = lq_n;
+        const float4 sel = sel_n;
+        const float4* __restrict__ pts = pts_n;
+        unsigned int rl[9], rh[9];
+        int rounds = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+          const unsigned int a0 = __shfl_sync(0xffffffffu, lo[j / SUB], gbase + (j % SUB));
+          rh[j] = __shfl_sync(0xffffffffu, hi[j / SUB], gbase + (j % SUB));
+          rounds = max(rounds, (int)(rh[j] - a0 + SUB - 1) / SUB);
+          rl[j] = a0 + sub;
+        }
+        if (e0 + QPW * (GN_NT / 32) < n_own) lookup(e0 + QPW * (GN_NT / 32));
         unsigned long long k0 = GN_EMPTY, k1 = GN_EMPTY, k2 = GN_EMPTY, k3 = GN_EMPTY, k4 = GN_EMPTY;
         unsigned int p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
-#pragma unroll 1
-        for (int j = 0; j < 9; j++) {
-          const unsigned int rlo = j < 8 ? __shfl_sync(gmask, lo, grp * GN_SUB + j) : __shfl_sync(gmask, lo8, grp * GN_SUB);
-          const unsigned int rhi = j < 8 ? __shfl_sync(gmask, hi, grp * GN_SUB + j) : __shfl_sync(gmask, hi8, grp * GN_SUB);
-          for (unsigned int i = rlo + sub; i < rhi; i += GN_SUB) {
-            const float4 p = __ldg(&pts[i]);
-            const float d2 = lg_sqdist(p.x, p.y, p.z, sel.x, sel.y, sel.z);
-            if (d2 < 1.0f) {
-              const unsigned long long c = lg_pack_nbr(d2, __float_as_int(p.w));
-              if (c < k4) GN_INSERT(c, i);
+        // every lane takes points sub, sub + SUB, ... of each of the nine runs; the (up to) nine loads of a round are issued
+        // together before the first distance is formed, so a lane has nine L2 / DRAM requests in flight instead of one
+        for (int rd = 0; rd < rounds; rd++) {
+          float4 pf[9];
+#pragma unroll
+          for (int j = 0; j < 9; j++)
+            if (rl[j] < rh[j]) pf[j] = __ldg(&pts[rl[j]]);
+#pragma unroll
+          for (int j = 0; j < 9; j++) {
+            if (rl[j] < rh[j]) {
+              const float d2 = lg_sqdist(pf[j].x, pf[j].y, pf[j].z, sel.x, sel.y, sel.z);
+              if (d2 < 1.0f) {
+                const unsigned long long c = lg_pack_nbr(d2, __float_as_int(pf[j].w));
+                if (c < k4) GN_INSERT(c, rl[j]);
+              }
             }
+            rl[j] += SUB;
           }
         }
-        // merge inside the group: five rounds of "minimum of the lanes' heads"; keys are unique (they embed the index)
-        unsigned long long res4 = GN_EMPTY;
-        unsigned int mypos = 0;  // lane r < 5 of the group ends with the position of neighbour r
-        int nbr_idx = -1;
+        // merge inside the group: five rounds of "smallest head of the lanes' sorted lists".  The minimum of the distance
+        // bits is found with xor-shuffles (they stay inside the group for every group of the warp at once); an exact tie
+        // between two lanes' heads (rare) is broken by the smaller original index the same way.
+        unsigned int pos_a = 0, pos_b = 0;  // lane `sub` ends with the positions of neighbours sub and sub + SUB
+        int idx_a = -1, idx_b = -1;
+        bool found = false;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
-          const unsigned int hi32 = (unsigned int)(k0 >> 32);
-          const unsigned int mhi = __reduce_min_sync(gmask, hi32);
-          const unsigned int lo32 = (hi32 == mhi) ? (unsigned int)k0 : 0xffffffffu;
-          const unsigned int mlo = __reduce_min_sync(gmask, lo32);
-          const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
-          const bool mine = k0 == m && m != GN_EMPTY;
-          const unsigned int pos = __reduce_max_sync(gmask, mine ? p0 : 0u);
-          if (sub == r) {
-            mypos = pos;
-            nbr_idx = (int)mlo;
+          const unsigned int hi32 = (unsigned int)(k0 >> 32), lo32 = (unsigned int)k0;
+          unsigned int m = hi32;
+#pragma unroll
+          for (int o = 1; o < SUB; o <<= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+          bool cand = hi32 == m && m != 0xffffffffu;
+          unsigned int bal = (__ballot_sync(0xffffffffu, cand) >> gbase) & ((1u << SUB) - 1u);
+          if (__any_sync(0xffffffffu, (bal & (bal - 1u)) != 0u)) {  // some group of the warp has a tie on d2
+            unsigned int ml = cand ? lo32 : 0xffffffffu;
+#pragma unroll
+            for (int o = 1; o < SUB; o <<= 1) ml = min(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+            cand = cand && lo32 == ml;
+            bal = (__ballot_sync(0xffffffffu, cand) >> gbase) & ((1u << SUB) - 1u);
           }
-          if (r == 4) res4 = m;
-          if (mine) {
+          const int wl = gbase + (bal ? __ffs(bal) - 1 : 0);
+          const unsigned int pos = __shfl_sync(0xffffffffu, p0, wl);
+          const unsigned int idx = __shfl_sync(0xffffffffu, lo32, wl);
+          if (sub == (r % SUB)) {
+            if (r < SUB) {
+              pos_a = pos;
+              idx_a = (int)idx;
+            } else {
+              pos_b = pos;
+              idx_b = (int)idx;
+            }
+          }
+          if (r == 4) found = active && bal != 0u;
+          if (cand) {
             k0 = k1; k1 = k2; k2 = k3; k3 = k4; k4 = GN_EMPTY;
             p0 = p1; p1 = p2; p2 = p3; p3 = p4;
           }
         }
-        const bool found = active && res4 != GN_EMPTY;
         if (sub < 5 && found) {
-          const float4 p = __ldg(&pts[mypos]);
+          const float4 p = __ldg(&pts[pos_a]);
           S.nb[lq][sub][0] = p.x;
           S.nb[lq][sub][1] = p.y;
           S.nb[lq][sub][2] = p.z;
         }
+        if (SUB < 5 && sub + SUB < 5 && found) {
+          const float4 p = __ldg(&pts[pos_b]);
+          S.nb[lq][sub + SUB][0] = p.x;
+          S.nb[lq][sub + SUB][1] = p.y;
+          S.nb[lq][sub + SUB][2] = p.z;
+        }
+        if (A.nbr != nullptr && active) {
+          int* o = A.nbr + (size_t)(tile * tq + lq) * 5;
+          if (sub < 5) o[sub] = found ? idx_a : -1;
+          if (SUB < 5 && sub + SUB < 5) o[sub + SUB] = found ? idx_b : -1;
+        }
         if (sub == 0 && found) S.ok[lq] = 1;
-        if (A.nbr != nullptr && sub < 5 && active) A.nbr[(size_t)(tile * GN_TILE + lq) * 5 + sub] = found ? nbr_idx : -1;
       }
       __syncthreads();
       // ---- phase 2: fit + Jacobian row, one query per thread; the warp's 28 sums go to its shared accumulator
-      {
-        Acc28 acc;
-        acc.clear();
+      if (w * 32 < tq) {  // warp-uniform: only the warps that hold queries of this tile
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = 0.f;
+        bool keep = false;
         if (S.ok[tid]) {
-          float px[5], py[5], pz[5], a[6], b;
+          float px[5], py[5], pz[5];
 #pragma unroll
           for (int j = 0; j < 5; j++) {
             px[j] = S.nb[tid][j][0];
             py[j] = S.nb[tid][j][1];
             pz[j] = S.nb[tid][j][2];
           }
-          if (gn_fit_row(sc, q < A.n_cs, S.ori[tid], S.sel[tid], px, py, pz, a, &b)) acc.add_row(a, b);
+          keep = gn_fit_row(sc, q < A.n_cs, S.ori[tid], S.sel[tid], px, py, pz, a, &b);
         }
-        if (__any_sync(0xffffffffu, S.ok[tid])) {
-          const double r = lg_warp_reduce28(acc.v, lane);
-          if (lane < 28) S.acc[w][lane] += r;
+        if (__any_sync(0xffffffffu, keep)) {
+          // the rows of this warp go through shared memory; lane L < 28 then adds "its" product over the 32 rows in row
+          // order (exact float products, double sums): 21 upper-triangle terms of AtA, 6 of AtB, the row count
+#pragma unroll
+          for (int i = 0; i < 6; i++) S.row[tid][i] = keep ? a[i] : 0.f;
+          S.row[tid][6] = keep ? b : 0.f;
+          S.row[tid][7] = keep ? 1.f : 0.f;
+          __syncwarp();
+          if (lane < 28) {
+            // lane -> (i, j): 0..20 upper triangle row-major, 21..26 (i, 6) = AtB, 27 (7, 7) = count
+            int i = 0, j = lane;
+            if (lane < 21) {
+              int rem = lane;
+#pragma unroll
+              for (int r = 0; r < 6; r++)
+                if (rem >= 6 - r && i == r) {
+                  rem -= 6 - r;
+                  i = r + 1;
+                }
+              j = i + rem;
+            } else if (lane < 27) {
+              i = lane - 21;
+              j = 6;
+            } else {
+              i = 7;
+              j = 7;
+            }
+            double sum = 0.0;
+            const float(*rw)[8] = &S.row[w * 32];
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) sum += (double)rw[r][i] * (double)rw[r][j];
+            S.acc[w][lane] += sum;
+          }
+          __syncwarp();
         }
       }
       __syncthreads();
@@ -686,23 +764,30 @@ int lg_csr_bbox_launch(const float4* pts0, int n0, const float4* pts1, int n1, i
   return LOAM_OK;
 }
 
-int lg_map_gn_grid(int nq, int device) {
+static int lg_map_gn_grid(int nq, int device, int* tile_out) {
   static int per_sm[64] = {0}, sms[64] = {0};
   const int d = device & 63;
   if (!per_sm[d]) {
     int occ = 0, n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_gn_kernel, GN_NT, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, map_gn_kernel<8>, GN_NT, 0) != cudaSuccess || occ < 1) occ = 1;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n < 1) n = 1;
     per_sm[d] = occ;
     sms[d] = n;
   }
-  const int ntiles = std::max(1, (nq + GN_TILE - 1) / GN_TILE);
-  return std::min(ntiles, per_sm[d] * sms[d]);
+  // tile: the largest of 256 / 128 / 64 / 32 stack points per CTA step that still gives every resident CTA a tile
+  // small problems (one sweep's stack against the local map): one CTA per SM at most -- a cooperative grid that fills
+  // the register files would lock the kernels of the other pipeline stages (extraction, odometry) out while it runs
+  const int resident = nq <= (1 << 16) ? sms[d] : per_sm[d] * sms[d];
+  int tile = GN_TILE;
+  while (tile > 32 && (nq + tile - 1) / tile < resident) tile >>= 1;
+  *tile_out = tile;
+  const int ntiles = std::max(1, (nq + tile - 1) / tile);
+  return std::min(ntiles, resident);
 }
 
 int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, long long* launches) {
   const int nq = A.n_cs + A.n_ss;
-  const int grid = lg_map_gn_grid(nq, device);
+  const int grid = lg_map_gn_grid(nq, device, &A.tile);
   LG_CHECK(ws.partials.ensure((size_t)grid * 28 * 8 + 64, st));
   if (!ws.sync.p) {
     LG_CHECK(ws.sync.ensure(64 * 4, st));
@@ -714,7 +799,9 @@ int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, lon
   A.state = ws.sync.as<float>() + 16;
   LgProfScope prof_scope(LGK_MAP_KNN, st, (double)nq);
   void* args[] = {(void*)&A};
-  LG_CHECK(cudaLaunchCooperativeKernel((const void*)map_gn_kernel, dim3(grid), dim3(GN_NT), args, 0, st));
+  static const int sub_env = getenv("LOAM_GN_SUB") ? atoi(getenv("LOAM_GN_SUB")) : 8;  // experiment switch: 4 lanes per query
+  const void* fn = sub_env == 4 ? (const void*)map_gn_kernel<4> : (const void*)map_gn_kernel<8>;
+  LG_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GN_NT), args, 0, st));
   (*launches)++;
   return LOAM_OK;
 }

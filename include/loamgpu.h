@@ -214,7 +214,23 @@ int loam_map_finish_reduced(const double reduced28_host[28], float AtA[36], floa
  *   loam_shard_export   allocate this rank's exchange buffer, return its 64-byte cudaIpcMemHandle_t
  *   loam_shard_connect  handles = world x 64 bytes gathered from all ranks (any transport), in rank order
  *   loam_map_iter_allreduce  loam_map_iter over the union of all ranks' queries; every rank must call it (<= 8 ranks) */
+/* The whole Gauss-Newton loop LM:753-1017 for the inputs of loam_map_set_inputs in ONE launch: kNN-5, fit, normal
+ * equations, 6x6 solve, pose update and convergence test all run on the device (the eigen-decomposition of iteration 0,
+ * LM:970-997, is verified by the host afterwards; a degenerate problem is replayed iteration by iteration).  T is updated
+ * in place; *iterations = iterations executed (<= max_iters; the reference uses 10).  On a handle connected with
+ * loam_shard_connect every rank calls it with the same T: the ranks exchange their 28 sums inside the kernel each
+ * iteration and end with bit-identical poses.
+ *   loam_shard_set_slab  owner rule of a sharded map: this rank evaluates the stack points whose MAP-FRAME x (under the
+ *                        current pose, re-evaluated every iteration on the device, LM:244-262) lies in [x_lo, x_hi); the
+ *                        caller gives every rank the whole stack and the map points of its slab + 1 m halo */
+int loam_map_optimize(loam_handle* h, float T[6], int max_iters, int* iterations);
+int loam_shard_set_slab(loam_handle* h, float x_lo, float x_hi);
 int loam_shard_export(loam_handle* h, unsigned char handle64[64]);
+/* Emulation hook for boxes with fewer GPUs than ranks: deposits rank `from_rank`'s 28 partial sums for the NEXT iteration in
+ * this handle's exchange buffer and raises its flag, exactly what that peer's kernel would do over NVLink.  Kernels of
+ * several ranks must never wait for one another on ONE GPU (nothing guarantees they run at the same time), so the tests
+ * run the ranks one after the other and inject the peers' sums. */
+int loam_shard_inject(loam_handle* h, int from_rank, const double sums28_host[28]);
 int loam_shard_connect(loam_handle* h, const unsigned char* handles, int world, int rank);
 int loam_map_iter_allreduce(loam_handle* h, int iter, const float T[6], float AtA[36], float AtB[6], int* n_sel);
 

@@ -214,6 +214,14 @@ class OdomIter:
         return AtA, AtB, n.value
 
 
+def associate_to_map(pts4, T):
+    """pointAssociateToMap (LM:244-262) of a cloud."""
+    a, T = _f32(pts4), _f32(T)
+    out = np.empty_like(a)
+    lib().orc_associate_to_map(a.ctypes.data, a.shape[0], T.ctypes.data, out.ctypes.data)
+    return out
+
+
 def map_iteration(corner_stack, surf_stack, corner_map, surf_map, T, brute=False):
     a, b, c, d, T = _f32(corner_stack), _f32(surf_stack), _f32(corner_map), _f32(surf_map), _f32(T)
     cc, cs = np.empty((a.shape[0], 5), np.int32), np.empty((b.shape[0], 5), np.int32)

@@ -15,6 +15,8 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     from gpscalibration_b200 import capi, sharding, SweepGenerator
     from oracle import orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers.routing import owner_mask
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -31,10 +33,11 @@ def _worker(rank, world, port, q):
     T = np.array(pipe.process(gen.sweep(8)[0]).mapped, np.float32)
     # the map clouds above live in different frames than a real local map; what matters here is only that sharded ==
     # unsharded on identical inputs, so bring the map into the query frame with the same pose
-    surf_map = sharding.associate_to_map(orc.voxel_grid(f["less_flat"], 0.2), T)
-    corner_map = sharding.associate_to_map(orc.voxel_grid(f["less_sharp"], 0.1), T)
+    surf_map = orc.associate_to_map(orc.voxel_grid(f["less_flat"], 0.2), T)
+    corner_map = orc.associate_to_map(orc.voxel_grid(f["less_sharp"], 0.1), T)
     edges = sharding.slab_edges(float(surf_map[:, 0].min()), float(surf_map[:, 0].max()), world)
-    my = orc.map_iteration_sums28(sharding.route_queries(corner_stack, T, edges, rank), sharding.route_queries(surf_stack, T, edges, rank),
+    my = orc.map_iteration_sums28(corner_stack[owner_mask(orc, corner_stack, T, edges, rank)],
+                                  surf_stack[owner_mask(orc, surf_stack, T, edges, rank)],
                                   sharding.shard_map(corner_map, edges, rank), sharding.shard_map(surf_map, edges, rank), T)
     t = torch.from_numpy(my.copy())
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
