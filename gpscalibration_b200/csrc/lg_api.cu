@@ -132,6 +132,7 @@ struct loam_handle {
   CsrWs csr;     // cell-sorted grids over the gathered corner / surf map (replace the kd-trees, LM:750-751)
   MapGnWs gn;    // workspace of the fused Gauss-Newton kernel
   bool grids_valid = false;
+  bool nbr_valid = false;  // gn.nbr holds the neighbours of the last stage-level iteration
   float slab_lo = -INFINITY, slab_hi = INFINITY;  // sharded map: this rank evaluates queries whose map-frame x is in [lo, hi)
   DevBuf d_ents, d_segs, d_ints, d_seg_off, d_seg_leaf, d_out_se;
   VoxBigWs vb;
@@ -500,8 +501,14 @@ int map_gn_enqueue(loam_handle* h, const float* T, int it0, int it1, int solve, 
   A.gs = h->csr.d[1];
   A.slab_lo = h->slab_lo;
   A.slab_hi = h->slab_hi;
-  LG_CHECK(h->gn.nbr.ensure((size_t)(A.n_cs + A.n_ss + 1) * 5 * 4, h->st));
-  A.nbr = h->gn.nbr.as<int>();
+  // pointSearchInd is internal to the reference (LM:760, 867): the stage-level calls keep it for loam_map_get_corr, the
+  // device loop does not write 20 bytes per stack point and iteration nobody reads
+  A.nbr = nullptr;
+  if (!solve) {
+    LG_CHECK(h->gn.nbr.ensure((size_t)(A.n_cs + A.n_ss + 1) * 5 * 4, h->st));
+    A.nbr = h->gn.nbr.as<int>();
+  }
+  h->nbr_valid = !solve;
   A.out = out_dev ? out_dev : h->d_mail;
   A.seq = out_dev ? 0ull : ++h->mail_seq;
   if (!out_dev) h->h_mail[40] = 0.0;
@@ -1556,7 +1563,7 @@ int loam_map_iter(loam_handle* h, int iter, const float* T, float* AtA, float* A
 int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int cap_s) {
   if (!h) return LOAM_EINVAL;
   if (cap_c < h->n_stack_c || cap_s < h->n_stack_s) return LOAM_ENOSPC;
-  if (!h->gn.nbr.p) return LOAM_ESTATE;
+  if (!h->gn.nbr.p || !h->nbr_valid) return LOAM_ESTATE;  // only after a stage-level iteration (loam_map_iter*)
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   if (h->n_stack_c) LG_D2H(h, corner5, h->gn.nbr.p, (size_t)h->n_stack_c * 20);

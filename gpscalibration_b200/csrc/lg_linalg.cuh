@@ -214,6 +214,77 @@ LG_HD void lg_jacobi_eigen(const float* A0, float* W, float* V) {
   }
 }
 
+#ifdef __CUDACC__
+// lg_jacobi_eigen<3> with every index static (the generic version indexes A, W, V with the pivot position, which puts them
+// into local memory on the device): the three possible pivots are three copies of the same rotation.  Same operations in
+// the same order, element for element -- bit-identical results.  Only the upper triangle of A is ever read.
+__device__ __forceinline__ void lg_jacobi_eigen3(const float* A0, float* W, float* V) {
+  float a01 = A0[1], a02 = A0[2], a12 = A0[5];
+  float w0 = A0[0], w1 = A0[4], w2 = A0[8];
+  float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+  const float eps = 1.1920929e-07f;
+#define LG_ROT(v0, v1) a0 = (v0), b0 = (v1), (v0) = a0 * c - b0 * s, (v1) = a0 * s + b0 * c
+#define LG_JAC3(P, WK, WL, R0, R1, VK0, VK1, VK2, VL0, VL1, VL2)   \
+  {                                                                \
+    const float p = P;                                             \
+    const float y = (WL - WK) * 0.5f;                              \
+    float t = fabsf(y) + sqrtf(p * p + y * y);                     \
+    float s = sqrtf(p * p + t * t);                                \
+    const float c = t / s;                                         \
+    s = p / s;                                                     \
+    t = (p / t) * p;                                               \
+    if (y < 0.f) {                                                 \
+      s = -s;                                                      \
+      t = -t;                                                      \
+    }                                                              \
+    P = 0.f;                                                       \
+    WK = WK - t;                                                   \
+    WL = WL + t;                                                   \
+    float a0, b0;                                                  \
+    LG_ROT(R0, R1);                                                \
+    LG_ROT(VK0, VL0);                                              \
+    LG_ROT(VK1, VL1);                                              \
+    LG_ROT(VK2, VL2);                                              \
+  }
+#pragma unroll 1
+  for (int it = 0; it < 3 * 3 * 30; it++) {
+    int piv = 0;
+    float mv = fabsf(a01);
+    if (mv < fabsf(a02)) {
+      mv = fabsf(a02);
+      piv = 1;
+    }
+    if (mv < fabsf(a12)) {
+      mv = fabsf(a12);
+      piv = 2;
+    }
+    if (mv <= eps) break;  // |pivot| <= eps
+    if (piv == 0) {         // (k, l) = (0, 1): i > l rotates (A[0][2], A[1][2])
+      LG_JAC3(a01, w0, w1, a02, a12, v00, v01, v02, v10, v11, v12)
+    } else if (piv == 1) {  // (0, 2): k < i < l rotates (A[0][1], A[1][2])
+      LG_JAC3(a02, w0, w2, a01, a12, v00, v01, v02, v20, v21, v22)
+    } else {                // (1, 2): i < k rotates (A[0][1], A[0][2])
+      LG_JAC3(a12, w1, w2, a01, a02, v10, v11, v12, v20, v21, v22)
+    }
+  }
+#undef LG_JAC3
+#undef LG_ROT
+#define LG_SWAPF(x, y) { const float t_ = (x); (x) = (y); (y) = t_; }
+  {  // selection sort, descending, first maximum wins (k = 0)
+    int m = 0;
+    float wm = w0;
+    if (wm < w1) { m = 1; wm = w1; }
+    if (wm < w2) { m = 2; }
+    if (m == 1) { LG_SWAPF(w0, w1) LG_SWAPF(v00, v10) LG_SWAPF(v01, v11) LG_SWAPF(v02, v12) }
+    if (m == 2) { LG_SWAPF(w0, w2) LG_SWAPF(v00, v20) LG_SWAPF(v01, v21) LG_SWAPF(v02, v22) }
+  }
+  if (w1 < w2) { LG_SWAPF(w1, w2) LG_SWAPF(v10, v20) LG_SWAPF(v11, v21) LG_SWAPF(v12, v22) }
+#undef LG_SWAPF
+  W[0] = w0; W[1] = w1; W[2] = w2;
+  V[0] = v00; V[1] = v01; V[2] = v02; V[3] = v10; V[4] = v11; V[5] = v12; V[6] = v20; V[7] = v21; V[8] = v22;
+}
+#endif
+
 // ---- the pieces of the Gauss-Newton update the reference keeps on the CPU ------------------------------------------
 #ifdef __CUDACC__
 __host__ __device__

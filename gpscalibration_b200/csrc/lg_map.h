@@ -65,6 +65,8 @@ struct MapGnArgs {
   unsigned int* ticket;
   unsigned int* gen;
   float* state;
+  unsigned int* work;       // one thread per query: next chunk of 32 stack points (chunks are handed out dynamically)
+  unsigned long long* fx;   // one thread per query: [28][4] fixed-point totals of the iteration (order-independent sums)
 };
 int lg_csr_reserve(CsrWs& ws, size_t table_entries, int n_points, cudaStream_t st);
 // Box corners in cells (inclusive) per grid; points outside are clamped into the boundary cells (still exact).

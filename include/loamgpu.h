@@ -198,7 +198,8 @@ int loam_map_set_inputs(loam_handle* h, const float* corner_stack, int n_cs, con
 /* One Gauss-Newton iteration body without the solve, LM:754-967: kNN-5, line / plane fit, rows, AtA, AtB.
  * n_sel < 50 => AtA/AtB zeroed (LM:929-932). */
 int loam_map_iter(loam_handle* h, int iter, const float T[6], float AtA[36], float AtB[6], int* n_sel);
-/* pointSearchInd (LM:760,867): 5 int32 per stack point, -1 x5 when the 5th neighbour is not within 1 m. */
+/* pointSearchInd (LM:760,867) of the last stage-level iteration (loam_map_iter / _partial / _allreduce): 5 int32 per stack
+ * point, -1 x5 when the 5th neighbour is not within 1 m.  LOAM_ESTATE after loam_map_optimize (the device loop keeps none). */
 int loam_map_get_corr(loam_handle* h, int* corner5, int cap_c, int* surf5, int cap_s);
 /* The 6x6 solve + degeneracy handling the host keeps (LO:975-1004 / LM:968-997).  state37 = matP (36) + isDegenerate. */
 int loam_gn_solve(const float AtA[36], const float AtB[6], int iter, float eig_threshold, float state37[37], float X[6]);
