@@ -13,6 +13,11 @@ sequence (BASELINE configs[3], no data-path collective): weak scaling, value = a
   roofline : dominant kernel class from a separate CUDA-event pass (loam_profile), algorithmic bytes per DESIGN.md
   cpu_baseline : the CPU oracle (restatement of the reference; oracle/_ref when built) on this box's host cores
 
+Extra objects on the same line: "cfg1" (configs[0]: microseconds per odometry refresh / iteration of one registration
+against the launch-latency floor), "cfg3" (configs[2] at spec size: mapping stage against a 2.0 M-point local map, N = 1),
+"cfg5" (configs[4]: 1 M-point stack against a 50 M-point map sharded over the N ranks, NCCL all-reduce and the exchange
+fused into the kernel), "multi_segment", "parity".
+
 `--impl reference` times the reference's CPU implementation of the same path on the same workload (bounded sample).
 """
 import argparse
@@ -159,6 +164,10 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=150, help="bounded CPU sample (first sweeps of the same sequence)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi-segments", type=int, default=4, help="extra: independent segments sharing one GPU (0/1 = skip)")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg 3 object (mapping stage against a 2 M-point local map)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg 5 object (1 M-point stack against the 50 M-point sharded map)")
+    ap.add_argument("--cfg5-map-points", type=int, default=50_000_000)
+    ap.add_argument("--cfg5-queries", type=int, default=1_000_000)
     args = ap.parse_args()
 
     # exactly ONE line on stdout (the JSON): libraries that print banners to fd 1 (NCCL version line) go to stderr
@@ -425,10 +434,79 @@ def main():
         g2.close()
         out["parity"] = {"sweeps": n, "mapping_runs": n_map, "against": kind, "max_abs_pose_diff_odometry": worst_o,
                          "max_abs_pose_diff_mapping": worst_m}
-    if rank == 0:
-        emit(out)
+    # cfg 1 (configs[0]): ONE registration of a sweep pair (extract + scan-to-scan odometry), the case that can only be
+    # latency bound: microseconds per stage against the floor the launches and host hand-overs of that stage set
+    if world == 1:
+        lat = torch.zeros(1, device=dev_t)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(2000):
+            lat.add_(1.0)
+        eb.record()
+        torch.cuda.synchronize()
+        launch_period_us = 1e3 * ea.elapsed_time(eb) / 2000  # back-to-back one-CTA kernels on one stream
+        w0 = time.perf_counter()
+        for _ in range(300):
+            lat.add_(1.0)
+            torch.cuda.synchronize()
+        roundtrip_us = 1e6 * (time.perf_counter() - w0) / 300  # launch + host-visible completion
+        g1 = LoamGpu(device=local_rank)
+        st1 = torch.cuda.ExternalStream(g1.stream, device=dev_t)
+        reg_us, ext_us, iters, launches_reg, launches_ext, syncs_reg = [], [], 0, 0, 0, 0
+        for rep in range(12):
+            g1.reset()
+            for k in range(2):  # sweep 0 initialises (LO:519-563); sweep 1 finds laserCloudCornerLastNum == 0 and only
+                g1.extract(arr[offs[k]:offs[k + 1]])  # hands its clouds on (LO:572, 1119-1121); sweep 2 is the first registration
+                g1.odometry_process()
+            s_a = g1.stats()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(st1)
+            g1.extract(arr[offs[2]:offs[3]])
+            s_b = g1.stats()
+            e1.record(st1)
+            ro = g1.odometry_process()
+            e2.record(st1)
+            torch.cuda.synchronize()
+            s_c = g1.stats()
+            if rep >= 2:
+                ext_us.append(1e3 * e0.elapsed_time(e1))
+                reg_us.append(1e3 * e1.elapsed_time(e2))
+            iters = ro.iterations
+            launches_ext, launches_reg = s_b["launches"] - s_a["launches"], s_c["launches"] - s_b["launches"]
+            syncs_reg = s_c["syncs"] - s_b["syncs"]
+        g1.close()
+        refreshes = (iters + 4) // 5  # LO:595: correspondences are re-searched every fifth iteration
+        floor_us = launches_reg * launch_period_us + syncs_reg * roundtrip_us
+        out["cfg1"] = {"workload": "cfg1: one VLP-16-shaped sweep pair (28.8 k points each): extract of the second sweep + its scan-to-scan registration against the first",
+                       "extract_us": float(np.median(ext_us)), "extract_launches": int(launches_ext),
+                       "registration_us": float(np.median(reg_us)), "iterations": int(iters), "refreshes": int(refreshes),
+                       "registration_launches": int(launches_reg), "registration_host_handovers": int(syncs_reg),
+                       "us_per_iteration": float(np.median(reg_us)) / max(1, iters),
+                       "launch_period_us": launch_period_us, "host_roundtrip_us": roundtrip_us,
+                       "latency_floor_us": floor_us, "registration_over_floor": float(np.median(reg_us)) / floor_us if floor_us > 0 else None,
+                       "note": "floor = launches x back-to-back launch period + host hand-overs x (launch + host-visible completion), both measured here"}
     gpu.close()
     pipe.close()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    if world == 1 and not args.no_cfg3:
+        import bench_cfg3
+        try:
+            out["cfg3"] = bench_cfg3.run_stage(local=local_rank, log=log)
+        except Exception as e:  # an extra must not take the headline down
+            out["cfg3"] = {"error": repr(e)}
+    if not args.no_cfg5:
+        import bench_cfg5
+        try:
+            c5 = bench_cfg5.run(args.cfg5_map_points, args.cfg5_queries, 10, rank, local_rank, world, dist if world > 1 else None, log=log)
+            if "fused" in c5:
+                c5["fused"]["frac_of_hbm_peak_per_gpu"] = c5["fused"]["per_gpu_GBps_algorithmic"] / peak_gbs
+            out["cfg5"] = c5
+        except Exception as e:
+            out["cfg5"] = {"error": repr(e)}
+    if rank == 0:
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0

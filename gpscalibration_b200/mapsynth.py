@@ -62,14 +62,17 @@ def voxel_order(c, leaf):
     return c[np.lexsort((ijk[:, 0], ijk[:, 1], ijk[:, 2]))]
 
 
-def synth_queries(corner_map, surf_map, n_queries, T_true, seed=11, ordered=True):
+def synth_queries(corner_map, surf_map, n_queries, T_true, seed=11, ordered=True, take_all=False):
     """Query stacks = a random subset of the map moved by the inverse of the rigid transform T_true = {rx, ry, rz, tx, ty, tz}
     (pointAssociateTobeMapped, LM:264-282, in float64), so that Gauss-Newton started at zero converges towards T_true.
     Returns (corner_stack, surf_stack) in voxel-grid order (or random order)."""
     rng = np.random.default_rng(seed)
-    n_c = min(n_queries // 5, len(corner_map) // 2)
-    qi_c = rng.choice(len(corner_map), n_c, replace=False)
-    qi_s = rng.choice(len(surf_map), min(n_queries - n_c, len(surf_map)), replace=False)
+    if take_all:  # the caller has chosen the points
+        qi_c, qi_s = np.arange(len(corner_map)), np.arange(len(surf_map))
+    else:
+        n_c = min(n_queries // 5, len(corner_map) // 2)
+        qi_c = rng.choice(len(corner_map), n_c, replace=False)
+        qi_s = rng.choice(len(surf_map), min(n_queries - n_c, len(surf_map)), replace=False)
     rx, ry, rz, tx, ty, tz = (float(v) for v in T_true)
 
     def inv(p):
@@ -87,4 +90,18 @@ def synth_queries(corner_map, surf_map, n_queries, T_true, seed=11, ordered=True
     cs, ss = inv(corner_map[qi_c]), inv(surf_map[qi_s])
     if ordered:
         cs, ss = voxel_order(cs, 0.2), voxel_order(ss, 0.4)
+    return cs, ss
+
+
+def synth_queries_local(corner_map, surf_map, n_corner, n_surf, T_true, center=(0.0, 0.0), radius=80.0, seed=13):
+    """Query stacks shaped like ONE sweep's (LM:736-747): map points within `radius` of a sensor position in the ground
+    plane (x, z), n_corner + n_surf of them, moved by the inverse of T_true, in voxel-grid order."""
+    rng = np.random.default_rng(seed)
+
+    def pick(m, n):
+        near = np.flatnonzero((m[:, 0] - center[0]) ** 2 + (m[:, 2] - center[1]) ** 2 < radius * radius)
+        return m[rng.choice(near, min(n, len(near)), replace=False)]
+
+    sub_c, sub_s = pick(corner_map, n_corner), pick(surf_map, n_surf)
+    cs, ss = synth_queries(sub_c, sub_s, 0, T_true, ordered=True, take_all=True)
     return cs, ss

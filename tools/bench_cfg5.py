@@ -23,14 +23,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-T_TRUE = np.array([0.002, 0.01, -0.003, 0.05, -0.02, 0.08], np.float32)
+# The stack is the map moved by the inverse of this pose.  The map is 3.2 km wide: rotations of 1e-5 rad move its far end
+# by 1.6 cm -- the size of error scan-to-map registration corrects (it starts from the odometry pose, LM:465) -- so the
+# Gauss-Newton loop converges like it does in the pipeline.  (Round 1 used 1e-2 rad: 16 m at the far end, where a point's
+# nearest neighbours are no longer its own surface and the loop just runs into the 10-iteration limit.)
+T_TRUE = np.array([2e-6, 1e-5, -3e-6, 0.05, -0.02, 0.08], np.float32)
 
 
 def run(map_points=50_000_000, queries=1_000_000, iters=10, rank=0, local=0, world=1, dist=None, unfiltered=False,
-        random_order=False, fused=True, log=lambda *a: None):
+        random_order=False, fused=True, log=lambda *a: None, t_true=None):
     import torch
     from gpscalibration_b200 import LoamGpu, capi, mapsynth, sharding
     dev = torch.device("cuda", local)
+    T_TRUE = np.asarray(t_true, np.float32) if t_true is not None else globals()["T_TRUE"]
     t0 = time.time()
     if unfiltered:
         corner_map, surf_map, extent = mapsynth.synth_map_unfiltered(map_points - map_points // 5, map_points // 5, 2000.0)
