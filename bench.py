@@ -437,22 +437,9 @@ def main():
     # cfg 1 (configs[0]): ONE registration of a sweep pair (extract + scan-to-scan odometry), the case that can only be
     # latency bound: microseconds per stage against the floor the launches and host hand-overs of that stage set
     if world == 1:
-        lat = torch.zeros(1, device=dev_t)
-        torch.cuda.synchronize()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        for _ in range(2000):
-            lat.add_(1.0)
-        eb.record()
-        torch.cuda.synchronize()
-        launch_period_us = 1e3 * ea.elapsed_time(eb) / 2000  # back-to-back one-CTA kernels on one stream
-        w0 = time.perf_counter()
-        for _ in range(300):
-            lat.add_(1.0)
-            torch.cuda.synchronize()
-        roundtrip_us = 1e6 * (time.perf_counter() - w0) / 300  # launch + host-visible completion
         g1 = LoamGpu(device=local_rank)
         st1 = torch.cuda.ExternalStream(g1.stream, device=dev_t)
+        launch_period_us, roundtrip_us = g1.launch_latency(2000)  # empty kernel: back-to-back period, launch + host-visible completion
         reg_us, ext_us, iters, launches_reg, launches_ext, syncs_reg = [], [], 0, 0, 0, 0
         for rep in range(12):
             g1.reset()

@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_extract", "loam_extract_device", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -96,6 +96,7 @@ def load_library():
     lib.loam_stats.argtypes = [vp, vp]
     lib.loam_profile.argtypes = [vp, C.c_int]
     lib.loam_host_times.argtypes = [vp, vp, C.c_int]
+    lib.loam_launch_latency.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
@@ -213,6 +214,12 @@ class LoamGpu:
         out = np.zeros(16)
         self._check(self.lib.loam_host_times(self._h, out.ctypes.data, int(clear)), "loam_host_times")
         return {k: float(out[i]) for i, k in enumerate(self.HOST_SECTIONS)}
+
+    def launch_latency(self, n=2000):
+        """(us per back-to-back empty launch, us per launch + host-visible completion) on the handle's stream."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.loam_launch_latency(self._h, int(n), C.byref(a), C.byref(b)), "loam_launch_latency")
+        return a.value, b.value
 
     def profile(self, enable):
         self._check(self.lib.loam_profile(self._h, int(enable)), "loam_profile")

@@ -754,6 +754,33 @@ int loam_host_times(loam_handle* h, double* out16, int clear) {
   }
   return LOAM_OK;
 }
+int loam_launch_latency(loam_handle* h, int n, double* period_us, double* roundtrip_us) {
+  if (!h || n < 1 || !period_us || !roundtrip_us) return LOAM_EINVAL;
+  LG_CHECK(cudaSetDevice(h->device));
+  cudaEvent_t a, b;
+  LG_CHECK(cudaEventCreate(&a));
+  LG_CHECK(cudaEventCreate(&b));
+  for (int i = 0; i < 16; i++) lg_empty_launch(h->st);
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  LG_CHECK(cudaEventRecord(a, h->st));
+  for (int i = 0; i < n; i++) lg_empty_launch(h->st);
+  LG_CHECK(cudaEventRecord(b, h->st));
+  LG_CHECK(cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  LG_CHECK(cudaEventElapsedTime(&ms, a, b));
+  *period_us = 1e3 * ms / n;
+  const int m = n < 200 ? n : 200;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < m; i++) {
+    lg_empty_launch(h->st);
+    LG_CHECK(cudaStreamSynchronize(h->st));
+  }
+  *roundtrip_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / m;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return LOAM_OK;
+}
+
 int loam_profile(loam_handle* h, int enable) {
   if (!h) return LOAM_EINVAL;
   cudaSetDevice(h->device);

@@ -39,8 +39,8 @@ struct CsrWs {
   void release() { tab.release(); sorted.release(); sums.release(); bb.release(); }
 };
 struct MapGnWs {
-  DevBuf partials, sync, nbr;
-  void release() { partials.release(); sync.release(); nbr.release(); }
+  DevBuf partials, sync, nbr, dbg;
+  void release() { partials.release(); sync.release(); nbr.release(); dbg.release(); }
 };
 struct MapGnArgs {
   float T[6], sc[6];       // transformTobeMapped (LM:108) and sin / cos of its angles (host libm) at entry
@@ -67,6 +67,7 @@ struct MapGnArgs {
   float* state;
   unsigned int* work;       // one thread per query: next chunk of 32 stack points (chunks are handed out dynamically)
   unsigned long long* fx;   // one thread per query: [28][4] fixed-point totals of the iteration (order-independent sums)
+  unsigned long long* dbg;  // LOAM_GN_DEBUG: phase stamps [iteration][8], else null
 };
 int lg_csr_reserve(CsrWs& ws, size_t table_entries, int n_points, cudaStream_t st);
 // Box corners in cells (inclusive) per grid; points outside are clamped into the boundary cells (still exact).
@@ -75,3 +76,4 @@ int lg_csr_build2(CsrWs& ws, const float4* pts0, int n0, const int lo0[3], const
 // d_bb12 <- {min cell x y z, max cell x y z} of both clouds (stage-level API: the caller reads it back)
 int lg_csr_bbox_launch(const float4* pts0, int n0, const float4* pts1, int n1, int* d_bb12, cudaStream_t st, long long* launches);
 int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, long long* launches);
+void lg_empty_launch(cudaStream_t st);

@@ -272,6 +272,16 @@ __device__ __forceinline__ bool gn_fit_row(const float* sc, bool is_c, float4 or
   return true;
 }
 
+// LOAM_GN_DEBUG=1: nanosecond stamps of the phases of every iteration (dbg[iteration][8]), printed by the host after the
+// launch -- how the phase costs quoted in DESIGN.md were measured
+#define GN_STAMP(k, cond)                                                              \
+  do {                                                                                 \
+    if (A.dbg != nullptr && (cond)) {                                                  \
+      unsigned long long t_;                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                            \
+      A.dbg[(size_t)(iter - A.it0) * 8 + (k)] = t_;                                    \
+    }                                                                                  \
+  } while (0)
 constexpr int GN_NT = 256;           // threads per CTA
 constexpr int GN_TILE = 256;         // largest number of stack points per CTA step (one per thread in the fit phase)
 constexpr unsigned long long GN_EMPTY = ~0ull;
@@ -544,6 +554,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
   __syncthreads();
   for (int iter = A.it0; iter < A.it1; iter++) {
     float T[6], sc[6];
+    GN_STAMP(0, blockIdx.x == 0 && tid == 0);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
       T[i] = S.T[i];
@@ -727,6 +738,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
         if (sub == 0 && found) S.ok[lq] = 1;
       }
       __syncthreads();
+      if (tile == (int)blockIdx.x) GN_STAMP(6, blockIdx.x == 0 && tid == 0);
       // ---- phase 2: fit + Jacobian row, one query per thread; the warp's 28 sums go to its shared accumulator
       if (w * 32 < tq) {  // warp-uniform: only the warps that hold queries of this tile
         float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = 0.f;
@@ -747,6 +759,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
       __syncthreads();
     }
     }
+    GN_STAMP(1, blockIdx.x == 0 && tid == 0);
     // ---- grid reduction.  Lanes-per-query layouts: CTA partial -> global, the last CTA adds them in CTA order; one thread
     // per query: the fixed-point totals are already in global memory, the last CTA converts them
     __syncthreads();
@@ -763,6 +776,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
     if (tid == 0) {
       const unsigned int t = atomicAdd(A.ticket, 1u);
       S.last = (t == gridDim.x - 1);
+      if (S.last) GN_STAMP(2, true);
     }
     __syncthreads();
     if (S.last) {
@@ -826,6 +840,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
         }
       }
       if (tid < 28) S.tot[tid] = s;
+      GN_STAMP(3, tid == 0);
       __syncthreads();
       if (!A.solve) {
         if (tid < 28) A.out[tid] = S.tot[tid];
@@ -904,6 +919,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
       }
       __threadfence();
       __syncthreads();
+      GN_STAMP(4, tid == 0);
       if (tid == 0) atomicAdd(A.gen, 1u);  // release the grid barrier
     }
     if (!A.solve) return;
@@ -921,6 +937,7 @@ __global__ void __launch_bounds__(GN_NT, MINB) map_gn_kernel(MapGnArgs A) {
     }
     if (tid == 0) S.done = __float_as_int(__ldcg(&A.state[12]));
     __syncthreads();
+    GN_STAMP(5, blockIdx.x == 0 && tid == 0);
     if (S.done) break;
   }
 }
@@ -1046,9 +1063,27 @@ int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, lon
   A.state = ws.sync.as<float>() + 16;
   A.work = ws.sync.as<unsigned int>() + 2;
   A.fx = reinterpret_cast<unsigned long long*>(ws.sync.as<unsigned int>() + 64);
+  static const bool dbg_env = getenv("LOAM_GN_DEBUG") != nullptr;
+  A.dbg = nullptr;
+  if (dbg_env) {
+    LG_CHECK(ws.dbg.ensure(16 * 8 * 8, st));
+    LG_CHECK(cudaMemsetAsync(ws.dbg.p, 0, 16 * 8 * 8, st));
+    A.dbg = ws.dbg.as<unsigned long long>();
+  }
   LgProfScope prof_scope(LGK_MAP_KNN, st, (double)nq);
   void* args[] = {(void*)&A};
   LG_CHECK(cudaLaunchCooperativeKernel(gn_kernel_of(sub), dim3(grid), dim3(GN_NT), args, 0, st));
   (*launches)++;
+  if (dbg_env) {
+    unsigned long long hb[16 * 8];
+    LG_CHECK(cudaStreamSynchronize(st));
+    LG_CHECK(cudaMemcpy(hb, ws.dbg.p, sizeof(hb), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < A.it1 - A.it0 && i < 16 && hb[i * 8]; i++) {
+      const unsigned long long* t = hb + i * 8;
+      auto us = [&](int a, int b) { return t[a] && t[b] ? ((double)t[b] - (double)t[a]) * 1e-3 : 0.0; };
+      fprintf(stderr, "[gn] nq %d grid %d tile %d iter %d: CTA 0 search %5.1f us, fit + rows %5.1f | all CTAs done +%5.1f | totals +%4.1f | solve +%4.1f | barrier +%4.1f | iteration %6.1f\n",
+              nq, grid, A.tile, A.it0 + i, us(0, 6), us(6, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), us(0, 5));
+    }
+  }
   return LOAM_OK;
 }

@@ -135,6 +135,10 @@ int loam_stats(const loam_handle* h, long long out4[4]);
 int loam_host_times(loam_handle* h, double* out16, int clear);
 int loam_profile(loam_handle* h, int enable);
 int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scopes, int n);
+/* The two latencies every small launch of the library pays on this box, measured on the handle's stream with an empty
+ * kernel: period of n back-to-back launches (us per launch) and launch + host-visible completion (us).  bench.py prints
+ * the latency floor of one registration (BASELINE configs[0]) from them.  Diagnostics only. */
+int loam_launch_latency(loam_handle* h, int n, double* period_us, double* roundtrip_us);
 
 /* ---- scanRegistration: replaces the body of laserCloudHandler, SR:238-752 ------------------------------------
  * xyz: n points in the SENSOR frame (x fwd, y left, z up), `stride_bytes` apart: 12 for packed xyz, 16 for PointXYZ,
