@@ -28,7 +28,7 @@ class LoamError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("ring_mode", C.c_int), ("ring_ang_min", C.c_float), ("ring_ang_step", C.c_float),
                 ("skip_frame_num", C.c_int), ("max_points", C.c_int), ("max_map_points", C.c_int),
-                ("want_registered", C.c_int), ("want_surround", C.c_int)]
+                ("want_registered", C.c_int), ("want_surround", C.c_int), ("pose_message_hop", C.c_int)]
 
 
 class Counts(C.Structure):
@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -64,6 +64,16 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_replay_segments"]
+
+
+def pose_message_hop(transform_sum):
+    """loam_pose_message_hop: the odometry pose as it arrives after the quaternion message (LO:1066-1078 -> LM:322-332)."""
+    a = _f32(transform_sum)
+    out = np.zeros(6, np.float32)
+    rc = load_library().loam_pose_message_hop(a.ctypes.data, out.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_pose_message_hop")
+    return out
 
 
 def library_path():
@@ -96,6 +106,7 @@ def load_library():
     lib.loam_stats.argtypes = [vp, vp]
     lib.loam_profile.argtypes = [vp, C.c_int]
     lib.loam_host_times.argtypes = [vp, vp, C.c_int]
+    lib.loam_pose_message_hop.argtypes = [vp, vp]
     lib.loam_launch_latency.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
@@ -151,13 +162,14 @@ class LoamGpu:
     """One handle = one GPU + one stream + the state of the three LOAM stages (thin wrapper, no logic)."""
 
     def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
-                 want_registered=False, want_surround=False, max_points=None, max_map_points=None):
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
         p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
         p.skip_frame_num = skip_frame_num
         p.want_registered, p.want_surround = int(want_registered), int(want_surround)
+        p.pose_message_hop = int(pose_message_hop)
         if max_points:
             p.max_points = int(max_points)
         if max_map_points:
@@ -417,13 +429,14 @@ class LoamGpuPipeline:
     """Pipelined mode (loam_pipeline_*): submit sweeps, collect results in order; same results as LoamGpu.process_sweep."""
 
     def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
-                 want_registered=False, want_surround=False, max_points=None, max_map_points=None):
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
         p.n_scans, p.ring_mode, p.ring_ang_min, p.ring_ang_step = n_scans, ring_mode, ring_ang_min, ring_ang_step
         p.skip_frame_num = skip_frame_num
         p.want_registered, p.want_surround = int(want_registered), int(want_surround)
+        p.pose_message_hop = int(pose_message_hop)
         if max_points:
             p.max_points = int(max_points)
         if max_map_points:

@@ -639,6 +639,7 @@ void loam_default_params(loam_params* p) {
   p->max_map_points = 1 << 21;
   p->want_registered = 0;
   p->want_surround = 0;
+  p->pose_message_hop = 0;
 }
 
 // role bits: 1 = needs the per-sweep odometry buffers, 2 = needs the map storage (arena, sort workspace)
@@ -945,6 +946,12 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
 }
 
 // ============================================================================================ laserMapping
+int loam_pose_message_hop(const float* in6, float* out6) {
+  if (!in6 || !out6) return LOAM_EINVAL;
+  lgh::pose_message_hop(in6, out6);
+  return LOAM_OK;
+}
+
 int loam_mapping_odometry(loam_handle* h, const float* Tsum) {
   if (!h || !Tsum) return LOAM_EINVAL;
   if (fabs((double)Tsum[3]) < 0.000001 && fabs((double)Tsum[4]) < 0.000001 && fabs((double)Tsum[5]) < 0.000001) h->lm_inited = false;  // LM:316-319
@@ -1324,7 +1331,9 @@ static int process_common(loam_handle* h, loam_sweep_result* out) {
   if (rc) return rc;
   out->mapping_ran = 0;
   if (out->odom.odom_published) {
-    rc = loam_mapping_odometry(h, out->odom.transform_sum);
+    float hop[6];
+    if (h->prm.pose_message_hop) lgh::pose_message_hop(out->odom.transform_sum, hop);
+    rc = loam_mapping_odometry(h, h->prm.pose_message_hop ? hop : out->odom.transform_sum);
     if (rc) return rc;
   }
   if (out->odom.odom_published && out->odom.fullres_published) {
@@ -1960,7 +1969,11 @@ void stage_c(loam_pipeline* p) {
     int rc = pipe_error(p, j.epoch);
     const bool skip_c = rc != 0;
     int ran = 0;
-    if (!rc && j.odom_published) rc = loam_mapping_odometry(h, j.Tsum);
+    if (!rc && j.odom_published) {
+      float hop[6];
+      if (h->prm.pose_message_hop) lgh::pose_message_hop(j.Tsum, hop);
+      rc = loam_mapping_odometry(h, h->prm.pose_message_hop ? hop : j.Tsum);
+    }
     if (j.full) {
       loam_pipeline::MapIn& m = p->mapin[j.slot];
       if (!rc) {

@@ -111,4 +111,46 @@ static inline void associate_to_map(const float* T, const float* pi, float* po) 
   po[2] = -sinf(T[1]) * x2 + cosf(T[1]) * z2 + T[5];
 }
 
+
+// LO:1066-1078 -> LM:322-332 / TM:277-283: Euler angles -> quaternion message -> Euler angles, in double.
+// createQuaternionMsgFromRollPitchYaw(rz, -rx, -ry) gives g; the message carries (-g.y, -g.z, g.x, g.w); the handler
+// reads it as tf::Quaternion(o.z, -o.x, -o.y, o.w) = g again, builds the rotation matrix and calls getRPY.
+inline void pose_message_hop(const float* in, float* out) {
+  const double roll = in[2], pitch = -(double)in[0], yaw = -(double)in[1];
+  const double cr = std::cos(roll * 0.5), sr = std::sin(roll * 0.5);
+  const double cp = std::cos(pitch * 0.5), sp = std::sin(pitch * 0.5);
+  const double cy = std::cos(yaw * 0.5), sy = std::sin(yaw * 0.5);
+  const double gx = sr * cp * cy - cr * sp * sy;
+  const double gy = cr * sp * cy + sr * cp * sy;
+  const double gz = cr * cp * sy - sr * sp * cy;
+  const double gw = cr * cp * cy + sr * sp * sy;
+  const double msg[4] = {-gy, -gz, gx, gw};                       // geometry_msgs orientation {x, y, z, w}
+  const double q[4] = {msg[2], -msg[0], -msg[1], msg[3]};         // the handler's tf::Quaternion {x, y, z, w}
+  const double s2 = 2.0 / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double xs = q[0] * s2, ys = q[1] * s2, zs = q[2] * s2;
+  const double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+  const double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+  // the matrix entries getRPY reads
+  const double r00 = 1.0 - (yy + zz), r01 = xy - wz, r02 = xz + wy, r10 = xy + wz, r20 = xz - wy, r21 = yz + wx, r22 = 1.0 - (xx + yy);
+  double e_roll, e_pitch, e_yaw;
+  if (std::fabs(r20) >= 1) {  // gimbal lock branch of tf::Matrix3x3::getEulerYPR
+    e_yaw = 0;
+    if (r20 < 0) {
+      e_pitch = M_PI / 2.0;
+      e_roll = std::atan2(r01, r02);
+    } else {
+      e_pitch = -M_PI / 2.0;
+      e_roll = std::atan2(-r01, -r02);
+    }
+  } else {
+    e_pitch = -std::asin(r20);
+    e_roll = std::atan2(r21 / std::cos(e_pitch), r22 / std::cos(e_pitch));
+    e_yaw = std::atan2(r10 / std::cos(e_pitch), r00 / std::cos(e_pitch));
+  }
+  out[0] = (float)-e_pitch;
+  out[1] = (float)-e_yaw;
+  out[2] = (float)e_roll;
+  for (int i = 3; i < 6; i++) out[i] = (float)(double)in[i];  // position rides in float64 fields
+}
+
 }  // namespace lgh

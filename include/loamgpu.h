@@ -45,6 +45,8 @@ typedef struct loam_params {
   int max_map_points;  /* capacity hint: points of the gathered local map; grows on demand */
   int want_registered; /* 1: mapping also produces /velodyne_cloud_registered (LM:1103-1112) */
   int want_surround;   /* 1: mapping also produces /laser_cloud_surround every mapFrameNum runs (LM:1081-1101) */
+  int pose_message_hop; /* 1: loam_process_sweep / the pipeline hand the odometry pose to mapping through loam_pose_message_hop,
+                        * like the reference's nodes do through /laser_odom_to_init; 0 (default): the float[6] as it is */
 } loam_params;
 
 /* cloud selectors for loam_get_cloud */
@@ -157,6 +159,11 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out);
 /* ---- laserMapping: replaces laserOdometryHandler's reset test (LM:316-319) and the loop body LM:425-1139 ------
  * loam_mapping_odometry must be called for every published odometry message (every sweep), loam_mapping_process
  * only when odometry published the full message set (fullres_published). */
+/* What the odometry pose goes through between the two reference nodes: laserOdometry publishes transformSum as a
+ * quaternion message built from (rz, -rx, -ry) (LO:1066-1078), laserMapping's and transformMaintenance's handlers turn it
+ * back with getRPY (LM:322-332, TM:277-283), all in double, including the |pitch| >= pi/2 branch.  An identity up to an
+ * ulp; offered so that a caller can be bit-identical to nodes wired through messages.  Host arithmetic. */
+int loam_pose_message_hop(const float transform_sum_in[6], float transform_sum_out[6]);
 int loam_mapping_odometry(loam_handle* h, const float transform_sum[6]);
 int loam_mapping_process(loam_handle* h, loam_map_result* out);
 

@@ -85,6 +85,27 @@ def test_ros_pose_hop_is_identity_on_the_sequence(orc, golden):
         assert np.abs(a - b).max() <= 1e-6
 
 
+def test_library_pose_message_hop_equals_the_oracle(orc, golden):
+    """loam_pose_message_hop (host arithmetic of the library) against the oracle's restatement of LO:1066-1078 -> LM:322-332,
+    bit for bit: on the odometry poses of the golden sequence, on random poses and in the |pitch| >= pi/2 branch."""
+    from gpscalibration_b200 import capi
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    poses = [np.ascontiguousarray(golden["odom"][k], np.float32) for k in range(int(golden["n_sweeps"]))]
+    poses += [np.concatenate([rng.uniform(-3.2, 3.2, 3), rng.uniform(-500, 500, 3)]).astype(np.float32) for _ in range(2000)]
+    for rx in (np.pi / 2, -np.pi / 2, np.float32(np.pi / 2), -np.float32(np.pi / 2)):  # gimbal lock: pitch = -rx
+        for _ in range(20):
+            poses.append(np.array([rx, rng.uniform(-3, 3), rng.uniform(-3, 3), 1.0, 2.0, 3.0], np.float32))
+    moved = 0
+    for a in poses:
+        b = np.zeros(6, np.float32)
+        L.orc_odometry_ros_hop(a.ctypes.data, b.ctypes.data)
+        c = capi.pose_message_hop(a)
+        assert np.array_equal(b, c, equal_nan=True), (a, b, c)
+        moved += int(not np.array_equal(a, c))
+    assert moved > 0  # the hop is NOT an identity in general: that is why the library offers it
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_reference_golden(golden, seq):
     from gpscalibration_b200 import LoamGpu

@@ -199,6 +199,31 @@ def test_pipeline_parity_true_vlp16(orc):
     p.close()
 
 
+def test_pipeline_with_pose_message_hop(orc, sweeps16):
+    """pose_message_hop = 1: the odometry pose reaches mapping through the quaternion message (LO:1066-1078 -> LM:322-332) like
+    between the reference's nodes; equal, bit for bit, to the oracle wired the same way -- fused call and pipelined mode."""
+    from gpscalibration_b200 import LoamGpu, LoamGpuPipeline
+    gpu, pipe = LoamGpu(pose_message_hop=True), orc.Pipeline()
+    pipe.set_ros_hop(True)
+    res = []
+    for k, xyz in enumerate(sweeps16[:14]):
+        r, o = gpu.process_sweep(xyz), pipe.process(xyz)
+        res.append(r)
+        assert np.array_equal(np.array(r.odom.transform_sum, np.float32), np.array(o.odom, np.float32)), k
+        assert r.mapping_ran == o.mapping_ran
+        if r.mapping_ran:
+            assert np.array_equal(np.array(r.map.transform_aft_mapped, np.float32), np.array(o.mapped, np.float32)), k
+            assert r.map.iterations == o.map_iters
+    gpu.close()
+    p = LoamGpuPipeline(pose_message_hop=True)
+    for xyz in sweeps16[:14]:
+        p.submit(xyz)
+    for k in range(14):
+        r = p.wait()
+        assert list(r.map.transform_aft_mapped) == list(res[k].map.transform_aft_mapped), k
+    p.close()
+
+
 # ------------------------------------------------------------------------------------------------ odometry (a6-a12)
 def _odom_pair(orc, sweeps16, a=0, b=1):
     sr = orc.ScanRegistration()
