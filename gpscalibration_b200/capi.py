@@ -63,7 +63,8 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
-           "loam_pipeline_stats", "loam_replay_segments"]
+           "loam_pipeline_stats", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
+           "loam_track_icp", "loam_track_smooth", "loam_track_calibrate", "loam_track_calibrate_long"]
 
 
 def pose_message_hop(transform_sum):
@@ -150,6 +151,13 @@ def load_library():
     lib.loam_pipeline_stream.restype = vp
     lib.loam_pipeline_stream.argtypes = [vp, C.c_int]
     lib.loam_pipeline_stats.argtypes = [vp, vp]
+    lib.loam_track_svd3.argtypes = [vp, vp, vp, vp]
+    lib.loam_track_speed_weights.argtypes = [vp, C.c_int, vp]
+    lib.loam_track_residual_weights.argtypes = [vp, vp, vp, C.c_int, vp]
+    lib.loam_track_icp.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    lib.loam_track_smooth.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.loam_track_calibrate.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.loam_track_calibrate_long.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     _LIB = lib
     return lib
 
@@ -512,3 +520,78 @@ def finish_reduced(reduced28):
     if rc:
         raise LoamError(rc, "loam_map_finish_reduced")
     return AtA, AtB, n.value
+
+
+# ------------------------------------------------------------------------------------------------ N4 track calibration
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class TrackCalibration:
+    """Mirror of the reference's trackCalibration class (track_calibration.h:12-65): constructed from a SLAM track, the
+    matching ENU (GPS) track and per-point weights, then do_icp() and do_calibration() like SD:241-243 / LD:67-72.
+    mode 0 runs the smoothing loop TC:648-674 on the GPU in the serial loop's order, mode 1 its closed form on the host."""
+
+    def __init__(self, slam_xyzt, enu_xyzt, weights, mode=0, device=0):
+        self.slam, self.enu, self.w = _f64(slam_xyzt), _f64(enu_xyzt), _f64(weights)
+        if not (self.slam.shape == self.enu.shape and self.slam.shape[0] == self.w.shape[0] and self.slam.shape[1] == 4):
+            raise ValueError("there's something wrong in icp data no, please check it out")  # TC:46-50 (the reference exits)
+        self.n, self.mode, self.device = self.slam.shape[0], mode, device
+        self.T = None
+        self.rotated = None
+
+    def do_icp(self):
+        self.T = np.zeros((4, 4))
+        self.rotated = np.zeros((self.n, 2))
+        rc = load_library().loam_track_icp(self.slam.ctypes.data, self.enu.ctypes.data, self.w.ctypes.data, self.n, self.T.ctypes.data,
+                                           self.rotated.ctypes.data)
+        if rc:
+            raise LoamError(rc, "loam_track_icp")
+        return 1
+
+    def do_calibration(self):
+        if self.rotated is None:
+            raise LoamError(-4, "loam_track_smooth", "do_icp() first")
+        out = np.zeros((self.n, 4))
+        rc = load_library().loam_track_smooth(self.rotated.ctypes.data, self.enu.ctypes.data, self.n, self.mode, self.device, out.ctypes.data)
+        if rc:
+            raise LoamError(rc, "loam_track_smooth", load_library().loam_last_cuda_error(None).decode())
+        return out
+
+
+def track_speed_weights(slam_xyzt):
+    s = _f64(slam_xyzt)
+    w = np.zeros(s.shape[0])
+    rc = load_library().loam_track_speed_weights(s.ctypes.data, s.shape[0], w.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_track_speed_weights")
+    return w
+
+
+def track_residual_weights(slam_xyzt, enu_xyzt, cal_xyzt):
+    s, e, c = _f64(slam_xyzt), _f64(enu_xyzt), _f64(cal_xyzt)
+    w = np.zeros(s.shape[0])
+    rc = load_library().loam_track_residual_weights(s.ctypes.data, e.ctypes.data, c.ctypes.data, s.shape[0], w.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_track_residual_weights")
+    return w
+
+
+def track_calibrate_long(slam_xyzt, enu_xyzt, iterations=5, mode=0, device=0):
+    """LD:57-83: returns (weights merged into /gps_weight, last calibrated track)."""
+    s, e = _f64(slam_xyzt), _f64(enu_xyzt)
+    n = s.shape[0]
+    w, cal = np.zeros(n), np.zeros((n, 4))
+    rc = load_library().loam_track_calibrate_long(s.ctypes.data, e.ctypes.data, n, iterations, mode, device, w.ctypes.data, cal.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_track_calibrate_long", load_library().loam_last_cuda_error(None).decode())
+    return w, cal
+
+
+def track_svd3(H):
+    h = _f64(H).reshape(3, 3)
+    U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+    rc = load_library().loam_track_svd3(h.ctypes.data, U.ctypes.data, S.ctypes.data, V.ctypes.data)
+    if rc:
+        raise LoamError(rc, "loam_track_svd3")
+    return U, S, V

@@ -290,6 +290,31 @@ int loam_replay_segments(const int* messages_per_bag, int n_bags, double long_di
                          double overlap_distance, int first_pass, int last_pass, const loam_replay_callbacks* cb,
                          loam_replay_stats* stats);
 
+/* ---- N4: track calibration -- weighted rigid alignment of a SLAM track to its GPS (ENU) track -------
+ * Replaces the bodies of trackCalibration (gps_calibration/track_calibration.cc, TC), WeightCoeCal
+ * (gps_calibration/weight_calculation.cc, WC) and the re-weighting loop of longDisTrackPro
+ * (long_distance_track_process.cpp, LD:57-83).  Tracks are n rows of double {x, y, z, t} (COORDXYZT, CH:31-37), fp64 like
+ * the reference, same operation order (sequential sums).  Host arithmetic (north_star keeps the trajectory alignment on
+ * the host) except loam_track_smooth mode 0: the O(N^2) loop TC:648-674 as one kernel on `device`, every point's sum
+ * in the serial loop's order (bit-identical to it); mode 1 is the O(N) closed form on the host (agrees to ~1e-12
+ * relative, no GPU needed).  Eigen's JacobiSVD (TC:506) is restated as a two-sided Jacobi SVD (loam_track_svd3).
+ * Quirk fence: WC:18-19 / WC:41-42 read element n of an n-element track for the last point; the index is clamped. */
+int loam_track_svd3(const double* h9, double* u9, double* s3, double* v9);               /* H = U diag(S) V^T, row-major 3x3 */
+int loam_track_speed_weights(const double* slam_xyzt, int n, double* w);                 /* WC:4-27 */
+int loam_track_residual_weights(const double* slam_xyzt, const double* enu_xyzt, const double* cal_xyzt, int n,
+                                double* w);                                              /* WC:30-78 */
+/* constructor + doICP (TC:4-27, 39-201, 366-545, 583-618): T16 = the 4x4 transform (row-major), rotated_xy = n x 2 */
+int loam_track_icp(const double* slam_xyzt, const double* enu_xyzt, const double* w, int n, double* T16, double* rotated_xy);
+/* doCalibration (TC:631-689): cal_xyzt = n x 4 calibrated ENU track */
+int loam_track_smooth(const double* rotated_xy, const double* enu_xyzt, int n, int mode, int device, double* cal_xyzt);
+/* one trackCalibration object end to end, as SD:241-243 uses it; T16 may be NULL */
+int loam_track_calibrate(const double* slam_xyzt, const double* enu_xyzt, const double* w, int n, int mode, int device,
+                         double* cal_xyzt, double* T16);
+/* LD:57-83: speed weights, calibration, then `iterations` (MAXITERATOR = 5) rounds of residual re-weighting with the
+ * calibrated track as the new source; w_out = the weights merged into /gps_weight (LD:85), cal_xyzt = the last track */
+int loam_track_calibrate_long(const double* slam_xyzt, const double* enu_xyzt, int n, int iterations, int mode, int device,
+                              double* w_out, double* cal_xyzt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ def lib():
         L.orc_qr_solve.argtypes = [vp, vp, vp, C.c_int, C.c_int]
         L.orc_jacobi_eigen.argtypes = [vp, vp, vp, C.c_int]
         L.orc_lu_inverse.argtypes = [vp, vp, C.c_int]
+        L.orc_svd3.argtypes = [vp, vp, vp, vp]
         L.orc_gn_solve.argtypes = [vp, vp, C.c_int, C.c_float, vp, vp]
         L.orc_sr_create.restype = vp
         L.orc_sr_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float]
@@ -124,6 +125,14 @@ def lu_inverse(A):
     out = np.zeros_like(A)
     lib().orc_lu_inverse(A.ctypes.data, out.ctypes.data, A.shape[0])
     return out
+
+
+def svd3(H):
+    """Restated Eigen::JacobiSVD of a 3x3 fp64 matrix (orc_linalg.h svd3_jacobi): H = U diag(S) V^T."""
+    h = np.ascontiguousarray(H, np.float64).reshape(3, 3)
+    U, S, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+    lib().orc_svd3(h.ctypes.data, U.ctypes.data, S.ctypes.data, V.ctypes.data)
+    return U, S, V
 
 
 def gn_solve(AtA, AtB, it, thre, state37):

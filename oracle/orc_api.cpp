@@ -101,6 +101,7 @@ void orc_gemm(const float* A, const float* B, float* C, int m, int k, int n) { g
 int orc_qr_solve(const float* A, const float* b, float* x, int m, int n) { return qr_solve(A, b, x, m, n) ? 0 : 1; }
 void orc_jacobi_eigen(const float* A, float* W, float* V, int n) { jacobi_eigen(A, W, V, n); }
 int orc_lu_inverse(const float* A, float* out, int n) { return lu_inverse(A, out, n) ? 0 : 1; }
+void orc_svd3(const double* H, double* U, double* S, double* V) { svd3_jacobi(H, U, S, V); }
 // state: 36 floats matP + 1 float degenerate flag
 void orc_gn_solve(const float* AtA, const float* AtB, int iter, float thre, float* state37, float* X) {
   GNState st;

@@ -13,6 +13,7 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <utility>
 
 namespace orc {
 
@@ -187,6 +188,89 @@ inline void gn_solve_step(const float* AtA, const float* AtB, int iter, float ei
     float X2[6];
     for (int i = 0; i < 6; i++) X2[i] = X[i];
     gemm_f32_dacc(st.matP, X2, X, 6, 6, 1);
+  }
+}
+
+// Eigen::JacobiSVD<MatrixXd>(H, ComputeThinU | ComputeThinV) of the 3x3 cross-covariance (TC:297, TC:506; Eigen 3 is an
+// un-vendored dependency, CMakeLists.txt:17): restated as the two-sided Jacobi iteration it is published as -- every
+// off-diagonal pair (p, q) is annihilated by a left rotation that symmetrises the 2x2 block followed by the symmetric
+// Jacobi rotation -- in fp64, row-major.  H = U diag(S) V^T, S >= 0 descending.  Rows / columns that are exactly zero are
+// left alone (the track problem is planar: H(2,:) = H(:,2) = 0, so U(:,2) = V(:,2) = e3).
+inline void svd3_jacobi(const double* H, double* U, double* S, double* V) {
+  double W[9];
+  for (int i = 0; i < 9; i++) {
+    W[i] = H[i];
+    U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  auto mul = [](const double* X, const double* Y, double* Z) {  // Z = X * Y (ascending k), Z may not alias
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double s = X[i * 3 + 0] * Y[0 * 3 + j];
+        s += X[i * 3 + 1] * Y[1 * 3 + j];
+        s += X[i * 3 + 2] * Y[2 * 3 + j];
+        Z[i * 3 + j] = s;
+      }
+  };
+  const double tiny = 2.2250738585072014e-308, eps = 2.220446049250313e-16;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool any = false;
+    for (int q = 1; q < 3; q++)
+      for (int p = 0; p < q; p++) {
+        double dmax = std::fmax(std::fabs(W[0]), std::fmax(std::fabs(W[4]), std::fabs(W[8])));
+        double thr = std::fmax(tiny, eps * dmax);
+        if (!(std::fabs(W[p * 3 + q]) > thr || std::fabs(W[q * 3 + p]) > thr)) continue;
+        any = true;
+        double a = W[p * 3 + p], b = W[p * 3 + q], c = W[q * 3 + p], d = W[q * 3 + q];
+        double c1 = 1.0, s1 = 0.0;
+        double t = a + d, dd = c - b;
+        if (std::fabs(dd) >= tiny) {
+          double u = t / dd, tmp = std::sqrt(1.0 + u * u);
+          s1 = 1.0 / tmp;
+          c1 = u / tmp;
+        }
+        double x = c1 * a + s1 * c, y = c1 * b + s1 * d, z = -s1 * b + c1 * d;
+        double cj = 1.0, sj = 0.0;
+        if (std::fabs(y) >= tiny) {
+          double tau = (z - x) / (2.0 * y);
+          double tt = (tau >= 0.0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+          cj = 1.0 / std::sqrt(1.0 + tt * tt);
+          sj = tt * cj;
+        }
+        double Gt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, J[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        Gt[p * 3 + p] = c1; Gt[q * 3 + p] = s1; Gt[p * 3 + q] = -s1; Gt[q * 3 + q] = c1;  // transpose of [[c1, s1], [-s1, c1]]
+        J[p * 3 + p] = cj; J[p * 3 + q] = sj; J[q * 3 + p] = -sj; J[q * 3 + q] = cj;
+        double L[9], Lt[9], T1[9], T2[9];
+        mul(Gt, J, L);
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) Lt[i * 3 + j] = L[j * 3 + i];
+        mul(Lt, W, T1);
+        mul(T1, J, T2);
+        for (int i = 0; i < 9; i++) W[i] = T2[i];
+        W[p * 3 + q] = 0.0;
+        W[q * 3 + p] = 0.0;
+        mul(U, L, T1);
+        for (int i = 0; i < 9; i++) U[i] = T1[i];
+        mul(V, J, T1);
+        for (int i = 0; i < 9; i++) V[i] = T1[i];
+      }
+    if (!any) break;
+  }
+  for (int i = 0; i < 3; i++) {
+    S[i] = std::fabs(W[i * 4]);
+    if (W[i * 4] < 0.0)
+      for (int r = 0; r < 3; r++) U[r * 3 + i] = -U[r * 3 + i];
+  }
+  for (int i = 0; i < 2; i++) {
+    int best = i;
+    for (int j = i + 1; j < 3; j++)
+      if (S[j] > S[best]) best = j;
+    if (best != i) {
+      std::swap(S[i], S[best]);
+      for (int r = 0; r < 3; r++) {
+        std::swap(U[r * 3 + i], U[r * 3 + best]);
+        std::swap(V[r * 3 + i], V[r * 3 + best]);
+      }
+    }
   }
 }
 

@@ -275,3 +275,60 @@ def input_replay(messages_per_bag, stamps, long_distance, short_distance, overla
         return rc
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------ N4 track calibration
+_TC = None
+
+
+def tc_available():
+    return os.path.exists(os.path.join(_DIR, "libref_tc.so"))
+
+
+def _tc():
+    """The reference's own track_calibration.cc + weight_calculation.cc (oracle/ref_build/ref_tc.cpp)."""
+    global _TC
+    if _TC is None:
+        L = C.CDLL(os.path.join(_DIR, "libref_tc.so"))
+        vp = C.c_void_p
+        L.ref_wc_speed.argtypes = [vp, C.c_int, vp]
+        L.ref_wc_residual.argtypes = [vp, vp, vp, C.c_int, vp]
+        L.ref_tc_calibrate.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+        L.ref_ld_long.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        _TC = L
+    return _TC
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def tc_speed_weights(slam):
+    s = _d(slam)
+    w = np.zeros(s.shape[0])
+    _tc().ref_wc_speed(s.ctypes.data, s.shape[0], w.ctypes.data)
+    return w
+
+
+def tc_residual_weights(slam, enu, cal):
+    s, e, c = _d(slam), _d(enu), _d(cal)
+    w = np.zeros(s.shape[0])
+    _tc().ref_wc_residual(s.ctypes.data, e.ctypes.data, c.ctypes.data, s.shape[0], w.ctypes.data)
+    return w
+
+
+def tc_calibrate(slam, enu, w):
+    """(calibrated track n x 4, SLAMRotatedCoord n x 2) of one trackCalibration object."""
+    s, e, ww = _d(slam), _d(enu), _d(w)
+    n = s.shape[0]
+    cal, rot = np.zeros((n, 4)), np.zeros((n, 2))
+    _tc().ref_tc_calibrate(s.ctypes.data, e.ctypes.data, ww.ctypes.data, n, cal.ctypes.data, rot.ctypes.data)
+    return cal, rot
+
+
+def tc_long(slam, enu, iterations=5):
+    s, e = _d(slam), _d(enu)
+    n = s.shape[0]
+    w, cal = np.zeros(n), np.zeros((n, 4))
+    _tc().ref_ld_long(s.ctypes.data, e.ctypes.data, n, iterations, w.ctypes.data, cal.ctypes.data)
+    return w, cal

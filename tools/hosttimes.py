@@ -6,7 +6,8 @@ from gpscalibration_b200 import LoamGpu, SweepGenerator
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 gen = SweepGenerator()
 sw = [gen.sweep(k)[0].copy() for k in range(N)]
-gpu = LoamGpu()
+WANT = (len(sys.argv) > 2 and sys.argv[2] == "full")
+gpu = LoamGpu(want_registered=WANT, want_surround=WANT)
 for rep in range(3):
     gpu.reset()
     gpu.host_times()
