@@ -1,5 +1,5 @@
 """Per-source-line view of an ncu report (the --page source CSV is SASS-level): joins it with nvdisasm's line table of the
-same object by instruction order.  usage: ncu_lines.py <report.ncu-rep> <object.o> <kernel-substring> [top]"""
+same object by instruction order.  usage: ncu_lines.py <report.ncu-rep> <object.o> <mangled-kernel-substring> [top] [demangled-substring]"""
 import csv, re, subprocess, sys, tempfile, os, glob
 from collections import defaultdict
 
@@ -35,7 +35,8 @@ for r in rows:
         cur["hdr"] = r
     elif cur is not None:
         cur["rows"].append(r)
-blk = [b for b in blocks if kname.split("ILi")[0].replace("_ZN", "") in b["name"] or "map_gn" in b["name"]][0] if blocks else None
+human = sys.argv[5] if len(sys.argv) > 5 else kname  # substring of the demangled name as ncu prints it
+blk = [b for b in blocks if human in b["name"]][0]
 hdr = blk["hdr"]
 ix = {h: i for i, h in enumerate(hdr)}
 n = min(len(lines), len(blk["rows"]))
