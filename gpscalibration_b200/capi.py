@@ -63,7 +63,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
            "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
-           "loam_pipeline_stats", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
+           "loam_pipeline_stats", "loam_pipeline_stage_times", "loam_pipeline_handle", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
            "loam_track_icp", "loam_track_smooth", "loam_track_calibrate", "loam_track_calibrate_long"]
 
 
@@ -151,6 +151,9 @@ def load_library():
     lib.loam_pipeline_stream.restype = vp
     lib.loam_pipeline_stream.argtypes = [vp, C.c_int]
     lib.loam_pipeline_stats.argtypes = [vp, vp]
+    lib.loam_pipeline_stage_times.argtypes = [vp, vp, C.c_int]
+    lib.loam_pipeline_handle.restype = vp
+    lib.loam_pipeline_handle.argtypes = [vp, C.c_int]
     lib.loam_track_svd3.argtypes = [vp, vp, vp, vp]
     lib.loam_track_speed_weights.argtypes = [vp, C.c_int, vp]
     lib.loam_track_residual_weights.argtypes = [vp, vp, vp, C.c_int, vp]
@@ -494,6 +497,18 @@ class LoamGpuPipeline:
 
     def stream(self, which):
         return self.lib.loam_pipeline_stream(self._h, which)
+
+    def stage_host_times(self, which, clear=True):
+        """loam_host_times of the handle behind stage `which` (read when the pipeline is idle)."""
+        a = (C.c_double * 16)()
+        self._check(self.lib.loam_host_times(self.lib.loam_pipeline_handle(self._h, which), a, 1 if clear else 0), "loam_host_times")
+        return list(a)
+
+    def stage_times(self, clear=True):
+        """Seconds of work per stage thread (extract, odometry, mapping) since the last clear; read when idle."""
+        a = (C.c_double * 3)()
+        self._check(self.lib.loam_pipeline_stage_times(self._h, a, 1 if clear else 0), "loam_pipeline_stage_times")
+        return [a[0], a[1], a[2]]
 
     def stats(self):
         out = (C.c_longlong * 4)()

@@ -1836,6 +1836,7 @@ struct loam_pipeline {
   long long epoch = 0;
   std::map<long long, long long> epoch_of;  // sweep -> epoch (for loam_pipeline_wait)
   char err_text[512] = "";
+  double busy[3] = {0, 0, 0};  // seconds each stage thread spent working on sweeps (not waiting for its queue / a free slot)
   std::thread tA, tB, tC;
 };
 
@@ -1864,6 +1865,7 @@ void stage_a(loam_pipeline* p) {
       if (j.kind == JOB_STOP) return;
       continue;
     }
+    const auto t_busy0 = std::chrono::steady_clock::now();
     loam_counts c = {0, 0, 0, 0, 0};
     int rc = pipe_error(p, j.epoch);
     const bool skip_a = rc != 0;
@@ -1873,6 +1875,7 @@ void stage_a(loam_pipeline* p) {
       rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c);
     }
     if (j.slot >= 0) p->in_free.release();  // extract_common synchronised: the input slot is free again
+    p->busy[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
     p->feat_free.acquire();
     const int fs = (int)(p->feat_count++ % PNS);
     loam_pipeline::Feat& f = p->feat[fs];
@@ -1908,6 +1911,7 @@ void stage_b(loam_pipeline* p) {
       if (j.kind == JOB_STOP) return;
       continue;
     }
+    const auto t_busy0 = std::chrono::steady_clock::now();
     loam_pipeline::Feat& f = p->feat[j.slot];
     loam_odom_result o;
     memset(&o, 0, sizeof(o));
@@ -1927,6 +1931,7 @@ void stage_b(loam_pipeline* p) {
       cudaEventRecord(f.consumed, h->st);
     }
     p->feat_free.release();
+    p->busy[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
     if (!rc && o.odom_published && o.fullres_published) {
       p->map_free.acquire();
       ms = (int)(p->map_count++ % PNS);
@@ -1964,6 +1969,7 @@ void stage_c(loam_pipeline* p) {
     Job j = p->qC.pop();
     if (j.kind == JOB_STOP) return;
     if (j.kind != JOB_SWEEP) continue;
+    const auto t_busy0 = std::chrono::steady_clock::now();
     loam_map_result mr;
     memset(&mr, 0, sizeof(mr));
     int rc = pipe_error(p, j.epoch);
@@ -1992,6 +1998,7 @@ void stage_c(loam_pipeline* p) {
       p->map_free.release();
     }
     if (rc && !skip_c) pipe_fail(p, rc, j.epoch);
+    p->busy[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
     {
       std::lock_guard<std::mutex> l(p->rm);
       loam_sweep_result r = p->partial[j.k];
@@ -2035,6 +2042,20 @@ int loam_pipeline_create(const loam_params* prm, int device, loam_pipeline** out
   p->tB = std::thread(stage_b, p);
   p->tC = std::thread(stage_c, p);
   *out = p;
+  return LOAM_OK;
+}
+
+loam_handle* loam_pipeline_handle(loam_pipeline* p, int which) {
+  if (!p) return nullptr;
+  return which == 0 ? p->hA : which == 1 ? p->hB : which == 2 ? p->hC : nullptr;
+}
+
+int loam_pipeline_stage_times(loam_pipeline* p, double* out3, int clear) {
+  if (!p || !out3) return LOAM_EINVAL;
+  for (int i = 0; i < 3; i++) {
+    out3[i] = p->busy[i];
+    if (clear) p->busy[i] = 0.0;
+  }
   return LOAM_OK;
 }
 
