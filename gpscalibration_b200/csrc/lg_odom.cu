@@ -149,16 +149,11 @@ __device__ __forceinline__ float box_d2(float4 s, float4 lo, float4 hi) {
 // best distance so far.  Everything skipped holds only points that are strictly farther, so the result -- the minimum of
 // the same packed (fp32 d2, index) key as the brute-force kernel -- is identical, ties included.
 constexpr int KP_WARPS = 8;
-__global__ void __launch_bounds__(KP_WARPS * 32) odom_knn_pruned_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
-                                                                         const float4* __restrict__ flat, int n_flat,
-                                                                         const float4* __restrict__ corner_last, int n_cl,
-                                                                         const float4* __restrict__ surf_last, int n_sl,
-                                                                         const float4* __restrict__ box_c, const float4* __restrict__ sup_c,
-                                                                         const float4* __restrict__ box_s, const float4* __restrict__ sup_s,
-                                                                         unsigned long long* __restrict__ best) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * KP_WARPS + (threadIdx.x >> 5);
-  if (q >= n_sharp + n_flat) return;
+__device__ __forceinline__ unsigned long long odom_knn_pruned_warp(const OdomT& T, int q, int lane, const float4* __restrict__ sharp, int n_sharp,
+                                                                   const float4* __restrict__ flat, const float4* __restrict__ corner_last, int n_cl,
+                                                                   const float4* __restrict__ surf_last, int n_sl,
+                                                                   const float4* __restrict__ box_c, const float4* __restrict__ sup_c,
+                                                                   const float4* __restrict__ box_s, const float4* __restrict__ sup_s) {
   const bool is_c = q < n_sharp;
   const float4* pts = is_c ? corner_last : surf_last;
   const float4* box = is_c ? box_c : box_s;
@@ -222,7 +217,7 @@ __global__ void __launch_bounds__(KP_WARPS * 32) odom_knn_pruned_kernel(OdomT T,
       if (__shfl_sync(0xffffffffu, lb, p) <= lg_nbr_d2(bestkey)) open_super(base + p);
     }
   }
-  if (lane == 0) best[q] = bestkey;
+  return bestkey;
 }
 
 __device__ __forceinline__ float sqd(float4 a, float4 sel) {
@@ -374,17 +369,12 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_kernel(OdomT T, con
 // current best of its category (or is the one in which the reference's `break` fires, recognised by its ring range);
 // everything else holds only points at 5 m or more, or strictly farther than the best so far.  Inside an opened box the
 // literal rules of odom_corr_kernel apply, so the result is identical (tests compare both against the oracle).
-__global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_pruned_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
-                                                                            const float4* __restrict__ flat, int n_flat,
-                                                                            const float4* __restrict__ corner_last, int n_cl,
-                                                                            const float4* __restrict__ surf_last, int n_sl,
-                                                                            const float4* __restrict__ box_c, const float4* __restrict__ box_s,
-                                                                            const unsigned long long* __restrict__ best, int* __restrict__ c1,
-                                                                            int* __restrict__ c2, int* __restrict__ s1, int* __restrict__ s2,
-                                                                            int* __restrict__ s3) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * CORR_WARPS + (threadIdx.x >> 5);
-  if (q >= n_sharp + n_flat) return;
+__device__ __forceinline__ void odom_corr_pruned_warp(const OdomT& T, int q, int lane, unsigned long long b, const float4* __restrict__ sharp,
+                                                      int n_sharp, const float4* __restrict__ flat, int n_flat,
+                                                      const float4* __restrict__ corner_last, int n_cl, const float4* __restrict__ surf_last,
+                                                      int n_sl, const float4* __restrict__ box_c, const float4* __restrict__ box_s,
+                                                      int* __restrict__ c1, int* __restrict__ c2, int* __restrict__ s1, int* __restrict__ s2,
+                                                      int* __restrict__ s3) {
   const bool is_c = q < n_sharp;
   const int f = is_c ? q : q - n_sharp;
   const float4* pts = is_c ? corner_last : surf_last;
@@ -392,7 +382,6 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_pruned_kernel(OdomT
   const int nlast = is_c ? n_cl : n_sl;
   const int bound = min(is_c ? n_sharp : n_flat, nlast);  // FENCE (i): LO:620 / LO:776 bound by the CURRENT feature count
   const float4 sel = transform_to_start(T, is_c ? sharp[f] : flat[f]);
-  const unsigned long long b = best[q];
   const float inf = __int_as_float(0x7f800000);
   int closest = -1, r2 = -1, r3 = -1;
   if (b != NONE64 && lg_nbr_d2(b) < 25) {
@@ -527,6 +516,26 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) odom_corr_pruned_kernel(OdomT
       s3[f] = r3;
     }
   }
+}
+
+// One refresh of the correspondences (LO:598-677, 756-844) in one launch, one WARP per feature: exact nearest neighbour
+// over the box hierarchy, then the +-1-ring scans around it -- the key never leaves the warp's registers (it is still
+// written to `best` for the brute-force cross-check and diagnostics).
+__global__ void __launch_bounds__(KP_WARPS * 32) odom_refresh_pruned_kernel(OdomT T, const float4* __restrict__ sharp, int n_sharp,
+                                                                             const float4* __restrict__ flat, int n_flat,
+                                                                             const float4* __restrict__ corner_last, int n_cl,
+                                                                             const float4* __restrict__ surf_last, int n_sl,
+                                                                             const float4* __restrict__ box_c, const float4* __restrict__ sup_c,
+                                                                             const float4* __restrict__ box_s, const float4* __restrict__ sup_s,
+                                                                             unsigned long long* __restrict__ best, int* __restrict__ c1,
+                                                                             int* __restrict__ c2, int* __restrict__ s1, int* __restrict__ s2,
+                                                                             int* __restrict__ s3) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * KP_WARPS + (threadIdx.x >> 5);
+  if (q >= n_sharp + n_flat) return;
+  const unsigned long long b = odom_knn_pruned_warp(T, q, lane, sharp, n_sharp, flat, corner_last, n_cl, surf_last, n_sl, box_c, sup_c, box_s, sup_s);
+  if (lane == 0) best[q] = b;
+  odom_corr_pruned_warp(T, q, lane, b, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, box_c, box_s, c1, c2, s1, s2, s3);
 }
 
 constexpr int IT_NT = 128;
@@ -919,21 +928,18 @@ static int odom_refresh_corr(OdomWs& ws, const OdomT& T, const float4* sharp, in
     dim3 grid(tiles_c + tiles_s, chunks);
     odom_knn_kernel<<<grid, KNN_Q, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, tiles_c,
                                             ws.best.as<unsigned long long>());
-  } else {
-    const int nsup_c = lg_div_up(n_cl, 1024), nsup_s = lg_div_up(n_sl, 1024);
-    odom_knn_pruned_kernel<<<lg_div_up(nq, KP_WARPS), KP_WARPS * 32, 0, st>>>(
-        T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_c.as<float4>() + (size_t)nsup_c * 64,
-        ws.bounds_s.as<float4>(), ws.bounds_s.as<float4>() + (size_t)nsup_s * 64, ws.best.as<unsigned long long>());
-  }
-  if (brute)
     odom_corr_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl,
                                                                             ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(),
                                                                             ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
-  else
-    odom_corr_pruned_kernel<<<lg_div_up(nq, CORR_WARPS), CORR_WARPS * 32, 0, st>>>(
-        T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_s.as<float4>(),
-        ws.best.as<unsigned long long>(), ws.c1.as<int>(), ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
-  (*launches) += 2;
+    (*launches) += 2;
+  } else {
+    const int nsup_c = lg_div_up(n_cl, 1024), nsup_s = lg_div_up(n_sl, 1024);
+    odom_refresh_pruned_kernel<<<lg_div_up(nq, KP_WARPS), KP_WARPS * 32, 0, st>>>(
+        T, sharp, n_sharp, flat, n_flat, corner_last, n_cl, surf_last, n_sl, ws.bounds_c.as<float4>(), ws.bounds_c.as<float4>() + (size_t)nsup_c * 64,
+        ws.bounds_s.as<float4>(), ws.bounds_s.as<float4>() + (size_t)nsup_s * 64, ws.best.as<unsigned long long>(), ws.c1.as<int>(),
+        ws.c2.as<int>(), ws.s1.as<int>(), ws.s2.as<int>(), ws.s3.as<int>());
+    (*launches)++;
+  }
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;
 }

@@ -1,33 +1,44 @@
-"""Aggregate throughput of S independent sequences sharing ONE GPU (cfg 4 with more segments than GPUs):
-S pipelined handles driven by S host threads (ctypes releases the GIL)."""
-import sys, time, threading
+"""Aggregate throughput of S independent sequences sharing ONE GPU (cfg 4 with more segments than GPUs), two ways:
+  pipelined  S pipelined handles (3 stage threads + 3 streams each) driven by S host threads
+  blocking   S plain handles, one host thread each calling loam_process_sweep (1 thread + 1 stream per sequence)
+ctypes releases the GIL during the calls.  usage: multiseg.py [sweeps] [full]"""
+import sys, time, threading, os
 sys.path.insert(0, '.')
 import numpy as np
-from gpscalibration_b200 import LoamGpuPipeline, SweepGenerator
+from gpscalibration_b200 import LoamGpu, LoamGpuPipeline, SweepGenerator
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-for S in (1, 2, 4, 8):
-    seqs = []
-    for s in range(S):
-        gen = SweepGenerator(seed=0xC0FFEE + 1000 * s, t_offset=37.0 * s)
-        seqs.append([gen.sweep(k)[0].copy() for k in range(N)])
-    pipes = [LoamGpuPipeline() for _ in range(S)]
-    def run(p, sw, out):
-        for rep in range(2):
-            p.reset()
-            t0 = time.perf_counter()
-            for k, x in enumerate(sw):
-                p.submit(x)
-                if k >= 6:
-                    p.wait()
-            while p.pending:
-                p.wait()
-            out.append(time.perf_counter() - t0)
-    outs = [[] for _ in range(S)]
-    ths = [threading.Thread(target=run, args=(pipes[i], seqs[i], outs[i])) for i in range(S)]
-    t0 = time.perf_counter()
-    for t in ths: t.start()
-    for t in ths: t.join()
-    wall = time.perf_counter() - t0
-    last = max(o[1] for o in outs)
-    print("segments %d: second pass %.3f s -> aggregate %.0f sweeps/s (per segment %.0f)" % (S, last, S * N / last, N / last), flush=True)
-    for p in pipes: p.close()
+WANT = len(sys.argv) > 2 and sys.argv[2] == "full"
+print("host cores", os.cpu_count(), "registered+surround", WANT, flush=True)
+seqs_all = []
+for s in range(16):
+    gen = SweepGenerator(seed=0xC0FFEE + 1000 * s, t_offset=37.0 * s)
+    seqs_all.append([gen.sweep(k)[0].copy() for k in range(N)])
+for mode in ("pipelined", "blocking"):
+    for S in (1, 2, 4, 8, 12, 16):
+        seqs = seqs_all[:S]
+        if mode == "pipelined":
+            objs = [LoamGpuPipeline(want_registered=WANT, want_surround=WANT) for _ in range(S)]
+        else:
+            objs = [LoamGpu(want_registered=WANT, want_surround=WANT) for _ in range(S)]
+        def run(p, sw, out):
+            for rep in range(2):
+                p.reset()
+                t0 = time.perf_counter()
+                if mode == "pipelined":
+                    for k, x in enumerate(sw):
+                        p.submit(x)
+                        if k >= 6:
+                            p.wait()
+                    while p.pending:
+                        p.wait()
+                else:
+                    for x in sw:
+                        p.process_sweep(x)
+                out.append(time.perf_counter() - t0)
+        outs = [[] for _ in range(S)]
+        ths = [threading.Thread(target=run, args=(objs[i], seqs[i], outs[i])) for i in range(S)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+        last = max(o[1] for o in outs)
+        print("%s segments %2d: second pass %.3f s -> aggregate %6.0f sweeps/s (per segment %.0f)" % (mode, S, last, S * N / last, N / last), flush=True)
+        for p in objs: p.close()
