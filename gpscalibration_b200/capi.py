@@ -498,6 +498,20 @@ class LoamGpuPipeline:
     def stream(self, which):
         return self.lib.loam_pipeline_stream(self._h, which)
 
+    def output_cloud(self, which="surround"):
+        """Cloud held by the pipeline's output stage (loam_pipeline_handle(p, 3)): /laser_cloud_surround of the last run that
+        published it (want_surround).  Read when the pipeline is idle."""
+        h = self.lib.loam_pipeline_handle(self._h, 3)
+        if not h:
+            raise LoamError(-4, "loam_pipeline_handle", "created without want_surround")
+        n = C.c_int()
+        w = CLOUD[which] if isinstance(which, str) else which
+        self._check(self.lib.loam_get_cloud(h, w, None, 0, C.byref(n)), "loam_get_cloud")
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            self._check(self.lib.loam_get_cloud(h, w, out.ctypes.data, n.value, C.byref(n)), "loam_get_cloud")
+        return out
+
     def stage_host_times(self, which, clear=True):
         """loam_host_times of the handle behind stage `which` (read when the pipeline is idle)."""
         a = (C.c_double * 16)()

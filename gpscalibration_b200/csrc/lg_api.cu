@@ -79,6 +79,15 @@ struct loam_handle {
   unsigned long long mail_seq = 0;  // sequence number the reduction kernels publish into the mapped mailbox
   LgProf prof;
   double host_s[LOAM_HOST_SECTIONS] = {0};  // host wall-clock per section (diagnostics, loam_host_times)
+  // Pipelined mode only: /laser_cloud_surround (LM:1081-1101) is an output nobody downstream in the path waits for, so the
+  // mapping stage only ENQUEUES the gather of the cubes on the output handle's stream (`aux`) and goes on with the next
+  // sweep; the voxel grid and its count read-back run on the pipeline's output thread.  ev_map_done: this handle's map
+  // kernels of the run are finished; ev_aux_read: the gather has read the arena (awaited before the arena is written again).
+  loam_handle* aux = nullptr;
+  cudaEvent_t ev_map_done = nullptr, ev_aux_read = nullptr;
+  bool aux_read_pending = false;
+  bool aux_reserved = false;  // the pipeline holds the output handle's scratch for this run (else the surround cloud is made in line)
+  int aux_ns = 0;  // points gathered for the output thread
   // pinned host staging
   double* h_mail = nullptr;  // mapped: 28 doubles written by the reduction kernels
   double* d_mail = nullptr;
@@ -694,6 +703,12 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
       for (DevBuf* b : key_bufs) e = e == cudaSuccess ? b->ensure(mm * 8, h->st) : e;
       for (DevBuf* b : val_bufs) e = e == cudaSuccess ? b->ensure(mm * 4, h->st) : e;
     }
+    if (role & 4) {  // output handle of a pipeline: surround cloud scratch (gathered cubes, sort workspace, result)
+      DevBuf* sur_bufs[] = {&h->vg_in, &h->ds_in, &h->vg_out, &h->surround};
+      for (DevBuf* b : sur_bufs) e = e == cudaSuccess ? b->ensure(mm * 16, h->st) : e;
+      if (e == cudaSuccess) e = (cudaError_t)lg_radix_ensure(h->vb.rs, (int)mm, h->st) == cudaSuccess ? cudaSuccess : cudaErrorMemoryAllocation;
+      if (e == cudaSuccess) e = h->d_ents.ensure(4096 * sizeof(CopyEnt), h->st);
+    }
     if (e != cudaSuccess) {
       lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       loam_destroy(h);
@@ -726,6 +741,8 @@ int loam_destroy(loam_handle* h) {
     for (auto it = g_xchg_local.begin(); it != g_xchg_local.end();) it = (it->second == h->xchg) ? g_xchg_local.erase(it) : std::next(it);
     cudaFree(h->xchg);
   }
+  if (h->ev_map_done) cudaEventDestroy(h->ev_map_done);
+  if (h->ev_aux_read) cudaEventDestroy(h->ev_aux_read);
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_ints) cudaFreeHost(h->h_ints);
   if (h->st) cudaStreamDestroy(h->st);
@@ -965,6 +982,10 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
   HostTimer ht(&h->host_s[HT_MAP_PREP]);
+  if (h->aux_read_pending) {  // the output stream may still be reading cubes of the previous surround: order this run's arena writes behind it
+    LG_CHECK(cudaStreamWaitEvent(h->st, h->ev_aux_read, 0));
+    h->aux_read_pending = false;
+  }
   if (!h->lm_inited) {
     h->lm_inited = true;
     map_reset(h);
@@ -1262,7 +1283,33 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (h->mapFrameCount >= 5) {
     h->mapFrameCount = 0;
     out->surround_published = 1;
-    if (h->prm.want_surround) {
+    if (h->prm.want_surround && h->aux && h->aux_reserved) {
+      // pipelined: enqueue the gather of the 125 cubes on the output stream behind this run's map kernels and hand the rest
+      // (voxel grid 0.2 m + count) to the output thread; out->n_surround is filled in there
+      loam_handle* a = h->aux;
+      std::vector<CopyEnt> ents;
+      const float4* ar = h->arena.as<float4>();
+      int off = 0, max_n = 0;
+      for (int ind : surroundInd) {
+        for (auto& c : h->cubeC[ind])
+          if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+        for (auto& c : h->cubeS[ind])
+          if (c.n > 0) { ents.push_back(CopyEnt{ar + c.off, c.n, off}); off += c.n; max_n = std::max(max_n, c.n); }
+      }
+      LG_CHECK(cudaEventRecord(h->ev_map_done, h->st));
+      LG_CHECK(cudaStreamWaitEvent(a->st, h->ev_map_done, 0));
+      LG_CHECK(a->vg_in.ensure((size_t)(off + 16) * 16, a->st));
+      if (!ents.empty()) {
+        rc = upload(a, a->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));  // pageable source: staged before the call returns
+        if (rc) return rc;
+        rc = lg_gather(a->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, a->vg_in.as<float4>(), a->st, &a->launches);
+        if (rc) return rc;
+      }
+      LG_CHECK(cudaEventRecord(h->ev_aux_read, a->st));
+      h->aux_read_pending = true;
+      h->aux_ns = off;
+      out->n_surround = -1;
+    } else if (h->prm.want_surround) {
       DevBuf& tmp = h->vg_in;
       int ns = 0;
       rc = gather_cubes(h, surroundInd, true, true, tmp, &ns);
@@ -1809,6 +1856,7 @@ constexpr int PNS = 4;  // slots per ring
 
 struct loam_pipeline {
   loam_handle *hA = nullptr, *hB = nullptr, *hC = nullptr;
+  loam_handle* hD = nullptr;  // output handle: /laser_cloud_surround is finished here, off the mapping stage's critical path
   int device = 0;
   cudaStream_t copy_st = nullptr;
   DevBuf in_xyz[PNS];
@@ -1824,7 +1872,8 @@ struct loam_pipeline {
     cudaEvent_t ready, consumed;
   } mapin[PNS];
   Sem in_free{PNS}, feat_free{PNS}, map_free{PNS};
-  BQueue<Job> qA, qB, qC;
+  BQueue<Job> qA, qB, qC, qD;
+  Sem aux_free{1};  // one surround job in flight on the output handle
   std::mutex rm;
   std::condition_variable rcv;
   std::map<long long, loam_sweep_result> partial, done;
@@ -1837,7 +1886,7 @@ struct loam_pipeline {
   std::map<long long, long long> epoch_of;  // sweep -> epoch (for loam_pipeline_wait)
   char err_text[512] = "";
   double busy[3] = {0, 0, 0};  // seconds each stage thread spent working on sweeps (not waiting for its queue / a free slot)
-  std::thread tA, tB, tC;
+  std::thread tA, tB, tC, tD;
 };
 
 namespace {
@@ -1967,7 +2016,10 @@ void stage_c(loam_pipeline* p) {
   loam_handle* h = p->hC;
   for (;;) {
     Job j = p->qC.pop();
-    if (j.kind == JOB_STOP) return;
+    if (j.kind == JOB_STOP) {
+      p->qD.push(j);
+      return;
+    }
     if (j.kind != JOB_SWEEP) continue;
     const auto t_busy0 = std::chrono::steady_clock::now();
     loam_map_result mr;
@@ -1988,7 +2040,14 @@ void stage_c(loam_pipeline* p) {
         std::swap(h->surf_last, m.surf);
         std::swap(h->fullres3, m.full);
         h->n_corner_last = m.nc; h->n_surf_last = m.ns; h->n_fullres3 = m.nf;
+        // the run that publishes the surround cloud (LM:1081-1083; the first run after a reset does, LM:434-461) needs the
+        // output handle's scratch: wait for the previous surround job only then
+        const bool reserve = h->aux && (!h->lm_inited || h->mapFrameCount + 1 >= 5);
+        if (reserve) p->aux_free.acquire();
+        h->aux_reserved = reserve;
         rc = loam_mapping_process(h, &mr);
+        h->aux_reserved = false;
+        if (reserve && (rc || mr.n_surround != -1)) p->aux_free.release();  // no surround job was handed over after all
         cudaEventRecord(m.consumed, h->st);
         std::swap(h->corner_last, m.corner);
         std::swap(h->surf_last, m.surf);
@@ -1999,12 +2058,59 @@ void stage_c(loam_pipeline* p) {
     }
     if (rc && !skip_c) pipe_fail(p, rc, j.epoch);
     p->busy[2] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
+    const bool to_output = !rc && ran && mr.n_surround == -1;  // the surround cloud of this run is still being made
+    {
+      std::lock_guard<std::mutex> l(p->rm);
+      loam_sweep_result& pr = p->partial[j.k];
+      pr.map = mr;
+      pr.mapping_ran = ran;
+      if (!to_output) {
+        p->done[j.k] = pr;
+        p->partial.erase(j.k);
+      }
+    }
+    if (to_output) {
+      j.n = h->aux_ns;
+      p->qD.push(j);
+    } else {
+      p->rcv.notify_all();
+    }
+  }
+}
+
+// Output thread: LM:1092-1094 (VoxelGrid 0.2 m over the gathered surround cubes) on the output handle's stream, then the
+// sweep's result is released to loam_pipeline_wait.
+void stage_d(loam_pipeline* p) {
+  cudaSetDevice(p->device);
+  loam_handle* h = p->hD;
+  for (;;) {
+    Job j = p->qD.pop();
+    if (j.kind == JOB_STOP) return;
+    int rc = pipe_error(p, j.epoch);
+    const bool skip_d = rc != 0;
+    int n_out = 0;
+    if (!rc) {
+      g_lg_prof = h->prof.on ? &h->prof : nullptr;
+      rc = (int)h->surround.ensure((size_t)(j.n + 16) * 16, h->st) == (int)cudaSuccess ? LOAM_OK : LOAM_ECUDA;
+      if (!rc) {
+        std::vector<VoxSegD> segs(1);
+        segs[0] = VoxSegD{h->vg_in.as<float4>(), nullptr, h->surround.as<float4>(), nullptr, j.n, 0.2f};
+        std::vector<int> cnt;
+        rc = voxel_segments(h, segs, cnt);
+        if (!rc) {
+          n_out = cnt[0];
+          h->n_surround = n_out;
+          rc = cudaStreamSynchronize(h->st) == cudaSuccess ? LOAM_OK : LOAM_ECUDA;
+        }
+      }
+    }
+    p->aux_free.release();
+    if (rc && !skip_d) pipe_fail(p, rc, j.epoch);
     {
       std::lock_guard<std::mutex> l(p->rm);
       loam_sweep_result r = p->partial[j.k];
       p->partial.erase(j.k);
-      r.map = mr;
-      r.mapping_ran = ran;
+      r.map.n_surround = n_out;
       p->done[j.k] = r;
     }
     p->rcv.notify_all();
@@ -2023,10 +2129,12 @@ int loam_pipeline_create(const loam_params* prm, int device, loam_pipeline** out
   int rc = create_internal(prm, device, 0, &p->hA);
   if (!rc) rc = create_internal(prm, device, 1, &p->hB);
   if (!rc) rc = create_internal(prm, device, 2, &p->hC);
+  if (!rc && p->hC->prm.want_surround) rc = create_internal(prm, device, 4, &p->hD);
   if (rc) {
     if (p->hA) loam_destroy(p->hA);
     if (p->hB) loam_destroy(p->hB);
     if (p->hC) loam_destroy(p->hC);
+    if (p->hD) loam_destroy(p->hD);
     delete p;
     return rc;
   }
@@ -2038,16 +2146,22 @@ int loam_pipeline_create(const loam_params* prm, int device, loam_pipeline** out
     cudaEventCreateWithFlags(&p->mapin[i].ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&p->mapin[i].consumed, cudaEventDisableTiming);
   }
+  if (p->hD) {
+    p->hC->aux = p->hD;
+    cudaEventCreateWithFlags(&p->hC->ev_map_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->hC->ev_aux_read, cudaEventDisableTiming);
+  }
   p->tA = std::thread(stage_a, p);
   p->tB = std::thread(stage_b, p);
   p->tC = std::thread(stage_c, p);
+  p->tD = std::thread(stage_d, p);
   *out = p;
   return LOAM_OK;
 }
 
 loam_handle* loam_pipeline_handle(loam_pipeline* p, int which) {
   if (!p) return nullptr;
-  return which == 0 ? p->hA : which == 1 ? p->hB : which == 2 ? p->hC : nullptr;
+  return which == 0 ? p->hA : which == 1 ? p->hB : which == 2 ? p->hC : which == 3 ? p->hD : nullptr;
 }
 
 int loam_pipeline_stage_times(loam_pipeline* p, double* out3, int clear) {
@@ -2068,6 +2182,7 @@ int loam_pipeline_destroy(loam_pipeline* p) {
   p->tA.join();
   p->tB.join();
   p->tC.join();
+  p->tD.join();
   cudaSetDevice(p->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < PNS; i++) {
@@ -2082,6 +2197,7 @@ int loam_pipeline_destroy(loam_pipeline* p) {
   loam_destroy(p->hA);
   loam_destroy(p->hB);
   loam_destroy(p->hC);
+  if (p->hD) loam_destroy(p->hD);
   delete p;
   return LOAM_OK;
 }
@@ -2190,7 +2306,8 @@ int loam_pipeline_pending(loam_pipeline* p) {
 int loam_pipeline_stats(loam_pipeline* p, long long out4[4]) {
   if (!p || !out4) return LOAM_EINVAL;
   for (int i = 0; i < 4; i++) out4[i] = 0;
-  for (loam_handle* h : {p->hA, p->hB, p->hC}) {
+  for (loam_handle* h : {p->hA, p->hB, p->hC, p->hD}) {
+    if (!h) continue;
     out4[0] += h->launches; out4[1] += h->h2d_bytes; out4[2] += h->d2h_bytes; out4[3] += h->syncs;
   }
   return LOAM_OK;

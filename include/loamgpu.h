@@ -269,8 +269,8 @@ int loam_pipeline_stats(loam_pipeline* p, long long out4[4]);
 /* diagnostic: seconds each stage thread (0 extract, 1 odometry, 2 mapping) spent working on sweeps, i.e. not waiting for its
  * queue or a free hand-over slot; read when the pipeline is idle */
 int loam_pipeline_stage_times(loam_pipeline* p, double* out3, int clear);
-/* diagnostic: the handle behind stage `which` (for loam_host_times / loam_stats / loam_get_cloud while the pipeline is idle);
- * owned by the pipeline */
+/* the handle behind stage `which` (0 extract, 1 odometry, 2 mapping, 3 output: holds LOAM_CLOUD_SURROUND when the pipeline was
+ * created with want_surround) for loam_host_times / loam_stats / loam_get_cloud while the pipeline is idle; owned by the pipeline */
 loam_handle* loam_pipeline_handle(loam_pipeline* p, int which);
 
 /* ---- N1: segment scheduler, replaces the replay loop of input_data.cpp (IN:244-446) -----------------

@@ -447,6 +447,39 @@ def test_pipelined_mode_equals_fused(sweeps16):
     p.close()
 
 
+def test_pipelined_surround_cloud_equals_blocking_call():
+    """want_surround in pipelined mode: the cloud is finished on the pipeline's output stage (gather enqueued by the mapping
+    stage, voxel grid + count on the output thread) -- count of every surround run and the last cloud must equal what the
+    blocking call (which does LM:1081-1101 in line) produces, over enough sweeps for several surround runs and a reset."""
+    from gpscalibration_b200 import LoamGpu, LoamGpuPipeline, SweepGenerator
+    gen = SweepGenerator(sensor=0, scene=0, seed=0xC0FFEE)
+    sweeps = [gen.sweep(k)[0].copy() for k in range(44)]
+    a = LoamGpu(want_registered=True, want_surround=True)
+    p = LoamGpuPipeline(want_registered=True, want_surround=True)
+    for rep in range(2):
+        a.reset()
+        ref, last_cloud = [], None
+        for x in sweeps:
+            r = a.process_sweep(x)
+            ref.append((r.mapping_ran, r.map.surround_published, r.map.n_surround, r.map.n_registered, list(r.map.transform_aft_mapped)))
+            if r.mapping_ran and r.map.surround_published:
+                last_cloud = a.cloud("surround")
+        p.reset()
+        for x in sweeps:
+            p.submit(x)
+        got = [p.wait() for _ in sweeps]
+        assert p.pending == 0
+        n_sur = 0
+        for k, (r, g) in enumerate(zip(ref, got)):
+            assert r == (g.mapping_ran, g.map.surround_published, g.map.n_surround, g.map.n_registered, list(g.map.transform_aft_mapped)), (rep, k)
+            n_sur += int(bool(g.mapping_ran and g.map.surround_published))
+        assert n_sur >= 4 and all(r[2] > 0 for r in ref if r[0] and r[1])
+        cloud = p.output_cloud("surround")
+        assert cloud.shape == last_cloud.shape and np.array_equal(cloud.view(np.uint32), last_cloud.view(np.uint32))
+    a.close()
+    p.close()
+
+
 def test_mapping_cube_grid_rolls_like_the_reference(orc, sweeps16):
     """K11 / a14 / a18: drive laserMapping alone with odometry poses that travel hundreds of metres (and back), so the
     21 x 11 x 21 cube grid re-centres in every direction (LM:497-657), cubes get cleared, points land in cubes outside
