@@ -83,6 +83,18 @@ struct loam_handle {
   // mapping stage only ENQUEUES the gather of the cubes on the output handle's stream (`aux`) and goes on with the next
   // sweep; the voxel grid and its count read-back run on the pipeline's output thread.  ev_map_done: this handle's map
   // kernels of the run are finished; ev_aux_read: the gather has read the arena (awaited before the arena is written again).
+  // The per-cube voxel grids at the end of a mapping run (LM:1061-1079) only change what the NEXT run gathers, so their
+  // counts are not waited for: the read-back is enqueued, and the cube descriptors are brought up to date when the next run
+  // starts (by then the kernels are long finished) -- unless this run still needs them for the surround cloud.
+  struct PendingDS {
+    bool active = false, merged = false;
+    int nseg = 0, Mtot = 0, max_n = 0;
+    std::vector<int> validInd, seg_off;
+    std::vector<float> leaf;
+    std::vector<CopyEnt> ents;  // segment-major input layout, for the (rare) fall-back from the merge path to the full sort
+    cudaEvent_t ev = nullptr;
+  } pds;
+  int* h_ints2 = nullptr;  // pinned: [start | end | merge flag] of the pending read-back
   loam_handle* aux = nullptr;
   cudaEvent_t ev_map_done = nullptr, ev_aux_read = nullptr;
   bool aux_read_pending = false;
@@ -677,6 +689,8 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_mail, 64 * sizeof(double), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->d_mail, h->h_mail, 0);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_ints, loam_handle::H_INTS * sizeof(int), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_ints2, loam_handle::H_INTS * sizeof(int), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pds.ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
     delete h;
@@ -745,6 +759,8 @@ int loam_destroy(loam_handle* h) {
   if (h->ev_aux_read) cudaEventDestroy(h->ev_aux_read);
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->h_ints) cudaFreeHost(h->h_ints);
+  if (h->h_ints2) cudaFreeHost(h->h_ints2);
+  if (h->pds.ev) cudaEventDestroy(h->pds.ev);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return LOAM_OK;
@@ -976,12 +992,57 @@ int loam_mapping_odometry(loam_handle* h, const float* Tsum) {
   return LOAM_OK;
 }
 
+// Applies the read-back of the previous run's per-cube voxel grids (see loam_handle::PendingDS).
+static int finish_cube_ds(loam_handle* h) {
+  loam_handle::PendingDS& pd = h->pds;
+  if (!pd.active) return LOAM_OK;
+  pd.active = false;
+  h->syncs++;
+  LG_CHECK(cudaEventSynchronize(pd.ev));
+  const int nseg = pd.nseg;
+  if (pd.merged && h->h_ints2[2 * nseg] != 0) {  // a cube's old cloud was not in voxel order after all: full sort path
+    h->merge_fallbacks++;
+    int* d_start = h->d_out_se.as<int>();
+    int* d_end = d_start + nseg;
+    int rc = upload(h, h->d_ents, pd.ents.data(), pd.ents.size() * sizeof(CopyEnt));
+    if (rc) return rc;
+    rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)pd.ents.size(), pd.max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+    if (rc) return rc;
+    rc = upload(h, h->d_seg_off, pd.seg_off.data(), (nseg + 1) * 4);
+    if (rc) return rc;
+    rc = upload(h, h->d_seg_leaf, pd.leaf.data(), nseg * 4);
+    if (rc) return rc;
+    LG_CHECK(h->ds_in.ensure((size_t)(pd.Mtot + 16) * 16, h->st));
+    rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, pd.Mtot,
+                    h->arena.as<float4>() + h->bump, d_start, d_end, h->st, &h->launches);
+    if (rc) return rc;
+    LG_D2H(h, h->h_ints2, d_start, (size_t)nseg * 8);
+    LG_SYNC(h);
+  }
+  int total = 0, s = 0;
+  for (int ind : pd.validInd)
+    for (int type = 0; type < 2; type++) {
+      auto& cube = type == 0 ? h->cubeC[ind] : h->cubeS[ind];
+      int st0 = h->h_ints2[s], en0 = h->h_ints2[nseg + s];
+      cube.clear();
+      if (en0 > st0) cube.push_back(Chunk{(int)h->bump + st0, en0 - st0});
+      total = std::max(total, en0);
+      s++;
+    }
+  h->bump += total;
+  return LOAM_OK;
+}
+
 int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (!h || !out) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
   HostTimer ht(&h->host_s[HT_MAP_PREP]);
+  {
+    int rcf = finish_cube_ds(h);
+    if (rcf) return rcf;
+  }
   if (h->aux_read_pending) {  // the output stream may still be reading cubes of the previous surround: order this run's arena writes behind it
     LG_CHECK(cudaStreamWaitEvent(h->st, h->ev_aux_read, 0));
     h->aux_read_pending = false;
@@ -1226,8 +1287,16 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       rc = upload(h, h->d_seg_leaf, leaf.data(), nseg * 4);
       if (rc) return rc;
       if (2 * nseg + 1 > loam_handle::H_INTS) return LOAM_ENOSPC;
-      bool done = false;
-      if (merge_ok && h->use_merge_path) {
+      loam_handle::PendingDS& pd = h->pds;
+      pd.nseg = nseg;
+      pd.Mtot = Mtot;
+      pd.max_n = max_n;
+      pd.validInd = validInd;
+      pd.seg_off = seg_off;
+      pd.merged = merge_ok && h->use_merge_path;
+      if (pd.merged) {
+        pd.ents = ents;
+        pd.leaf = leaf;
         std::vector<int> offs3;  // [old | new | merged] offset tables in one upload
         offs3.insert(offs3.end(), off_old.begin(), off_old.end());
         offs3.insert(offs3.end(), off_new.begin(), off_new.end());
@@ -1244,12 +1313,8 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
                           n_old, n_new, outp, d_start, d_end, d_flags, h->st, &h->launches);
         if (rc) return rc;
         ht.lap(&h->host_s[15]);
-        LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8 + 4);
-        LG_SYNC(h);
-        done = h->h_ints[2 * nseg] == 0;
-        if (!done) h->merge_fallbacks++;
-      }
-      if (!done) {
+        LG_D2H(h, h->h_ints2, d_start, (size_t)nseg * 8 + 4);
+      } else {
         rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
         if (rc) return rc;
         rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
@@ -1261,20 +1326,15 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
                         &h->launches);
         if (rc) return rc;
         ht.lap(&h->host_s[15]);
-        LG_D2H(h, h->h_ints, d_start, (size_t)nseg * 8);
-        LG_SYNC(h);
+        LG_D2H(h, h->h_ints2, d_start, (size_t)nseg * 8);
       }
-      int total = 0, s = 0;
-      for (int ind : validInd)
-        for (int type = 0; type < 2; type++) {
-          auto& cube = type == 0 ? h->cubeC[ind] : h->cubeS[ind];
-          int st0 = h->h_ints[s], en0 = h->h_ints[nseg + s];
-          cube.clear();
-          if (en0 > st0) cube.push_back(Chunk{(int)h->bump + st0, en0 - st0});
-          total = std::max(total, en0);
-          s++;
-        }
-      h->bump += total;
+      LG_CHECK(cudaEventRecord(pd.ev, h->st));
+      pd.active = true;
+      // this run's surround cloud (LM:1081-1101) gathers the cubes just written: it needs the descriptors now
+      if (h->prm.want_surround && h->mapFrameCount + 1 >= 5) {
+        rc = finish_cube_ds(h);
+        if (rc) return rc;
+      }
     }
   }
   ht.lap(&h->host_s[HT_MAP_REST]);
