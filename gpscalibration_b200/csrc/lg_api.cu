@@ -94,6 +94,10 @@ struct loam_handle {
     std::vector<CopyEnt> ents;  // segment-major input layout, for the (rare) fall-back from the merge path to the full sort
     cudaEvent_t ev = nullptr;
   } pds;
+  // the voxel-grid chain itself runs on a second stream behind the run's insert / sort (ev_pre_ds), so that the NEXT run's
+  // stack transform and stack voxel grid (which need neither the cubes nor this chain's scratch) overlap with it
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_pre_ds = nullptr;
   int* h_ints2 = nullptr;  // pinned: [start | end | merge flag] of the pending read-back
   loam_handle* aux = nullptr;
   cudaEvent_t ev_map_done = nullptr, ev_aux_read = nullptr;
@@ -164,12 +168,13 @@ struct loam_handle {
 
 namespace {
 
-int upload(loam_handle* h, DevBuf& dst, const void* src, size_t bytes) {
+int upload_on(loam_handle* h, cudaStream_t st, DevBuf& dst, const void* src, size_t bytes) {
   h->h2d_bytes += (long long)bytes;
-  LG_CHECK(dst.ensure(bytes + 16, h->st));
-  if (bytes) LG_CHECK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->st));
+  LG_CHECK(dst.ensure(bytes + 16, st));
+  if (bytes) LG_CHECK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, st));
   return LOAM_OK;
 }
+int upload(loam_handle* h, DevBuf& dst, const void* src, size_t bytes) { return upload_on(h, h->st, dst, src, bytes); }
 
 // ------------------------------------------------------------------------------------------------ map storage
 size_t live_points(const loam_handle* h) {
@@ -309,7 +314,9 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
     for (int i = 0; i < nseg; i++) counts[i] = h->h_ints[i];
     return LOAM_OK;
   }
-  // big path: stage the segments contiguously
+  // big path: stage the segments contiguously (it shares the sort workspace and the staging buffers with the per-cube voxel
+  // grids of the previous mapping run, which may still be running on the second stream)
+  if (h->pds.active) LG_CHECK(cudaStreamWaitEvent(h->st, h->pds.ev, 0));
   std::vector<CopyEnt> ents;
   std::vector<int> seg_off(nseg + 1, 0);
   std::vector<float> leaf(nseg);
@@ -691,6 +698,8 @@ static int create_internal(const loam_params* p, int device, int role, loam_hand
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_ints, loam_handle::H_INTS * sizeof(int), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_ints2, loam_handle::H_INTS * sizeof(int), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pds.ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pre_ds, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
     delete h;
@@ -739,6 +748,7 @@ int loam_destroy(loam_handle* h) {
   if (!h) return LOAM_EINVAL;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
+  if (h->st2) cudaStreamSynchronize(h->st2);
   h->prof.resolve(h->st);
   h->prof.release();
   h->sr.release(); h->od.release(); h->csr.release(); h->gn.release(); h->vb.release();
@@ -761,6 +771,8 @@ int loam_destroy(loam_handle* h) {
   if (h->h_ints) cudaFreeHost(h->h_ints);
   if (h->h_ints2) cudaFreeHost(h->h_ints2);
   if (h->pds.ev) cudaEventDestroy(h->pds.ev);
+  if (h->ev_pre_ds) cudaEventDestroy(h->ev_pre_ds);
+  if (h->st2) cudaStreamDestroy(h->st2);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return LOAM_OK;
@@ -1039,7 +1051,7 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   memset(out, 0, sizeof(*out));
   HostTimer ht(&h->host_s[HT_MAP_PREP]);
-  {
+  if (!h->lm_inited) {  // a reset clears the cubes: bring them up to date first
     int rcf = finish_cube_ds(h);
     if (rcf) return rcf;
   }
@@ -1063,6 +1075,22 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   LG_CHECK(h->stack_s.ensure((size_t)(nsl + 16) * 16, h->st));
   int rc = lg_map_stack_launch(mt, h->corner_last.as<float4>(), h->stack2_c.as<float4>(), ncl, h->surf_last.as<float4>(),
                                h->stack2_s.as<float4>(), nsl, h->st, &h->launches);
+  if (rc) return rc;
+  ht.lap(&h->host_s[11]);
+  // LM:736-747 down-sample the stacks.  Done ahead of the cube bookkeeping (it needs neither the cubes nor their scratch): the
+  // per-cube voxel grids of the previous run may still be running on the second stream and are only waited for below.
+  {
+    std::vector<VoxSegD> segs(2);
+    segs[0] = VoxSegD{h->stack2_c.as<float4>(), nullptr, h->stack_c.as<float4>(), nullptr, ncl, 0.2f};
+    segs[1] = VoxSegD{h->stack2_s.as<float4>(), nullptr, h->stack_s.as<float4>(), nullptr, nsl, 0.4f};
+    std::vector<int> cnt;
+    rc = voxel_segments(h, segs, cnt);
+    if (rc) return rc;
+    h->n_stack_c = cnt[0];
+    h->n_stack_s = cnt[1];
+  }
+  ht.lap(&h->host_s[HT_MAP_PREP]);
+  rc = finish_cube_ds(h);
   if (rc) return rc;
 
   ht.lap(&h->host_s[9]);
@@ -1115,18 +1143,6 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
   if (rc) return rc;
   rc = gather_cubes(h, validInd, false, true, h->map_s, &h->n_map_s);
   if (rc) return rc;
-  ht.lap(&h->host_s[11]);
-  // LM:736-747 down-sample the stacks
-  {
-    std::vector<VoxSegD> segs(2);
-    segs[0] = VoxSegD{h->stack2_c.as<float4>(), nullptr, h->stack_c.as<float4>(), nullptr, ncl, 0.2f};
-    segs[1] = VoxSegD{h->stack2_s.as<float4>(), nullptr, h->stack_s.as<float4>(), nullptr, nsl, 0.4f};
-    std::vector<int> cnt;
-    rc = voxel_segments(h, segs, cnt);
-    if (rc) return rc;
-    h->n_stack_c = cnt[0];
-    h->n_stack_s = cnt[1];
-  }
   out->n_corner_stack = h->n_stack_c;
   out->n_surf_stack = h->n_stack_s;
   out->n_corner_map = h->n_map_c;
@@ -1288,6 +1304,9 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
       if (rc) return rc;
       if (2 * nseg + 1 > loam_handle::H_INTS) return LOAM_ENOSPC;
       loam_handle::PendingDS& pd = h->pds;
+      cudaStream_t ds = h->st2;  // behind everything this run has enqueued so far (insert, sort, runs, raw appends, the leaf table)
+      LG_CHECK(cudaEventRecord(h->ev_pre_ds, h->st));
+      LG_CHECK(cudaStreamWaitEvent(ds, h->ev_pre_ds, 0));
       pd.nseg = nseg;
       pd.Mtot = Mtot;
       pd.max_n = max_n;
@@ -1301,34 +1320,36 @@ int loam_mapping_process(loam_handle* h, loam_map_result* out) {
         offs3.insert(offs3.end(), off_old.begin(), off_old.end());
         offs3.insert(offs3.end(), off_new.begin(), off_new.end());
         offs3.insert(offs3.end(), seg_off.begin(), seg_off.end());
-        rc = upload(h, h->d_ents, ents_m.data(), ents_m.size() * sizeof(CopyEnt));
+        rc = upload_on(h, ds, h->d_ents, ents_m.data(), ents_m.size() * sizeof(CopyEnt));
         if (rc) return rc;
-        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents_m.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents_m.size(), max_n, h->ds_in.as<float4>(), ds, &h->launches);
         if (rc) return rc;
-        rc = upload(h, h->d_seg_off, offs3.data(), offs3.size() * 4);
+        rc = upload_on(h, ds, h->d_seg_off, offs3.data(), offs3.size() * 4);
         if (rc) return rc;
         const int* d_off = h->d_seg_off.as<int>();
         ht.lap(&h->host_s[14]);
         rc = lg_vox_merge(h->vb, h->ds_in.as<float4>(), d_off, d_off + (nseg + 1), d_off + 2 * (nseg + 1), h->d_seg_leaf.as<float>(), nseg,
-                          n_old, n_new, outp, d_start, d_end, d_flags, h->st, &h->launches);
+                          n_old, n_new, outp, d_start, d_end, d_flags, ds, &h->launches);
         if (rc) return rc;
         ht.lap(&h->host_s[15]);
-        LG_D2H(h, h->h_ints2, d_start, (size_t)nseg * 8 + 4);
+        h->d2h_bytes += (long long)nseg * 8 + 4;
+        LG_CHECK(cudaMemcpyAsync(h->h_ints2, d_start, (size_t)nseg * 8 + 4, cudaMemcpyDeviceToHost, ds));
       } else {
-        rc = upload(h, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
+        rc = upload_on(h, ds, h->d_ents, ents.data(), ents.size() * sizeof(CopyEnt));
         if (rc) return rc;
-        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), h->st, &h->launches);
+        rc = lg_gather(h->d_ents.as<CopyEnt>(), (int)ents.size(), max_n, h->ds_in.as<float4>(), ds, &h->launches);
         if (rc) return rc;
-        rc = upload(h, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
+        rc = upload_on(h, ds, h->d_seg_off, seg_off.data(), (nseg + 1) * 4);
         if (rc) return rc;
         ht.lap(&h->host_s[14]);
-        rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, h->st,
+        rc = lg_vox_big(h->vb, h->ds_in.as<float4>(), h->d_seg_off.as<int>(), h->d_seg_leaf.as<float>(), nseg, Mtot, outp, d_start, d_end, ds,
                         &h->launches);
         if (rc) return rc;
         ht.lap(&h->host_s[15]);
-        LG_D2H(h, h->h_ints2, d_start, (size_t)nseg * 8);
+        h->d2h_bytes += (long long)nseg * 8;
+        LG_CHECK(cudaMemcpyAsync(h->h_ints2, d_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, ds));
       }
-      LG_CHECK(cudaEventRecord(pd.ev, h->st));
+      LG_CHECK(cudaEventRecord(pd.ev, ds));
       pd.active = true;
       // this run's surround cloud (LM:1081-1101) gathers the cubes just written: it needs the descriptors now
       if (h->prm.want_surround && h->mapFrameCount + 1 >= 5) {
