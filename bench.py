@@ -16,7 +16,7 @@ sequence (BASELINE configs[3], no data-path collective): weak scaling, value = a
 Extra objects on the same line: "cfg1" (configs[0]: microseconds per odometry refresh / iteration of one registration
 against the launch-latency floor), "cfg3" (configs[2] at spec size: mapping stage against a 2.0 M-point local map, N = 1),
 "cfg5" (configs[4]: 1 M-point stack against a 50 M-point map sharded over the N ranks, NCCL all-reduce and the exchange
-fused into the kernel), "multi_segment", "parity".
+fused into the kernel), "extract_batch" (loam_extract_batch: B sequences per launch), "multi_segment", "parity".
 
 `--impl reference` times the reference's CPU implementation of the same path on the same workload (bounded sample).
 """
@@ -52,13 +52,12 @@ ALGO_BYTES = {
     "sr_select": ("16 F + 5 N per sweep (keys, flags, labels)", 5.0 + 16.0 * 0.2),
 }
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
-# (r1_ncu_full_<kernel>.csv, first 60 sweeps of the same sequence); None where no capture exists
-# DRAM bytes (read + write) per launch group of each class from the final `ncu --set full` capture
-# (profiles/r1_ncu_full_final.csv; ncu flushes caches between replays, so these are cold-cache upper bounds).
-NCU_TRAFFIC = {"odom_knn": 351000 + 381000,  # odom_knn_pruned_kernel + odom_corr_pruned_kernel of one refresh
-               "odom_iter": 358144,           # odom_loop_kernel (one launch = up to five iterations)
-               "sr_select": 172288, "map_knn": 2148608, "map_fit": 915200, "voxel": None, "extract": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch group of each class from the round-2 `ncu --set full` capture
+# (profiles/r2_ncu_full.csv; ncu flushes caches between replays, so these are cold-cache upper bounds); None where the
+# class is a chain of several kernels without one dominant launch
+NCU_TRAFFIC = {"odom_knn": None,              # odom_refresh_pruned_kernel: see profiles/r2_ncu_full.csv of the final build
+               "odom_iter": 386304,           # odom_loop_kernel (one launch = up to five iterations)
+               "sr_select": 185344, "map_knn": 1234944, "map_fit": None, "voxel": None, "extract": None}
 
 
 def log(*a):
@@ -166,6 +165,7 @@ def main():
     ap.add_argument("--multi-segments", type=int, default=4, help="extra: independent segments sharing one GPU (0/1 = skip)")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg 3 object (mapping stage against a 2 M-point local map)")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg 5 object (1 M-point stack against the 50 M-point sharded map)")
+    ap.add_argument("--no-extract-batch", action="store_true", help="skip the batched-extraction object (loam_extract_batch, B = 1 / 8 / 32)")
     ap.add_argument("--cfg5-map-points", type=int, default=50_000_000)
     ap.add_argument("--cfg5-queries", type=int, default=1_000_000)
     args = ap.parse_args()
@@ -483,6 +483,12 @@ def main():
             out["cfg3"] = bench_cfg3.run_stage(local=local_rank, log=log)
         except Exception as e:  # an extra must not take the headline down
             out["cfg3"] = {"error": repr(e)}
+    if world == 1 and not args.no_extract_batch:
+        import bench_extract_batch
+        try:  # SURVEY 8b `*_batch`: the extraction stage with one launch per kernel for B sequences (roofline on batched launches)
+            out["extract_batch"] = bench_extract_batch.run((1, 8, 32), 24, local_rank, peak_gbs, log=log)
+        except Exception as e:
+            out["extract_batch"] = {"error": repr(e)}
     if not args.no_cfg5:
         import bench_cfg5
         try:

@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_extract_batch", "loam_odometry_process",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -112,6 +112,7 @@ def load_library():
     lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
+    lib.loam_extract_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.loam_odometry_process.argtypes = [vp, C.POINTER(OdomResult)]
     lib.loam_mapping_odometry.argtypes = [vp, vp]
     lib.loam_mapping_process.argtypes = [vp, C.POINTER(MapResult)]
@@ -528,6 +529,21 @@ class LoamGpuPipeline:
         out = (C.c_longlong * 4)()
         self._check(self.lib.loam_pipeline_stats(self._h, out), "loam_pipeline_stats")
         return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
+
+
+def extract_batch(handles, sweeps, stride_bytes=12):
+    """loam_extract_batch: one sweep (float32 array (n, 3), or (n, k) rows of stride_bytes) per LoamGpu handle, every
+    extraction kernel launched once for the whole batch.  Returns the list of Counts."""
+    B = len(handles)
+    arrs = [_f32(x) for x in sweeps]
+    hs = (C.c_void_p * B)(*[h._h for h in handles])
+    ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    ns = (C.c_int * B)(*[a.shape[0] for a in arrs])
+    out = (Counts * B)()
+    rc = load_library().loam_extract_batch(hs, B, ptrs, ns, stride_bytes, None, out)
+    if rc:
+        raise LoamError(rc, "loam_extract_batch", load_library().loam_last_cuda_error(None).decode())
+    return list(out)
 
 
 def gn_solve(AtA, AtB, it, eig_threshold, state37):

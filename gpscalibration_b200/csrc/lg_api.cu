@@ -98,6 +98,7 @@ struct loam_handle {
   // stack transform and stack voxel grid (which need neither the cubes nor this chain's scratch) overlap with it
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_pre_ds = nullptr;
+  DevBuf batch_tab;        // argument table of loam_extract_batch (first handle of the batch)
   int* h_ints2 = nullptr;  // pinned: [start | end | merge flag] of the pending read-back
   loam_handle* aux = nullptr;
   cudaEvent_t ev_map_done = nullptr, ev_aux_read = nullptr;
@@ -355,9 +356,8 @@ int voxel_segments(loam_handle* h, const std::vector<VoxSegD>& segs_in, std::vec
   return LOAM_OK;
 }
 
-int read_sr_counts(loam_handle* h, loam_counts* out) {
-  LG_D2H(h, h->h_ints, h->sr.meta.p, SRM_HEAD * 4);
-  LG_SYNC(h);
+// h->h_ints holds the head of the extraction's meta array (read back by the caller): virtual rings, errors, counts
+int sr_counts_tail(loam_handle* h, loam_counts* out) {
   if (h->h_ints[SRM_VIRTUAL]) {
     // A ring whose scanStartInd was never written (empty rings: true VLP-16 angles leave rings 6 / 8 / 10 of the
     // reference's table empty): it spans [0, scanEndInd) and is replayed after the rings before it, serially (SR:480-490).
@@ -410,6 +410,11 @@ int read_sr_counts(loam_handle* h, loam_counts* out) {
   if (out) *out = h->counts;
   return LOAM_OK;
 }
+int read_sr_counts(loam_handle* h, loam_counts* out) {
+  LG_D2H(h, h->h_ints, h->sr.meta.p, SRM_HEAD * 4);
+  LG_SYNC(h);
+  return sr_counts_tail(h, out);
+}
 
 // sensor_msgs/PointCloud2 payloads whose point_step is not a multiple of four (the Velodyne driver's 22-byte
 // PointXYZIR: x y z @0, intensity @16, ring @20) cannot be read with aligned 4-byte loads: repack x y z first.
@@ -432,6 +437,16 @@ __global__ void pack_pcl32_kernel(const float4* __restrict__ src, int n, float4*
   dst[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
 }
 
+// the five clouds of the sweep become the handle's current features (what the node publishes, SR:689-726)
+void extract_publish(loam_handle* h) {
+  h->cur_sharp = h->sr.sharp.as<float4>();
+  h->cur_less_sharp = h->sr.less_sharp.as<float4>();
+  h->cur_flat = h->sr.flat.as<float4>();
+  h->cur_less_flat = h->sr.less_flat.as<float4>();
+  h->cur_full = h->sr.full.as<float4>();
+  h->have_features = true;
+}
+
 int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out) {
   HostTimer ht(&h->host_s[HT_EXTRACT]);
   if (n < 0 || stride_bytes < 12) return LOAM_EINVAL;
@@ -448,12 +463,7 @@ int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, 
   if (rc) return rc;
   rc = read_sr_counts(h, out);
   if (rc) return rc;
-  h->cur_sharp = h->sr.sharp.as<float4>();
-  h->cur_less_sharp = h->sr.less_sharp.as<float4>();
-  h->cur_flat = h->sr.flat.as<float4>();
-  h->cur_less_flat = h->sr.less_flat.as<float4>();
-  h->cur_full = h->sr.full.as<float4>();
-  h->have_features = true;
+  extract_publish(h);
   return LOAM_OK;
 }
 
@@ -755,7 +765,7 @@ int loam_destroy(loam_handle* h) {
   DevBuf* all[] = {&h->xyz_packed, &h->wire, &h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
-                   &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts};
+                   &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts, &h->batch_tab};
   for (DevBuf* b : all) b->release();
   if (h->px_connected)
     for (int r = 0; r < h->px.world; r++)
@@ -862,6 +872,69 @@ int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   return extract_common(h, xyz_dev, n, stride_bytes, imu_trans, out);
+}
+
+// One sweep of each of B independent sequences (SURVEY 8b `*_batch`): the eight extraction kernels are launched ONCE for
+// all members (grid.y = sequence) on the first handle's stream, the counts come back with one synchronisation.  Results
+// are those of B loam_extract calls, bit for bit.  Members the batched launch does not take (empty sweeps, unaligned
+// point layouts) and sweeps with virtual rings go through the per-handle path.
+int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_host, const int* n, int stride_bytes, const double*,
+                       loam_counts* out) {
+  if (!hs || !xyz_host || !n || B < 1 || B > 256 || stride_bytes < 12) return LOAM_EINVAL;
+  for (int b = 0; b < B; b++)
+    if (!hs[b] || n[b] < 0 || (!xyz_host[b] && n[b] > 0) || hs[b]->device != hs[0]->device || hs[b]->prm.n_scans != hs[0]->prm.n_scans)
+      return LOAM_EINVAL;
+  for (int b = 0; b < B; b++)
+    for (int c = 0; c < b; c++)
+      if (hs[b] == hs[c]) return LOAM_EINVAL;
+  loam_handle* h0 = hs[0];
+  LG_CHECK(cudaSetDevice(h0->device));
+  g_lg_prof = h0->prof.on ? &h0->prof : nullptr;
+  HostTimer ht(&h0->host_s[HT_EXTRACT]);
+  cudaStream_t st = h0->st;
+  std::vector<int> members;
+  std::vector<SrWs*> ws;
+  std::vector<SrParams> prm;
+  std::vector<const float*> dxyz;
+  std::vector<int> nn, strides;
+  for (int b = 0; b < B; b++) {
+    loam_handle* h = hs[b];
+    const bool batched = n[b] > 0 && (stride_bytes & 3) == 0;
+    if (!batched) {  // per-handle path
+      int rc = loam_extract(h, xyz_host[b], n[b], stride_bytes, 0.0, nullptr, out ? &out[b] : nullptr);
+      if (rc) return rc;
+      continue;
+    }
+    LG_CHECK(cudaStreamSynchronize(h->st));  // the member's own stream may still read the clouds of its previous sweep
+    int rc = upload_on(h, st, h->xyz_in, xyz_host[b], (size_t)n[b] * stride_bytes);
+    if (rc) return rc;
+    for (int i = 0; i < 12; i++) h->imu[i] = 0.f;
+    members.push_back(b);
+    ws.push_back(&h->sr);
+    prm.push_back(h->srp);
+    dxyz.push_back(h->xyz_in.as<float>());
+    nn.push_back(n[b]);
+    strides.push_back(stride_bytes);
+  }
+  if (members.empty()) return LOAM_OK;
+  int rc = lg_extract_launch_batch(ws.data(), prm.data(), dxyz.data(), nn.data(), strides.data(), (int)members.size(), h0->batch_tab, st,
+                                   &h0->launches);
+  if (rc) return rc;
+  for (int b : members) {
+    loam_handle* h = hs[b];
+    h->d2h_bytes += SRM_HEAD * 4;
+    LG_CHECK(cudaMemcpyAsync(h->h_ints, h->sr.meta.p, SRM_HEAD * 4, cudaMemcpyDeviceToHost, st));
+  }
+  h0->syncs++;
+  LG_CHECK(cudaStreamSynchronize(st));
+  for (int b : members) {
+    loam_handle* h = hs[b];
+    g_lg_prof = h->prof.on ? &h->prof : nullptr;
+    rc = sr_counts_tail(h, out ? &out[b] : nullptr);  // sweeps with virtual rings are finished on the member's own stream
+    if (rc) return rc;
+    extract_publish(h);
+  }
+  return LOAM_OK;
 }
 
 // ============================================================================================ laserOdometry

@@ -90,7 +90,7 @@ __device__ void sweep_ori(const float* xyz, int n, int stride_bytes, float* star
   *ok = 1;
 }
 
-__global__ void __launch_bounds__(SR_NT) sr_ring_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+__device__ __forceinline__ void sr_ring_kernel_body(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
                                                          signed char* __restrict__ ring8, float* __restrict__ ori_raw,
                                                          unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
   __shared__ unsigned int h[MAXR];
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SR_NT) sr_ring_kernel(SrParams prm, const floa
   if (tid < prm.n_scans) hist[tid * nblocks + blockIdx.x] = h[tid];
 }
 
-__global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
+__device__ __forceinline__ void sr_scan_kernel_body(SrParams prm, unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
   __shared__ int s_scan[34];
   const int total = prm.n_scans * nblocks;
   int per = (total + 1023) / 1024;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned in
   }
 }
 
-__global__ void __launch_bounds__(SR_NT) sr_scatter_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+__device__ __forceinline__ void sr_scatter_kernel_body(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
                                                             const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
                                                             const unsigned int* __restrict__ hist, int nblocks, const int* __restrict__ meta,
                                                             float4* __restrict__ full) {
@@ -242,7 +242,7 @@ __device__ __forceinline__ float gap2(float4 a, float4 b) {
   return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(256) sr_curv_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+__device__ __forceinline__ void sr_curv_kernel_body(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                        float* __restrict__ curv, unsigned char* __restrict__ cond, signed char* __restrict__ label) {
   const int n = meta[SRM_N_FULL];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +333,7 @@ constexpr int SEL_NT = 512;
 // step hide the shared-memory latency a single 300-key sort cannot), then warp 0 replays the reference's greedy walk
 // sector after sector, 32 candidates at a time: every lane knows its candidate's suppression interval, and the
 // sequential "picked earlier => suppress neighbours" dependency inside a batch is resolved with ballots.
-__global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+__device__ __forceinline__ void sr_select_kernel_body(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                             const float* __restrict__ curv, const unsigned char* __restrict__ cond,
                                                             unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
                                                             signed char* __restrict__ label, int* __restrict__ picks,
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(VIRT_NT) sr_virtual_kernel(SrParams prm, const
 }
 
 // Compacts picks to feature clouds, derives the less-flat mask (SR:670-674) and the per-ring voxel jobs (SR:677-683).
-__global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+__device__ __forceinline__ void sr_collect_kernel_body(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                           const signed char* __restrict__ label, const int* __restrict__ picks,
                                                           float4* __restrict__ sharp, float4* __restrict__ less_sharp, float4* __restrict__ flat,
                                                           unsigned char* __restrict__ lf_valid, float4* __restrict__ lf_tmp, VoxSegD* __restrict__ segs,
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const flo
   }
 }
 
-__global__ void __launch_bounds__(256) sr_concat_kernel(SrParams prm, int* __restrict__ meta, const VoxSegD* __restrict__ segs,
+__device__ __forceinline__ void sr_concat_kernel_body(SrParams prm, int* __restrict__ meta, const VoxSegD* __restrict__ segs,
                                                          float4* __restrict__ less_flat) {
   const int r = blockIdx.x, tid = threadIdx.x;
   const int R = prm.n_scans;
@@ -852,12 +852,110 @@ __global__ void __launch_bounds__(256) sr_concat_kernel(SrParams prm, int* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ launch forms
+// Every kernel above exists twice: for ONE sequence (arguments by value) and BATCHED over several sequences -- grid.y is
+// the sequence, whose arguments come from a device table (SURVEY 8b `*_batch`): eight launches extract B sweeps instead
+// of 8 B.  grid.x is the largest any member needs; a CTA beyond its member's own grid returns at once.
+struct SrK {
+  SrParams prm;
+  const float* xyz;
+  int n, stride, nblocks;
+  signed char* ring8;
+  float* ori_raw;
+  unsigned int* hist;
+  int* meta;
+  float4* full;
+  float* curv;
+  unsigned char *cond, *picked, *mask_diag;
+  signed char* label;
+  int *picks, *sort_ind;
+  unsigned char* stale;
+  float4 *sharp, *less_sharp, *flat;
+  unsigned char* lf_valid;
+  float4* lf_tmp;
+  VoxSegD* segs;
+  float4* less_flat;
+};
+
+__global__ void __launch_bounds__(SR_NT) sr_ring_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+                                                         signed char* __restrict__ ring8, float* __restrict__ ori_raw,
+                                                         unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
+  sr_ring_kernel_body(prm, xyz, n, stride_bytes, ring8, ori_raw, hist, nblocks, meta);
+}
+__global__ void __launch_bounds__(SR_NT) sr_ring_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)blockIdx.x >= A.nblocks) return;
+  sr_ring_kernel_body(A.prm, A.xyz, A.n, A.stride, A.ring8, A.ori_raw, A.hist, A.nblocks, A.meta);
+}
+__global__ void __launch_bounds__(1024) sr_scan_kernel(SrParams prm, unsigned int* __restrict__ hist, int nblocks, int* __restrict__ meta) {
+  sr_scan_kernel_body(prm, hist, nblocks, meta);
+}
+__global__ void __launch_bounds__(1024) sr_scan_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  sr_scan_kernel_body(A.prm, A.hist, A.nblocks, A.meta);
+}
+__global__ void __launch_bounds__(SR_NT) sr_scatter_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+                                                            const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
+                                                            const unsigned int* __restrict__ hist, int nblocks, const int* __restrict__ meta,
+                                                            float4* __restrict__ full) {
+  sr_scatter_kernel_body(prm, xyz, n, stride_bytes, ring8, ori_raw, hist, nblocks, meta, full);
+}
+__global__ void __launch_bounds__(SR_NT) sr_scatter_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)blockIdx.x >= A.nblocks) return;
+  sr_scatter_kernel_body(A.prm, A.xyz, A.n, A.stride, A.ring8, A.ori_raw, A.hist, A.nblocks, A.meta, A.full);
+}
+__global__ void __launch_bounds__(256) sr_curv_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                       float* __restrict__ curv, unsigned char* __restrict__ cond, signed char* __restrict__ label) {
+  sr_curv_kernel_body(prm, c, meta, curv, cond, label);
+}
+__global__ void __launch_bounds__(256) sr_curv_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)(blockIdx.x * blockDim.x) >= A.n) return;
+  sr_curv_kernel_body(A.prm, A.full, A.meta, A.curv, A.cond, A.label);
+}
+__global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                            const float* __restrict__ curv, const unsigned char* __restrict__ cond,
+                                                            unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
+                                                            signed char* __restrict__ label, int* __restrict__ picks,
+                                                            int* __restrict__ sort_ind, unsigned char* __restrict__ stale) {
+  sr_select_kernel_body(prm, c, meta, curv, cond, picked, mask_diag, label, picks, sort_ind, stale);
+}
+__global__ void __launch_bounds__(SEL_NT) sr_select_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)blockIdx.x >= A.prm.n_scans) return;
+  sr_select_kernel_body(A.prm, A.full, A.meta, A.curv, A.cond, A.picked, A.mask_diag, A.label, A.picks, A.sort_ind, A.stale);
+}
+__global__ void __launch_bounds__(256) sr_collect_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+                                                          const signed char* __restrict__ label, const int* __restrict__ picks,
+                                                          float4* __restrict__ sharp, float4* __restrict__ less_sharp, float4* __restrict__ flat,
+                                                          unsigned char* __restrict__ lf_valid, float4* __restrict__ lf_tmp, VoxSegD* __restrict__ segs,
+                                                          int features_only) {
+  sr_collect_kernel_body(prm, c, meta, label, picks, sharp, less_sharp, flat, lf_valid, lf_tmp, segs, features_only);
+}
+__global__ void __launch_bounds__(256) sr_collect_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)blockIdx.x >= A.prm.n_scans) return;
+  sr_collect_kernel_body(A.prm, A.full, A.meta, A.label, A.picks, A.sharp, A.less_sharp, A.flat, A.lf_valid, A.lf_tmp, A.segs, 0);
+}
+__global__ void __launch_bounds__(256) sr_concat_kernel(SrParams prm, int* __restrict__ meta, const VoxSegD* __restrict__ segs,
+                                                         float4* __restrict__ less_flat) {
+  sr_concat_kernel_body(prm, meta, segs, less_flat);
+}
+__global__ void __launch_bounds__(256) sr_concat_batch_kernel(const SrK* __restrict__ tab) {
+  const SrK A = tab[blockIdx.y];
+  if ((int)blockIdx.x >= A.prm.n_scans) return;
+  sr_concat_kernel_body(A.prm, A.meta, A.segs, A.less_flat);
+}
+
 }  // namespace
 
-int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches) {
+// buffers of one sequence for a sweep of n points (grown on demand; nothing is allocated in steady state)
+static int lg_extract_prepare(SrWs& ws, const SrParams& prm, int n, cudaStream_t st, int* nblocks_out) {
   const int R = prm.n_scans;
   if (R > MAXR || R < 1) return LOAM_EINVAL;
   const int nblocks = std::max(1, lg_div_up(n, SR_TILE));
+  *nblocks_out = nblocks;
   LG_CHECK(ws.ring8.ensure((size_t)n + 16, st));
   LG_CHECK(ws.ori_raw.ensure((size_t)(n + 16) * 4, st));
   LG_CHECK(ws.hist.ensure((size_t)R * nblocks * 4, st));
@@ -886,6 +984,16 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
     int big = 0x7fffffff;
     LG_CHECK(cudaMemcpyAsync(ws.meta.as<int>() + SRM_JSTAR, &big, 4, cudaMemcpyHostToDevice, st));
     LG_CHECK(cudaStreamSynchronize(st));
+  }
+  return LOAM_OK;
+}
+
+int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches) {
+  const int R = prm.n_scans;
+  int nblocks = 1;
+  {
+    int rcp = lg_extract_prepare(ws, prm, n, st, &nblocks);
+    if (rcp) return rcp;
   }
   int* meta = ws.meta.as<int>();
   if (n <= 0) {
@@ -965,5 +1073,80 @@ int lg_extract_finish_launch(SrWs& ws, const SrParams& prm, cudaStream_t st, lon
   sr_concat_kernel<<<R, 256, 0, st>>>(prm, ws.meta.as<int>(), ws.segs.as<VoxSegD>(), ws.less_flat.as<float4>());
   (*launches) += 2;
   LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+// One sweep of each of B sequences with eight launches in all (SURVEY 8b `*_batch`): see SrK above.  Members must have
+// n > 0 (the caller handles empty sweeps); the table travels through `tab` (device) on `st`.
+int lg_extract_launch_batch(SrWs* const* ws, const SrParams* prm, const float* const* d_xyz, const int* n, const int* stride_bytes, int B,
+                            DevBuf& tab, cudaStream_t st, long long* launches) {
+  if (B <= 0) return LOAM_OK;
+  std::vector<SrK> host(B);
+  int max_blocks = 1, max_R = 1, max_n = 1;
+  bool small_rings = true;
+  for (int b = 0; b < B; b++) {
+    if (n[b] <= 0) return LOAM_EINVAL;
+    int nblocks = 1;
+    int rc = lg_extract_prepare(*ws[b], prm[b], n[b], st, &nblocks);
+    if (rc) return rc;
+    SrWs& w = *ws[b];
+    SrK& k = host[b];
+    k.prm = prm[b];
+    k.xyz = d_xyz[b]; k.n = n[b]; k.stride = stride_bytes[b]; k.nblocks = nblocks;
+    k.ring8 = w.ring8.as<signed char>(); k.ori_raw = w.ori_raw.as<float>(); k.hist = w.hist.as<unsigned int>(); k.meta = w.meta.as<int>();
+    k.full = w.full.as<float4>(); k.curv = w.curv.as<float>(); k.cond = w.cond.as<unsigned char>(); k.picked = w.picked.as<unsigned char>();
+    k.mask_diag = w.mask_diag.as<unsigned char>(); k.label = w.label.as<signed char>(); k.picks = w.picks.as<int>();
+    k.sort_ind = w.sort_ind.as<int>(); k.stale = w.stale.as<unsigned char>(); k.sharp = w.sharp.as<float4>();
+    k.less_sharp = w.less_sharp.as<float4>(); k.flat = w.flat.as<float4>(); k.lf_valid = w.lf_valid.as<unsigned char>();
+    k.lf_tmp = w.lf_tmp.as<float4>(); k.segs = w.segs.as<VoxSegD>(); k.less_flat = w.less_flat.as<float4>();
+    max_blocks = std::max(max_blocks, nblocks);
+    max_R = std::max(max_R, prm[b].n_scans);
+    max_n = std::max(max_n, n[b]);
+    small_rings = small_rings && (n[b] / prm[b].n_scans) * 2 + 64 <= 4096;
+  }
+  LG_CHECK(tab.ensure((size_t)B * sizeof(SrK) + 2 * (size_t)B * sizeof(void*) + 64, st));
+  LG_CHECK(cudaMemcpyAsync(tab.p, host.data(), (size_t)B * sizeof(SrK), cudaMemcpyHostToDevice, st));
+  const SrK* d_tab = tab.as<SrK>();
+  static bool sel_attr[64] = {};
+  constexpr int sel_smem = 6 * SEL_CAP * 8;
+  int dev = 0;
+  LG_CHECK(cudaGetDevice(&dev));
+  if (!sel_attr[dev & 63]) {
+    LG_CHECK(cudaFuncSetAttribute(sr_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sel_smem));
+    sel_attr[dev & 63] = true;
+  }
+  double units = 0;
+  for (int b = 0; b < B; b++) units += n[b];
+  {
+    LgProfScope prof_scope(LGK_EXTRACT, st, units);
+    sr_ring_batch_kernel<<<dim3(max_blocks, B), SR_NT, 0, st>>>(d_tab);
+    sr_scan_batch_kernel<<<dim3(1, B), 1024, 0, st>>>(d_tab);
+    sr_scatter_batch_kernel<<<dim3(max_blocks, B), SR_NT, 0, st>>>(d_tab);
+    sr_curv_batch_kernel<<<dim3(lg_div_up(max_n, 256), B), 256, 0, st>>>(d_tab);
+  }
+  {
+    LgProfScope prof_scope(LGK_SR_SELECT, st, units);
+    sr_select_batch_kernel<<<dim3(max_R, B), SEL_NT, sel_smem, st>>>(d_tab);
+  }
+  LgProfScope prof_scope(LGK_EXTRACT, st, 0.0);
+  sr_collect_batch_kernel<<<dim3(max_R, B), 256, 0, st>>>(d_tab);
+  (*launches) += 6;
+  // per-ring voxel grids of all members in one launch: a table of {segment array, overflow flag} behind the SrK table
+  std::vector<const VoxSegD*> seg_tab(B);
+  std::vector<int*> ovf_tab(B);
+  for (int b = 0; b < B; b++) {
+    seg_tab[b] = host[b].segs;
+    ovf_tab[b] = host[b].meta + SRM_VOX_OVERFLOW;
+  }
+  char* extra = (char*)tab.p + (((size_t)B * sizeof(SrK) + 15) & ~(size_t)15);
+  LG_CHECK(cudaMemcpyAsync(extra, seg_tab.data(), (size_t)B * sizeof(void*), cudaMemcpyHostToDevice, st));
+  LG_CHECK(cudaMemcpyAsync(extra + (size_t)B * sizeof(void*), ovf_tab.data(), (size_t)B * sizeof(void*), cudaMemcpyHostToDevice, st));
+  int rc = lg_vox_small_batch((const VoxSegD* const*)extra, (int* const*)(extra + (size_t)B * sizeof(void*)), max_R, B, small_rings ? 4096 : 16384, st,
+                              launches);
+  if (rc) return rc;
+  sr_concat_batch_kernel<<<dim3(max_R, B), 256, 0, st>>>(d_tab);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  LG_CHECK(cudaStreamSynchronize(st));  // the tables above are host vectors
   return LOAM_OK;
 }

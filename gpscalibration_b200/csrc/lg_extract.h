@@ -50,6 +50,10 @@ struct SrWs {
 
 // Enqueues the whole extraction of one sweep on `st`; results and counts (meta) stay on the device.
 int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches);
+// The same for one sweep of each of B sequences with one launch per kernel (grid.y = sequence): members need n > 0, same
+// device; `tab` is scratch for the argument table.  Synchronises `st` before it returns.
+int lg_extract_launch_batch(SrWs* const* ws, const SrParams* prm, const float* const* d_xyz, const int* n, const int* stride_bytes, int B,
+                            DevBuf& tab, cudaStream_t st, long long* launches);
 // Sweeps with virtual rings (SRM_VIRTUAL set after the first pass).  lg_extract_virtual_launch replays those rings in the
 // reference's serial order; `stage_points` = sum of their scanEndInd (capacity of the less-flat staging).  It leaves
 // {offset, count} per ring in ws.lf_meta; the caller voxel-grids ws.lf_stage[offset .. +count) into ws.lf_vout + offset,

@@ -50,7 +50,7 @@ __device__ __forceinline__ int vox_cell(const VoxGrid& g, float4 p) {
 
 // ------------------------------------------------------------------------------------------------ small path
 template <int CAP, int NT>
-__global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict__ segs, int* __restrict__ overflow) {
+__device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs, int* __restrict__ overflow) {
   extern __shared__ unsigned long long skeys[];
   __shared__ float s_red[6][NT / 32];
   __shared__ int s_cnt[NT / 32];
@@ -172,6 +172,16 @@ __global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict
 
 
 // ------------------------------------------------------------------------------------------------ split path
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) vox_small_kernel(const VoxSegD* __restrict__ segs, int* __restrict__ overflow) {
+  vox_small_body<CAP, NT>(segs, overflow);
+}
+// several segment arrays in one launch: blockIdx.y picks the array (one per sequence of a batched extraction)
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT) vox_small_batch_kernel(const VoxSegD* const* __restrict__ seg_tab, int* const* __restrict__ overflow_tab) {
+  vox_small_body<CAP, NT>(seg_tab[blockIdx.y], overflow_tab[blockIdx.y]);
+}
+
 // Medium segments (a sweep-sized stack, 4 k .. 64 k points): the cell-id range of the segment is cut into `gridDim.x`
 // equal sub-ranges, one CTA each.  Every CTA scans the whole segment (L2-resident), keeps the points of its
 // sub-range, sorts them in shared memory and writes their centroids to its staging slice; a second kernel
@@ -799,6 +809,25 @@ int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overf
   return LOAM_OK;
 }
 
+
+int lg_vox_small_batch(const VoxSegD* const* d_seg_tab, int* const* d_overflow_tab, int max_nseg, int B, int max_seg_hint, cudaStream_t st,
+                       long long* launches) {
+  if (max_nseg <= 0 || B <= 0) return LOAM_OK;
+  if (max_seg_hint <= 4096) {
+    vox_small_batch_kernel<4096, 256><<<dim3(max_nseg, B), 256, 4096 * sizeof(unsigned long long), st>>>(d_seg_tab, d_overflow_tab);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(vox_small_batch_kernel<16384, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           16384 * (int)sizeof(unsigned long long));
+      attr_set = true;
+    }
+    vox_small_batch_kernel<16384, 1024><<<dim3(max_nseg, B), 1024, 16384 * sizeof(unsigned long long), st>>>(d_seg_tab, d_overflow_tab);
+  }
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
 
 int lg_vox_split(DevBuf& staging, DevBuf& counts, const VoxSegD* d_segs, int nseg, int* d_overflow, cudaStream_t st, long long* launches) {
   if (nseg <= 0) return LOAM_OK;

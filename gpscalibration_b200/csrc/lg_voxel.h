@@ -41,6 +41,9 @@ int lg_vox_split(DevBuf& staging, DevBuf& counts, const VoxSegD* d_segs, int nse
 int lg_vox_big(VoxBigWs& ws, const float4* d_in, const int* d_seg_off, const float* d_seg_leaf, int nseg, int M, float4* d_out,
                int* d_out_start, int* d_out_end, cudaStream_t st, long long* launches);
 // Merge path for cube-sized segments whose old cloud is already voxel-gridded (see lg_voxel.cu): d_in = [old | new].
+// lg_vox_small over several segment arrays at once: grid.y picks {segment array, overflow flag} from the device tables
+int lg_vox_small_batch(const VoxSegD* const* d_seg_tab, int* const* d_overflow_tab, int max_nseg, int B, int max_seg_hint, cudaStream_t st,
+                       long long* launches);
 int lg_vox_merge(VoxBigWs& ws, const float4* d_in, const int* d_seg_off_old, const int* d_seg_off_new, const int* d_seg_off,
                  const float* d_seg_leaf, int nseg, int n_old, int n_new, float4* d_out, int* d_out_start, int* d_out_end, int* d_flags,
                  cudaStream_t st, long long* launches);

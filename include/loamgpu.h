@@ -152,6 +152,14 @@ int loam_launch_latency(loam_handle* h, int n, double* period_us, double* roundt
 int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* Same, the sweep already resident in device memory of this handle's GPU. */
 int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
+/* Batched form of loam_extract (SURVEY 8b `*_batch`): one sweep of each of B independent sequences (B handles on the same
+ * device, same n_scans).  Every extraction kernel is launched ONCE for the whole batch (grid.y = sequence) and the counts
+ * come back with one synchronisation, so B sweeps cost eight launches instead of 8 B; results are those of B loam_extract
+ * calls bit for bit (empty sweeps, point_step not a multiple of 4 and sweeps with empty rings fall back to the per-handle
+ * path inside the call).  xyz_host[b] / n[b]: member b's sweep; stamps may be NULL; out[b] receives its counts.  Only the
+ * extraction is batched: odometry and mapping are data-dependent loops per sequence. */
+int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_host, const int* n, int stride_bytes,
+                       const double* stamps, loam_counts* out);
 
 /* ---- laserOdometry: replaces the loop body LO:502-1147 for the message set of the last loam_extract ---------- */
 int loam_odometry_process(loam_handle* h, loam_odom_result* out);

@@ -1,0 +1,89 @@
+"""SURVEY §8b `*_batch`: loam_extract_batch launches every extraction kernel once for B sequences (grid.y = sequence).
+Its results must be those of B loam_extract calls bit for bit -- counts and all five clouds -- for ragged batches (different
+point counts, NaNs, an empty sweep, a sweep with empty rings that takes the serial replay), over several sweeps per
+sequence (the per-sequence state between sweeps stays separate), and the features must feed the unbatched odometry /
+mapping of each sequence unchanged."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CLOUDS = ("full", "sharp", "less_sharp", "flat", "less_flat")
+
+
+def _counts(c):
+    return (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat)
+
+
+def _sequences(B, n_sweeps):
+    from gpscalibration_b200 import SweepGenerator
+    seqs = []
+    for b in range(B):
+        sensor = 1 if b == 2 else 0  # member 2: true VLP-16 angles -> rings 6 / 8 / 10 of the reference's table stay empty
+        g = SweepGenerator(sensor=sensor, scene=b % 2, seed=0xC0FFEE + 1000 * b, t_offset=37.0 * b)
+        sw = [g.sweep(k)[0].copy() for k in range(n_sweeps)]
+        if b == 1:  # ragged + invalid points
+            sw = [x[: x.shape[0] - 500 * (k + 1)].copy() for k, x in enumerate(sw)]
+            sw[0][::97, 1] = np.nan
+        seqs.append(sw)
+    return seqs
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_batched_extraction_equals_single_calls(B):
+    from gpscalibration_b200 import LoamGpu, capi
+    n_sweeps = 3
+    seqs = _sequences(B, n_sweeps)
+    single = [LoamGpu() for _ in range(B)]
+    batch = [LoamGpu() for _ in range(B)]
+    for k in range(n_sweeps):
+        sweeps = [seqs[b][k] for b in range(B)]
+        if B >= 3 and k == 1:
+            sweeps[0] = sweeps[0][:0]  # an empty sweep inside the batch
+        ref = [single[b].extract(sweeps[b]) for b in range(B)]
+        got = capi.extract_batch(batch, sweeps)
+        for b in range(B):
+            assert _counts(got[b]) == _counts(ref[b]), (k, b)
+            for name in CLOUDS:
+                a, c = single[b].cloud(name), batch[b].cloud(name)
+                assert a.shape == c.shape and np.array_equal(a.view(np.uint32), c.view(np.uint32)), (k, b, name)
+    launches_single = sum(h.stats()["launches"] for h in single)
+    launches_batch = sum(h.stats()["launches"] for h in batch)
+    if B == 8:
+        assert launches_batch < launches_single / 3  # the point of batching (the fall-back members launch on their own)
+    for h in single + batch:
+        h.close()
+
+
+def test_batched_features_drive_the_unbatched_pipeline():
+    """Extraction batched over four sequences, odometry + mapping per sequence: poses equal to loam_process_sweep."""
+    from gpscalibration_b200 import LoamGpu, capi
+    B, n_sweeps = 4, 12
+    seqs = _sequences(B, n_sweeps)
+    ref = [LoamGpu() for _ in range(B)]
+    bat = [LoamGpu() for _ in range(B)]
+    for k in range(n_sweeps):
+        capi.extract_batch(bat, [seqs[b][k] for b in range(B)])
+        for b in range(B):
+            r = ref[b].process_sweep(seqs[b][k])
+            o = bat[b].odometry_process()
+            assert list(o.transform_sum) == list(r.odom.transform_sum) and o.iterations == r.odom.iterations, (k, b)
+            if o.odom_published:
+                bat[b].mapping_odometry(np.array(o.transform_sum, np.float32))
+            if o.odom_published and o.fullres_published:
+                m = bat[b].mapping_process()
+                assert r.mapping_ran and list(m.transform_aft_mapped) == list(r.map.transform_aft_mapped), (k, b)
+    for h in ref + bat:
+        h.close()
+
+
+def test_batch_rejects_bad_arguments():
+    from gpscalibration_b200 import LoamGpu, capi
+    a, b = LoamGpu(), LoamGpu(n_scans=64, ring_mode=1, ring_ang_min=-24.8, ring_ang_step=26.8 / 63.0)
+    x = np.zeros((10, 3), np.float32)
+    with pytest.raises(capi.LoamError):
+        capi.extract_batch([a, b], [x, x])  # different ring tables in one batch
+    with pytest.raises(capi.LoamError):
+        capi.extract_batch([a, a], [x, x])  # the same handle twice
+    a.close()
+    b.close()
