@@ -61,7 +61,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect", "loam_shard_set_slab", "loam_shard_inject",
            "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
-           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_batch", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_pipeline_stage_times", "loam_pipeline_handle", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
            "loam_track_icp", "loam_track_smooth", "loam_track_calibrate", "loam_track_calibrate_long"]
@@ -147,6 +147,7 @@ def load_library():
     lib.loam_pipeline_last_error.argtypes = [vp]
     lib.loam_pipeline_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
+    lib.loam_pipeline_submit_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
     lib.loam_pipeline_pending.argtypes = [vp]
     lib.loam_pipeline_stream.restype = vp
@@ -529,6 +530,18 @@ class LoamGpuPipeline:
         out = (C.c_longlong * 4)()
         self._check(self.lib.loam_pipeline_stats(self._h, out), "loam_pipeline_stats")
         return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
+
+
+def pipeline_submit_batch(pipes, sweeps, stride_bytes=12):
+    """loam_pipeline_submit_batch: one sweep per LoamGpuPipeline, the extraction of all of them in one batched launch chain."""
+    B = len(pipes)
+    arrs = [_f32(x) for x in sweeps]
+    ps = (C.c_void_p * B)(*[p._h for p in pipes])
+    ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    ns = (C.c_int * B)(*[a.shape[0] for a in arrs])
+    rc = load_library().loam_pipeline_submit_batch(ps, B, ptrs, ns, stride_bytes, None)
+    if rc:
+        raise LoamError(rc, "loam_pipeline_submit_batch", load_library().loam_last_cuda_error(None).decode())
 
 
 def extract_batch(handles, sweeps, stride_bytes=12):

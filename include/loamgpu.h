@@ -269,6 +269,12 @@ const char* loam_pipeline_last_error(loam_pipeline* p);
 int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double stamp);
 /* device-resident sweep: the buffer must stay valid until the sweep's result has been returned */
 int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp);
+/* One sweep for each of B pipelines (B independent sequences on one device) with the extraction batched: the B sweeps go
+ * through loam_extract_batch in the caller's thread (one launch per extraction kernel for the whole batch), every
+ * pipeline's own stages do the rest.  Per-pipeline results are those of loam_pipeline_submit; collect them with
+ * loam_pipeline_wait on each pipeline.  Do not mix with loam_pipeline_submit calls in flight on the same pipelines. */
+int loam_pipeline_submit_batch(loam_pipeline* const* ps, int B, const float* const* xyz_host, const int* n, int stride_bytes,
+                               const double* stamps);
 int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out);
 int loam_pipeline_pending(loam_pipeline* p);
 /* cudaStream_t of stage `which` (0 extract, 1 odometry, 2 mapping), for CUDA-event timing by the caller */

@@ -87,3 +87,42 @@ def test_batch_rejects_bad_arguments():
         capi.extract_batch([a, a], [x, x])  # the same handle twice
     a.close()
     b.close()
+
+
+def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines():
+    """loam_pipeline_submit_batch: four pipelines, the extraction of their sweeps batched in the caller's thread, odometry /
+    mapping / output stages per pipeline -- every result equal to the same pipelines fed with loam_pipeline_submit, across a
+    reset."""
+    from gpscalibration_b200 import LoamGpuPipeline, capi
+    B, n_sweeps = 4, 30
+    seqs = _sequences(B, n_sweeps)
+
+    def key(r):
+        t = (r.counts.n_full, r.counts.n_less_flat, list(r.odom.transform_sum), r.odom.iterations, r.mapping_ran)
+        if r.mapping_ran:
+            t += (list(r.map.transform_aft_mapped), r.map.iterations, r.map.n_corner_map, r.map.n_surf_map, r.map.n_surround, r.map.n_registered)
+        return t
+
+    plain = [LoamGpuPipeline(want_registered=True, want_surround=True) for _ in range(B)]
+    batched = [LoamGpuPipeline(want_registered=True, want_surround=True) for _ in range(B)]
+    ref = [[] for _ in range(B)]
+    got = [[] for _ in range(B)]
+    for k in range(n_sweeps):
+        if k == 17:
+            for p in plain + batched:
+                p.reset()
+        for b in range(B):
+            plain[b].submit(seqs[b][k])
+        capi.pipeline_submit_batch(batched, [seqs[b][k] for b in range(B)])
+        if k >= 4:
+            for b in range(B):
+                ref[b].append(key(plain[b].wait()))
+                got[b].append(key(batched[b].wait()))
+    for b in range(B):
+        while plain[b].pending:
+            ref[b].append(key(plain[b].wait()))
+        while batched[b].pending:
+            got[b].append(key(batched[b].wait()))
+        assert len(ref[b]) == n_sweeps and ref[b] == got[b], b
+    for p in plain + batched:
+        p.close()

@@ -1,5 +1,6 @@
-"""Aggregate throughput of S independent sequences sharing ONE GPU (cfg 4 with more segments than GPUs), two ways:
+"""Aggregate throughput of S independent sequences sharing ONE GPU (cfg 4 with more segments than GPUs), three ways:
   pipelined  S pipelined handles (3 stage threads + 3 streams each) driven by S host threads
+  batched    the same pipelines fed by ONE thread through loam_pipeline_submit_batch (extraction of the S sweeps batched)
   blocking   S plain handles, one host thread each calling loam_process_sweep (1 thread + 1 stream per sequence)
 ctypes releases the GIL during the calls.  usage: multiseg.py [sweeps] [full]"""
 import sys, time, threading, os
@@ -13,10 +14,10 @@ seqs_all = []
 for s in range(16):
     gen = SweepGenerator(seed=0xC0FFEE + 1000 * s, t_offset=37.0 * s)
     seqs_all.append([gen.sweep(k)[0].copy() for k in range(N)])
-for mode in ("pipelined", "blocking"):
+for mode in ("pipelined", "batched", "blocking"):
     for S in (1, 2, 4, 8, 12, 16):
         seqs = seqs_all[:S]
-        if mode == "pipelined":
+        if mode in ("pipelined", "batched"):
             objs = [LoamGpuPipeline(want_registered=WANT, want_surround=WANT) for _ in range(S)]
         else:
             objs = [LoamGpu(want_registered=WANT, want_surround=WANT) for _ in range(S)]
@@ -36,9 +37,23 @@ for mode in ("pipelined", "blocking"):
                         p.process_sweep(x)
                 out.append(time.perf_counter() - t0)
         outs = [[] for _ in range(S)]
-        ths = [threading.Thread(target=run, args=(objs[i], seqs[i], outs[i])) for i in range(S)]
-        for t in ths: t.start()
-        for t in ths: t.join()
+        if mode == "batched":  # ONE feeder thread: loam_pipeline_submit_batch extracts the S sweeps with one launch per kernel
+            from gpscalibration_b200 import capi
+            for rep in range(2):
+                for p in objs: p.reset()
+                t0 = time.perf_counter()
+                for k in range(N):
+                    capi.pipeline_submit_batch(objs, [seqs[i][k] for i in range(S)])
+                    if k >= 6:
+                        for p in objs: p.wait()
+                for p in objs:
+                    while p.pending: p.wait()
+                dt = time.perf_counter() - t0
+                for o in outs: o.append(dt)
+        else:
+            ths = [threading.Thread(target=run, args=(objs[i], seqs[i], outs[i])) for i in range(S)]
+            for t in ths: t.start()
+            for t in ths: t.join()
         last = max(o[1] for o in outs)
         print("%s segments %2d: second pass %.3f s -> aggregate %6.0f sweeps/s (per segment %.0f)" % (mode, S, last, S * N / last, N / last), flush=True)
         for p in objs: p.close()
