@@ -409,6 +409,33 @@ def main():
                                 "note": "independent sequences sharing one B200 (host buffers, wall clock of the slowest segment, second pass)"}
         for p in seg_pipes[1:]:
             p.close()
+        # the same with more sequences than threads can usefully drive: EIGHT pipelines fed by ONE thread through
+        # loam_pipeline_submit_batch (the extraction of the eight sweeps is one launch per kernel)
+        try:
+            from gpscalibration_b200 import capi as _capi
+            SEGB, NSB = 8, min(300, S)
+            bdata = seg_data + [make_sequence(NSB, 200 + i, pinned=True)[1:] for i in range(len(seg_data), SEGB)]
+            bpipes = [pipe] + [LoamGpuPipeline(device=local_rank, want_registered=True, want_surround=True) for _ in range(1, SEGB)]
+            tb = 0.0
+            for rep in range(2):
+                for p in bpipes:
+                    p.reset()
+                t0 = time.perf_counter()
+                for k in range(NSB):
+                    _capi.pipeline_submit_batch(bpipes, [bdata[i][0][bdata[i][1][k]:bdata[i][1][k + 1]] for i in range(SEGB)])
+                    if k >= DEPTH:
+                        for p in bpipes:
+                            p.wait()
+                for p in bpipes:
+                    while p.pending:
+                        p.wait()
+                tb = time.perf_counter() - t0
+            out["multi_segment"]["batched_feeder"] = {"segments_on_one_gpu": SEGB, "sweeps_per_segment": NSB, "value": SEGB * NSB / tb, "unit": UNIT,
+                                                      "note": "eight pipelines fed by one thread, extraction batched (loam_pipeline_submit_batch), second pass"}
+            for p in bpipes[1:]:
+                p.close()
+        except Exception as e:
+            out["multi_segment"]["batched_feeder"] = {"error": repr(e)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(args.cpu_sweeps, S)
