@@ -55,13 +55,13 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_extract_batch", "loam_odometry_process",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_extract_batch", "loam_odometry_process", "loam_odometry_process_batch",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect", "loam_shard_set_slab", "loam_shard_inject",
            "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
-           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_batch", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_batch", "loam_pipeline_submit_lockstep", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_pipeline_stage_times", "loam_pipeline_handle", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
            "loam_track_icp", "loam_track_smooth", "loam_track_calibrate", "loam_track_calibrate_long"]
@@ -114,6 +114,7 @@ def load_library():
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
     lib.loam_odometry_process.argtypes = [vp, C.POINTER(OdomResult)]
+    lib.loam_odometry_process_batch.argtypes = [vp, C.c_int, vp]
     lib.loam_mapping_odometry.argtypes = [vp, vp]
     lib.loam_mapping_process.argtypes = [vp, C.POINTER(MapResult)]
     lib.loam_integrate_odometry.argtypes = [vp, vp, C.c_double, vp, vp]
@@ -148,6 +149,7 @@ def load_library():
     lib.loam_pipeline_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_submit_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
+    lib.loam_pipeline_submit_lockstep.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
     lib.loam_pipeline_pending.argtypes = [vp]
     lib.loam_pipeline_stream.restype = vp
@@ -532,16 +534,30 @@ class LoamGpuPipeline:
         return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
 
 
-def pipeline_submit_batch(pipes, sweeps, stride_bytes=12):
-    """loam_pipeline_submit_batch: one sweep per LoamGpuPipeline, the extraction of all of them in one batched launch chain."""
+def pipeline_submit_batch(pipes, sweeps, stride_bytes=12, lockstep=False):
+    """loam_pipeline_submit_batch: one sweep per LoamGpuPipeline, the extraction of all of them in one batched launch chain;
+    lockstep=True (loam_pipeline_submit_lockstep) batches the scan-to-scan odometry as well."""
     B = len(pipes)
     arrs = [_f32(x) for x in sweeps]
     ps = (C.c_void_p * B)(*[p._h for p in pipes])
     ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
     ns = (C.c_int * B)(*[a.shape[0] for a in arrs])
-    rc = load_library().loam_pipeline_submit_batch(ps, B, ptrs, ns, stride_bytes, None)
+    fn = load_library().loam_pipeline_submit_lockstep if lockstep else load_library().loam_pipeline_submit_batch
+    rc = fn(ps, B, ptrs, ns, stride_bytes, None)
     if rc:
-        raise LoamError(rc, "loam_pipeline_submit_batch", load_library().loam_last_cuda_error(None).decode())
+        raise LoamError(rc, "loam_pipeline_submit_lockstep" if lockstep else "loam_pipeline_submit_batch", "loam_pipeline_submit_lockstep", load_library().loam_last_cuda_error(None).decode())
+
+
+def odometry_process_batch(handles):
+    """loam_odometry_process_batch: scan-to-scan odometry of the current sweep of every handle in lock-step (one launch per
+    kernel and round for the whole batch).  Returns the list of OdomResult."""
+    B = len(handles)
+    hs = (C.c_void_p * B)(*[h._h for h in handles])
+    out = (OdomResult * B)()
+    rc = load_library().loam_odometry_process_batch(hs, B, out)
+    if rc:
+        raise LoamError(rc, "loam_odometry_process_batch", load_library().loam_last_cuda_error(None).decode())
+    return list(out)
 
 
 def extract_batch(handles, sweeps, stride_bytes=12):

@@ -938,21 +938,19 @@ int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_ho
 }
 
 // ============================================================================================ laserOdometry
-int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
-  if (!h || !out) return LOAM_EINVAL;
-  if (!h->have_features) return LOAM_ESTATE;
-  LG_CHECK(cudaSetDevice(h->device));
-  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+// LO:519-572 -- the part of a sweep before its Gauss-Newton iterations.  *state: 0 = the sweep only initialised the node
+// (LO:519-563), 1 = iterate (LO:572 holds), 2 = go straight to the pose accumulation.  Device work goes to `st`.
+static int lo_begin(loam_handle* h, loam_odom_result* out, cudaStream_t st, int* state) {
   memset(out, 0, sizeof(*out));
   const loam_counts& c = h->counts;
   const float* imu = h->imu;
   if (!h->lo_inited) {  // LO:519-563
     h->cornerLastNum = 0;
     h->surfLastNum = 0;
-    LG_CHECK(h->corner_last.ensure((size_t)(c.n_less_sharp + 16) * 16, h->st));
-    LG_CHECK(h->surf_last.ensure((size_t)(c.n_less_flat + 16) * 16, h->st));
-    if (c.n_less_sharp) LG_CHECK(cudaMemcpyAsync(h->corner_last.p, h->cur_less_sharp, (size_t)c.n_less_sharp * 16, cudaMemcpyDeviceToDevice, h->st));
-    if (c.n_less_flat) LG_CHECK(cudaMemcpyAsync(h->surf_last.p, h->cur_less_flat, (size_t)c.n_less_flat * 16, cudaMemcpyDeviceToDevice, h->st));
+    LG_CHECK(h->corner_last.ensure((size_t)(c.n_less_sharp + 16) * 16, st));
+    LG_CHECK(h->surf_last.ensure((size_t)(c.n_less_flat + 16) * 16, st));
+    if (c.n_less_sharp) LG_CHECK(cudaMemcpyAsync(h->corner_last.p, h->cur_less_sharp, (size_t)c.n_less_sharp * 16, cudaMemcpyDeviceToDevice, st));
+    if (c.n_less_flat) LG_CHECK(cudaMemcpyAsync(h->surf_last.p, h->cur_less_flat, (size_t)c.n_less_flat * 16, cudaMemcpyDeviceToDevice, st));
     h->n_corner_last = c.n_less_sharp;
     h->n_surf_last = c.n_less_flat;
     h->od.bounds_valid = false;
@@ -963,14 +961,109 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
     out->clouds_published = 1;
     out->n_corner_last = h->n_corner_last;
     out->n_surf_last = h->n_surf_last;
+    *state = 0;
     return LOAM_OK;
   }
-  HostTimer ht(&h->host_s[HT_ODOM_ITERS]);
   const float scanPeriod = 0.1f;  // LO:50
   h->T[3] -= imu[9] * scanPeriod;
   h->T[4] -= imu[10] * scanPeriod;
   h->T[5] -= imu[11] * scanPeriod;
-  if (h->cornerLastNum > 10 && h->surfLastNum > 100) {  // LO:572
+  *state = (h->cornerLastNum > 10 && h->surfLastNum > 100) ? 1 : 2;  // LO:572
+  return LOAM_OK;
+}
+
+// LO:904-907, 975-1031 for iteration 0 on the host (it carries the eigen-decomposition / degeneracy test): true = converged
+static bool lo_iter0_host(loam_handle* h, const float* AtA, const float* AtB, int n_sel) {
+  if (n_sel < 10) return false;  // LO:904-907
+  float X[6];
+  lg_gn_solve_step(AtA, AtB, 0, 10.f, h->lo_gn, X);
+  for (int i = 0; i < 6; i++) h->T[i] += X[i];
+  for (int i = 0; i < 6; i++)
+    if (isnan(h->T[i])) h->T[i] = 0;
+  float deltaR = (float)sqrt(pow(X[0] * 180.0 / M_PI, 2) + pow(X[1] * 180.0 / M_PI, 2) + pow(X[2] * 180.0 / M_PI, 2));
+  float deltaT = (float)sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
+  return deltaR < 0.1 && deltaT < 0.1;
+}
+
+// LO:1035-1121 -- pose accumulation, TransformToEnd of the clouds, swap.  k == nullptr: launches the kernel on `st`; else the
+// kernel arguments go into the member's row of a batched launch (lg_odom_batch_to_end on the same stream).
+static int lo_finish(loam_handle* h, loam_odom_result* out, cudaStream_t st, OdK* k) {
+  const loam_counts& c = h->counts;
+  const float* imu = h->imu;
+  // LO:1035-1064
+  float* T = h->T;
+  float* S = h->Tsum;
+  float rx, ry, rz, tx, ty, tz;
+  lgh::accumulate_rotation(S[0], S[1], S[2], -T[0], (float)(-T[1] * 1.05), -T[2], rx, ry, rz);
+  float x1 = cosf(rz) * (T[3] - imu[6]) - sinf(rz) * (T[4] - imu[7]);
+  float y1 = sinf(rz) * (T[3] - imu[6]) + cosf(rz) * (T[4] - imu[7]);
+  float z1 = (float)(T[5] * 1.05 - imu[8]);
+  float x2 = x1;
+  float y2 = cosf(rx) * y1 - sinf(rx) * z1;
+  float z2 = sinf(rx) * y1 + cosf(rx) * z1;
+  tx = S[3] - (cosf(ry) * x2 + sinf(ry) * z2);
+  ty = S[4] - y2;
+  tz = S[5] - (-sinf(ry) * x2 + cosf(ry) * z2);
+  lgh::plugin_imu_rotation(rx, ry, rz, imu[0], imu[1], imu[2], imu[3], imu[4], imu[5], rx, ry, rz);
+  S[0] = rx; S[1] = ry; S[2] = rz; S[3] = tx; S[4] = ty; S[5] = tz;
+  out->odom_published = 1;
+
+  // LO:1087-1121
+  h->frameCount++;
+  const bool pub = h->frameCount >= h->prm.skip_frame_num + 1;
+  LG_CHECK(h->corner_new.ensure((size_t)(c.n_less_sharp + 16) * 16, st));
+  LG_CHECK(h->surf_new.ensure((size_t)(c.n_less_flat + 16) * 16, st));
+  if (pub) LG_CHECK(h->fullres3.ensure((size_t)(c.n_full + 16) * 16, st));
+  OdomT ot;
+  for (int i = 0; i < 6; i++) ot.t[i] = T[i];
+  if (k) {
+    k->do_to_end = 1;
+    k->T = ot; k->sT = host_sincos3(T); k->imu = imu_sc(imu);
+    k->in0 = h->cur_less_sharp; k->out0 = h->corner_new.as<float4>(); k->n0 = c.n_less_sharp;
+    k->in1 = h->cur_less_flat; k->out1 = h->surf_new.as<float4>(); k->n1 = c.n_less_flat;
+    k->in2 = h->cur_full; k->out2 = h->fullres3.as<float4>(); k->n2 = pub ? c.n_full : 0;
+  } else {
+    int rc = lg_odom_to_end_launch(ot, host_sincos3(T), imu_sc(imu), h->cur_less_sharp, h->corner_new.as<float4>(), c.n_less_sharp,
+                                   h->cur_less_flat, h->surf_new.as<float4>(), c.n_less_flat, h->cur_full, h->fullres3.as<float4>(),
+                                   pub ? c.n_full : 0, st, &h->launches);
+    if (rc) return rc;
+  }
+  std::swap(h->corner_last, h->corner_new);
+  std::swap(h->surf_last, h->surf_new);
+  h->od.bounds_valid = false;
+  h->n_corner_last = c.n_less_sharp;
+  h->n_surf_last = c.n_less_flat;
+  h->cornerLastNum = h->n_corner_last;
+  h->surfLastNum = h->n_surf_last;
+  if (pub) {
+    h->frameCount = 0;
+    h->n_fullres3 = c.n_full;
+    out->clouds_published = 1;
+    out->fullres_published = 1;
+  }
+  for (int i = 0; i < 6; i++) {
+    out->transform_sum[i] = S[i];
+    out->transformation[i] = T[i];
+  }
+  out->n_corner_last = h->n_corner_last;
+  out->n_surf_last = h->n_surf_last;
+  return LOAM_OK;
+}
+
+int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
+  if (!h || !out) return LOAM_EINVAL;
+  if (!h->have_features) return LOAM_ESTATE;
+  LG_CHECK(cudaSetDevice(h->device));
+  g_lg_prof = h->prof.on ? &h->prof : nullptr;
+  int state = 0;
+  {
+    int rcb = lo_begin(h, out, h->st, &state);
+    if (rcb) return rcb;
+    if (state == 0) return LOAM_OK;
+  }
+  const loam_counts& c = h->counts;
+  HostTimer ht(&h->host_s[HT_ODOM_ITERS]);
+  if (state == 1) {  // LO:572
     static const bool host_loop = getenv("LOAM_HOST_GN_LOOP") != nullptr;  // diagnostic: every iteration through the host
     for (int iter = 0; iter < 25;) {
       if (iter == 0 || host_loop) {  // iteration 0 carries the eigen-decomposition / degeneracy test (LO:977-999): host
@@ -980,7 +1073,11 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
         int rc = odom_iter(h, iter, h->T, AtA, AtB, &n_sel);
         if (rc) return rc;
         iter++;
-        if (n_sel < 10) continue;  // LO:904-907
+        if (!host_loop || iter == 1) {
+          if (lo_iter0_host(h, AtA, AtB, n_sel)) break;
+          continue;
+        }
+        if (n_sel < 10) continue;  // LO:904-907 (diagnostic path: later iterations through the host)
         lg_gn_solve_step(AtA, AtB, iter - 1, 10.f, h->lo_gn, X);
         for (int i = 0; i < 6; i++) h->T[i] += X[i];
         for (int i = 0; i < 6; i++)
@@ -1011,55 +1108,133 @@ int loam_odometry_process(loam_handle* h, loam_odom_result* out) {
     }
   }
   ht.lap(&h->host_s[HT_ODOM_END]);
-  // LO:1035-1064
-  float* T = h->T;
-  float* S = h->Tsum;
-  float rx, ry, rz, tx, ty, tz;
-  lgh::accumulate_rotation(S[0], S[1], S[2], -T[0], (float)(-T[1] * 1.05), -T[2], rx, ry, rz);
-  float x1 = cosf(rz) * (T[3] - imu[6]) - sinf(rz) * (T[4] - imu[7]);
-  float y1 = sinf(rz) * (T[3] - imu[6]) + cosf(rz) * (T[4] - imu[7]);
-  float z1 = (float)(T[5] * 1.05 - imu[8]);
-  float x2 = x1;
-  float y2 = cosf(rx) * y1 - sinf(rx) * z1;
-  float z2 = sinf(rx) * y1 + cosf(rx) * z1;
-  tx = S[3] - (cosf(ry) * x2 + sinf(ry) * z2);
-  ty = S[4] - y2;
-  tz = S[5] - (-sinf(ry) * x2 + cosf(ry) * z2);
-  lgh::plugin_imu_rotation(rx, ry, rz, imu[0], imu[1], imu[2], imu[3], imu[4], imu[5], rx, ry, rz);
-  S[0] = rx; S[1] = ry; S[2] = rz; S[3] = tx; S[4] = ty; S[5] = tz;
-  out->odom_published = 1;
+  return lo_finish(h, out, h->st, nullptr);
+}
 
-  // LO:1087-1121
-  h->frameCount++;
-  const bool pub = h->frameCount >= h->prm.skip_frame_num + 1;
-  LG_CHECK(h->corner_new.ensure((size_t)(c.n_less_sharp + 16) * 16, h->st));
-  LG_CHECK(h->surf_new.ensure((size_t)(c.n_less_flat + 16) * 16, h->st));
-  if (pub) LG_CHECK(h->fullres3.ensure((size_t)(c.n_full + 16) * 16, h->st));
-  OdomT ot;
-  for (int i = 0; i < 6; i++) ot.t[i] = T[i];
-  int rc = lg_odom_to_end_launch(ot, host_sincos3(T), imu_sc(imu), h->cur_less_sharp, h->corner_new.as<float4>(), c.n_less_sharp,
-                                 h->cur_less_flat, h->surf_new.as<float4>(), c.n_less_flat, h->cur_full, h->fullres3.as<float4>(),
-                                 pub ? c.n_full : 0, h->st, &h->launches);
+// SURVEY 8b `*_batch`: one sweep of B independent sequences through scan-to-scan odometry in LOCK-STEP.  Every kernel of a
+// round (box hierarchy, correspondence refresh, iteration 0, a block of device iterations, TransformToEnd) is launched once
+// for all members that take part in it (grid.y = sequence); the host parts (LO:519-572, the eigen-decomposition of
+// iteration 0, LO:1035-1084) run per member between the rounds.  Results are those of B loam_odometry_process calls, bit
+// for bit.  Members whose feature count exceeds what the cluster kernels hold go through the per-handle call.
+int loam_odometry_process_batch(loam_handle* const* hs, int B, loam_odom_result* out) {
+  if (!hs || !out || B < 1 || B > 256) return LOAM_EINVAL;
+  for (int b = 0; b < B; b++) {
+    if (!hs[b] || hs[b]->device != hs[0]->device) return LOAM_EINVAL;
+    if (!hs[b]->have_features) return LOAM_ESTATE;
+    for (int c = 0; c < b; c++)
+      if (hs[b] == hs[c]) return LOAM_EINVAL;
+  }
+  loam_handle* h0 = hs[0];
+  LG_CHECK(cudaSetDevice(h0->device));
+  g_lg_prof = h0->prof.on ? &h0->prof : nullptr;
+  HostTimer ht(&h0->host_s[HT_ODOM_ITERS]);
+  cudaStream_t st = h0->st;
+  std::vector<OdK> tab(B);
+  std::vector<int> state(B, 0), iter(B, 0);
+  std::vector<char> active(B, 0), batched(B, 0);
+  for (int b = 0; b < B; b++) {
+    loam_handle* h = hs[b];
+    memset(&tab[b], 0, sizeof(OdK));
+    if (!lg_odom_batch_fits(h->counts.n_sharp, h->counts.n_flat)) {  // per-handle path (own stream, blocking)
+      int rc = loam_odometry_process(h, &out[b]);
+      if (rc) return rc;
+      continue;
+    }
+    batched[b] = 1;
+    if (h != h0) LG_CHECK(cudaStreamSynchronize(h->st));  // the member's own stream may still use the clouds this call replaces
+    int rc = lo_begin(h, &out[b], st, &state[b]);
+    if (rc) return rc;
+    if (state[b] != 1) continue;
+    OdK& k = tab[b];
+    rc = lg_odom_batch_prepare(h->od, h->counts.n_sharp, h->counts.n_flat, h->n_corner_last, h->n_surf_last, st, &k);
+    if (rc) return rc;
+    k.sharp = h->cur_sharp; k.flat = h->cur_flat; k.corner_last = h->corner_last.as<float4>(); k.surf_last = h->surf_last.as<float4>();
+    k.n_sharp = h->counts.n_sharp; k.n_flat = h->counts.n_flat; k.n_cl = h->n_corner_last; k.n_sl = h->n_surf_last;
+    k.out = h->d_mail;
+    active[b] = 1;
+  }
+  // ---- round 0: box hierarchy (once per sweep), correspondences, iteration 0 (its sums go to the host: LO:977-999)
+  bool any = false;
+  for (int b = 0; b < B; b++) {
+    OdK& k = tab[b];
+    k.do_bounds = k.do_refresh = k.do_iter0 = k.do_loop = 0;
+    if (!active[b]) continue;
+    loam_handle* h = hs[b];
+    any = true;
+    k.do_bounds = h->od.bounds_valid ? 0 : 1;
+    k.do_refresh = 1;
+    k.do_iter0 = 1;
+    for (int i = 0; i < 6; i++) k.T.t[i] = h->T[i];
+    k.sc = host_sincos3(h->T);
+    k.iter = 0;
+    k.seq = ++h->mail_seq;
+  }
+  if (any) {
+    int rc = lg_odom_batch_round(tab.data(), B, h0->batch_tab, st, &h0->launches);
+    if (rc) return rc;
+    for (int b = 0; b < B; b++) {
+      if (!active[b]) continue;
+      loam_handle* h = hs[b];
+      h->od.bounds_valid = true;
+      rc = mailbox_wait(h);
+      if (rc) return rc;
+      h->d2h_bytes += 28 * 8;
+      float AtA[36], AtB[6];
+      int n_sel = 0;
+      lg_unpack28(h->h_mail, AtA, AtB, &n_sel);
+      out[b].iterations = 1;
+      iter[b] = 1;
+      if (lo_iter0_host(h, AtA, AtB, n_sel)) active[b] = 0;
+    }
+  }
+  // ---- rounds 1..: blocks of device iterations up to the next correspondence refresh (LO:595), members drop out as they converge
+  for (;;) {
+    any = false;
+    for (int b = 0; b < B; b++) {
+      OdK& k = tab[b];
+      k.do_bounds = k.do_refresh = k.do_iter0 = k.do_loop = 0;
+      if (!active[b]) continue;
+      loam_handle* h = hs[b];
+      any = true;
+      OdomLoopArgs& la = k.la;
+      for (int i = 0; i < 6; i++) la.T.t[i] = h->T[i];
+      la.sc = host_sincos3(h->T);
+      memcpy(la.matP, h->lo_gn.matP, sizeof(la.matP));
+      la.degenerate = h->lo_gn.degenerate ? 1 : 0;
+      la.it0 = iter[b];
+      la.it1 = std::min(25, (iter[b] / 5 + 1) * 5);
+      k.T = la.T;
+      k.do_refresh = la.it0 % 5 == 0 ? 1 : 0;
+      k.do_loop = 1;
+      k.seq = ++h->mail_seq;
+    }
+    if (!any) break;
+    int rc = lg_odom_batch_round(tab.data(), B, h0->batch_tab, st, &h0->launches);
+    if (rc) return rc;
+    for (int b = 0; b < B; b++) {
+      if (!active[b]) continue;
+      loam_handle* h = hs[b];
+      rc = mailbox_wait(h);
+      if (rc) return rc;
+      h->d2h_bytes += 8 * 8;
+      for (int i = 0; i < 6; i++) h->T[i] = (float)h->h_mail[i];
+      out[b].iterations = (int)h->h_mail[6] + 1;
+      iter[b] = tab[b].la.it1;
+      if (h->h_mail[7] != 0.0 || iter[b] >= 25) active[b] = 0;
+    }
+  }
+  ht.lap(&h0->host_s[HT_ODOM_END]);
+  // ---- LO:1035-1121 per member on the host, TransformToEnd of all members in one launch
+  for (int b = 0; b < B; b++) {
+    tab[b].do_to_end = 0;
+    if (!batched[b] || state[b] == 0) continue;
+    int rc = lo_finish(hs[b], &out[b], st, &tab[b]);
+    if (rc) return rc;
+  }
+  int rc = lg_odom_batch_to_end(tab.data(), B, h0->batch_tab, st, &h0->launches);
   if (rc) return rc;
-  std::swap(h->corner_last, h->corner_new);
-  std::swap(h->surf_last, h->surf_new);
-  h->od.bounds_valid = false;
-  h->n_corner_last = c.n_less_sharp;
-  h->n_surf_last = c.n_less_flat;
-  h->cornerLastNum = h->n_corner_last;
-  h->surfLastNum = h->n_surf_last;
-  if (pub) {
-    h->frameCount = 0;
-    h->n_fullres3 = c.n_full;
-    out->clouds_published = 1;
-    out->fullres_published = 1;
-  }
-  for (int i = 0; i < 6; i++) {
-    out->transform_sum[i] = S[i];
-    out->transformation[i] = T[i];
-  }
-  out->n_corner_last = h->n_corner_last;
-  out->n_surf_last = h->n_surf_last;
+  h0->syncs++;
+  LG_CHECK(cudaStreamSynchronize(st));  // the members go on with their own streams
   return LOAM_OK;
 }
 
@@ -2041,6 +2216,7 @@ struct loam_pipeline {
   long long epoch = 0;
   std::map<long long, long long> epoch_of;  // sweep -> epoch (for loam_pipeline_wait)
   char err_text[512] = "";
+  long long resets_pushed = 0, resets_at_b = 0;  // loam_pipeline_reset calls / those the odometry stage has seen (guarded by rm)
   long long pre_submitted = 0, pre_handled = 0;  // batch-extracted sweeps pushed / handed on by stage A (guarded by rm)
   double busy[3] = {0, 0, 0};  // seconds each stage thread spent working on sweeps (not waiting for its queue / a free slot)
   std::thread tA, tB, tC, tD;
@@ -2115,7 +2291,14 @@ void stage_b(loam_pipeline* p) {
   loam_handle* h = p->hB;
   for (;;) {
     Job j = p->qB.pop();
-    if (j.kind == JOB_RESET) h->lo_inited = false;
+    if (j.kind == JOB_RESET) {
+      h->lo_inited = false;
+      {
+        std::lock_guard<std::mutex> l(p->rm);
+        p->resets_at_b++;
+      }
+      p->rcv.notify_all();
+    }
     if (j.kind != JOB_SWEEP) {
       p->qC.push(j);
       if (j.kind == JOB_STOP) return;
@@ -2371,6 +2554,7 @@ int loam_pipeline_reset(loam_pipeline* p) {
   {
     std::lock_guard<std::mutex> l(p->rm);
     p->epoch++;  // an error of the epoch that ends here no longer blocks submit / stages
+    p->resets_pushed++;
   }
   p->qA.push(j);
   return LOAM_OK;
@@ -2478,6 +2662,87 @@ int loam_pipeline_submit_batch(loam_pipeline* const* ps, int B, const float* con
       p->pre_submitted++;
     }
     p->qA.push(j);
+  }
+  return LOAM_OK;
+}
+
+// One sweep for each of B pipelines with extraction AND scan-to-scan odometry batched in lock-step in the caller's thread
+// (loam_extract_batch + loam_odometry_process_batch: one launch per kernel and round for all B sequences); the mapping and
+// output stages stay per pipeline.  Per-pipeline results are those of loam_pipeline_submit.  Blocks for the extraction and
+// the odometry of the batch (and for a free mapping slot); use it INSTEAD of loam_pipeline_submit on these pipelines.
+int loam_pipeline_submit_lockstep(loam_pipeline* const* ps, int B, const float* const* xyz_host, const int* n, int stride_bytes, const double* stamps) {
+  if (!ps || B < 1 || B > 256 || !xyz_host || !n) return LOAM_EINVAL;
+  std::vector<loam_handle*> hA(B), hB(B);
+  std::vector<long long> epochs(B);
+  for (int b = 0; b < B; b++) {
+    if (!ps[b] || ps[b]->device != ps[0]->device) return LOAM_EINVAL;
+    hA[b] = ps[b]->hA;
+    hB[b] = ps[b]->hB;
+    std::unique_lock<std::mutex> l(ps[b]->rm);
+    // a reset travels through the stage threads: the odometry handle is only touched here once it has arrived
+    ps[b]->rcv.wait(l, [&] { return ps[b]->resets_at_b == ps[b]->resets_pushed && ps[b]->pre_handled == ps[b]->pre_submitted; });
+    epochs[b] = ps[b]->epoch;
+  }
+  for (int b = 0; b < B; b++)
+    if (int e = pipe_error(ps[b], epochs[b])) return e;
+  std::vector<loam_counts> counts(B);
+  int rc = loam_extract_batch(hA.data(), B, xyz_host, n, stride_bytes, stamps, counts.data());
+  if (rc) return rc;
+  for (int b = 0; b < B; b++) {  // the odometry handles read the features where the extraction left them
+    loam_handle *a = hA[b], *h = hB[b];
+    h->counts = counts[b];
+    h->cur_full = a->cur_full; h->cur_sharp = a->cur_sharp; h->cur_less_sharp = a->cur_less_sharp;
+    h->cur_flat = a->cur_flat; h->cur_less_flat = a->cur_less_flat;
+    for (int i = 0; i < 12; i++) h->imu[i] = 0.f;
+    h->have_features = true;
+  }
+  std::vector<loam_odom_result> od(B);
+  rc = loam_odometry_process_batch(hB.data(), B, od.data());
+  if (rc) return rc;
+  for (int b = 0; b < B; b++) {  // what the odometry stage does after its sweep: hand the clouds to the mapping stage
+    loam_pipeline* p = ps[b];
+    loam_handle* h = hB[b];
+    const loam_odom_result& o = od[b];
+    int ms = -1;
+    if (o.odom_published && o.fullres_published) {
+      p->map_free.acquire();
+      ms = (int)(p->map_count++ % PNS);
+      loam_pipeline::MapIn& m = p->mapin[ms];
+      m.nc = h->n_corner_last; m.ns = h->n_surf_last; m.nf = h->n_fullres3;
+      cudaStreamWaitEvent(h->st, m.consumed, 0);
+      cudaError_t e = m.corner.ensure((size_t)(m.nc + 16) * 16, h->st);
+      if (e == cudaSuccess) e = m.surf.ensure((size_t)(m.ns + 16) * 16, h->st);
+      if (e == cudaSuccess) e = m.full.ensure((size_t)(m.nf + 16) * 16, h->st);
+      if (e != cudaSuccess) {
+        lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+        p->map_free.release();
+        return LOAM_ECUDA;
+      }
+      if (m.nc) cudaMemcpyAsync(m.corner.p, h->corner_last.p, (size_t)m.nc * 16, cudaMemcpyDeviceToDevice, h->st);
+      if (m.ns) cudaMemcpyAsync(m.surf.p, h->surf_last.p, (size_t)m.ns * 16, cudaMemcpyDeviceToDevice, h->st);
+      if (m.nf) cudaMemcpyAsync(m.full.p, h->fullres3.p, (size_t)m.nf * 16, cudaMemcpyDeviceToDevice, h->st);
+      cudaEventRecord(m.ready, h->st);
+    }
+    Job j;
+    memset(&j, 0, sizeof(j));
+    j.kind = JOB_SWEEP;
+    j.n = n[b];
+    j.stride = stride_bytes;
+    j.epoch = epochs[b];
+    j.slot = ms;
+    j.odom_published = o.odom_published;
+    j.full = ms >= 0;
+    for (int i = 0; i < 6; i++) j.Tsum[i] = o.transform_sum[i];
+    {
+      std::lock_guard<std::mutex> l(p->rm);
+      j.k = p->next_submit++;
+      loam_sweep_result& pr = p->partial[j.k];
+      memset(&pr, 0, sizeof(pr));
+      pr.counts = counts[b];
+      pr.odom = o;
+      p->epoch_of[j.k] = epochs[b];
+    }
+    p->qC.push(j);
   }
   return LOAM_OK;
 }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(KNN_Q) odom_knn_kernel(OdomT T, const float4* 
 // Two levels of axis-aligned boxes over a ring-ordered cloud: a BOX bounds 32 consecutive points, a SUPER-BOX bounds 32
 // consecutive boxes (1024 points).  box[2c] / box[2c + 1] = component-wise minimum / maximum (.w of the pair = smallest /
 // largest ring id); super[2s], super[2s + 1] likewise.  One CTA of 1024 threads per super-box builds both.
-__global__ void __launch_bounds__(1024) odom_bounds_kernel(const float4* __restrict__ corner_last, int n_cl, const float4* __restrict__ surf_last,
+__device__ __forceinline__ void odom_bounds_body(const float4* __restrict__ corner_last, int n_cl, const float4* __restrict__ surf_last,
                                                             int n_sl, float4* __restrict__ box_c, float4* __restrict__ sup_c,
                                                             float4* __restrict__ box_s, float4* __restrict__ sup_s) {
   __shared__ float s_red[8][32];
@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(IT_NT) odom_iter_kernel(OdomT T, SinCos3 sc, i
 // (DSMEM) in rank order before publishing to the host mailbox — no global partials, no ticket atomic, no second
 // pass.  Used whenever the features fit one cluster's grid-stride budget (any VLP-16-sized sweep).
 constexpr int CL_CTAS = 8, CL_NT = 256;
-__global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
-    odom_iter_cluster_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
+__device__ __forceinline__ void
+    odom_iter_cluster_body(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
                              int n_flat, const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
                              const int* __restrict__ c1, const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2,
                              const int* __restrict__ s3, double* __restrict__ out28, unsigned long long seq) {
@@ -709,8 +709,8 @@ struct OdomLoopShared {
   float sc[6];  // srx crx sry cry srz crz
   int done, last_iter;
 };
-__global__ void __launch_bounds__(LP_NT)
-    odom_loop_kernel(OdomLoopArgs A, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
+__device__ __forceinline__ void
+    odom_loop_body(const OdomLoopArgs& A, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
                      const float4* __restrict__ corner_last, const float4* __restrict__ surf_last, const int* __restrict__ c1,
                      const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
                      double* __restrict__ out, unsigned long long seq) {
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(LP_NT)
 }
 
 // LO:156-227.  sT = sin/cos of the full transform, imu sin/cos evaluated on the host.
-__global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
+__device__ __forceinline__ void odom_to_end_body(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
                                                            int n0, const float4* __restrict__ in1, float4* __restrict__ out1, int n1,
                                                            const float4* __restrict__ in2, float4* __restrict__ out2, int n2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -879,6 +879,68 @@ __global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, I
   po.z = z11;
   po.w = int(pi.w);
   out[i] = po;
+}
+
+// ------------------------------------------------------------------------------------------------ launch forms
+// Like the extraction kernels (lg_extract.cu), every odometry kernel exists for ONE sequence (arguments by value) and
+// BATCHED over several sequences in lock-step (grid.y = sequence, arguments from a device table of OdK, see lg_odom.h): a
+// member that does not take part in a kernel of the round (converged, no refresh due) returns at once.
+__global__ void __launch_bounds__(1024) odom_bounds_kernel(const float4* __restrict__ corner_last, int n_cl, const float4* __restrict__ surf_last,
+                                                            int n_sl, float4* __restrict__ box_c, float4* __restrict__ sup_c,
+                                                            float4* __restrict__ box_s, float4* __restrict__ sup_s) {
+  odom_bounds_body(corner_last, n_cl, surf_last, n_sl, box_c, sup_c, box_s, sup_s);
+}
+__global__ void __launch_bounds__(1024) odom_bounds_batch_kernel(const OdK* __restrict__ tab) {
+  const OdK& A = tab[blockIdx.y];
+  if (!A.do_bounds || (int)blockIdx.x >= ((A.n_cl + 1023) >> 10) + ((A.n_sl + 1023) >> 10)) return;
+  odom_bounds_body(A.corner_last, A.n_cl, A.surf_last, A.n_sl, A.box_c, A.sup_c, A.box_s, A.sup_s);
+}
+__global__ void __launch_bounds__(KP_WARPS * 32) odom_refresh_batch_kernel(const OdK* __restrict__ tab) {
+  const OdK& A = tab[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * KP_WARPS + (threadIdx.x >> 5);
+  if (!A.do_refresh || q >= A.n_sharp + A.n_flat) return;
+  const OdomT T = A.do_loop ? A.la.T : A.T;
+  const unsigned long long b =
+      odom_knn_pruned_warp(T, q, lane, A.sharp, A.n_sharp, A.flat, A.corner_last, A.n_cl, A.surf_last, A.n_sl, A.box_c, A.sup_c, A.box_s, A.sup_s);
+  if (lane == 0) A.best[q] = b;
+  odom_corr_pruned_warp(T, q, lane, b, A.sharp, A.n_sharp, A.flat, A.n_flat, A.corner_last, A.n_cl, A.surf_last, A.n_sl, A.box_c, A.box_s, A.c1, A.c2,
+                        A.s1, A.s2, A.s3);
+}
+__global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT)
+    odom_iter_cluster_kernel(OdomT T, SinCos3 sc, int iter, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat,
+                             int n_flat, const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
+                             const int* __restrict__ c1, const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2,
+                             const int* __restrict__ s3, double* __restrict__ out28, unsigned long long seq) {
+  odom_iter_cluster_body(T, sc, iter, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, out28, seq);
+}
+__global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT) odom_iter_cluster_batch_kernel(const OdK* __restrict__ tab) {
+  const OdK& A = tab[blockIdx.y];
+  if (!A.do_iter0) return;  // the whole cluster of this member
+  odom_iter_cluster_body(A.T, A.sc, A.iter, A.sharp, A.n_sharp, A.flat, A.n_flat, A.corner_last, A.surf_last, A.c1, A.c2, A.s1, A.s2, A.s3, A.out,
+                         A.seq);
+}
+__global__ void __launch_bounds__(LP_NT)
+    odom_loop_kernel(OdomLoopArgs A, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
+                     const float4* __restrict__ corner_last, const float4* __restrict__ surf_last, const int* __restrict__ c1,
+                     const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
+                     double* __restrict__ out, unsigned long long seq) {
+  odom_loop_body(A, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, out, seq);
+}
+__global__ void __launch_bounds__(LP_NT) odom_loop_batch_kernel(const OdK* __restrict__ tab) {
+  const OdK& A = tab[blockIdx.y];
+  if (!A.do_loop) return;
+  odom_loop_body(A.la, A.sharp, A.n_sharp, A.flat, A.n_flat, A.corner_last, A.surf_last, A.c1, A.c2, A.s1, A.s2, A.s3, A.out, A.seq);
+}
+__global__ void __launch_bounds__(256) odom_to_end_kernel(OdomT T, SinCos3 sT, ImuSC imu, const float4* __restrict__ in0, float4* __restrict__ out0,
+                                                           int n0, const float4* __restrict__ in1, float4* __restrict__ out1, int n1,
+                                                           const float4* __restrict__ in2, float4* __restrict__ out2, int n2) {
+  odom_to_end_body(T, sT, imu, in0, out0, n0, in1, out1, n1, in2, out2, n2);
+}
+__global__ void __launch_bounds__(256) odom_to_end_batch_kernel(const OdK* __restrict__ tab) {
+  const OdK& A = tab[blockIdx.y];
+  if (!A.do_to_end || (int)(blockIdx.x * blockDim.x) >= A.n0 + A.n1 + A.n2) return;
+  odom_to_end_body(A.T, A.sT, A.imu, A.in0, A.out0, A.n0, A.in1, A.out1, A.n1, A.in2, A.out2, A.n2);
 }
 
 }  // namespace
@@ -1022,6 +1084,113 @@ int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, c
   if (n <= 0) return LOAM_OK;
   LgProfScope prof_scope(LGK_TO_END, st, (double)n);
   odom_to_end_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(T, sT, imu, in0, out0, n0, in1, out1, n1, in2, out2, n2);
+  (*launches)++;
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched launches
+int lg_odom_batch_prepare(OdomWs& ws, int n_sharp, int n_flat, int n_cl, int n_sl, cudaStream_t st, OdK* k) {
+  int rc = odom_ensure(ws, n_sharp, n_flat, st);
+  if (rc) return rc;
+  const int nsup_c = lg_div_up(n_cl, 1024), nsup_s = lg_div_up(n_sl, 1024);
+  LG_CHECK(ws.bounds_c.ensure((size_t)(nsup_c + 1) * 66 * 16, st));
+  LG_CHECK(ws.bounds_s.ensure((size_t)(nsup_s + 1) * 66 * 16, st));
+  k->box_c = ws.bounds_c.as<float4>(); k->sup_c = ws.bounds_c.as<float4>() + (size_t)nsup_c * 64;
+  k->box_s = ws.bounds_s.as<float4>(); k->sup_s = ws.bounds_s.as<float4>() + (size_t)nsup_s * 64;
+  k->best = ws.best.as<unsigned long long>();
+  k->c1 = ws.c1.as<int>(); k->c2 = ws.c2.as<int>(); k->s1 = ws.s1.as<int>(); k->s2 = ws.s2.as<int>(); k->s3 = ws.s3.as<int>();
+  return LOAM_OK;
+}
+bool lg_odom_batch_fits(int n_sharp, int n_flat) { return n_sharp + n_flat <= CL_CTAS * CL_NT * 3; }
+
+// One lock-step round for B members: bounds -> refresh -> iteration 0 / loop block, each kernel launched once if any member
+// takes part in it.  The table is copied to `tab` first (it is small: B x sizeof(OdK)).
+int lg_odom_batch_round(const OdK* host_tab, int B, DevBuf& tab, cudaStream_t st, long long* launches) {
+  bool any_bounds = false, any_refresh = false, any_iter0 = false, any_loop = false;
+  int g_bounds = 1, g_q = 1;
+  double units_r = 0, units_i = 0;
+  for (int b = 0; b < B; b++) {
+    const OdK& k = host_tab[b];
+    any_bounds |= k.do_bounds != 0; any_refresh |= k.do_refresh != 0; any_iter0 |= k.do_iter0 != 0; any_loop |= k.do_loop != 0;
+    g_bounds = std::max(g_bounds, lg_div_up(k.n_cl, 1024) + lg_div_up(k.n_sl, 1024));
+    g_q = std::max(g_q, lg_div_up(k.n_sharp + k.n_flat, KP_WARPS));
+    if (k.do_refresh) units_r += k.n_sharp + k.n_flat;
+    if (k.do_iter0) units_i += k.n_sharp + k.n_flat;
+    if (k.do_loop) units_i += (double)(k.n_sharp + k.n_flat) * (k.la.it1 - k.la.it0);
+  }
+  if (!(any_bounds || any_refresh || any_iter0 || any_loop)) return LOAM_OK;
+  LG_CHECK(tab.ensure((size_t)B * sizeof(OdK) + 64, st));
+  LG_CHECK(cudaMemcpyAsync(tab.p, host_tab, (size_t)B * sizeof(OdK), cudaMemcpyHostToDevice, st));
+  const OdK* d = tab.as<OdK>();
+  if (any_bounds || any_refresh) {
+    LgProfScope prof_scope(LGK_ODOM_KNN, st, units_r);
+    if (any_bounds) {
+      odom_bounds_batch_kernel<<<dim3(g_bounds, B), 1024, 0, st>>>(d);
+      (*launches)++;
+    }
+    if (any_refresh) {
+      odom_refresh_batch_kernel<<<dim3(g_q, B), KP_WARPS * 32, 0, st>>>(d);
+      (*launches)++;
+    }
+  }
+  if (any_iter0 || any_loop) {
+    LgProfScope prof_scope(LGK_ODOM_ITER, st, units_i);
+    if (any_iter0) {
+      odom_iter_cluster_batch_kernel<<<dim3(CL_CTAS, B), CL_NT, 0, st>>>(d);
+      (*launches)++;
+    }
+    if (any_loop) {
+      static int cluster_ctas_dev[64] = {};
+      int dev = 0;
+      LG_CHECK(cudaGetDevice(&dev));
+      int& cluster_ctas = cluster_ctas_dev[dev & 63];
+      if (cluster_ctas == 0) {
+        cluster_ctas = 8;
+        if (cudaFuncSetAttribute(odom_loop_batch_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(16);
+          cfg.blockDim = dim3(LP_NT);
+          cudaLaunchAttribute at;
+          at.id = cudaLaunchAttributeClusterDimension;
+          at.val.clusterDim.x = 16; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+          cfg.attrs = &at;
+          cfg.numAttrs = 1;
+          int n_clusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&n_clusters, odom_loop_batch_kernel, &cfg) == cudaSuccess && n_clusters > 0) cluster_ctas = 16;
+        }
+        (void)cudaGetLastError();
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cluster_ctas, B);
+      cfg.blockDim = dim3(LP_NT);
+      cfg.stream = st;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = cluster_ctas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = 1;
+      LG_CHECK(cudaLaunchKernelEx(&cfg, odom_loop_batch_kernel, d));
+      (*launches)++;
+    }
+  }
+  LG_CHECK(cudaGetLastError());
+  return LOAM_OK;
+}
+
+int lg_odom_batch_to_end(const OdK* host_tab, int B, DevBuf& tab, cudaStream_t st, long long* launches) {
+  int g = 0;
+  double units = 0;
+  for (int b = 0; b < B; b++)
+    if (host_tab[b].do_to_end) {
+      g = std::max(g, lg_div_up(host_tab[b].n0 + host_tab[b].n1 + host_tab[b].n2, 256));
+      units += host_tab[b].n0 + host_tab[b].n1 + host_tab[b].n2;
+    }
+  if (g == 0) return LOAM_OK;
+  LG_CHECK(tab.ensure((size_t)B * sizeof(OdK) + 64, st));
+  LG_CHECK(cudaMemcpyAsync(tab.p, host_tab, (size_t)B * sizeof(OdK), cudaMemcpyHostToDevice, st));
+  LgProfScope prof_scope(LGK_TO_END, st, units);
+  odom_to_end_batch_kernel<<<dim3(g, B), 256, 0, st>>>(tab.as<OdK>());
   (*launches)++;
   LG_CHECK(cudaGetLastError());
   return LOAM_OK;

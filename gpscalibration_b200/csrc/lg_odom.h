@@ -45,3 +45,31 @@ int lg_odom_loop_launch(OdomWs& ws, const OdomLoopArgs& args, const float4* shar
                         long long* launches);
 int lg_odom_to_end_launch(const OdomT& T, const SinCos3& sT, const ImuSC& imu, const float4* in0, float4* out0, int n0, const float4* in1,
                           float4* out1, int n1, const float4* in2, float4* out2, int n2, cudaStream_t st, long long* launches);
+
+// ---- batched (lock-step) form: one row of this table per sequence, grid.y of every odometry kernel picks the row ----------
+struct OdK {
+  const float4 *sharp, *flat, *corner_last, *surf_last;
+  int n_sharp, n_flat, n_cl, n_sl;
+  float4 *box_c, *sup_c, *box_s, *sup_s;
+  unsigned long long* best;
+  int *c1, *c2, *s1, *s2, *s3;
+  // this round
+  int do_bounds, do_refresh, do_iter0, do_loop, do_to_end;
+  OdomT T;            // iteration 0 / TransformToEnd
+  SinCos3 sc;
+  int iter;
+  OdomLoopArgs la;    // loop block
+  double* out;        // the member's host mailbox (mapped pinned memory)
+  unsigned long long seq;
+  // TransformToEnd (LO:1087-1106)
+  SinCos3 sT;
+  ImuSC imu;
+  const float4 *in0, *in1, *in2;
+  float4 *out0, *out1, *out2;
+  int n0, n1, n2;
+};
+// fills the workspace pointers of `k` (boxes, correspondence arrays) after growing them for these sizes
+int lg_odom_batch_prepare(OdomWs& ws, int n_sharp, int n_flat, int n_cl, int n_sl, cudaStream_t st, OdK* k);
+bool lg_odom_batch_fits(int n_sharp, int n_flat);  // the cluster kernels hold this many features (else: per-handle path)
+int lg_odom_batch_round(const OdK* host_tab, int B, DevBuf& tab, cudaStream_t st, long long* launches);
+int lg_odom_batch_to_end(const OdK* host_tab, int B, DevBuf& tab, cudaStream_t st, long long* launches);

@@ -163,6 +163,12 @@ int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_ho
 
 /* ---- laserOdometry: replaces the loop body LO:502-1147 for the message set of the last loam_extract ---------- */
 int loam_odometry_process(loam_handle* h, loam_odom_result* out);
+/* Batched (lock-step) form (SURVEY 8b `*_batch`): the current sweep of B independent sequences (handles on one device, each
+ * after its loam_extract / loam_extract_batch).  Every odometry kernel of a round -- box hierarchy, correspondence refresh,
+ * iteration 0, a block of device iterations, TransformToEnd -- is launched once for all members taking part (grid.y =
+ * sequence); the per-member host steps run between the rounds.  out[b] and the handles' state are those of B
+ * loam_odometry_process calls bit for bit. */
+int loam_odometry_process_batch(loam_handle* const* hs, int B, loam_odom_result* out);
 
 /* ---- laserMapping: replaces laserOdometryHandler's reset test (LM:316-319) and the loop body LM:425-1139 ------
  * loam_mapping_odometry must be called for every published odometry message (every sweep), loam_mapping_process
@@ -275,6 +281,11 @@ int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, i
  * loam_pipeline_wait on each pipeline.  Do not mix with loam_pipeline_submit calls in flight on the same pipelines. */
 int loam_pipeline_submit_batch(loam_pipeline* const* ps, int B, const float* const* xyz_host, const int* n, int stride_bytes,
                                const double* stamps);
+/* The same with the scan-to-scan odometry batched as well (loam_extract_batch + loam_odometry_process_batch in the caller's
+ * thread, lock-step over the B sequences); mapping and output stages stay per pipeline.  Use it INSTEAD of
+ * loam_pipeline_submit on these pipelines (loam_pipeline_reset is fine: the call waits until the reset has arrived). */
+int loam_pipeline_submit_lockstep(loam_pipeline* const* ps, int B, const float* const* xyz_host, const int* n, int stride_bytes,
+                                  const double* stamps);
 int loam_pipeline_wait(loam_pipeline* p, loam_sweep_result* out);
 int loam_pipeline_pending(loam_pipeline* p);
 /* cudaStream_t of stage `which` (0 extract, 1 odometry, 2 mapping), for CUDA-event timing by the caller */

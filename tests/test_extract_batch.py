@@ -89,10 +89,11 @@ def test_batch_rejects_bad_arguments():
     b.close()
 
 
-def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines():
-    """loam_pipeline_submit_batch: four pipelines, the extraction of their sweeps batched in the caller's thread, odometry /
-    mapping / output stages per pipeline -- every result equal to the same pipelines fed with loam_pipeline_submit, across a
-    reset."""
+@pytest.mark.parametrize("lockstep", [False, True])
+def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines(lockstep):
+    """loam_pipeline_submit_batch (extraction batched) / loam_pipeline_submit_lockstep (extraction + odometry batched in the
+    caller's thread): four pipelines, mapping / output stages per pipeline -- every result equal to the same pipelines fed
+    with loam_pipeline_submit, across a reset."""
     from gpscalibration_b200 import LoamGpuPipeline, capi
     B, n_sweeps = 4, 30
     seqs = _sequences(B, n_sweeps)
@@ -113,7 +114,7 @@ def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines():
                 p.reset()
         for b in range(B):
             plain[b].submit(seqs[b][k])
-        capi.pipeline_submit_batch(batched, [seqs[b][k] for b in range(B)])
+        capi.pipeline_submit_batch(batched, [seqs[b][k] for b in range(B)], lockstep=lockstep)
         if k >= 4:
             for b in range(B):
                 ref[b].append(key(plain[b].wait()))
@@ -126,3 +127,37 @@ def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines():
         assert len(ref[b]) == n_sweeps and ref[b] == got[b], b
     for p in plain + batched:
         p.close()
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_lockstep_odometry_batch_equals_single_calls(B):
+    """loam_extract_batch + loam_odometry_process_batch (lock-step rounds, one launch per kernel for the batch) + per-handle
+    mapping against loam_process_sweep per sequence: every pose, iteration count and flag equal, over enough sweeps for
+    members to converge in different rounds, a reset of one member in mid-stream and a member with empty rings."""
+    from gpscalibration_b200 import LoamGpu, capi
+    n_sweeps = 16
+    seqs = _sequences(B, n_sweeps)
+    ref = [LoamGpu() for _ in range(B)]
+    bat = [LoamGpu() for _ in range(B)]
+    for k in range(n_sweeps):
+        if k == 9 and B > 1:
+            ref[1].reset()
+            bat[1].reset()
+        capi.extract_batch(bat, [seqs[b][k] for b in range(B)])
+        outs = capi.odometry_process_batch(bat)
+        for b in range(B):
+            r = ref[b].process_sweep(seqs[b][k])
+            o = outs[b]
+            assert list(o.transform_sum) == list(r.odom.transform_sum) and list(o.transformation) == list(r.odom.transformation), (k, b)
+            assert (o.iterations, o.odom_published, o.clouds_published, o.fullres_published, o.n_corner_last, o.n_surf_last) == \
+                (r.odom.iterations, r.odom.odom_published, r.odom.clouds_published, r.odom.fullres_published, r.odom.n_corner_last,
+                 r.odom.n_surf_last), (k, b)
+            if o.odom_published:
+                bat[b].mapping_odometry(np.array(o.transform_sum, np.float32))
+            if o.odom_published and o.fullres_published:
+                m = bat[b].mapping_process()
+                assert r.mapping_ran and list(m.transform_aft_mapped) == list(r.map.transform_aft_mapped) and m.iterations == r.map.iterations, (k, b)
+    if B > 1:
+        assert sum(h.stats()["launches"] for h in bat) < 0.8 * sum(h.stats()["launches"] for h in ref)
+    for h in ref + bat:
+        h.close()
