@@ -545,7 +545,7 @@ def pipeline_submit_batch(pipes, sweeps, stride_bytes=12, lockstep=False):
     fn = load_library().loam_pipeline_submit_lockstep if lockstep else load_library().loam_pipeline_submit_batch
     rc = fn(ps, B, ptrs, ns, stride_bytes, None)
     if rc:
-        raise LoamError(rc, "loam_pipeline_submit_lockstep" if lockstep else "loam_pipeline_submit_batch", "loam_pipeline_submit_lockstep", load_library().loam_last_cuda_error(None).decode())
+        raise LoamError(rc, "loam_pipeline_submit_lockstep" if lockstep else "loam_pipeline_submit_batch", load_library().loam_last_cuda_error(None).decode())
 
 
 def odometry_process_batch(handles):

@@ -471,7 +471,8 @@ int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, 
 // mailbox.  Spinning on host memory the GPU writes over PCIe costs ~2 us; cudaStreamSynchronize costs 10-20 us, and
 // there is one such hand-over per host-visited Gauss-Newton iteration (every mapping iteration, the first odometry
 // iteration of a sweep and once per device loop launch).
-int mailbox_wait(loam_handle* h) {
+int mailbox_wait(loam_handle* h, cudaStream_t watch = nullptr) {  // watch: the stream the publishing kernel runs on (default: the handle's)
+  if (!watch) watch = h->st;
   volatile unsigned long long* flag = (volatile unsigned long long*)(h->h_mail + 31);
   h->syncs++;
   for (long spin = 0;; spin++) {
@@ -481,7 +482,7 @@ int mailbox_wait(loam_handle* h) {
     }
     _mm_pause();
     if ((spin & 0xffff) == 0xffff) {  // every ~65k polls make sure the stream has not died
-      cudaError_t e = cudaStreamQuery(h->st);
+      cudaError_t e = cudaStreamQuery(watch);
       if (e != cudaSuccess && e != cudaErrorNotReady) {
         lg_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
         return LOAM_ECUDA;
@@ -1176,7 +1177,7 @@ int loam_odometry_process_batch(loam_handle* const* hs, int B, loam_odom_result*
       if (!active[b]) continue;
       loam_handle* h = hs[b];
       h->od.bounds_valid = true;
-      rc = mailbox_wait(h);
+      rc = mailbox_wait(h, st);
       if (rc) return rc;
       h->d2h_bytes += 28 * 8;
       float AtA[36], AtB[6];
@@ -1214,7 +1215,7 @@ int loam_odometry_process_batch(loam_handle* const* hs, int B, loam_odom_result*
     for (int b = 0; b < B; b++) {
       if (!active[b]) continue;
       loam_handle* h = hs[b];
-      rc = mailbox_wait(h);
+      rc = mailbox_wait(h, st);
       if (rc) return rc;
       h->d2h_bytes += 8 * 8;
       for (int i = 0; i < 6; i++) h->T[i] = (float)h->h_mail[i];

@@ -1,6 +1,7 @@
 """Aggregate throughput of S independent sequences sharing ONE GPU (cfg 4 with more segments than GPUs), three ways:
   pipelined  S pipelined handles (3 stage threads + 3 streams each) driven by S host threads
   batched    the same pipelines fed by ONE thread through loam_pipeline_submit_batch (extraction of the S sweeps batched)
+  lockstep   ... through loam_pipeline_submit_lockstep (extraction AND odometry batched in lock-step, mapping per pipeline)
   blocking   S plain handles, one host thread each calling loam_process_sweep (1 thread + 1 stream per sequence)
 ctypes releases the GIL during the calls.  usage: multiseg.py [sweeps] [full]"""
 import sys, time, threading, os
@@ -14,10 +15,10 @@ seqs_all = []
 for s in range(16):
     gen = SweepGenerator(seed=0xC0FFEE + 1000 * s, t_offset=37.0 * s)
     seqs_all.append([gen.sweep(k)[0].copy() for k in range(N)])
-for mode in ("pipelined", "batched", "blocking"):
+for mode in ("pipelined", "batched", "lockstep", "blocking"):
     for S in (1, 2, 4, 8, 12, 16):
         seqs = seqs_all[:S]
-        if mode in ("pipelined", "batched"):
+        if mode in ("pipelined", "batched", "lockstep"):
             objs = [LoamGpuPipeline(want_registered=WANT, want_surround=WANT) for _ in range(S)]
         else:
             objs = [LoamGpu(want_registered=WANT, want_surround=WANT) for _ in range(S)]
@@ -37,13 +38,33 @@ for mode in ("pipelined", "batched", "blocking"):
                         p.process_sweep(x)
                 out.append(time.perf_counter() - t0)
         outs = [[] for _ in range(S)]
-        if mode == "batched":  # ONE feeder thread: loam_pipeline_submit_batch extracts the S sweeps with one launch per kernel
+        if mode == "lockstep" and S >= 4:  # lock-step groups: G feeder threads, S / G pipelines each (rounds of different groups overlap)
+            from gpscalibration_b200 import capi
+            G = 2 if S < 8 else 4
+            groups = [list(range(g, S, G)) for g in range(G)]
+            def feed(idx, res):
+                for rep in range(2):
+                    for i in idx: objs[i].reset()
+                    t0 = time.perf_counter()
+                    for k in range(N):
+                        capi.pipeline_submit_batch([objs[i] for i in idx], [seqs[i][k] for i in idx], lockstep=True)
+                        if k >= 6:
+                            for i in idx: objs[i].wait()
+                    for i in idx:
+                        while objs[i].pending: objs[i].wait()
+                    res.append(time.perf_counter() - t0)
+            gres = [[] for _ in range(G)]
+            ths = [threading.Thread(target=feed, args=(groups[g], gres[g])) for g in range(G)]
+            for t in ths: t.start()
+            for t in ths: t.join()
+            for o in outs: o.extend([max(r[0] for r in gres), max(r[1] for r in gres)])
+        elif mode in ("batched", "lockstep"):  # ONE feeder thread: loam_pipeline_submit_batch extracts the S sweeps with one launch per kernel
             from gpscalibration_b200 import capi
             for rep in range(2):
                 for p in objs: p.reset()
                 t0 = time.perf_counter()
                 for k in range(N):
-                    capi.pipeline_submit_batch(objs, [seqs[i][k] for i in range(S)])
+                    capi.pipeline_submit_batch(objs, [seqs[i][k] for i in range(S)], lockstep=(mode == "lockstep"))
                     if k >= 6:
                         for p in objs: p.wait()
                 for p in objs:
