@@ -415,7 +415,8 @@ def main():
             from gpscalibration_b200 import capi as _capi
             SEGB, NSB = 8, min(300, S)
             bdata = seg_data + [make_sequence(NSB, 200 + i, pinned=True)[1:] for i in range(len(seg_data), SEGB)]
-            bpipes = [pipe] + [LoamGpuPipeline(device=local_rank, want_registered=True, want_surround=True) for _ in range(1, SEGB)]
+            # gn_max_ctas: the mapping loops of the eight sequences run side by side (20 CTAs each) instead of queueing for all the SMs
+            bpipes = [LoamGpuPipeline(device=local_rank, want_registered=True, want_surround=True, gn_max_ctas=20) for _ in range(SEGB)]
             tb = 0.0
             for rep in range(2):
                 for p in bpipes:
@@ -431,8 +432,8 @@ def main():
                         p.wait()
                 tb = time.perf_counter() - t0
             out["multi_segment"]["batched_feeder"] = {"segments_on_one_gpu": SEGB, "sweeps_per_segment": NSB, "value": SEGB * NSB / tb, "unit": UNIT,
-                                                      "note": "eight pipelines fed by one thread, extraction batched (loam_pipeline_submit_batch), second pass"}
-            for p in bpipes[1:]:
+                                                      "note": "eight pipelines fed by one thread, extraction batched (loam_pipeline_submit_batch), loam_params.gn_max_ctas = 20, second pass"}
+            for p in bpipes:
                 p.close()
         except Exception as e:
             out["multi_segment"]["batched_feeder"] = {"error": repr(e)}

@@ -28,7 +28,7 @@ class LoamError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("ring_mode", C.c_int), ("ring_ang_min", C.c_float), ("ring_ang_step", C.c_float),
                 ("skip_frame_num", C.c_int), ("max_points", C.c_int), ("max_map_points", C.c_int),
-                ("want_registered", C.c_int), ("want_surround", C.c_int), ("pose_message_hop", C.c_int)]
+                ("want_registered", C.c_int), ("want_surround", C.c_int), ("pose_message_hop", C.c_int), ("gn_max_ctas", C.c_int)]
 
 
 class Counts(C.Structure):
@@ -177,7 +177,7 @@ class LoamGpu:
     """One handle = one GPU + one stream + the state of the three LOAM stages (thin wrapper, no logic)."""
 
     def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
-                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False):
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False, gn_max_ctas=0):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
@@ -185,6 +185,7 @@ class LoamGpu:
         p.skip_frame_num = skip_frame_num
         p.want_registered, p.want_surround = int(want_registered), int(want_surround)
         p.pose_message_hop = int(pose_message_hop)
+        p.gn_max_ctas = int(gn_max_ctas)
         if max_points:
             p.max_points = int(max_points)
         if max_map_points:
@@ -444,7 +445,7 @@ class LoamGpuPipeline:
     """Pipelined mode (loam_pipeline_*): submit sweeps, collect results in order; same results as LoamGpu.process_sweep."""
 
     def __init__(self, device=0, n_scans=16, ring_mode=0, ring_ang_min=-15.0, ring_ang_step=2.0, skip_frame_num=1,
-                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False):
+                 want_registered=False, want_surround=False, max_points=None, max_map_points=None, pose_message_hop=False, gn_max_ctas=0):
         self.lib = load_library()
         p = Params()
         self.lib.loam_default_params(C.byref(p))
@@ -452,6 +453,7 @@ class LoamGpuPipeline:
         p.skip_frame_num = skip_frame_num
         p.want_registered, p.want_surround = int(want_registered), int(want_surround)
         p.pose_message_hop = int(pose_message_hop)
+        p.gn_max_ctas = int(gn_max_ctas)
         if max_points:
             p.max_points = int(max_points)
         if max_map_points:

@@ -538,6 +538,7 @@ int map_gn_enqueue(loam_handle* h, const float* T, int it0, int it1, int solve, 
   A.n_ss = h->n_stack_s;
   A.gc = h->csr.d[0];
   A.gs = h->csr.d[1];
+  A.max_ctas = h->prm.gn_max_ctas;
   A.slab_lo = h->slab_lo;
   A.slab_hi = h->slab_hi;
   // pointSearchInd is internal to the reference (LM:760, 867): the stage-level calls keep it for loam_map_get_corr, the
@@ -679,6 +680,7 @@ void loam_default_params(loam_params* p) {
   p->want_registered = 0;
   p->want_surround = 0;
   p->pose_message_hop = 0;
+  p->gn_max_ctas = 0;
 }
 
 // role bits: 1 = needs the per-sweep odometry buffers, 2 = needs the map storage (arena, sort workspace)

@@ -53,6 +53,7 @@ struct MapGnArgs {
   const float4* sstack;
   int n_ss;
   CsrGridD gc, gs;
+  int max_ctas;            // > 0: cap of the cooperative grid for sweep-sized stacks (loam_params.gn_max_ctas)
   float slab_lo, slab_hi;  // owner rule of a sharded map: map-frame x in [lo, hi); (-inf, +inf) otherwise
   int* nbr;                // [n_cs + n_ss][5] pointSearchInd of the last iteration (optional)
   double* out;             // mailbox / device buffer, 64 doubles: [0..27] sums (solve: of iteration 0), [28] peer timeout,

@@ -1022,7 +1022,7 @@ static const void* gn_kernel_of(int sub) {
   return sub == 4 ? (const void*)map_gn_kernel<4, 2> : (const void*)map_gn_kernel<8, 2>;
 }
 
-static int lg_map_gn_grid(int nq, int device, int sub, int* tile_out) {
+static int lg_map_gn_grid(int nq, int device, int sub, int max_ctas, int* tile_out) {
   static int per_sm[3][64] = {{0}}, sms[64] = {0};
   const int d = device & 63, m = sub == 1 ? 0 : (sub == 4 ? 1 : 2);
   if (!per_sm[m][d]) {
@@ -1035,7 +1035,12 @@ static int lg_map_gn_grid(int nq, int device, int sub, int* tile_out) {
   // tile: the largest of 256 / 128 / 64 / 32 stack points per CTA step that still gives every resident CTA a tile
   // small problems (one sweep's stack against the local map): one CTA per SM at most -- a cooperative grid that fills
   // the register files would lock the kernels of the other pipeline stages (extraction, odometry) out while it runs
-  const int resident = nq <= (1 << 16) ? sms[d] : per_sm[m][d] * sms[d];
+  // loam_params.gn_max_ctas (LOAM_GN_MAX_CTAS overrides it): cap of the cooperative grid for sweep-sized stacks -- several
+  // sequences sharing one GPU run their mapping loops side by side instead of queueing for all the SMs
+  static const int cap_env = getenv("LOAM_GN_MAX_CTAS") ? atoi(getenv("LOAM_GN_MAX_CTAS")) : 0;
+  const int cap = cap_env > 0 ? cap_env : max_ctas;
+  int resident = nq <= (1 << 16) ? sms[d] : per_sm[m][d] * sms[d];
+  if (cap > 0 && nq <= (1 << 16)) resident = std::min(resident, cap);
   int tile = GN_TILE;
   while (tile > 32 && (nq + tile - 1) / tile < resident) tile >>= 1;
   *tile_out = tile;
@@ -1051,7 +1056,7 @@ int lg_map_gn_launch(MapGnWs& ws, MapGnArgs& A, int device, cudaStream_t st, lon
   // them give the same neighbours and rows, the sums up to the order of addition.
   static const int sub_env = getenv("LOAM_GN_SUB") ? atoi(getenv("LOAM_GN_SUB")) : 0;
   const int sub = sub_env == 1 || sub_env == 4 || sub_env == 8 ? sub_env : (nq > (1 << 19) ? 1 : 8);
-  const int grid = lg_map_gn_grid(nq, device, sub, &A.tile);
+  const int grid = lg_map_gn_grid(nq, device, sub, A.max_ctas, &A.tile);
   LG_CHECK(ws.partials.ensure((size_t)grid * 28 * 8 + 64, st));
   if (!ws.sync.p) {
     LG_CHECK(ws.sync.ensure(64 * 4 + 28 * 4 * 8, st));

@@ -105,7 +105,8 @@ def test_pipelines_fed_by_batched_extraction_equal_plain_pipelines(lockstep):
         return t
 
     plain = [LoamGpuPipeline(want_registered=True, want_surround=True) for _ in range(B)]
-    batched = [LoamGpuPipeline(want_registered=True, want_surround=True) for _ in range(B)]
+    # gn_max_ctas: a smaller cooperative grid for the mapping loop (several sequences side by side) must not change a result
+    batched = [LoamGpuPipeline(want_registered=True, want_surround=True, gn_max_ctas=20) for _ in range(B)]
     ref = [[] for _ in range(B)]
     got = [[] for _ in range(B)]
     for k in range(n_sweeps):

@@ -19,7 +19,8 @@ for mode in ("pipelined", "batched", "lockstep", "blocking"):
     for S in (1, 2, 4, 8, 12, 16):
         seqs = seqs_all[:S]
         if mode in ("pipelined", "batched", "lockstep"):
-            objs = [LoamGpuPipeline(want_registered=WANT, want_surround=WANT) for _ in range(S)]
+            cap = 20 if (S > 1 and mode != "pipelined") else 0  # loam_params.gn_max_ctas: mapping loops side by side
+            objs = [LoamGpuPipeline(want_registered=WANT, want_surround=WANT, gn_max_ctas=cap) for _ in range(S)]
         else:
             objs = [LoamGpu(want_registered=WANT, want_surround=WANT) for _ in range(S)]
         def run(p, sw, out):
