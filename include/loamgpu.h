@@ -160,7 +160,8 @@ int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_
  * come back with one synchronisation, so B sweeps cost eight launches instead of 8 B; results are those of B loam_extract
  * calls bit for bit (empty sweeps, point_step not a multiple of 4 and sweeps with empty rings fall back to the per-handle
  * path inside the call).  xyz_host[b] / n[b]: member b's sweep; stamps may be NULL; out[b] receives its counts.  Only the
- * extraction is batched: odometry and mapping are data-dependent loops per sequence. */
+ * extraction is batched here; loam_odometry_process_batch is the lock-step form of the odometry; the mapping stays per sequence
+ * (DESIGN.md §6).  If the call fails part-way the members are in an unspecified state: reset those sequences. */
 int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_host, const int* n, int stride_bytes,
                        const double* stamps, loam_counts* out);
 
