@@ -44,6 +44,8 @@ def lib():
         L.orc_sr_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float]
         L.orc_sr_destroy.argtypes = [vp]
         L.orc_sr_extract.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.orc_sr_imu.argtypes = [vp, C.c_double, vp, vp, vp]
+        L.orc_sr_extract_imu.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp]
         L.orc_sr_cloud.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_sr_ints.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_sr_curvature.argtypes = [vp, vp, C.c_int]
@@ -159,6 +161,18 @@ class ScanRegistration:
         xyz = _f32(xyz)
         lib().orc_sr_extract(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] // 4)
         return {k: self.cloud(k) for k in self.CLOUDS}
+
+    def imu(self, stamp, quat_xyzw, angular_velocity, linear_acceleration):
+        """One /imu/data message (imuHandler SR:754-837)."""
+        q, a, l = (np.ascontiguousarray(v, np.float64) for v in (quat_xyzw, angular_velocity, linear_acceleration))
+        lib().orc_sr_imu(self._h, float(stamp), q.ctypes.data, a.ctypes.data, l.ctypes.data)
+
+    def extract_imu(self, xyz, stamp):
+        """laserCloudHandler with the IMU branch (SR:364-434): returns (clouds, the 12 floats of /imu_trans)."""
+        xyz = _f32(xyz)
+        tr = np.zeros(12, np.float32)
+        lib().orc_sr_extract_imu(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] // 4, float(stamp), tr.ctypes.data)
+        return {k: self.cloud(k) for k in self.CLOUDS}, tr
 
     def cloud(self, which):
         w = self.CLOUDS.index(which)

@@ -46,6 +46,7 @@ struct SRH {
   SRParams prm;
   SRState st;
   SROut out;
+  ImuState imu;
 };
 
 struct PipelineResult {  // mirrored by ctypes in tests/bench
@@ -125,6 +126,14 @@ void orc_sr_destroy(void* h) { delete (SRH*)h; }
 int orc_sr_extract(void* hv, const float* xyz, int n, int stride_floats) {
   SRH* h = (SRH*)hv;
   extract(h->prm, h->st, xyz, n, stride_floats, h->out);
+  return 0;
+}
+// the IMU branch: one /imu/data message (SR:754-837); then extract with the sweep's stamp; imu_trans = the 12 floats of /imu_trans
+void orc_sr_imu(void* hv, double stamp, const double* q4, const double* av3, const double* la3) { imu_handler(((SRH*)hv)->imu, stamp, q4, av3, la3); }
+int orc_sr_extract_imu(void* hv, const float* xyz, int n, int stride_floats, double stamp, float* imu_trans12) {
+  SRH* h = (SRH*)hv;
+  extract(h->prm, h->st, xyz, n, stride_floats, h->out, &h->imu, stamp);
+  if (imu_trans12) h->imu.trans12(imu_trans12);
   return 0;
 }
 // which: 0 full, 1 sharp, 2 less sharp, 3 flat, 4 less flat.  Returns the count (copies when cap suffices).

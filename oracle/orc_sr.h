@@ -1,8 +1,9 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orc_linalg.h header).
 //
 // CPU restatement of the reference's per-sweep feature extraction,
-// src/gpsCalibration/src/lidar_slam/loam/scanRegistration.cpp (SR), laserCloudHandler SR:238-752, IMU branch
-// excluded (dormant in the shipped pipeline: input_data only replays velodyne_points, so imuPointerLast stays -1).
+// src/gpsCalibration/src/lidar_slam/loam/scanRegistration.cpp (SR), laserCloudHandler SR:238-752, incl. the IMU branch
+// (imuHandler SR:754-837, AccumulateIMUShift SR:187-233, the per-point de-skew SR:364-434 with SR:121-184; dormant in the
+// shipped pipeline -- input_data only replays velodyne_points, so imuPointerLast stays -1 -- but live code).
 // fp32 with the reference's expression order and its fp64 promotions (unsuffixed literals, M_PI, scanPeriod).
 #pragma once
 #include <cmath>
@@ -94,8 +95,207 @@ inline void suppress_neighbours(const Cloud& c, int* picked, int ind, int cloudS
   }
 }
 
+// ---- IMU state of the node (file-scope globals SR:76-110): a ring of 200 messages with integrated velocity / shift, the
+// "Start" values latched at the sweep's first point, the "Cur" values interpolated per point -- all persistent between sweeps.
+struct ImuState {
+  static const int Q = 200;  // imuQueLength SR:78
+  int front = 0, last = -1;  // imuPointerFront, imuPointerLast
+  double time[Q] = {0};
+  float roll[Q] = {0}, pitch[Q] = {0}, yaw[Q] = {0}, accX[Q] = {0}, accY[Q] = {0}, accZ[Q] = {0};
+  float veloX[Q] = {0}, veloY[Q] = {0}, veloZ[Q] = {0}, shiftX[Q] = {0}, shiftY[Q] = {0}, shiftZ[Q] = {0};
+  float rollStart = 0, pitchStart = 0, yawStart = 0, rollCur = 0, pitchCur = 0, yawCur = 0;
+  float veloXStart = 0, veloYStart = 0, veloZStart = 0, shiftXStart = 0, shiftYStart = 0, shiftZStart = 0;
+  float veloXCur = 0, veloYCur = 0, veloZCur = 0, shiftXCur = 0, shiftYCur = 0, shiftZCur = 0;
+  float shiftFromStartXCur = 0, shiftFromStartYCur = 0, shiftFromStartZCur = 0;
+  float veloFromStartXCur = 0, veloFromStartYCur = 0, veloFromStartZCur = 0;
+  int imuMesg = 0;      // SR:59
+  double initYaw = 0;   // SR:60
+  // /imu_trans as published SR:730-745
+  void trans12(float* v) const {
+    v[0] = pitchStart; v[1] = yawStart; v[2] = rollStart; v[3] = pitchCur; v[4] = yawCur; v[5] = rollCur;
+    v[6] = shiftFromStartXCur; v[7] = shiftFromStartYCur; v[8] = shiftFromStartZCur;
+    v[9] = veloFromStartXCur; v[10] = veloFromStartYCur; v[11] = veloFromStartZCur;
+  }
+};
+
+// tf::Matrix3x3(q).getRPY (double), as the shim and odometry_ros_hop state it
+inline void quat_to_rpy(double qx, double qy, double qz, double qw, double& roll, double& pitch, double& yaw) {
+  double d = qx * qx + qy * qy + qz * qz + qw * qw, s = 2.0 / d;
+  double xs = qx * s, ys = qy * s, zs = qz * s;
+  double wx = qw * xs, wy = qw * ys, wz = qw * zs, xx = qx * xs, xy = qx * ys, xz = qx * zs, yy = qy * ys, yz = qy * zs, zz = qz * zs;
+  double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  if (std::fabs(m20) >= 1) {
+    yaw = 0;
+    if (m20 < 0) { pitch = M_PI / 2.0; roll = std::atan2(m01, m02); } else { pitch = -M_PI / 2.0; roll = std::atan2(-m01, -m02); }
+  } else {
+    pitch = -std::asin(m20);
+    roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+    yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+  }
+}
+
+// AccumulateIMUShift SR:187-233 (std::cos / std::sin of float arguments are the float overloads: SR:51-52)
+inline void imu_accumulate(ImuState& s) {
+  const int L = s.last;
+  float roll = s.roll[L];
+  float accX = s.accX[L], accY = s.accY[L], accZ = s.accZ[L];
+  float x1 = cosf(roll) * accX - sinf(roll) * accY;
+  float y1 = sinf(roll) * accX + cosf(roll) * accY;
+  float z1 = accZ;
+  accX = x1; accY = y1; accZ = z1;
+  int back = (L + ImuState::Q - 1) % ImuState::Q;
+  double timeDiff = s.time[L] - s.time[back];
+  if (timeDiff < 0.2) {  // rfansScanPeriod SR:58
+    s.shiftX[L] = (float)(s.shiftX[back] + s.veloX[back] * timeDiff + accX * timeDiff * timeDiff / 2);
+    s.shiftY[L] = (float)(s.shiftY[back] + s.veloY[back] * timeDiff + accY * timeDiff * timeDiff / 2);
+    s.shiftZ[L] = (float)(s.shiftZ[back] + s.veloZ[back] * timeDiff + accZ * timeDiff * timeDiff / 2);
+    s.veloX[L] = (float)(s.veloX[back] + accX * timeDiff);
+    s.veloY[L] = (float)(s.veloY[back] + accY * timeDiff);
+    s.veloZ[L] = (float)(s.veloZ[back] + accZ * timeDiff);
+  }
+}
+
+// imuHandler SR:754-837.  q = orientation {x, y, z, w}, av = angular velocity, la = linear acceleration.
+inline void imu_handler(ImuState& s, double stamp, const double* q, const double* av, const double* la) {
+  double roll, pitch, yaw;
+  bool flag = false;
+  s.imuMesg++;
+  if (std::fabs(std::pow(q[0], 2) + std::pow(q[1], 2) + std::pow(q[2], 2) + std::pow(q[3], 2) - 1) < 0.1) {
+    quat_to_rpy(q[0], q[1], q[2], q[3], roll, pitch, yaw);
+    if (s.imuMesg == 1) s.initYaw = yaw;
+  } else {
+    return;
+  }
+  float accY = (float)(la[1] - std::sin(roll) * std::cos(pitch) * 9.81);
+  float accZ = (float)(la[2] - std::cos(roll) * std::cos(pitch) * 9.81);
+  float accX = (float)(la[0] + std::sin(pitch) * 9.81);
+  s.last = (s.last + 1) % ImuState::Q;
+  int back = (s.last + ImuState::Q - 1) % ImuState::Q;
+  const double PI_CH = 3.141592653589;  // CH:17 #define PI
+  if (s.imuMesg != 1) {
+    if (av[2] > 3) {  // IMUANGULARNOISE CH:23
+      if (s.yaw[back] > yaw) {
+        if (std::fabs(s.yaw[back]) < PI_CH) { flag = true; yaw = s.yaw[back]; }
+      }
+    } else if (std::fabs(av[2]) < 3) {
+      if (s.yaw[back] != yaw) { flag = true; yaw = s.yaw[back]; }
+    } else if (av[2] < -1 * 3) {
+      if (s.yaw[back] < yaw) {
+        if (std::fabs(s.yaw[back]) < PI_CH) { flag = true; yaw = s.yaw[back]; }
+      }
+    }
+  }
+  s.time[s.last] = stamp;
+  s.roll[s.last] = (float)roll;
+  s.pitch[s.last] = (float)pitch;
+  if (s.imuMesg != 1) {
+    if (flag) s.yaw[s.last] = (float)yaw; else s.yaw[s.last] = (float)(yaw - s.initYaw);
+  } else {
+    s.yaw[s.last] = 0;
+  }
+  if (std::fabs(accX) > 2 || std::fabs(accY) > 2) return;
+  s.accX[s.last] = accX; s.accY[s.last] = accY; s.accZ[s.last] = accZ;
+  imu_accumulate(s);
+}
+
+// SR:364-434 for one kept point: advance imuPointerFront, interpolate the Cur values, latch the Start values at the sweep's
+// first point (i == 0 in the NaN-filtered cloud) or de-skew the point (SR:121-184).
+inline void imu_point(ImuState& s, double timeScanCur, float relTime, double scanPeriod, bool first_point, P4& point) {
+  const int Q = ImuState::Q;
+  float pointTime = (float)(relTime * scanPeriod);
+  while (s.front != s.last) {
+    if (timeScanCur + pointTime < s.time[s.front]) break;
+    s.front = (s.front + 1) % Q;
+  }
+  const int F = s.front;
+  if (timeScanCur + pointTime > s.time[F]) {
+    if ((timeScanCur + pointTime) - s.time[F] < 0.2) {
+      s.rollCur = s.roll[F]; s.pitchCur = s.pitch[F]; s.yawCur = s.yaw[F];
+      s.veloXCur = s.veloX[F]; s.veloYCur = s.veloY[F]; s.veloZCur = s.veloZ[F];
+      s.shiftXCur = s.shiftX[F]; s.shiftYCur = s.shiftY[F]; s.shiftZCur = s.shiftZ[F];
+    }
+  } else {
+    if (s.time[F] - timeScanCur - pointTime < 0.2) {
+      int B = (F + Q - 1) % Q;
+      float ratioFront = (float)((timeScanCur + pointTime - s.time[B]) / (s.time[F] - s.time[B]));
+      float ratioBack = (float)((s.time[F] - timeScanCur - pointTime) / (s.time[F] - s.time[B]));
+      s.rollCur = s.roll[F] * ratioFront + s.roll[B] * ratioBack;
+      s.pitchCur = s.pitch[F] * ratioFront + s.pitch[B] * ratioBack;
+      if (s.yaw[F] - s.yaw[B] > M_PI) {
+        s.yawCur = (float)(s.yaw[F] * ratioFront + (s.yaw[B] + 2 * M_PI) * ratioBack);
+      } else if (s.yaw[F] - s.yaw[B] < -M_PI) {
+        s.yawCur = (float)(s.yaw[F] * ratioFront + (s.yaw[B] - 2 * M_PI) * ratioBack);
+      } else {
+        s.yawCur = s.yaw[F] * ratioFront + s.yaw[B] * ratioBack;
+      }
+      s.veloXCur = s.veloX[F] * ratioFront + s.veloX[B] * ratioBack;
+      s.veloYCur = s.veloY[F] * ratioFront + s.veloY[B] * ratioBack;
+      s.veloZCur = s.veloZ[F] * ratioFront + s.veloZ[B] * ratioBack;
+      s.shiftXCur = s.shiftX[F] * ratioFront + s.shiftX[B] * ratioBack;
+      s.shiftYCur = s.shiftY[F] * ratioFront + s.shiftY[B] * ratioBack;
+      s.shiftZCur = s.shiftZ[F] * ratioFront + s.shiftZ[B] * ratioBack;
+    }
+  }
+  if (first_point) {
+    s.rollStart = s.rollCur; s.pitchStart = s.pitchCur; s.yawStart = s.yawCur;
+    s.veloXStart = s.veloXCur; s.veloYStart = s.veloYCur; s.veloZStart = s.veloZCur;
+    s.shiftXStart = s.shiftXCur; s.shiftYStart = s.shiftYCur; s.shiftZStart = s.shiftZCur;
+    return;
+  }
+  {  // ShiftToStartIMU SR:121-139
+    s.shiftFromStartXCur = s.shiftXCur - s.shiftXStart - s.veloXStart * pointTime;
+    s.shiftFromStartYCur = s.shiftYCur - s.shiftYStart - s.veloYStart * pointTime;
+    s.shiftFromStartZCur = s.shiftZCur - s.shiftZStart - s.veloZStart * pointTime;
+    float x1 = cosf(s.yawStart) * s.shiftFromStartXCur - sinf(s.yawStart) * s.shiftFromStartZCur;
+    float y1 = s.shiftFromStartYCur;
+    float z1 = sinf(s.yawStart) * s.shiftFromStartXCur + cosf(s.yawStart) * s.shiftFromStartZCur;
+    float x2 = x1;
+    float y2 = cosf(s.pitchStart) * y1 + sinf(s.pitchStart) * z1;
+    float z2 = -sinf(s.pitchStart) * y1 + cosf(s.pitchStart) * z1;
+    s.shiftFromStartXCur = cosf(s.rollStart) * x2 + sinf(s.rollStart) * y2;
+    s.shiftFromStartYCur = -sinf(s.rollStart) * x2 + cosf(s.rollStart) * y2;
+    s.shiftFromStartZCur = z2;
+  }
+  {  // VeloToStartIMU SR:142-160
+    s.veloFromStartXCur = s.veloXCur - s.veloXStart;
+    s.veloFromStartYCur = s.veloYCur - s.veloYStart;
+    s.veloFromStartZCur = s.veloZCur - s.veloZStart;
+    float x1 = cosf(s.yawStart) * s.veloFromStartXCur - sinf(s.yawStart) * s.veloFromStartZCur;
+    float y1 = s.veloFromStartYCur;
+    float z1 = sinf(s.yawStart) * s.veloFromStartXCur + cosf(s.yawStart) * s.veloFromStartZCur;
+    float x2 = x1;
+    float y2 = cosf(s.pitchStart) * y1 + sinf(s.pitchStart) * z1;
+    float z2 = -sinf(s.pitchStart) * y1 + cosf(s.pitchStart) * z1;
+    s.veloFromStartXCur = cosf(s.rollStart) * x2 + sinf(s.rollStart) * y2;
+    s.veloFromStartYCur = -sinf(s.rollStart) * x2 + cosf(s.rollStart) * y2;
+    s.veloFromStartZCur = z2;
+  }
+  {  // TransformToStartIMU SR:163-184
+    float x1 = cosf(s.rollCur) * point.x - sinf(s.rollCur) * point.y;
+    float y1 = sinf(s.rollCur) * point.x + cosf(s.rollCur) * point.y;
+    float z1 = point.z;
+    float x2 = x1;
+    float y2 = cosf(s.pitchCur) * y1 - sinf(s.pitchCur) * z1;
+    float z2 = sinf(s.pitchCur) * y1 + cosf(s.pitchCur) * z1;
+    float x3 = cosf(s.yawCur) * x2 + sinf(s.yawCur) * z2;
+    float y3 = y2;
+    float z3 = -sinf(s.yawCur) * x2 + cosf(s.yawCur) * z2;
+    float x4 = cosf(s.yawStart) * x3 - sinf(s.yawStart) * z3;
+    float y4 = y3;
+    float z4 = sinf(s.yawStart) * x3 + cosf(s.yawStart) * z3;
+    float x5 = x4;
+    float y5 = cosf(s.pitchStart) * y4 + sinf(s.pitchStart) * z4;
+    float z5 = -sinf(s.pitchStart) * y4 + cosf(s.pitchStart) * z4;
+    point.x = cosf(s.rollStart) * x5 + sinf(s.rollStart) * y5 + s.shiftFromStartXCur;
+    point.y = -sinf(s.rollStart) * x5 + cosf(s.rollStart) * y5 + s.shiftFromStartYCur;
+    point.z = z5 + s.shiftFromStartZCur;
+  }
+}
+
 // xyz: n points, `stride` floats apart, sensor frame (x fwd, y left, z up).
-inline void extract(const SRParams& prm, SRState& st, const float* xyz, int n, int stride, SROut& out) {
+// imu != nullptr with imu->last >= 0: the IMU branch SR:364-434 runs (timeScanCur = the sweep's stamp).
+inline void extract(const SRParams& prm, SRState& st, const float* xyz, int n, int stride, SROut& out, ImuState* imu = nullptr,
+                    double timeScanCur = 0.0) {
   const int R = prm.n_scans;
   out.full.clear(); out.sharp.clear(); out.lessSharp.clear(); out.flat.clear(); out.lessFlat.clear();
   out.scanStart.assign(R, 0);
@@ -151,6 +351,7 @@ inline void extract(const SRParams& prm, SRState& st, const float* xyz, int n, i
     }
     float relTime = (ori - startOri) / (endOri - startOri);
     pt.i = (float)(scanID + prm.scan_period * relTime);
+    if (imu && imu->last >= 0) imu_point(*imu, timeScanCur, relTime, prm.scan_period, t == 0, pt);  // SR:364-434
     scans[scanID].push_back(pt);
   }
   // SR:444-447

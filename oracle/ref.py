@@ -332,3 +332,34 @@ def tc_long(slam, enu, iterations=5):
     w, cal = np.zeros(n), np.zeros((n, 4))
     _tc().ref_ld_long(s.ctypes.data, e.ctypes.data, n, iterations, w.ctypes.data, cal.ctypes.data)
     return w, cal
+
+
+# ------------------------------------------------------------------------------------------------ SR with the IMU branch
+class SrWithImu:
+    """A PRIVATE copy of the reference's scanRegistration.cpp (its IMU state lives in file-scope globals and would leak into
+    every later sweep of the process): imuHandler (SR:754-837) + laserCloudHandler with the de-skew branch (SR:364-434)."""
+
+    def __init__(self):
+        import shutil
+        import tempfile
+        self._dir = tempfile.mkdtemp(prefix="refsr_")
+        so = os.path.join(self._dir, "libref_sr_imu.so")
+        shutil.copy(os.path.join(_DIR, "libref_sr.so"), so)
+        L = C.CDLL(so)
+        vp = C.c_void_p
+        L.ref_sr_process.argtypes = [vp, C.c_int, C.c_double]
+        L.ref_sr_cloud.argtypes = [C.c_int, vp, C.c_int]
+        L.ref_sr_imu.argtypes = [C.c_double, vp, vp, vp]
+        L.ref_sr_imu_trans.argtypes = [vp]
+        self.L = L
+
+    def imu(self, stamp, quat_xyzw, angular_velocity, linear_acceleration):
+        q, a, l = (np.ascontiguousarray(v, np.float64) for v in (quat_xyzw, angular_velocity, linear_acceleration))
+        self.L.ref_sr_imu(float(stamp), q.ctypes.data, a.ctypes.data, l.ctypes.data)
+
+    def process(self, xyz, stamp):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        self.L.ref_sr_process(xyz.ctypes.data, xyz.shape[0], float(stamp))
+        tr = np.zeros(12, np.float32)
+        self.L.ref_sr_imu_trans(tr.ctypes.data)
+        return [_cloud(self.L.ref_sr_cloud, w) for w in range(5)], tr

@@ -1,0 +1,80 @@
+"""The IMU branch of scanRegistration (imuHandler SR:754-837, AccumulateIMUShift SR:187-233, the per-point de-skew SR:364-434
+with SR:121-184; dormant in the shipped pipeline but live code).  CPU: the oracle restatement against the reference's own
+scanRegistration.cpp (a private copy of oracle/_ref/libref_sr.so: the node keeps its IMU state in globals) bit for bit --
+clouds and the 12 floats of /imu_trans -- on IMU streams that exercise both interpolation branches, the 0.2 s staleness
+gates, the yaw filter, the acceleration gate and a yaw wrap.  GPU: loam_imu_push + loam_extract against the oracle."""
+import numpy as np
+import pytest
+
+
+def quat(roll, pitch, yaw):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    return np.array([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy])
+
+
+def imu_stream(t0, t1, rate, seed, yaw0=0.0, gap=None):
+    """(stamp, quaternion, angular velocity, linear acceleration) at `rate` Hz; `gap` = (a, b): no messages in that interval."""
+    rng = np.random.default_rng(seed)
+    out = []
+    t = t0
+    while t < t1:
+        if not (gap and gap[0] <= t < gap[1]):
+            yaw = yaw0 + 0.35 * (t - t0) + 0.02 * np.sin(3 * t)
+            yaw = (yaw + np.pi) % (2 * np.pi) - np.pi  # wraps through +-pi on long streams
+            roll, pitch = 0.03 * np.sin(1.3 * t), 0.02 * np.cos(0.7 * t)
+            wz = 0.35 + 0.06 * np.cos(3 * t) if rng.random() > 0.1 else rng.choice([4.0, -4.0, 0.0])  # the yaw filter's branches
+            la = np.array([0.4 * np.sin(t) - np.sin(pitch) * 9.81, 0.3 * np.cos(2 * t) + np.sin(roll) * np.cos(pitch) * 9.81,
+                           np.cos(roll) * np.cos(pitch) * 9.81 + 0.1 * rng.standard_normal()])
+            if rng.random() < 0.03:
+                la[0] += 5.0  # trips the |acc| > 2 gate: the message's integration is skipped
+            out.append((t, quat(roll, pitch, yaw), np.array([0.0, 0.0, wz]), la))
+        t += 1.0 / rate
+    return out
+
+
+def scenario(seed):
+    """Sweeps at 10 Hz with stamps, IMU messages delivered before each sweep up to a little PAST its end (so both the
+    'IMU newer' and the 'IMU older' branch run), one gap longer than 0.2 s, one sweep whose first point is invalid."""
+    from gpscalibration_b200 import SweepGenerator
+    gen = SweepGenerator(sensor=0, scene=seed % 2, seed=0xC0FFEE + seed)
+    msgs = imu_stream(99.95, 101.3, 100.0, seed, yaw0=2.9, gap=(100.52, 100.78))
+    events = []
+    k_msg = 0
+    for k in range(10):
+        stamp = 100.0 + 0.1 * k
+        lead = 0.13 if k % 3 else 0.04  # how far past the sweep's stamp the IMU has been heard
+        while k_msg < len(msgs) and msgs[k_msg][0] <= stamp + lead:
+            events.append(("imu",) + msgs[k_msg])
+            k_msg += 1
+        xyz = gen.sweep(k)[0].copy()
+        if k == 4:
+            xyz[0] = np.nan  # the first finite point moves
+        if k == 6:
+            xyz[0, 2] = 40.0  # the first point leaves the ring table: the Start values are NOT latched in this sweep
+        events.append(("sweep", stamp, xyz))
+    return events
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_imu_branch_matches_reference(orc, seed):
+    from oracle import ref
+    import os
+    if not os.path.exists(os.path.join(ref._DIR, "libref_sr.so")):
+        pytest.skip("oracle/_ref/libref_sr.so not built (needs /root/reference)")
+    r = ref.SrWithImu()
+    o = orc.ScanRegistration()
+    n_sweeps = 0
+    for ev in scenario(seed):
+        if ev[0] == "imu":
+            r.imu(*ev[1:])
+            o.imu(*ev[1:])
+        else:
+            _, stamp, xyz = ev
+            rc, rtr = r.process(xyz, stamp)
+            oc, otr = o.extract_imu(xyz, stamp)
+            assert np.array_equal(rtr.view(np.uint32), otr.view(np.uint32)), (n_sweeps, rtr, otr)
+            for name, a in zip(o.CLOUDS, rc):
+                b = oc[name]
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_sweeps, name)
+            n_sweeps += 1
+    assert n_sweeps == 10 and np.abs(otr).max() > 1e-3  # the de-skew did something
