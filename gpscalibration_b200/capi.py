@@ -55,7 +55,7 @@ class SweepResult(C.Structure):
 
 # every symbol include/loamgpu.h declares (tests check the library exports all of them)
 SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam_create", "loam_destroy", "loam_reset",
-           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_extract", "loam_extract_device", "loam_extract_batch", "loam_odometry_process", "loam_odometry_process_batch",
+           "loam_stream", "loam_launch_count", "loam_stats", "loam_profile", "loam_profile_read", "loam_host_times", "loam_launch_latency", "loam_pose_message_hop", "loam_imu_push", "loam_get_imu_trans", "loam_extract", "loam_extract_device", "loam_extract_batch", "loam_odometry_process", "loam_odometry_process_batch",
            "loam_mapping_odometry", "loam_mapping_process", "loam_integrate_odometry", "loam_integrate_mapping", "loam_process_sweep", "loam_process_sweep_device",
            "loam_get_cloud", "loam_get_cloud_wire", "loam_get_diag", "loam_voxel_grid", "loam_odom_set_inputs", "loam_odom_iter",
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
@@ -110,6 +110,8 @@ def load_library():
     lib.loam_pose_message_hop.argtypes = [vp, vp]
     lib.loam_launch_latency.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.loam_profile_read.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.loam_imu_push.argtypes = [vp, C.c_double, vp, vp, vp]
+    lib.loam_get_imu_trans.argtypes = [vp, vp]
     lib.loam_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(Counts)]
     lib.loam_extract_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
@@ -265,6 +267,17 @@ class LoamGpu:
         self._check(self.lib.loam_extract(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] if xyz.shape[0] > 1 else 12, stamp, None, C.byref(c)),
                     "loam_extract")
         return c
+
+    def imu_push(self, stamp, quat_xyzw, angular_velocity, linear_acceleration):
+        """loam_imu_push: one /imu/data message (imuHandler SR:754-837)."""
+        q, a, l = (np.ascontiguousarray(v, np.float64) for v in (quat_xyzw, angular_velocity, linear_acceleration))
+        self._check(self.lib.loam_imu_push(self._h, float(stamp), q.ctypes.data, a.ctypes.data, l.ctypes.data), "loam_imu_push")
+
+    def imu_trans(self):
+        """The 12 floats of /imu_trans of the last extracted sweep (SR:730-745)."""
+        out = np.zeros(12, np.float32)
+        self._check(self.lib.loam_get_imu_trans(self._h, out.ctypes.data), "loam_get_imu_trans")
+        return out
 
     def extract_device(self, dev_ptr, n, stride_bytes=12, stamp=0.0):
         c = Counts()

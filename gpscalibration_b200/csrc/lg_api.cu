@@ -118,6 +118,13 @@ struct loam_handle {
   loam_counts counts = {0, 0, 0, 0, 0};
   bool have_features = false;
   float imu[12] = {0};
+  // the node's IMU state (SR:76-110): ring of integrated messages (host copy + device copy), the device-resident carry of the
+  // per-point de-skew; inactive until the first loam_imu_push (imuPointerLast == -1, SR:364)
+  lgh::ImuHost imu_host;
+  SrImuRing imu_ring = {};
+  DevBuf d_imu_ring, d_imu_carry;
+  SrImuCarry imu_carry = {};  // host mirror of the device carry after the last sweep
+  bool imu_ring_dirty = false;
   // current message set for odometry (device pointers; either sr.* or the explicit test buffers)
   const float4 *cur_sharp = nullptr, *cur_less_sharp = nullptr, *cur_flat = nullptr, *cur_less_flat = nullptr, *cur_full = nullptr;
   DevBuf t_sharp, t_flat;  // loam_odom_set_inputs
@@ -447,7 +454,7 @@ void extract_publish(loam_handle* h) {
   h->have_features = true;
 }
 
-int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out) {
+int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, const float* imu_trans, loam_counts* out, double stamp = 0.0) {
   HostTimer ht(&h->host_s[HT_EXTRACT]);
   if (n < 0 || stride_bytes < 12) return LOAM_EINVAL;
   if (n > 0 && ((stride_bytes & 3) || ((uintptr_t)d_xyz & 3))) {  // unaligned wire layout: repack to 12-byte points
@@ -459,10 +466,34 @@ int extract_common(loam_handle* h, const float* d_xyz, int n, int stride_bytes, 
     stride_bytes = 12;
   }
   for (int i = 0; i < 12; i++) h->imu[i] = imu_trans ? imu_trans[i] : 0.f;
-  int rc = lg_extract_launch(h->sr, h->srp, d_xyz, n, stride_bytes, h->st, &h->launches);
+  SrImuJob job;
+  const bool with_imu = h->imu_host.last >= 0 && n > 0;  // SR:364: the IMU branch runs once a message has arrived
+  if (with_imu) {
+    if (!h->d_imu_carry.p) {
+      LG_CHECK(h->d_imu_carry.ensure(sizeof(SrImuCarry), h->st));
+      LG_CHECK(cudaMemsetAsync(h->d_imu_carry.p, 0, sizeof(SrImuCarry), h->st));
+    }
+    if (h->imu_ring_dirty || !h->d_imu_ring.p) {
+      int rcu = upload(h, h->d_imu_ring, &h->imu_ring, sizeof(SrImuRing));  // pageable source: staged before the call returns
+      if (rcu) return rcu;
+      h->imu_ring_dirty = false;
+    }
+    job.ring = h->d_imu_ring.as<SrImuRing>();
+    job.carry = h->d_imu_carry.as<SrImuCarry>();
+    job.last = h->imu_host.last;
+    job.time_scan = stamp;
+  }
+  int rc = lg_extract_launch(h->sr, h->srp, d_xyz, n, stride_bytes, h->st, &h->launches, with_imu ? &job : nullptr);
   if (rc) return rc;
+  if (with_imu) LG_D2H(h, &h->imu_carry, h->d_imu_carry.p, sizeof(SrImuCarry));  // lands with the counts below
   rc = read_sr_counts(h, out);
   if (rc) return rc;
+  if (with_imu) {  // /imu_trans as the node publishes it (SR:730-745); it overrides a caller-supplied imu_trans
+    const SrImuCarry& c = h->imu_carry;
+    const float tr[12] = {c.start[1], c.start[2], c.start[0], c.cur[1], c.cur[2], c.cur[0], c.shift_from_start[0], c.shift_from_start[1],
+                          c.shift_from_start[2], c.velo_from_start[0], c.velo_from_start[1], c.velo_from_start[2]};
+    for (int i = 0; i < 12; i++) h->imu[i] = tr[i];
+  }
   extract_publish(h);
   return LOAM_OK;
 }
@@ -768,7 +799,7 @@ int loam_destroy(loam_handle* h) {
   DevBuf* all[] = {&h->xyz_packed, &h->wire, &h->xyz_in, &h->t_sharp, &h->t_flat, &h->corner_last, &h->surf_last, &h->corner_new, &h->surf_new, &h->fullres3,
                    &h->arena, &h->arena2, &h->stack2_c, &h->stack2_s, &h->stack_c, &h->stack_s, &h->map_c, &h->map_s, &h->d_ents, &h->d_segs,
                    &h->d_ints, &h->d_seg_off, &h->d_seg_leaf, &h->d_out_se, &h->ds_in, &h->ins_sel, &h->ins_sorted, &h->d_runs,
-                   &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts, &h->batch_tab};
+                   &h->surround, &h->registered, &h->vg_in, &h->vg_out, &h->vs_staging, &h->vs_counts, &h->batch_tab, &h->d_imu_ring, &h->d_imu_carry};
   for (DevBuf* b : all) b->release();
   if (h->px_connected)
     for (int r = 0; r < h->px.world; r++)
@@ -862,26 +893,40 @@ int loam_profile_read(loam_handle* h, double* ms, double* units, long long* scop
 long long loam_launch_count(const loam_handle* h) { return h ? h->launches : 0; }
 
 // ============================================================================================ scanRegistration
-int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
+int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out) {
   if (!h || (!xyz_host && n > 0)) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
   int rc = upload(h, h->xyz_in, xyz_host, (size_t)n * stride_bytes);
   if (rc) return rc;
-  return extract_common(h, h->xyz_in.as<float>(), n, stride_bytes, imu_trans, out);
+  return extract_common(h, h->xyz_in.as<float>(), n, stride_bytes, imu_trans, out, stamp);
 }
-int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double, const float* imu_trans, loam_counts* out) {
+int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out) {
   if (!h || (!xyz_dev && n > 0)) return LOAM_EINVAL;
   LG_CHECK(cudaSetDevice(h->device));
   g_lg_prof = h->prof.on ? &h->prof : nullptr;
-  return extract_common(h, xyz_dev, n, stride_bytes, imu_trans, out);
+  return extract_common(h, xyz_dev, n, stride_bytes, imu_trans, out, stamp);
+}
+
+// imuHandler SR:754-837: one /imu/data message.  From the first message on, loam_extract de-skews every sweep (SR:364-434)
+// and produces /imu_trans itself.
+int loam_imu_push(loam_handle* h, double stamp, const double* orientation_xyzw, const double* angular_velocity, const double* linear_acceleration) {
+  if (!h || !orientation_xyzw || !angular_velocity || !linear_acceleration) return LOAM_EINVAL;
+  lgh::imu_handler(h->imu_host, h->imu_ring, stamp, orientation_xyzw, angular_velocity, linear_acceleration);
+  h->imu_ring_dirty = true;
+  return LOAM_OK;
+}
+int loam_get_imu_trans(loam_handle* h, float* out12) {
+  if (!h || !out12) return LOAM_EINVAL;
+  for (int i = 0; i < 12; i++) out12[i] = h->imu[i];
+  return LOAM_OK;
 }
 
 // One sweep of each of B independent sequences (SURVEY 8b `*_batch`): the eight extraction kernels are launched ONCE for
 // all members (grid.y = sequence) on the first handle's stream, the counts come back with one synchronisation.  Results
 // are those of B loam_extract calls, bit for bit.  Members the batched launch does not take (empty sweeps, unaligned
 // point layouts) and sweeps with virtual rings go through the per-handle path.
-int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_host, const int* n, int stride_bytes, const double*,
+int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_host, const int* n, int stride_bytes, const double* stamps,
                        loam_counts* out) {
   if (!hs || !xyz_host || !n || B < 1 || B > 256 || stride_bytes < 12) return LOAM_EINVAL;
   for (int b = 0; b < B; b++)
@@ -902,9 +947,9 @@ int loam_extract_batch(loam_handle* const* hs, int B, const float* const* xyz_ho
   std::vector<int> nn, strides;
   for (int b = 0; b < B; b++) {
     loam_handle* h = hs[b];
-    const bool batched = n[b] > 0 && (stride_bytes & 3) == 0;
+    const bool batched = n[b] > 0 && (stride_bytes & 3) == 0 && h->imu_host.last < 0;  // the IMU de-skew is a per-handle pass
     if (!batched) {  // per-handle path
-      int rc = loam_extract(h, xyz_host[b], n[b], stride_bytes, 0.0, nullptr, out ? &out[b] : nullptr);
+      int rc = loam_extract(h, xyz_host[b], n[b], stride_bytes, stamps ? stamps[b] : 0.0, nullptr, out ? &out[b] : nullptr);
       if (rc) return rc;
       continue;
     }

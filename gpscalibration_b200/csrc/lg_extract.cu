@@ -178,7 +178,7 @@ __device__ __forceinline__ void sr_scan_kernel_body(SrParams prm, unsigned int* 
 __device__ __forceinline__ void sr_scatter_kernel_body(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
                                                             const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
                                                             const unsigned int* __restrict__ hist, int nblocks, const int* __restrict__ meta,
-                                                            float4* __restrict__ full) {
+                                                            float4* __restrict__ full, const float* __restrict__ imu_pts = nullptr) {
   __shared__ unsigned int s_base[MAXR];
   __shared__ unsigned int s_wcnt[SR_NT / 32][MAXR];
   __shared__ float s_ori[2];
@@ -224,7 +224,8 @@ __device__ __forceinline__ void sr_scatter_kernel_body(SrParams prm, const float
       }
       float relTime = (ori - startOri) / (endOri - startOri);
       float inten = (float)(ring + prm.scan_period * relTime);  // SR:362, scanPeriod is a double
-      full[off] = make_float4(p[1], p[2], p[0], inten);
+      if (imu_pts) full[off] = make_float4(imu_pts[3 * (size_t)i], imu_pts[3 * (size_t)i + 1], imu_pts[3 * (size_t)i + 2], inten);  // SR:364-434 ran
+      else full[off] = make_float4(p[1], p[2], p[0], inten);
     }
     __syncthreads();
     if (tid < MAXR) {
@@ -852,6 +853,232 @@ __device__ __forceinline__ void sr_concat_kernel_body(SrParams prm, int* __restr
   }
 }
 
+// ---- SR:364-434, the IMU branch: every kept point advances imuPointerFront, interpolates the "Cur" IMU values at its own
+// time, and is rotated / shifted back to the sweep's start (SR:121-184).  The reference does this point by point with
+// state that persists from point to point; here ONE CTA walks the sweep in chunks of 1024 points in input order:
+//   imuPointerFront is monotone: front_i = max(front_(i-1), g_i), g_i = first ring offset whose stamp exceeds the point's
+//     time (exact while the ring's stamps increase with the offset, as IMU streams do) -> an inclusive max-scan;
+//   the Cur values are those of the LAST point whose update passed its 0.2 s gate (SR:375, 390) -> a second max-scan over
+//     "index if valid"; a point then recomputes that source point's interpolation (same arithmetic, same result);
+//   the Start values are latched at the sweep's first finite point if it is kept (SR:410-421), which precedes every
+//     other kept point; ShiftToStartIMU / VeloToStartIMU / TransformToStartIMU are pure functions of (Cur_i, Start, time_i).
+// sinf / cosf are the libm-exact ports (lg_libm.cuh), products are not contracted: bit-identical to the host arithmetic.
+constexpr int IMU_NT = 1024;
+struct ImuCur { float v[9]; };
+__device__ __forceinline__ int imu_scan_max(int v, int carry, int* s_w /* >= 33 */) {  // inclusive max-scan over the CTA + carry-in; ends with a barrier
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, t);
+  }
+  if (lane == 31) s_w[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x = max(x, t);
+    }
+    s_w[lane] = x;
+  }
+  __syncthreads();
+  int r = max(v, carry);
+  if (w > 0) r = max(r, s_w[w - 1]);
+  __syncthreads();
+  return r;
+}
+// the interpolation of SR:373-408 for a point at time t whose imuPointerFront is ring index F; false = its gate failed
+__device__ __forceinline__ bool imu_interp(const SrImuRing& R, double t, int F, ImuCur& c) {
+  const double tf = R.time[F];
+  if (t > tf) {
+    if (!(t - tf < 0.2)) return false;
+    c.v[0] = R.roll[F]; c.v[1] = R.pitch[F]; c.v[2] = R.yaw[F];
+    c.v[3] = R.veloX[F]; c.v[4] = R.veloY[F]; c.v[5] = R.veloZ[F];
+    c.v[6] = R.shiftX[F]; c.v[7] = R.shiftY[F]; c.v[8] = R.shiftZ[F];
+    return true;
+  }
+  if (!(tf - t < 0.2)) return false;
+  const int B = (F + SR_IMU_Q - 1) % SR_IMU_Q;
+  const float rf = (float)((t - R.time[B]) / (tf - R.time[B]));
+  const float rb = (float)((tf - t) / (tf - R.time[B]));
+  c.v[0] = R.roll[F] * rf + R.roll[B] * rb;
+  c.v[1] = R.pitch[F] * rf + R.pitch[B] * rb;
+  if (R.yaw[F] - R.yaw[B] > M_PI) {
+    c.v[2] = (float)(R.yaw[F] * rf + (R.yaw[B] + 2 * M_PI) * rb);
+  } else if (R.yaw[F] - R.yaw[B] < -M_PI) {
+    c.v[2] = (float)(R.yaw[F] * rf + (R.yaw[B] - 2 * M_PI) * rb);
+  } else {
+    c.v[2] = R.yaw[F] * rf + R.yaw[B] * rb;
+  }
+  c.v[3] = R.veloX[F] * rf + R.veloX[B] * rb;
+  c.v[4] = R.veloY[F] * rf + R.veloY[B] * rb;
+  c.v[5] = R.veloZ[F] * rf + R.veloZ[B] * rb;
+  c.v[6] = R.shiftX[F] * rf + R.shiftX[B] * rb;
+  c.v[7] = R.shiftY[F] * rf + R.shiftY[B] * rb;
+  c.v[8] = R.shiftZ[F] * rf + R.shiftZ[B] * rb;
+  return true;
+}
+// SR:121-160: the shift / velocity of the point relative to the sweep's start, in the start frame
+__device__ __forceinline__ void imu_from_start(const ImuCur& c, const float* S, float pointTime, float* sh, float* ve) {
+  const float cy = lgm_cosf(S[2]), sy = lgm_sinf(S[2]), cp = lgm_cosf(S[1]), sp = lgm_sinf(S[1]), cr = lgm_cosf(S[0]), sr = lgm_sinf(S[0]);
+  {
+    const float fx = c.v[6] - S[6] - S[3] * pointTime, fy = c.v[7] - S[7] - S[4] * pointTime, fz = c.v[8] - S[8] - S[5] * pointTime;
+    const float x1 = cy * fx - sy * fz, y1 = fy, z1 = sy * fx + cy * fz;
+    const float x2 = x1, y2 = cp * y1 + sp * z1, z2 = -sp * y1 + cp * z1;
+    sh[0] = cr * x2 + sr * y2;
+    sh[1] = -sr * x2 + cr * y2;
+    sh[2] = z2;
+  }
+  {
+    const float fx = c.v[3] - S[3], fy = c.v[4] - S[4], fz = c.v[5] - S[5];
+    const float x1 = cy * fx - sy * fz, y1 = fy, z1 = sy * fx + cy * fz;
+    const float x2 = x1, y2 = cp * y1 + sp * z1, z2 = -sp * y1 + cp * z1;
+    ve[0] = cr * x2 + sr * y2;
+    ve[1] = -sr * x2 + cr * y2;
+    ve[2] = z2;
+  }
+}
+__global__ void __launch_bounds__(IMU_NT) sr_imu_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
+                                                         const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
+                                                         const int* __restrict__ meta, SrImuJob J, float* __restrict__ pts,
+                                                         double* __restrict__ g_t, int2* __restrict__ g_fs) {
+  __shared__ SrImuRing R;
+  __shared__ int s_w[33];
+  __shared__ float s_ori[2];
+  __shared__ int s_ok, s_f0;
+  __shared__ float s_start[9];
+  const int tid = threadIdx.x;
+  for (int k = tid; k < (int)(sizeof(SrImuRing) / 4); k += IMU_NT) reinterpret_cast<int*>(&R)[k] = reinterpret_cast<const int*>(J.ring)[k];
+  if (tid == 0) {
+    sweep_ori(xyz, n, stride_bytes, &s_ori[0], &s_ori[1], &s_ok);
+    s_f0 = 0x7fffffff;
+  }
+  if (tid < 9) s_start[tid] = J.carry->start[tid];
+  __syncthreads();
+  {  // i == 0 of the NaN-filtered cloud (SR:410): the first finite point
+    int f = 0x7fffffff;
+    for (int i = tid; i < n && f == 0x7fffffff; i += IMU_NT)
+      if (finite3(pt_at(xyz, stride_bytes, i))) f = i;
+    if (f != 0x7fffffff) atomicMin(&s_f0, f);
+  }
+  __syncthreads();
+  const int f0 = s_f0;
+  const float startOri = s_ori[0], endOri = s_ori[1];
+  const int jstar = meta[SRM_JSTAR];
+  const int front0 = J.carry->front;
+  const int L = (J.last - front0 + SR_IMU_Q) % SR_IMU_Q;  // offsets 0 .. L: the ring entries the pointer can reach
+  auto point_time = [&](int i) {  // relTime as sr_scatter_kernel forms it (SR:341-362), times scanPeriod (SR:365)
+    float ori = ori_raw[i];
+    if (i <= jstar) {
+      if (ori < startOri - M_PI / 2) {
+        ori = (float)(ori + 2 * M_PI);
+      } else if (ori > startOri + M_PI * 3 / 2) {
+        ori = (float)(ori - 2 * M_PI);
+      }
+    } else {
+      ori = (float)(ori + 2 * M_PI);
+      if (ori < endOri - M_PI * 3 / 2) {
+        ori = (float)(ori + 2 * M_PI);
+      } else if (ori > endOri + M_PI / 2) {
+        ori = (float)(ori - 2 * M_PI);
+      }
+    }
+    const float relTime = (ori - startOri) / (endOri - startOri);
+    return (float)(relTime * prm.scan_period);
+  };
+  ImuCur carry_cur;
+#pragma unroll
+  for (int k = 0; k < 9; k++) carry_cur.v[k] = J.carry->cur[k];
+  int cF = 0, cS = -1, cK = -1;  // carries: front offset, last valid source, last kept point
+  for (int base = 0; base < n; base += IMU_NT) {
+    const int i = base + tid;
+    const bool kept = s_ok && i < n && ring8[i] >= 0;
+    float pointTime = 0.f;
+    double t = 0.0;
+    int g = 0;
+    if (kept) {
+      pointTime = point_time(i);
+      t = J.time_scan + pointTime;
+      while (g < L && !(t < R.time[(front0 + g) % SR_IMU_Q])) g++;  // SR:366-371 from the sweep's first pointer
+    }
+    const int F = imu_scan_max(g, cF, s_w);
+    ImuCur mine;
+    bool valid = false;
+    if (kept) valid = imu_interp(R, t, (front0 + F) % SR_IMU_Q, mine);
+    const int S = imu_scan_max(valid ? i : -1, cS, s_w);
+    const int K = imu_scan_max(kept ? i : -1, cK, s_w);
+    if (i < n) {
+      g_t[i] = t;
+      g_fs[i] = make_int2(F, S);
+    }
+    __syncthreads();  // the source point of a lane may sit anywhere in this or an earlier chunk
+    ImuCur cur = carry_cur;
+    if (kept) {
+      if (S == i) cur = mine;
+      else if (S >= 0) imu_interp(R, g_t[S], (front0 + g_fs[S].x) % SR_IMU_Q, cur);
+      if (i == f0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) s_start[k] = cur.v[k];  // SR:410-421
+      }
+    }
+    __syncthreads();
+    if (kept) {
+      const float* p = pt_at(xyz, stride_bytes, i);
+      float px = p[1], py = p[2], pz = p[0];  // SR:293-295
+      if (i != f0) {
+        float sh[3], ve[3];
+        imu_from_start(cur, s_start, pointTime, sh, ve);
+        // TransformToStartIMU SR:163-184
+        const float crc = lgm_cosf(cur.v[0]), src = lgm_sinf(cur.v[0]), cpc = lgm_cosf(cur.v[1]), spc = lgm_sinf(cur.v[1]);
+        const float cyc = lgm_cosf(cur.v[2]), syc = lgm_sinf(cur.v[2]);
+        const float cys = lgm_cosf(s_start[2]), sys = lgm_sinf(s_start[2]), cps = lgm_cosf(s_start[1]), sps = lgm_sinf(s_start[1]);
+        const float crs = lgm_cosf(s_start[0]), srs = lgm_sinf(s_start[0]);
+        const float x1 = crc * px - src * py, y1 = src * px + crc * py, z1 = pz;
+        const float x2 = x1, y2 = cpc * y1 - spc * z1, z2 = spc * y1 + cpc * z1;
+        const float x3 = cyc * x2 + syc * z2, y3 = y2, z3 = -syc * x2 + cyc * z2;
+        const float x4 = cys * x3 - sys * z3, y4 = y3, z4 = sys * x3 + cys * z3;
+        const float x5 = x4, y5 = cps * y4 + sps * z4, z5 = -sps * y4 + cps * z4;
+        px = crs * x5 + srs * y5 + sh[0];
+        py = -srs * x5 + crs * y5 + sh[1];
+        pz = z5 + sh[2];
+      }
+      pts[3 * (size_t)i] = px;
+      pts[3 * (size_t)i + 1] = py;
+      pts[3 * (size_t)i + 2] = pz;
+    }
+    // carries of this chunk (its last lane holds the inclusive results)
+    __shared__ int s_c[3];
+    if (tid == IMU_NT - 1) {
+      s_c[0] = F; s_c[1] = S; s_c[2] = K;
+    }
+    __syncthreads();
+    cF = s_c[0]; cS = s_c[1]; cK = s_c[2];
+    __syncthreads();
+  }
+  // ---- what persists into the next sweep (and goes out as /imu_trans, SR:730-745): the state after the LAST kept point
+  if (tid == 0) {
+    SrImuCarry out = *J.carry;
+    if (cK >= 0) {
+      ImuCur cur = carry_cur;
+      const int S = g_fs[cK].y;
+      if (S >= 0) imu_interp(R, g_t[S], (front0 + g_fs[S].x) % SR_IMU_Q, cur);
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        out.cur[k] = cur.v[k];
+        out.start[k] = s_start[k];
+      }
+      if (cK != f0) {
+        const float pointTime = point_time(cK);
+        imu_from_start(cur, s_start, pointTime, out.shift_from_start, out.velo_from_start);
+      }
+      out.front = (front0 + cF) % SR_IMU_Q;
+    }
+    *J.carry = out;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ launch forms
 // Every kernel above exists twice: for ONE sequence (arguments by value) and BATCHED over several sequences -- grid.y is
 // the sequence, whose arguments come from a device table (SURVEY 8b `*_batch`): eight launches extract B sweeps instead
@@ -897,8 +1124,8 @@ __global__ void __launch_bounds__(1024) sr_scan_batch_kernel(const SrK* __restri
 __global__ void __launch_bounds__(SR_NT) sr_scatter_kernel(SrParams prm, const float* __restrict__ xyz, int n, int stride_bytes,
                                                             const signed char* __restrict__ ring8, const float* __restrict__ ori_raw,
                                                             const unsigned int* __restrict__ hist, int nblocks, const int* __restrict__ meta,
-                                                            float4* __restrict__ full) {
-  sr_scatter_kernel_body(prm, xyz, n, stride_bytes, ring8, ori_raw, hist, nblocks, meta, full);
+                                                            float4* __restrict__ full, const float* __restrict__ imu_pts) {
+  sr_scatter_kernel_body(prm, xyz, n, stride_bytes, ring8, ori_raw, hist, nblocks, meta, full, imu_pts);
 }
 __global__ void __launch_bounds__(SR_NT) sr_scatter_batch_kernel(const SrK* __restrict__ tab) {
   const SrK A = tab[blockIdx.y];
@@ -988,7 +1215,8 @@ static int lg_extract_prepare(SrWs& ws, const SrParams& prm, int n, cudaStream_t
   return LOAM_OK;
 }
 
-int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches) {
+int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches,
+                      const SrImuJob* imu) {
   const int R = prm.n_scans;
   int nblocks = 1;
   {
@@ -1005,8 +1233,18 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
   sr_ring_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
                                             ws.hist.as<unsigned int>(), nblocks, meta);
   sr_scan_kernel<<<1, 1024, 0, st>>>(prm, ws.hist.as<unsigned int>(), nblocks, meta);
+  const float* imu_pts = nullptr;
+  if (imu) {  // SR:364-434: de-skew the kept points (input order) before they are bucketed
+    LG_CHECK(ws.imu_pts.ensure((size_t)(n + 16) * 12, st));
+    LG_CHECK(ws.imu_t.ensure((size_t)(n + 16) * 8, st));
+    LG_CHECK(ws.imu_fs.ensure((size_t)(n + 16) * 8, st));
+    sr_imu_kernel<<<1, IMU_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(), meta, *imu,
+                                        ws.imu_pts.as<float>(), ws.imu_t.as<double>(), ws.imu_fs.as<int2>());
+    (*launches)++;
+    imu_pts = ws.imu_pts.as<float>();
+  }
   sr_scatter_kernel<<<nblocks, SR_NT, 0, st>>>(prm, d_xyz, n, stride_bytes, ws.ring8.as<signed char>(), ws.ori_raw.as<float>(),
-                                               ws.hist.as<unsigned int>(), nblocks, meta, ws.full.as<float4>());
+                                               ws.hist.as<unsigned int>(), nblocks, meta, ws.full.as<float4>(), imu_pts);
   sr_curv_kernel<<<lg_div_up(n, 256), 256, 0, st>>>(prm, ws.full.as<float4>(), meta, ws.curv.as<float>(), ws.cond.as<unsigned char>(),
                                                     ws.label.as<signed char>());
   }

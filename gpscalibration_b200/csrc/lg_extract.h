@@ -33,6 +33,27 @@ enum {
 };
 enum { SR_PICK_SHARP = 0, SR_PICK_LESS = 96, SR_PICK_FLAT = 216, SR_PICKS_PER_RING = 408 };  // 6*16, 6*20, 6*32
 
+// ---- IMU branch (SR:364-434): what the de-skew kernel needs from the node's IMU state (see loam_imu_push) ------------------
+constexpr int SR_IMU_Q = 200;  // imuQueLength SR:78
+struct SrImuRing {   // the ring of integrated IMU messages, in ring order
+  double time[SR_IMU_Q];
+  float roll[SR_IMU_Q], pitch[SR_IMU_Q], yaw[SR_IMU_Q];
+  float veloX[SR_IMU_Q], veloY[SR_IMU_Q], veloZ[SR_IMU_Q], shiftX[SR_IMU_Q], shiftY[SR_IMU_Q], shiftZ[SR_IMU_Q];
+};
+struct SrImuCarry {  // persistent between points AND sweeps: Cur, Start, FromStart values, imuPointerFront (SR:76-92)
+  float cur[9];      // roll pitch yaw, velo xyz, shift xyz
+  float start[9];
+  float shift_from_start[3], velo_from_start[3];
+  int front;
+  int pad;
+};
+struct SrImuJob {    // one sweep's de-skew: device pointers + scalars
+  const SrImuRing* ring;
+  SrImuCarry* carry;   // in / out
+  int last;            // imuPointerLast
+  double time_scan;    // timeScanCur SR:257
+};
+
 struct SrWs {
   DevBuf ring8, ori_raw, hist, meta;
   DevBuf full, curv, cond, picked, mask_diag, label;
@@ -40,16 +61,19 @@ struct SrWs {
   DevBuf lf_valid, lf_tmp, less_flat, segs;
   DevBuf sort_ind, stale;                          // cloudSortInd; pick flags / labels of the five never re-initialised entries
   DevBuf reach, lf_stage, lf_vout, lf_meta, gkeys;  // virtual-ring pass only
+  DevBuf imu_pts, imu_t, imu_fs;                    // IMU branch only: de-skewed points, point times, (front offset, source) per point
   void release() {
     DevBuf* all[] = {&ring8, &ori_raw, &hist, &meta, &full, &curv, &cond, &picked, &mask_diag, &label,
                      &picks, &sharp, &less_sharp, &flat, &lf_valid, &lf_tmp, &less_flat, &segs,
-                     &sort_ind, &stale, &reach, &lf_stage, &lf_vout, &lf_meta, &gkeys};
+                     &sort_ind, &stale, &reach, &lf_stage, &lf_vout, &lf_meta, &gkeys, &imu_pts, &imu_t, &imu_fs};
     for (DevBuf* b : all) b->release();
   }
 };
 
 // Enqueues the whole extraction of one sweep on `st`; results and counts (meta) stay on the device.
-int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches);
+// imu != nullptr: the IMU branch runs (the points are de-skewed before they are bucketed; imu->carry is updated on the device).
+int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, int stride_bytes, cudaStream_t st, long long* launches,
+                      const SrImuJob* imu = nullptr);
 // The same for one sweep of each of B sequences with one launch per kernel (grid.y = sequence): members need n > 0, same
 // device; `tab` is scratch for the argument table.  Synchronises `st` before it returns.
 int lg_extract_launch_batch(SrWs* const* ws, const SrParams* prm, const float* const* d_xyz, const int* n, const int* stride_bytes, int B,

@@ -153,4 +153,71 @@ inline void pose_message_hop(const float* in, float* out) {
   for (int i = 3; i < 6; i++) out[i] = (float)(double)in[i];  // position rides in float64 fields
 }
 
+// ---- the IMU side of scanRegistration that stays on the host: imuHandler (SR:754-837) and AccumulateIMUShift (SR:187-233).
+// One message -> one ring entry with the integrated velocity / shift; the per-point de-skew (SR:364-434) is a kernel.
+// R is lg_extract.h's SrImuRing (same layout on the device).
+struct ImuHost {
+  int last = -1;        // imuPointerLast
+  int imuMesg = 0;      // SR:59
+  double initYaw = 0;   // SR:60
+  float accX[200] = {0}, accY[200] = {0}, accZ[200] = {0};
+};
+template <class Ring>
+inline void imu_handler(ImuHost& s, Ring& R, double stamp, const double* q, const double* av, const double* la) {
+  const int Q = 200;
+  double roll, pitch, yaw;
+  bool flag = false;
+  s.imuMesg++;
+  if (!(std::fabs(std::pow(q[0], 2) + std::pow(q[1], 2) + std::pow(q[2], 2) + std::pow(q[3], 2) - 1) < 0.1)) return;  // SR:760-768
+  {  // tf::Matrix3x3(orientation).getRPY
+    const double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], sc = 2.0 / d;
+    const double xs = q[0] * sc, ys = q[1] * sc, zs = q[2] * sc;
+    const double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs, xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs,
+                 zz = q[2] * zs;
+    const double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    if (std::fabs(m20) >= 1) {
+      yaw = 0;
+      if (m20 < 0) { pitch = M_PI / 2.0; roll = std::atan2(m01, m02); } else { pitch = -M_PI / 2.0; roll = std::atan2(-m01, -m02); }
+    } else {
+      pitch = -std::asin(m20);
+      roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+      yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+    }
+  }
+  if (s.imuMesg == 1) s.initYaw = yaw;
+  const float accY = (float)(la[1] - std::sin(roll) * std::cos(pitch) * 9.81);  // SR:770-772
+  const float accZ = (float)(la[2] - std::cos(roll) * std::cos(pitch) * 9.81);
+  const float accX = (float)(la[0] + std::sin(pitch) * 9.81);
+  s.last = (s.last + 1) % Q;
+  const int L = s.last, back = (L + Q - 1) % Q;
+  if (s.imuMesg != 1) {  // SR:777-809: the yaw may only move the way the angular velocity says
+    const double PI_CH = 3.141592653589;  // CH:17
+    if (av[2] > 3) {
+      if (R.yaw[back] > yaw && std::fabs(R.yaw[back]) < PI_CH) { flag = true; yaw = R.yaw[back]; }
+    } else if (std::fabs(av[2]) < 3) {
+      if (R.yaw[back] != yaw) { flag = true; yaw = R.yaw[back]; }
+    } else if (av[2] < -1 * 3) {
+      if (R.yaw[back] < yaw && std::fabs(R.yaw[back]) < PI_CH) { flag = true; yaw = R.yaw[back]; }
+    }
+  }
+  R.time[L] = stamp;
+  R.roll[L] = (float)roll;
+  R.pitch[L] = (float)pitch;
+  if (s.imuMesg != 1) R.yaw[L] = flag ? (float)yaw : (float)(yaw - s.initYaw); else R.yaw[L] = 0;
+  if (std::fabs(accX) > 2 || std::fabs(accY) > 2) return;  // SR:826-829: the entry keeps whatever the ring held there
+  s.accX[L] = accX; s.accY[L] = accY; s.accZ[L] = accZ;
+  // AccumulateIMUShift SR:187-233
+  const float r = R.roll[L];
+  const float ax = cosf(r) * accX - sinf(r) * accY, ay = sinf(r) * accX + cosf(r) * accY, az = accZ;
+  const double timeDiff = R.time[L] - R.time[back];
+  if (timeDiff < 0.2) {
+    R.shiftX[L] = (float)(R.shiftX[back] + R.veloX[back] * timeDiff + ax * timeDiff * timeDiff / 2);
+    R.shiftY[L] = (float)(R.shiftY[back] + R.veloY[back] * timeDiff + ay * timeDiff * timeDiff / 2);
+    R.shiftZ[L] = (float)(R.shiftZ[back] + R.veloZ[back] * timeDiff + az * timeDiff * timeDiff / 2);
+    R.veloX[L] = (float)(R.veloX[back] + ax * timeDiff);
+    R.veloY[L] = (float)(R.veloY[back] + ay * timeDiff);
+    R.veloZ[L] = (float)(R.veloZ[back] + az * timeDiff);
+  }
+}
+
 }  // namespace lgh

@@ -154,6 +154,17 @@ int loam_launch_latency(loam_handle* h, int n, double* period_us, double* roundt
  * Results stay device-resident for loam_odometry_process; counts are returned; clouds via loam_get_cloud. */
 int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* Same, the sweep already resident in device memory of this handle's GPU. */
+/* The IMU branch of scanRegistration (dormant in the shipped pipeline -- input_data replays only velodyne_points -- but
+ * live code).  loam_imu_push replaces the body of imuHandler (SR:754-837 incl. AccumulateIMUShift SR:187-233): one
+ * sensor_msgs/Imu message (orientation quaternion {x, y, z, w}, angular velocity, linear acceleration, header stamp).
+ * From the first message on, loam_extract / loam_extract_device de-skew every kept point of a sweep with the IMU
+ * values interpolated at the point's own time (SR:364-434, SR:121-184: a kernel in front of the ring bucketing; `stamp`
+ * = the sweep's header stamp, timeScanCur SR:257) and compute /imu_trans themselves (loam_get_imu_trans: the 12 floats
+ * as published SR:730-745; they replace a caller-supplied imu_trans and feed the odometry of the same handle).
+ * Stated assumption: the stamps in the 200-message ring increase with the ring order (as IMU streams do). */
+int loam_imu_push(loam_handle* h, double stamp, const double orientation_xyzw[4], const double angular_velocity[3],
+                  const double linear_acceleration[3]);
+int loam_get_imu_trans(loam_handle* h, float out12[12]);
 int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* Batched form of loam_extract (SURVEY 8b `*_batch`): one sweep of each of B independent sequences (B handles on the same
  * device, same n_scans).  Every extraction kernel is launched ONCE for the whole batch (grid.y = sequence) and the counts

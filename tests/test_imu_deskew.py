@@ -78,3 +78,55 @@ def test_oracle_imu_branch_matches_reference(orc, seed):
                 assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_sweeps, name)
             n_sweeps += 1
     assert n_sweeps == 10 and np.abs(otr).max() > 1e-3  # the de-skew did something
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1])
+def test_gpu_imu_deskew_equals_oracle(orc, seed):
+    """loam_imu_push (host: imuHandler + AccumulateIMUShift) + loam_extract with the de-skew kernel (prefix-max scans in
+    place of the reference's point-to-point state) against the oracle: all five clouds and /imu_trans bit for bit."""
+    from gpscalibration_b200 import LoamGpu
+    gpu = LoamGpu()
+    o = orc.ScanRegistration()
+    n_sweeps = 0
+    for ev in scenario(seed):
+        if ev[0] == "imu":
+            gpu.imu_push(*ev[1:])
+            o.imu(*ev[1:])
+        else:
+            _, stamp, xyz = ev
+            c = gpu.extract(xyz, stamp)
+            oc, otr = o.extract_imu(xyz, stamp)
+            assert (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat) == tuple(oc[k].shape[0] for k in o.CLOUDS), n_sweeps
+            gtr = gpu.imu_trans()
+            assert np.array_equal(gtr.view(np.uint32), otr.view(np.uint32)), (n_sweeps, gtr, otr)
+            for name in o.CLOUDS:
+                a, b = gpu.cloud(name), oc[name]
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_sweeps, name)
+            n_sweeps += 1
+    assert n_sweeps == 10
+    gpu.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_runs_with_imu():
+    """The whole path with IMU messages: the de-skewed clouds and /imu_trans feed odometry and mapping of the same handle
+    (LO:201-225, 566-568, 1053-1064 use the 12 floats); without messages nothing changes."""
+    from gpscalibration_b200 import LoamGpu
+    with_imu, without = LoamGpu(), LoamGpu()
+    last = None
+    for ev in scenario(0):
+        if ev[0] == "imu":
+            with_imu.imu_push(*ev[1:])
+        else:
+            _, stamp, xyz = ev
+            a = with_imu.process_sweep(xyz, stamp)
+            b = without.process_sweep(xyz, stamp)
+            last = (a, b)
+    a, b = last
+    assert a.odom.odom_published and b.odom.odom_published
+    assert np.isfinite(np.array(a.odom.transform_sum)).all()
+    assert list(a.odom.transform_sum) != list(b.odom.transform_sum)  # the IMU prior and the de-skew changed the registration
+    assert np.abs(with_imu.imu_trans()).max() > 1e-3 and np.abs(without.imu_trans()).max() == 0.0
+    with_imu.close()
+    without.close()
