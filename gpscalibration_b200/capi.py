@@ -61,7 +61,7 @@ SYMBOLS = ["loam_strerror", "loam_last_cuda_error", "loam_default_params", "loam
            "loam_odom_get_corr", "loam_transform_to_end", "loam_map_set_inputs", "loam_map_iter", "loam_map_get_corr",
            "loam_gn_solve", "loam_map_iter_partial", "loam_map_finish_reduced", "loam_shard_export", "loam_shard_connect", "loam_shard_set_slab", "loam_shard_inject",
            "loam_map_iter_allreduce", "loam_map_optimize", "loam_pipeline_create", "loam_pipeline_destroy",
-           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_batch", "loam_pipeline_submit_lockstep", "loam_pipeline_submit_device", "loam_pipeline_wait", "loam_pipeline_pending",
+           "loam_pipeline_reset", "loam_pipeline_last_error", "loam_pipeline_submit", "loam_pipeline_submit_batch", "loam_pipeline_submit_lockstep", "loam_pipeline_submit_device", "loam_pipeline_imu_push", "loam_pipeline_wait", "loam_pipeline_pending",
            "loam_pipeline_stream",
            "loam_pipeline_stats", "loam_pipeline_stage_times", "loam_pipeline_handle", "loam_replay_segments", "loam_track_svd3", "loam_track_speed_weights", "loam_track_residual_weights",
            "loam_track_icp", "loam_track_smooth", "loam_track_calibrate", "loam_track_calibrate_long"]
@@ -150,6 +150,7 @@ def load_library():
     lib.loam_pipeline_last_error.argtypes = [vp]
     lib.loam_pipeline_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     lib.loam_pipeline_submit_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
+    lib.loam_pipeline_imu_push.argtypes = [vp, C.c_double, vp, vp, vp]
     lib.loam_pipeline_submit_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     lib.loam_pipeline_submit_lockstep.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     lib.loam_pipeline_wait.argtypes = [vp, C.POINTER(SweepResult)]
@@ -502,6 +503,11 @@ class LoamGpuPipeline:
         self._check(self.lib.loam_pipeline_submit(self._h, xyz.ctypes.data, xyz.shape[0], xyz.strides[0] if xyz.shape[0] > 1 else 12, stamp),
                     "loam_pipeline_submit")
 
+    def imu_push(self, stamp, quat_xyzw, angular_velocity, linear_acceleration):
+        """loam_pipeline_imu_push: one /imu/data message, applied in submission order with the sweeps."""
+        q, a, l = (np.ascontiguousarray(v, np.float64) for v in (quat_xyzw, angular_velocity, linear_acceleration))
+        self._check(self.lib.loam_pipeline_imu_push(self._h, float(stamp), q.ctypes.data, a.ctypes.data, l.ctypes.data), "loam_pipeline_imu_push")
+
     def submit_device(self, dev_ptr, n, stride_bytes=12, stamp=0.0):
         self._check(self.lib.loam_pipeline_submit_device(self._h, dev_ptr, n, stride_bytes, stamp), "loam_pipeline_submit_device")
 
@@ -549,7 +555,7 @@ class LoamGpuPipeline:
         return dict(launches=out[0], h2d_bytes=out[1], d2h_bytes=out[2], syncs=out[3])
 
 
-def pipeline_submit_batch(pipes, sweeps, stride_bytes=12, lockstep=False):
+def pipeline_submit_batch(pipes, sweeps, stride_bytes=12, lockstep=False, stamps=None):
     """loam_pipeline_submit_batch: one sweep per LoamGpuPipeline, the extraction of all of them in one batched launch chain;
     lockstep=True (loam_pipeline_submit_lockstep) batches the scan-to-scan odometry as well."""
     B = len(pipes)
@@ -558,7 +564,8 @@ def pipeline_submit_batch(pipes, sweeps, stride_bytes=12, lockstep=False):
     ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
     ns = (C.c_int * B)(*[a.shape[0] for a in arrs])
     fn = load_library().loam_pipeline_submit_lockstep if lockstep else load_library().loam_pipeline_submit_batch
-    rc = fn(ps, B, ptrs, ns, stride_bytes, None)
+    st = (C.c_double * B)(*[float(t) for t in stamps]) if stamps is not None else None
+    rc = fn(ps, B, ptrs, ns, stride_bytes, st)
     if rc:
         raise LoamError(rc, "loam_pipeline_submit_lockstep" if lockstep else "loam_pipeline_submit_batch", load_library().loam_last_cuda_error(None).decode())
 

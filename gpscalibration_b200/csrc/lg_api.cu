@@ -2216,7 +2216,7 @@ struct Sem {
     cv.notify_one();
   }
 };
-enum { JOB_SWEEP = 0, JOB_RESET = 1, JOB_STOP = 2 };
+enum { JOB_SWEEP = 0, JOB_RESET = 1, JOB_STOP = 2, JOB_IMU = 3 };
 struct Job {
   long long k;
   int kind;
@@ -2228,6 +2228,8 @@ struct Job {
   long long epoch;    // number of loam_pipeline_reset calls before this job: an error only poisons its own epoch
   int pre;            // the sweep was extracted by loam_pipeline_submit_batch already: stage A only hands the clouds on
   loam_counts counts;
+  double stamp;       // header stamp of the sweep (timeScanCur SR:257) or of the IMU message
+  double imu_msg[10]; // JOB_IMU: orientation {x, y, z, w}, angular velocity, linear acceleration
 };
 constexpr int PNS = 4;  // slots per ring
 
@@ -2243,6 +2245,7 @@ struct loam_pipeline {
   struct Feat {
     DevBuf b[5];
     loam_counts c;
+    float imu[12];  // /imu_trans of the sweep (SR:730-745), consumed by the odometry stage (LO:201-225, 566-568, 1053-1064)
     cudaEvent_t ready, consumed;
   } feat[PNS];
   struct MapIn {
@@ -2266,6 +2269,7 @@ struct loam_pipeline {
   char err_text[512] = "";
   long long resets_pushed = 0, resets_at_b = 0;  // loam_pipeline_reset calls / those the odometry stage has seen (guarded by rm)
   long long pre_submitted = 0, pre_handled = 0;  // batch-extracted sweeps pushed / handed on by stage A (guarded by rm)
+  long long imu_pushed = 0, imu_handled = 0;     // loam_pipeline_imu_push calls / those stage A has applied (guarded by rm)
   double busy[3] = {0, 0, 0};  // seconds each stage thread spent working on sweeps (not waiting for its queue / a free slot)
   std::thread tA, tB, tC, tD;
 };
@@ -2290,6 +2294,15 @@ void stage_a(loam_pipeline* p) {
   loam_handle* h = p->hA;
   for (;;) {
     Job j = p->qA.pop();
+    if (j.kind == JOB_IMU) {  // imuHandler SR:754-837, in submission order with the sweeps
+      loam_imu_push(h, j.stamp, j.imu_msg, j.imu_msg + 4, j.imu_msg + 7);
+      {
+        std::lock_guard<std::mutex> l(p->rm);
+        p->imu_handled++;
+      }
+      p->rcv.notify_all();
+      continue;
+    }
     if (j.kind != JOB_SWEEP) {
       p->qB.push(j);
       if (j.kind == JOB_STOP) return;
@@ -2304,7 +2317,7 @@ void stage_a(loam_pipeline* p) {
     } else if (!rc) {
       if (j.slot >= 0) cudaStreamWaitEvent(h->st, p->in_copied[j.slot], 0);
       g_lg_prof = h->prof.on ? &h->prof : nullptr;
-      rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c);
+      rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c, j.stamp);
     }
     if (j.slot >= 0) p->in_free.release();  // extract_common synchronised: the input slot is free again
     p->busy[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
@@ -2313,6 +2326,7 @@ void stage_a(loam_pipeline* p) {
     loam_pipeline::Feat& f = p->feat[fs];
     if (!rc) {
       f.c = c;
+      memcpy(f.imu, h->imu, sizeof(f.imu));
       const void* src[5] = {h->cur_full, h->cur_sharp, h->cur_less_sharp, h->cur_flat, h->cur_less_flat};
       const int cnt[5] = {c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat};
       cudaStreamWaitEvent(h->st, f.consumed, 0);  // odometry of the sweep that used this slot has finished reading it
@@ -2367,6 +2381,7 @@ void stage_b(loam_pipeline* p) {
       h->cur_less_sharp = f.b[2].as<float4>();
       h->cur_flat = f.b[3].as<float4>();
       h->cur_less_flat = f.b[4].as<float4>();
+      memcpy(h->imu, f.imu, sizeof(f.imu));
       h->have_features = true;
       rc = loam_odometry_process(h, &o);
       cudaEventRecord(f.consumed, h->st);
@@ -2615,7 +2630,7 @@ const char* loam_pipeline_last_error(loam_pipeline* p) {
   return buf;
 }
 
-static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride_bytes, bool host) {
+static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride_bytes, bool host, double stamp) {
   // any point_step >= 12 and any alignment is accepted, like loam_extract: extract_common repacks unaligned layouts
   if (!p || n < 0 || (!xyz && n > 0) || stride_bytes < 12) return LOAM_EINVAL;
   long long epoch;
@@ -2633,6 +2648,7 @@ static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride
   j.slot = -1;
   j.xyz = xyz;
   j.epoch = epoch;
+  j.stamp = stamp;
   if (host) {
     p->in_free.acquire();
     const int s = (int)(p->in_count % PNS);  // the slot is only taken once the copy has succeeded
@@ -2663,11 +2679,29 @@ static int pipeline_submit(loam_pipeline* p, const float* xyz, int n, int stride
   p->qA.push(j);
   return LOAM_OK;
 }
-int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double) {
-  return pipeline_submit(p, xyz_host, n, stride_bytes, true);
+int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double stamp) {
+  return pipeline_submit(p, xyz_host, n, stride_bytes, true, stamp);
 }
-int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double) {
-  return pipeline_submit(p, xyz_dev, n, stride_bytes, false);
+int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp) {
+  return pipeline_submit(p, xyz_dev, n, stride_bytes, false, stamp);
+}
+// One /imu/data message for the pipeline's extraction stage (loam_imu_push), applied in submission order: sweeps submitted
+// before it do not see it, sweeps submitted after it do -- the pipelined results equal the blocking calls'.
+int loam_pipeline_imu_push(loam_pipeline* p, double stamp, const double* orientation_xyzw, const double* angular_velocity,
+                           const double* linear_acceleration) {
+  if (!p || !orientation_xyzw || !angular_velocity || !linear_acceleration) return LOAM_EINVAL;
+  Job j;
+  memset(&j, 0, sizeof(j));
+  j.kind = JOB_IMU;
+  j.stamp = stamp;
+  for (int i = 0; i < 4; i++) j.imu_msg[i] = orientation_xyzw[i];
+  for (int i = 0; i < 3; i++) j.imu_msg[4 + i] = angular_velocity[i], j.imu_msg[7 + i] = linear_acceleration[i];
+  {
+    std::lock_guard<std::mutex> l(p->rm);
+    p->imu_pushed++;
+  }
+  p->qA.push(j);
+  return LOAM_OK;
 }
 
 // One sweep for each of B pipelines (independent sequences on one device): the extraction of all B sweeps is done here, in
@@ -2684,7 +2718,7 @@ int loam_pipeline_submit_batch(loam_pipeline* const* ps, int B, const float* con
     std::unique_lock<std::mutex> l(ps[b]->rm);
     epochs[b] = ps[b]->epoch;
     // stage A must have handed on the previous batch's clouds before they are overwritten
-    ps[b]->rcv.wait(l, [&] { return ps[b]->pre_handled == ps[b]->pre_submitted; });
+    ps[b]->rcv.wait(l, [&] { return ps[b]->pre_handled == ps[b]->pre_submitted && ps[b]->imu_handled == ps[b]->imu_pushed; });
   }
   for (int b = 0; b < B; b++)
     if (int e = pipe_error(ps[b], epochs[b])) return e;
@@ -2728,7 +2762,9 @@ int loam_pipeline_submit_lockstep(loam_pipeline* const* ps, int B, const float* 
     hB[b] = ps[b]->hB;
     std::unique_lock<std::mutex> l(ps[b]->rm);
     // a reset travels through the stage threads: the odometry handle is only touched here once it has arrived
-    ps[b]->rcv.wait(l, [&] { return ps[b]->resets_at_b == ps[b]->resets_pushed && ps[b]->pre_handled == ps[b]->pre_submitted; });
+    ps[b]->rcv.wait(l, [&] {
+      return ps[b]->resets_at_b == ps[b]->resets_pushed && ps[b]->pre_handled == ps[b]->pre_submitted && ps[b]->imu_handled == ps[b]->imu_pushed;
+    });
     epochs[b] = ps[b]->epoch;
   }
   for (int b = 0; b < B; b++)
@@ -2741,7 +2777,7 @@ int loam_pipeline_submit_lockstep(loam_pipeline* const* ps, int B, const float* 
     h->counts = counts[b];
     h->cur_full = a->cur_full; h->cur_sharp = a->cur_sharp; h->cur_less_sharp = a->cur_less_sharp;
     h->cur_flat = a->cur_flat; h->cur_less_flat = a->cur_less_flat;
-    for (int i = 0; i < 12; i++) h->imu[i] = 0.f;
+    for (int i = 0; i < 12; i++) h->imu[i] = a->imu[i];
     h->have_features = true;
   }
   std::vector<loam_odom_result> od(B);

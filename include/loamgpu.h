@@ -290,6 +290,12 @@ const char* loam_pipeline_last_error(loam_pipeline* p);
 int loam_pipeline_submit(loam_pipeline* p, const float* xyz_host, int n, int stride_bytes, double stamp);
 /* device-resident sweep: the buffer must stay valid until the sweep's result has been returned */
 int loam_pipeline_submit_device(loam_pipeline* p, const float* xyz_dev, int n, int stride_bytes, double stamp);
+/* loam_imu_push for a pipeline (imuHandler SR:754-837): applied by the extraction stage in submission order -- sweeps
+ * submitted before the message do not see it, sweeps submitted after it do; `stamp` of the submit calls is timeScanCur
+ * (SR:257).  /imu_trans travels with the features to the odometry stage (LO:201-225, 566-568, 1053-1064).  Results equal
+ * loam_imu_push + loam_process_sweep on one handle. */
+int loam_pipeline_imu_push(loam_pipeline* p, double stamp, const double orientation_xyzw[4], const double angular_velocity[3],
+                           const double linear_acceleration[3]);
 /* One sweep for each of B pipelines (B independent sequences on one device) with the extraction batched: the B sweeps go
  * through loam_extract_batch in the caller's thread (one launch per extraction kernel for the whole batch), every
  * pipeline's own stages do the rest.  Per-pipeline results are those of loam_pipeline_submit; collect them with

@@ -130,3 +130,35 @@ def test_gpu_pipeline_runs_with_imu():
     assert np.abs(with_imu.imu_trans()).max() > 1e-3 and np.abs(without.imu_trans()).max() == 0.0
     with_imu.close()
     without.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["submit", "batch", "lockstep"])
+def test_gpu_pipelined_imu_equals_blocking(mode):
+    """loam_pipeline_imu_push: the messages are applied by the extraction stage in submission order and /imu_trans travels
+    with the features to the odometry stage -- every result field of the pipelined modes equals loam_imu_push +
+    loam_process_sweep on one handle."""
+    from gpscalibration_b200 import LoamGpu, LoamGpuPipeline
+    from gpscalibration_b200.capi import pipeline_submit_batch
+    blocking, pipe = LoamGpu(want_registered=1, want_surround=1), LoamGpuPipeline(want_registered=1, want_surround=1)
+    want, n = [], 0
+    for ev in scenario(1):
+        if ev[0] == "imu":
+            blocking.imu_push(*ev[1:])
+            pipe.imu_push(*ev[1:])
+        else:
+            _, stamp, xyz = ev
+            want.append(blocking.process_sweep(xyz, stamp))
+            if mode == "submit":
+                pipe.submit(xyz, stamp)
+            else:
+                pipeline_submit_batch([pipe], [xyz], lockstep=(mode == "lockstep"), stamps=[stamp])
+            n += 1
+    got = [pipe.wait() for _ in range(n)]
+    moved = False
+    for k, (a, b) in enumerate(zip(want, got)):
+        assert bytes(a) == bytes(b), (mode, k)
+        moved = moved or any(abs(v) > 1e-3 for v in a.odom.transform_sum)
+    assert moved
+    blocking.close()
+    pipe.close()
