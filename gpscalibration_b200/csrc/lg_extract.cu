@@ -6,8 +6,8 @@
 //   sr_scan_kernel     SR:444-447  exclusive scan of (ring, CTA) counts -> ring-major offsets (stable bucket by ring)
 //   sr_scatter_kernel  SR:340-362,436  relTime / intensity, stable scatter to the ring-major float4 cloud
 //   sr_curv_kernel     SR:454-549  11-tap curvature, ring bounds, occlusion / parallel-beam conditions, gap flags
-//   sr_select_kernel   SR:559-675  one CTA per ring: per-sector stable sort (shared-memory bitonic on (curvature,
-//                                  index) keys) + the sequential greedy pick with +-5 suppression
+//   sr_select_kernel   SR:559-675  one CTA per ring: per-sector stable sort as ranks (counting) + the greedy pick with +-5
+//                                  suppression resolved in index space (dominator rounds instead of a serial walk)
 //   sr_collect_kernel  SR:587-633  compacts the picks into the four feature clouds, sets up the per-ring voxel jobs
 //   (lg_vox_small)     SR:677-683  per-ring 0.2 m voxel grid of the less-flat points
 //   sr_concat_kernel   SR:683      concatenates the per-ring results
@@ -328,23 +328,263 @@ __device__ __forceinline__ unsigned char suppress_reach(const unsigned char* s_c
 }
 
 constexpr int SEL_NT = 512;
+constexpr int SEL_WORDS = SEL_CAP / 32 + 2;  // candidate bit sets of one sector, one guard word on either side
+// dynamic shared memory of sr_select_kernel: curvature key (4 B), rank / walk order / dominator mask (2 B each) per ring point
+constexpr int SEL_SMEM = RING_CAP * (4 + 2 + 2 + 2);
+#ifdef LG_SEL_DEBUG  // phase stamps of ring 1's CTA (tools/probe/sel_time.py): cycles in setup / ranks / dominators / rounds / numbering
+__device__ long long g_sel_dbg[8];
+#define SEL_STAMP(k) do { const long long t_ = clock64(); dbg_acc[k] += t_ - dbg_t; dbg_t = t_; } while (0)
+#define SEL_DBG_ARGS dbg_acc, dbg_t
+#else
+#define SEL_STAMP(k) do { } while (0)
+#define SEL_DBG_ARGS nullptr, sel_dbg_dummy
+#endif
 
-// One CTA per ring.  The six sectors' (curvature, index) keys are sorted TOGETHER (one shared-memory bitonic network
-// over six padded segments: the keys do not depend on the picks, and six independent compare-exchanges per thread and
-// step hide the shared-memory latency a single 300-key sort cannot), then warp 0 replays the reference's greedy walk
-// sector after sector, 32 candidates at a time: every lane knows its candidate's suppression interval, and the
-// sequential "picked earlier => suppress neighbours" dependency inside a batch is resolved with ballots.
+// SR:568-576 as ranks: the position of every point in its sector's stable sort = the number of keys (curvature bits,
+// index) below its own.  One work item = four points of a sector (they share the key stream).  The fast form compares the
+// 31-bit curvature keys alone (one subtract, one shift-accumulate per pair); equal curvatures make ranks collide, which the
+// caller detects (an order slot stays empty) and then repeats the pass with EXACT = true (index as tie-break).
+template <bool EXACT>
+__device__ __forceinline__ void sel_rank_pass(const unsigned int* s_key, unsigned short* s_rank, unsigned short* s_sorted,
+                                              const int* s_spl, const int* s_m, const int* s_qoff) {
+  for (int item = threadIdx.x; item < s_qoff[6]; item += SEL_NT) {
+    int j = 0;
+    while (item >= s_qoff[j + 1]) j++;
+    const int m = s_m[j], spl = s_spl[j], Q = (m + 3) >> 2, q = item - s_qoff[j];
+    const unsigned int* sk = s_key + spl;
+    const int t0 = q, t1 = q + Q, t2 = q + 2 * Q, t3 = q + 3 * Q;
+    const unsigned int k0 = sk[t0], k1 = t1 < m ? sk[t1] : 0u, k2 = t2 < m ? sk[t2] : 0u, k3 = t3 < m ? sk[t3] : 0u;
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll 8
+    for (int t = 0; t < m; t++) {
+      const unsigned int k = sk[t];
+      if (EXACT) {
+        r0 += (k < k0) || (k == k0 && t < t0);
+        r1 += (k < k1) || (k == k1 && t < t1);
+        r2 += (k < k2) || (k == k2 && t < t2);
+        r3 += (k < k3) || (k == k3 && t < t3);
+      } else {  // keys are below 2^31: the sign of the difference is the comparison
+        r0 += (k - k0) >> 31;
+        r1 += (k - k1) >> 31;
+        r2 += (k - k2) >> 31;
+        r3 += (k - k3) >> 31;
+      }
+    }
+    s_rank[spl + t0] = (unsigned short)r0;
+    s_sorted[spl + r0] = (unsigned short)(spl + t0);
+    if (t1 < m) s_rank[spl + t1] = (unsigned short)r1, s_sorted[spl + r1] = (unsigned short)(spl + t1);
+    if (t2 < m) s_rank[spl + t2] = (unsigned short)r2, s_sorted[spl + r2] = (unsigned short)(spl + t2);
+    if (t3 < m) s_rank[spl + t3] = (unsigned short)r3, s_sorted[spl + r3] = (unsigned short)(spl + t3);
+  }
+}
+
+// Named barrier of the warps that run the walks (the others wait at the CTA barrier behind them).
+__device__ __forceinline__ void sel_bar(int nthr) { asm volatile("barrier.sync 1, %0;" ::"r"(nthr) : "memory"); }
+__device__ __forceinline__ bool sel_bar_or(int nthr, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, 1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"((int)pred), "r"(nthr)
+      : "memory");
+  return r != 0;
+}
+
+// The twelve walks of a ring (six sectors, sharp then flat) on bit sets; NCH = sector points per thread (1: sectors of up
+// to SEL_NT points, the usual case; 4: up to SEL_CAP).  Run by the first nthr / 32 warps of the CTA.  See the kernel's
+// header for the scheme.  s_sb: IN candidates by walk position (set when a candidate turns IN) -> pick numbers by popcount.
+template <int NCH>
+__device__ __forceinline__ void sel_walks(const unsigned short* s_rank, const unsigned short* s_dom, const unsigned char* s_reach,
+                                          unsigned char* s_picked, signed char* s_label, unsigned int (*s_bits)[2][SEL_WORDS],
+                                          unsigned int* s_sb, int (*s_base)[3], const int* s_spl, const int* s_m, int a, int* my_picks,
+                                          int nthr, int* phases_out, long long* dbg_acc, long long& dbg_t) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int phase = 0;
+  for (int j = 0; j < 6; j++) {
+    const int m = s_m[j];
+    if (m <= 0) continue;
+    const int spl = s_spl[j], nw = (m + 31) >> 5;
+    unsigned int d_lo[NCH], d_mid[NCH], d_hi[NCH];  // the point's dominators as masks of its own and the two adjacent words
+    int rk[NCH];
+    unsigned int kinds[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int t = c * SEL_NT + tid;
+      const unsigned int dm = t < m ? s_dom[spl + t] : 0u;
+      rk[c] = t < m ? s_rank[spl + t] : 0;
+      kinds[c] = dm >> 11;
+      const unsigned long long x = (unsigned long long)(dm & 0x7ffu) << (lane + 27);  // window bit k <-> position lane + k - 5
+      d_lo[c] = (unsigned int)x;
+      d_mid[c] = (unsigned int)(x >> 32);
+      d_hi[c] = lane >= 27 ? (dm & 0x7ffu) >> (37 - lane) : 0u;
+    }
+    for (int kind = 0; kind < 2; kind++, phase++) {  // 0: SR:578-624 from the largest curvature down, 1: SR:626-668 from the smallest up
+      int cur = 0;
+      bool have = false;
+      int pos[NCH];
+      bool is_in[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {  // candidates of this walk that no earlier pick has marked
+        const int t = c * SEL_NT + tid;
+        pos[c] = kind == 0 ? m - 1 - rk[c] : rk[c];
+        is_in[c] = false;
+        if (c * SEL_NT + (warp << 5) < m) {
+          const bool cand = t < m && ((kinds[c] >> kind) & 1u) && s_picked[spl + t] == 0;
+          const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+          if (lane == 0) {
+            s_bits[0][0][(t >> 5) + 1] = 0u;
+            s_bits[0][1][(t >> 5) + 1] = bal;
+          }
+          have |= bal != 0u;
+        }
+      }
+      if (tid < 8) s_bits[tid >> 2][(tid >> 1) & 1][(tid & 1) ? nw + 1 : 0] = 0u;  // guard words of both buffers
+      for (int w = tid; w < (NCH == 1 ? SEL_NT / 32 : nw); w += nthr) s_sb[w] = 0u;
+      const bool any_cand = sel_bar_or(nthr, have);
+      SEL_STAMP(2);
+      if (!any_cand) {
+        if (tid == 0) s_base[phase + 1][0] = s_base[phase][0], s_base[phase + 1][1] = s_base[phase][1], s_base[phase + 1][2] = s_base[phase][2];
+        continue;
+      }
+      for (;;) {  // one round: every undecided candidate looks at its dominators' state of the previous round
+        bool und = false;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          if (c * SEL_NT + (warp << 5) >= m) continue;  // warp-uniform
+          const int w = c * (SEL_NT / 32) + warp + 1;
+          const unsigned int i_lo = s_bits[cur][0][w - 1], i_hi = s_bits[cur][0][w + 1];
+          const unsigned int u_lo = s_bits[cur][1][w - 1], u_hi = s_bits[cur][1][w + 1];
+          unsigned int i_mid = s_bits[cur][0][w], u_mid = s_bits[cur][1][w];
+          // the warp's own 32 points may resolve several steps of a chain on what it already knows (the neighbour words
+          // keep the previous round's state, which is only ever less decided)
+          for (int sub = 0; sub < 4; sub++) {
+            const bool mine = (u_mid >> lane) & 1u;
+            const unsigned int in_hit = (i_lo & d_lo[c]) | (i_mid & d_mid[c]) | (i_hi & d_hi[c]);
+            const unsigned int un_hit = (u_lo & d_lo[c]) | (u_mid & d_mid[c]) | (u_hi & d_hi[c]);
+            const bool to_out = mine && in_hit != 0u;
+            const bool to_in = mine && (in_hit | un_hit) == 0u;
+            const unsigned int b_in = __ballot_sync(0xffffffffu, to_in), b_out = __ballot_sync(0xffffffffu, to_out);
+            if (to_in) {
+              is_in[c] = true;
+              atomicOr(&s_sb[pos[c] >> 5], 1u << (pos[c] & 31));
+            }
+            i_mid |= b_in;
+            u_mid &= ~(b_in | b_out);
+            if (u_mid == 0u || (b_in | b_out) == 0u) break;  // warp-uniform
+          }
+          const unsigned int n_und = u_mid;
+          if (lane == 0) {
+            s_bits[cur ^ 1][0][w] = i_mid;
+            s_bits[cur ^ 1][1][w] = n_und;
+          }
+          und |= n_und != 0u;
+        }
+        cur ^= 1;
+#ifdef LG_SEL_DEBUG
+        dbg_acc[6]++;
+#endif
+        if (!sel_bar_or(nthr, und)) break;
+      }
+      SEL_STAMP(3);
+      // the pick number = position among the IN candidates in walk order; the count limit keeps a prefix, and only kept
+      // picks leave marks
+      const int keep = kind == 0 ? 20 : 32, marking = kind == 0 ? 20 : 31;
+      const int base_sharp = s_base[phase][0], base_less = s_base[phase][1], base_flat = s_base[phase][2];
+      int total = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        int num = 1;
+        const int pw = pos[c] >> 5;
+        const unsigned int low = (1u << (pos[c] & 31)) - 1u;
+        if (NCH == 1) {  // sixteen words at most: independent loads, no serial loop (words beyond the sector are zero)
+          if (__any_sync(0xffffffffu, is_in[c]) || tid == 0) {
+#pragma unroll
+            for (int w = 0; w < SEL_NT / 32; w++) {
+              const unsigned int x = s_sb[w];
+              total += __popc(x);
+              num += __popc(x & (w < pw ? 0xffffffffu : (w == pw ? low : 0u)));
+            }
+          }
+        } else {
+          if (is_in[c]) {
+            num += __popc(s_sb[pw] & low);
+            for (int w = 0; w < pw; w++) num += __popc(s_sb[w]);
+          }
+          if (tid == 0 && c == 0)
+            for (int w = 0; w < nw; w++) total += __popc(s_sb[w]);
+        }
+        if (!is_in[c] || num > keep) continue;
+        const int li = spl + c * SEL_NT + tid;
+        if (kind == 0) {
+          if (num <= 16) {
+            s_label[li] = 2;
+            my_picks[SR_PICK_SHARP + base_sharp + num - 1] = li + a;
+          } else {
+            s_label[li] = 1;
+          }
+          my_picks[SR_PICK_LESS + base_less + num - 1] = li + a;
+        } else {
+          s_label[li] = -1;
+          my_picks[SR_PICK_FLAT + base_flat + num - 1] = li + a;
+        }
+        if (num <= marking) {  // SR:635-638: the 32nd flat point is kept but neither marked nor suppressing
+          const unsigned char rr = s_reach[li];
+          const int nf = rr & 15, nb = rr >> 4;
+#pragma unroll
+          for (int l = -5; l <= 5; l++)
+            if (l >= -nb && l <= nf) s_picked[li + l] = 1;
+        }
+      }
+      if (tid == 0) {
+        const int npick = min(total, keep);  // SR:592-594: the 21st sharp candidate only ends the walk
+        s_base[phase + 1][0] = base_sharp + (kind == 0 ? min(npick, 16) : 0);
+        s_base[phase + 1][1] = base_less + (kind == 0 ? npick : 0);
+        s_base[phase + 1][2] = base_flat + (kind == 0 ? 0 : npick);
+      }
+      sel_bar(nthr);
+      SEL_STAMP(4);
+    }
+  }
+  if (tid == 0) *phases_out = phase;
+}
+
+// One CTA per ring, no serial walk.  The reference sorts a sector by curvature and then walks it greedily ("take the
+// next candidate unless an earlier pick suppressed it", SR:578-668).  Both steps are restated in INDEX space:
+//   sort  -> ranks by counting (sel_rank_pass): no barriers, no exchanges;
+//   walk  -> a pick only suppresses points within +-5 of it, so whether a candidate is picked depends only on the
+//            candidates within +-5 that come EARLIER in the walk (better rank) and whose suppression span covers it: its
+//            "dominators", an 11-bit window mask fixed per point (a point is a candidate of exactly one of the two walks:
+//            curvature > 0.1 or < 0.1).  A candidate is picked iff no dominator is picked.  All candidates of a sector
+//            resolve this together in rounds on two bit sets (IN, UNDECIDED; one word per warp, neighbours read through
+//            a funnel shift): UNDECIDED -> IN once no dominator is IN or UNDECIDED, -> OUT as soon as one is IN.  The
+//            best-ranked undecided candidate always resolves; 3-4 rounds are typical.  By induction on the rank the result
+//            is the walk's pick set had it no count limit; the limit (16 + 4 sharp, 32 flat, SR:592-594, 635-638) cuts
+//            that set in walk order -- a prefix, since a pick never depends on later ones -- and only the kept picks
+//            leave marks for the next phase (flat after sharp, sector after sector, SR:561-668).
 __device__ __forceinline__ void sr_select_kernel_body(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                             const float* __restrict__ curv, const unsigned char* __restrict__ cond,
                                                             unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
                                                             signed char* __restrict__ label, int* __restrict__ picks,
                                                             int* __restrict__ sort_ind, unsigned char* __restrict__ stale) {
-  extern __shared__ unsigned long long skeys[];  // [6][P]
-  __shared__ unsigned char s_cond[RING_CAP];
+  extern __shared__ unsigned int s_key[];  // [RING_CAP] curvature bits (clamped below 2^31)
+  unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_key + RING_CAP);  // position of the point in its sector's sort
+  unsigned short* s_sorted = s_rank + RING_CAP;                                   // sector start + position -> local index
+  unsigned short* s_dom = s_sorted + RING_CAP;  // bit 5-d: li-d dominates, bit 5+d: li+d; bit 11 / 12: candidate of the sharp / flat walk
+  __shared__ unsigned char s_cond_raw[RING_CAP + 16];
   __shared__ unsigned char s_reach[RING_CAP];
   __shared__ unsigned char s_picked[RING_CAP];
   __shared__ signed char s_label[RING_CAP];
-  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  __shared__ unsigned int s_bits[2][2][SEL_WORDS];  // [buffer][IN, UNDECIDED][guard + word of 32 sector points]
+  __shared__ unsigned int s_sb[SEL_WORDS];  // IN candidates of the current walk by walk position
+  __shared__ int s_spl[6], s_m[6], s_qoff[7];
+  __shared__ int s_base[13][3];  // picks (sharp, less sharp, flat) of the ring before each of the twelve walks
+  __shared__ int s_phases;
+  unsigned char* s_cond = s_cond_raw + 8;  // [-8, len + 8): the flags of the points around the ring's range as well
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef LG_SEL_DEBUG
+  long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long dbg_t = clock64();
+#endif
   const int n = meta[SRM_N_FULL];
   const int R = prm.n_scans;
   const int S = (r == 0) ? 5 : meta[SRM_SCAN_START + r];         // SR:489
@@ -387,16 +627,17 @@ __device__ __forceinline__ void sr_select_kernel_body(SrParams prm, const float4
     }
     return;
   }
+  for (int x = tid - 8; x < len + 8; x += SEL_NT) {  // one global read per flag; the masks below come from shared memory
+    const int gi = a + x;
+    s_cond[x] = (gi >= 0 && gi < n) ? cond[gi] : (unsigned char)0;
+  }
   for (int li = tid; li < len; li += SEL_NT) {
-    unsigned char m = mask_at(cond, a + li, n);
-    s_cond[li] = cond[a + li];
-    s_picked[li] = m;
+    s_key[li] = min(__float_as_uint(curv[a + li]), 0x7fffffffu);
+    s_sorted[li] = 0xffffu;
     s_label[li] = 0;
-    mask_diag[a + li] = m;
   }
   // sector bounds (SR:561-562); a sector that does not fit is skipped and flagged, as before
   int sp6[6], m6[6];
-  int maxm = 2;
   bool too_big = false;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -409,143 +650,89 @@ __device__ __forceinline__ void sr_select_kernel_body(SrParams prm, const float4
     }
     sp6[j] = sp;
     m6[j] = max(m, 0);
-    maxm = max(maxm, m6[j]);
   }
-  int P = 2, lgP = 1;
-  while (P < maxm) P <<= 1, lgP++;
+  if (tid == 0) {
+    int q = 0;
 #pragma unroll
-  for (int j = 0; j < 6; j++)
-    for (int t = tid; t < P; t += SEL_NT)
-      skeys[j * P + t] = t < m6[j] ? (((unsigned long long)__float_as_uint(curv[sp6[j] + t]) << 32) | (unsigned int)(sp6[j] + t)) : ~0ull;
+    for (int j = 0; j < 6; j++) {
+      s_spl[j] = sp6[j] - a;
+      s_m[j] = m6[j];
+      s_qoff[j] = q;
+      q += (m6[j] + 3) >> 2;
+    }
+    s_qoff[6] = q;
+    s_base[0][0] = s_base[0][1] = s_base[0][2] = 0;
+    s_phases = 0;
+  }
   __syncthreads();
-  for (int li = tid; li < len; li += SEL_NT) s_reach[li] = suppress_reach(s_cond, li, len);
-  const int half = P >> 1;
-  for (int k = 2; k <= P; k <<= 1)
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int t = tid; t < 6 * half; t += SEL_NT) {
-        const int seg = t >> (lgP - 1), tt = t & (half - 1);
-        const int i = ((tt & ~(jj - 1)) << 1) | (tt & (jj - 1));
-        const int l = i | jj;
-        unsigned long long* sk = skeys + seg * P;
-        const unsigned long long x = sk[i], y = sk[l];
-        const bool asc = (i & k) == 0;
-        if ((x > y) == asc) {
-          sk[i] = y;
-          sk[l] = x;
-        }
-      }
+  for (int li = tid; li < len; li += SEL_NT) {  // cloudNeighborPicked after SR:492-549 (mask_at, from the staged flags)
+    unsigned char m = (s_cond[li] & C_C) ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j <= 5; j++) m |= (s_cond[li + j] & C_A) ? 1 : 0;
+#pragma unroll
+    for (int j = 1; j <= 6; j++) m |= (s_cond[li - j] & C_B) ? 1 : 0;
+    s_picked[li] = m;
+    mask_diag[a + li] = m;
+    s_reach[li] = suppress_reach(s_cond, li, len);
+  }
+  SEL_STAMP(0);
+  sel_rank_pass<false>(s_key, s_rank, s_sorted, s_spl, s_m, s_qoff);
+  __syncthreads();
+  {
+    int tie = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      for (int t = tid; t < m6[j]; t += SEL_NT) tie |= s_sorted[sp6[j] - a + t] == 0xffffu;
+    if (__syncthreads_or(tie)) {  // equal curvatures somewhere in the ring: the index decides (stable sort)
+      sel_rank_pass<true>(s_key, s_rank, s_sorted, s_spl, s_m, s_qoff);
       __syncthreads();
     }
-  int nsharp = 0, nless = 0, nflat = 0;
-  if (tid < 32) {
-    for (int j = 0; j < 6; j++) {
-      const int m = m6[j];
-      if (m <= 0) continue;
-      const unsigned long long* sk = skeys + j * P;
-      // ---- SR:578-624: walk down from the largest curvature
-      int count = 0;
-      bool done = false;
-      for (int k = m - 1; k >= 0 && !done; k -= 32) {
-        const int kk = k - lane;
-        const bool have = kk >= 0;
-        const unsigned long long key = have ? sk[kk] : 0ull;
-        const float cv = __uint_as_float((unsigned int)(key >> 32));
-        const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
-        const bool pass = have && (cv > 0.1);
-        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
-        int nf = 0, nb = 0;
-        if (pass) {
-          const unsigned char rr = s_reach[li];
-          nf = rr & 15;
-          nb = rr >> 4;
-        }
-        const int span = (li - nb) | ((li + nf) << 16);
-        const bool alive = pass && s_picked[li] == 0;
-        unsigned int am = __ballot_sync(0xffffffffu, alive);
-        int mynum = 0;
-        while (am) {
-          const int p = __ffs(am) - 1;
-          am &= ~(1u << p);
-          count++;
-          if (count > 20) {  // SR:592-594: the 21st candidate only ends the walk
-            done = true;
-            break;
-          }
-          if (lane == p) mynum = count;
-          const int ps = __shfl_sync(0xffffffffu, span, p);
-          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= (ps & 0xffff) && li <= (ps >> 16));
-        }
-        if (mynum > 0) {
-          const int ind = li + a;
-          if (mynum <= 16) {
-            s_label[li] = 2;
-            my_picks[SR_PICK_SHARP + nsharp + mynum - 1] = ind;
-          } else {
-            s_label[li] = 1;
-          }
-          my_picks[SR_PICK_LESS + nless + mynum - 1] = ind;
-          for (int l = -nb; l <= nf; l++) s_picked[li + l] = 1;
-        }
-        __syncwarp();
-        if (pm != 0xffffffffu) done = true;  // sorted: nothing below the first c <= 0.1 can pass
-      }
-      const int npick = min(count, 20);
-      nsharp += min(npick, 16);
-      nless += npick;
-      // ---- SR:626-668: walk up from the smallest curvature
-      count = 0;
-      done = false;
-      for (int k = 0; k < m && !done; k += 32) {
-        const int kk = k + lane;
-        const bool have = kk < m;
-        const unsigned long long key = have ? sk[kk] : 0ull;
-        const float cv = __uint_as_float((unsigned int)(key >> 32));
-        const int li = (int)(unsigned int)(key & 0xffffffffull) - a;
-        const bool pass = have && (cv < 0.1);
-        const unsigned int pm = __ballot_sync(0xffffffffu, pass);
-        int nf = 0, nb = 0;
-        if (pass) {
-          const unsigned char rr = s_reach[li];
-          nf = rr & 15;
-          nb = rr >> 4;
-        }
-        const int span = (li - nb) | ((li + nf) << 16);
-        const bool alive = pass && s_picked[li] == 0;
-        unsigned int am = __ballot_sync(0xffffffffu, alive);
-        int mynum = 0;
-        bool last32 = false;
-        while (am) {
-          const int p = __ffs(am) - 1;
-          am &= ~(1u << p);
-          count++;
-          if (lane == p) mynum = count;
-          if (count >= 32) {  // SR:635-638: the 32nd flat point is kept but neither marked nor suppressing
-            if (lane == p) last32 = true;
-            done = true;
-            break;
-          }
-          const int ps = __shfl_sync(0xffffffffu, span, p);
-          am &= ~__ballot_sync(0xffffffffu, alive && lane > p && li >= (ps & 0xffff) && li <= (ps >> 16));
-        }
-        if (mynum > 0) {
-          s_label[li] = -1;
-          my_picks[SR_PICK_FLAT + nflat + mynum - 1] = li + a;
-          if (!last32)
-            for (int l = -nb; l <= nf; l++) s_picked[li + l] = 1;
-        }
-        __syncwarp();
-        if (pm != 0xffffffffu) done = true;
-      }
-      nflat += count;
+  }
+  SEL_STAMP(1);
+  // dominators: which neighbours come earlier in the point's walk and reach it
+  for (int li = S - a + tid; li < E - a; li += SEL_NT) {
+    const int j = (li >= s_spl[1]) + (li >= s_spl[2]) + (li >= s_spl[3]) + (li >= s_spl[4]) + (li >= s_spl[5]);
+    const int spl = s_spl[j], epl = spl + s_m[j] - 1;
+    if (li < spl || li > epl) continue;  // a skipped sector
+    const float cv = __uint_as_float(s_key[li]);
+    const bool sharp = cv > 0.1, flat = cv < 0.1;
+    const int sgn = sharp ? 1 : -1, rk = s_rank[li] * sgn;  // sharp: larger rank first; flat: smaller rank first
+    unsigned int dom = 0;
+#pragma unroll
+    for (int d = 1; d <= 5; d++) {
+      const int lo = max(li - d, spl), hi = min(li + d, epl);
+      const int rl = s_rank[lo] * sgn, rh = s_rank[hi] * sgn;
+      const int xl = s_reach[lo] & 15, xh = s_reach[hi] >> 4;
+      const bool bl = (li - d >= spl) & (xl >= d) & (rl > rk);
+      const bool bh = (li + d <= epl) & (xh >= d) & (rh > rk);
+      dom |= (bl ? 1u : 0u) << (5 - d);
+      dom |= (bh ? 1u : 0u) << (5 + d);
+    }
+    s_dom[li] = (unsigned short)(dom | (sharp ? 1u << 11 : 0u) | (flat ? 1u << 12 : 0u));
+  }
+  __syncthreads();
+  SEL_STAMP(5);
+#ifndef LG_SEL_DEBUG
+  long long sel_dbg_dummy = 0;
+#endif
+  {
+    int maxm = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) maxm = max(maxm, m6[j]);
+    const int nwa = maxm <= SEL_NT ? max((maxm + 31) >> 5, 1) : SEL_NT / 32;  // warps that hold sector points
+    if (warp < nwa) {
+      if (maxm <= SEL_NT) sel_walks<1>(s_rank, s_dom, s_reach, s_picked, s_label, s_bits, s_sb, s_base, s_spl, s_m, a, my_picks, nwa * 32, &s_phases, SEL_DBG_ARGS);
+      else sel_walks<SEL_CAP / SEL_NT>(s_rank, s_dom, s_reach, s_picked, s_label, s_bits, s_sb, s_base, s_spl, s_m, a, my_picks, nwa * 32, &s_phases, SEL_DBG_ARGS);
     }
   }
   __syncthreads();
+  const int nsharp = s_base[s_phases][0], nless = s_base[s_phases][1], nflat = s_base[s_phases][2];
   for (int li = tid; li < len; li += SEL_NT) label[a + li] = s_label[li];
   if (any_virtual) {  // what a later, overlapping ring of the reference would find: pick flags and the sorted index order
     for (int li = tid; li < len; li += SEL_NT) picked[a + li] = s_picked[li];
 #pragma unroll
     for (int j = 0; j < 6; j++)
-      for (int t = tid; t < m6[j]; t += SEL_NT) sort_ind[sp6[j] + t] = (int)(unsigned int)(skeys[j * P + t] & 0xffffffffull);
+      for (int t = tid; t < m6[j]; t += SEL_NT) sort_ind[sp6[j] + t] = a + (int)s_sorted[sp6[j] - a + t];
   }
   // cloudNeighborPicked[0..4] is never re-initialised by the reference (SR:454 starts at 5): marks persist between sweeps
   if (a + tid < 5 && tid < len && s_picked[tid]) stale[a + tid] = 1;
@@ -555,6 +742,13 @@ __device__ __forceinline__ void sr_select_kernel_body(SrParams prm, const float4
     cnt[2] = nflat;
     if (too_big) atomicExch(&meta[SRM_ERR], 1);
   }
+  SEL_STAMP(5);
+#ifdef LG_SEL_DEBUG
+  if (blockIdx.x == 1 && blockIdx.y == 0 && tid == 0) {
+    for (int k = 0; k < 7; k++) g_sel_dbg[k] += dbg_acc[k];
+    g_sel_dbg[7]++;
+  }
+#endif
 }
 
 // Suppression reach with whole-cloud bounds (FENCE (iv) as in oracle/orc_sr.h suppress_neighbours).
@@ -1251,7 +1445,7 @@ int lg_extract_launch(SrWs& ws, const SrParams& prm, const float* d_xyz, int n, 
   {
   LgProfScope prof_scope(LGK_SR_SELECT, st, (double)n);
   static bool sel_attr[64] = {};  // the opt-in is per device
-  constexpr int sel_smem = 6 * SEL_CAP * 8;
+  constexpr int sel_smem = SEL_SMEM;
   int dev = 0;
   LG_CHECK(cudaGetDevice(&dev));
   if (!sel_attr[dev & 63]) {
@@ -1346,7 +1540,7 @@ int lg_extract_launch_batch(SrWs* const* ws, const SrParams* prm, const float* c
   LG_CHECK(cudaMemcpyAsync(tab.p, host.data(), (size_t)B * sizeof(SrK), cudaMemcpyHostToDevice, st));
   const SrK* d_tab = tab.as<SrK>();
   static bool sel_attr[64] = {};
-  constexpr int sel_smem = 6 * SEL_CAP * 8;
+  constexpr int sel_smem = SEL_SMEM;
   int dev = 0;
   LG_CHECK(cudaGetDevice(&dev));
   if (!sel_attr[dev & 63]) {
@@ -1388,3 +1582,15 @@ int lg_extract_launch_batch(SrWs* const* ws, const SrParams* prm, const float* c
   LG_CHECK(cudaStreamSynchronize(st));  // the tables above are host vectors
   return LOAM_OK;
 }
+
+#ifdef LG_SEL_DEBUG
+extern "C" int loam_debug_sel(long long* out8, int clear) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_sel_dbg, sizeof(long long) * 8);
+  if (clear) {
+    long long z[8] = {0};
+    cudaMemcpyToSymbol(g_sel_dbg, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -112,6 +112,27 @@ def test_extract_hdl64_parity(orc):
     gpu.close()
 
 
+def test_extract_dense_rings_large_sectors(gpu, orc):
+    """Rings of 4200 points (sectors of ~700: the multi-chunk form of the selection walks) and curvature ties (a
+    noise-free cylinder: equal curvatures -> the index decides, stable sort SR:568-576)."""
+    rng = np.random.default_rng(11)
+    per_ring, angles = 4200, np.array([-15, -13, -11, -9, -7, -5, -4, -3, -2, -1, 0, 1, 3, 5, 7, 9], np.float64)
+    az = np.linspace(0.0, 2 * np.pi, per_ring, endpoint=False)
+    cols = []
+    for k in range(per_ring):  # column-major like a spinning sensor: all rings at one azimuth, then the next
+        th = -az[k]
+        for e in angles:
+            rad = 8.0 + 2.5 * np.sin(3 * az[k]) + (0.6 if (k // 37) % 5 == 0 else 0.0)
+            if e > 4:
+                rad = 12.0  # noise-free cylinder: ties
+            else:
+                rad += rng.normal(0, 0.01)
+            cols.append((rad * np.cos(th), rad * np.sin(th), rad * np.tan(np.deg2rad(e))))
+    xyz = np.asarray(cols, np.float32)
+    ref = _check_extract(gpu, orc.ScanRegistration(), xyz)
+    assert ref["full"].shape[0] == xyz.shape[0] and ref["sharp"].shape[0] > 100
+
+
 def test_extract_empty_and_tiny(gpu, orc):
     c = gpu.extract(np.zeros((0, 3), np.float32))
     assert c.n_full == 0 and c.n_sharp == 0 and c.n_less_flat == 0
