@@ -2308,23 +2308,17 @@ void stage_a(loam_pipeline* p) {
       if (j.kind == JOB_STOP) return;
       continue;
     }
+    // the feature slot is taken BEFORE the extraction: the kernels write the five clouds straight into the slot's buffers
+    // (swapped into the workspace for the duration of the sweep), so nothing is copied between the two stages
+    p->feat_free.acquire();
+    const int fs = (int)(p->feat_count++ % PNS);
+    loam_pipeline::Feat& f = p->feat[fs];
     const auto t_busy0 = std::chrono::steady_clock::now();
     loam_counts c = {0, 0, 0, 0, 0};
     int rc = pipe_error(p, j.epoch);
     const bool skip_a = rc != 0;
     if (!rc && j.pre) {
       c = j.counts;  // extracted by loam_pipeline_submit_batch (one launch per kernel for all pipelines of the batch)
-    } else if (!rc) {
-      if (j.slot >= 0) cudaStreamWaitEvent(h->st, p->in_copied[j.slot], 0);
-      g_lg_prof = h->prof.on ? &h->prof : nullptr;
-      rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c, j.stamp);
-    }
-    if (j.slot >= 0) p->in_free.release();  // extract_common synchronised: the input slot is free again
-    p->busy[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
-    p->feat_free.acquire();
-    const int fs = (int)(p->feat_count++ % PNS);
-    loam_pipeline::Feat& f = p->feat[fs];
-    if (!rc) {
       f.c = c;
       memcpy(f.imu, h->imu, sizeof(f.imu));
       const void* src[5] = {h->cur_full, h->cur_sharp, h->cur_less_sharp, h->cur_flat, h->cur_less_flat};
@@ -2335,7 +2329,22 @@ void stage_a(loam_pipeline* p) {
         else if (cnt[i]) cudaMemcpyAsync(f.b[i].p, src[i], (size_t)cnt[i] * 16, cudaMemcpyDeviceToDevice, h->st);
       }
       cudaEventRecord(f.ready, h->st);
+    } else if (!rc) {
+      if (j.slot >= 0) cudaStreamWaitEvent(h->st, p->in_copied[j.slot], 0);
+      cudaStreamWaitEvent(h->st, f.consumed, 0);  // odometry of the sweep that used this slot has finished reading it
+      DevBuf* ws_out[5] = {&h->sr.full, &h->sr.sharp, &h->sr.less_sharp, &h->sr.flat, &h->sr.less_flat};
+      for (int i = 0; i < 5; i++) std::swap(*ws_out[i], f.b[i]);
+      g_lg_prof = h->prof.on ? &h->prof : nullptr;
+      rc = extract_common(h, j.xyz, j.n, j.stride, nullptr, &c, j.stamp);
+      for (int i = 0; i < 5; i++) std::swap(*ws_out[i], f.b[i]);  // the slot keeps the results, the workspace its other set
+      if (!rc) {
+        f.c = c;
+        memcpy(f.imu, h->imu, sizeof(f.imu));
+        cudaEventRecord(f.ready, h->st);
+      }
     }
+    if (j.slot >= 0) p->in_free.release();  // extract_common synchronised: the input slot is free again
+    p->busy[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_busy0).count();
     if (rc && !skip_a) pipe_fail(p, rc, j.epoch);
     {
       std::lock_guard<std::mutex> l(p->rm);

@@ -71,6 +71,11 @@ __device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs,
     if (tid == 0) *sg.out_count = 0;
     return;
   }
+  // small segments keep their points in shared memory: the segment is read from global memory once (the bounding-box
+  // pass), the key pass and the centroid gather -- a serial chain of dependent loads per voxel -- read the staged copy
+  constexpr bool STAGE = CAP <= 4096;
+  float4* s_pts = reinterpret_cast<float4*>(skeys + CAP);                      // [CAP] when STAGE
+  unsigned char* s_take = reinterpret_cast<unsigned char*>(s_pts + CAP);       // [CAP] when STAGE
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
   int cnt = 0;
   for (int i0 = tid; i0 < n; i0 += 4 * NT) {  // four loads in flight per thread
@@ -83,12 +88,17 @@ __device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs,
       if (i < n) p[u] = sg.in[i];
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++)
+    for (int u = 0; u < 4; u++) {
+      if (STAGE && i0 + u * NT < n) {
+        s_pts[i0 + u * NT] = p[u];
+        s_take[i0 + u * NT] = take[u];
+      }
       if (take[u]) {
         mn0 = fminf(mn0, p[u].x); mn1 = fminf(mn1, p[u].y); mn2 = fminf(mn2, p[u].z);
         mx0 = fmaxf(mx0, p[u].x); mx1 = fmaxf(mx1, p[u].y); mx2 = fmaxf(mx2, p[u].z);
         cnt++;
       }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -125,7 +135,12 @@ __device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs,
 #pragma unroll 4
   for (int i = tid; i < P; i += NT) {
     unsigned long long key = ~0ull;
-    if (i < n && (!sg.valid || sg.valid[i])) {
+    if (STAGE) {
+      if (i < n && s_take[i]) {
+        int cell = ok ? vox_cell(g, s_pts[i]) : i;
+        key = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
+      }
+    } else if (i < n && (!sg.valid || sg.valid[i])) {
       int cell = ok ? vox_cell(g, sg.in[i]) : i;
       key = ((unsigned long long)(unsigned int)cell << 32) | (unsigned int)i;
     }
@@ -159,7 +174,8 @@ __device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs,
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
       int j = i;
       while (j < nvalid && (unsigned int)(skeys[j] >> 32) == cell) {
-        float4 p = sg.in[(unsigned int)(skeys[j] & 0xffffffffull)];
+        const unsigned int src = (unsigned int)(skeys[j] & 0xffffffffull);
+        float4 p = STAGE ? s_pts[src] : sg.in[src];
         sx = sx + p.x; sy = sy + p.y; sz = sz + p.z; si = si + p.w;
         j++;
       }
@@ -169,6 +185,9 @@ __device__ __forceinline__ void vox_small_body(const VoxSegD* __restrict__ segs,
   }
   if (tid == 0) *sg.out_count = V;
 }
+// dynamic shared memory of vox_small_kernel<CAP, NT>: keys, and for small segments the staged points + validity flags
+template <int CAP>
+constexpr int vox_small_smem() { return CAP * 8 + (CAP <= 4096 ? CAP * 17 : 0); }
 
 
 // ------------------------------------------------------------------------------------------------ split path
@@ -795,7 +814,14 @@ __global__ void gather_kernel(const CopyEnt* __restrict__ ents, int nent, float4
 int lg_vox_small(const VoxSegD* d_segs, int nseg, int max_seg_hint, int* d_overflow, cudaStream_t st, long long* launches) {
   if (nseg <= 0) return LOAM_OK;
   if (max_seg_hint <= 4096) {
-    vox_small_kernel<4096, 256><<<nseg, 256, 4096 * sizeof(unsigned long long), st>>>(d_segs, d_overflow);
+    static bool attr_small[64] = {};  // the opt-in above 48 KB is per device
+    int dev = 0;
+    LG_CHECK(cudaGetDevice(&dev));
+    if (!attr_small[dev & 63]) {
+      LG_CHECK(cudaFuncSetAttribute(vox_small_kernel<4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, vox_small_smem<4096>()));
+      attr_small[dev & 63] = true;
+    }
+    vox_small_kernel<4096, 512><<<nseg, 512, vox_small_smem<4096>(), st>>>(d_segs, d_overflow);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -814,7 +840,14 @@ int lg_vox_small_batch(const VoxSegD* const* d_seg_tab, int* const* d_overflow_t
                        long long* launches) {
   if (max_nseg <= 0 || B <= 0) return LOAM_OK;
   if (max_seg_hint <= 4096) {
-    vox_small_batch_kernel<4096, 256><<<dim3(max_nseg, B), 256, 4096 * sizeof(unsigned long long), st>>>(d_seg_tab, d_overflow_tab);
+    static bool attr_small[64] = {};
+    int dev = 0;
+    LG_CHECK(cudaGetDevice(&dev));
+    if (!attr_small[dev & 63]) {
+      LG_CHECK(cudaFuncSetAttribute(vox_small_batch_kernel<4096, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, vox_small_smem<4096>()));
+      attr_small[dev & 63] = true;
+    }
+    vox_small_batch_kernel<4096, 512><<<dim3(max_nseg, B), 512, vox_small_smem<4096>(), st>>>(d_seg_tab, d_overflow_tab);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
