@@ -32,11 +32,11 @@ def imu_stream(t0, t1, rate, seed, yaw0=0.0, gap=None):
     return out
 
 
-def scenario(seed):
+def scenario(seed, sensor=0):
     """Sweeps at 10 Hz with stamps, IMU messages delivered before each sweep up to a little PAST its end (so both the
     'IMU newer' and the 'IMU older' branch run), one gap longer than 0.2 s, one sweep whose first point is invalid."""
     from gpscalibration_b200 import SweepGenerator
-    gen = SweepGenerator(sensor=0, scene=seed % 2, seed=0xC0FFEE + seed)
+    gen = SweepGenerator(sensor=sensor, scene=seed % 2, seed=0xC0FFEE + seed)
     msgs = imu_stream(99.95, 101.3, 100.0, seed, yaw0=2.9, gap=(100.52, 100.78))
     events = []
     k_msg = 0
@@ -105,6 +105,32 @@ def test_gpu_imu_deskew_equals_oracle(orc, seed):
                 assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_sweeps, name)
             n_sweeps += 1
     assert n_sweeps == 10
+    gpu.close()
+
+
+@pytest.mark.gpu
+def test_gpu_imu_deskew_with_empty_rings(orc):
+    """The IMU branch on true VLP-16 angles: rings 6, 8 and 10 of the reference's table stay empty, so every sweep also goes
+    through the virtual-ring replay (SR:480-490) -- on de-skewed points.  Clouds and /imu_trans equal to the oracle."""
+    from gpscalibration_b200 import LoamGpu
+    gpu = LoamGpu()
+    o = orc.ScanRegistration()
+    n_sweeps = 0
+    for ev in scenario(2, sensor=1):
+        if ev[0] == "imu":
+            gpu.imu_push(*ev[1:])
+            o.imu(*ev[1:])
+        else:
+            _, stamp, xyz = ev
+            c = gpu.extract(xyz, stamp)
+            oc, otr = o.extract_imu(xyz, stamp)
+            assert (c.n_full, c.n_sharp, c.n_less_sharp, c.n_flat, c.n_less_flat) == tuple(oc[k].shape[0] for k in o.CLOUDS), n_sweeps
+            assert np.array_equal(gpu.imu_trans().view(np.uint32), otr.view(np.uint32)), n_sweeps
+            for name in o.CLOUDS:
+                a, b = gpu.cloud(name), oc[name]
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n_sweeps, name)
+            n_sweeps += 1
+    assert n_sweeps == 10 and (o.ints("scan_start")[[6, 8, 10]] == 0).all()  # the three rings really were empty
     gpu.close()
 
 
