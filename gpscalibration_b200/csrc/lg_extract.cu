@@ -1335,14 +1335,14 @@ __global__ void __launch_bounds__(256) sr_curv_batch_kernel(const SrK* __restric
   if ((int)(blockIdx.x * blockDim.x) >= A.n) return;
   sr_curv_kernel_body(A.prm, A.full, A.meta, A.curv, A.cond, A.label);
 }
-__global__ void __launch_bounds__(SEL_NT) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
+__global__ void __launch_bounds__(SEL_NT, 2) sr_select_kernel(SrParams prm, const float4* __restrict__ c, int* __restrict__ meta,
                                                             const float* __restrict__ curv, const unsigned char* __restrict__ cond,
                                                             unsigned char* __restrict__ picked, unsigned char* __restrict__ mask_diag,
                                                             signed char* __restrict__ label, int* __restrict__ picks,
                                                             int* __restrict__ sort_ind, unsigned char* __restrict__ stale) {
   sr_select_kernel_body(prm, c, meta, curv, cond, picked, mask_diag, label, picks, sort_ind, stale);
 }
-__global__ void __launch_bounds__(SEL_NT) sr_select_batch_kernel(const SrK* __restrict__ tab) {
+__global__ void __launch_bounds__(SEL_NT, 2) sr_select_batch_kernel(const SrK* __restrict__ tab) {
   const SrK A = tab[blockIdx.y];
   if ((int)blockIdx.x >= A.prm.n_scans) return;
   sr_select_kernel_body(A.prm, A.full, A.meta, A.curv, A.cond, A.picked, A.mask_diag, A.label, A.picks, A.sort_ind, A.stale);

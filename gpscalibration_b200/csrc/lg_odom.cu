@@ -920,14 +920,14 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_NT) odom_it
   odom_iter_cluster_body(A.T, A.sc, A.iter, A.sharp, A.n_sharp, A.flat, A.n_flat, A.corner_last, A.surf_last, A.c1, A.c2, A.s1, A.s2, A.s3, A.out,
                          A.seq);
 }
-__global__ void __launch_bounds__(LP_NT)
+__global__ void __launch_bounds__(LP_NT, 2)
     odom_loop_kernel(OdomLoopArgs A, const float4* __restrict__ sharp, int n_sharp, const float4* __restrict__ flat, int n_flat,
                      const float4* __restrict__ corner_last, const float4* __restrict__ surf_last, const int* __restrict__ c1,
                      const int* __restrict__ c2, const int* __restrict__ s1, const int* __restrict__ s2, const int* __restrict__ s3,
                      double* __restrict__ out, unsigned long long seq) {
   odom_loop_body(A, sharp, n_sharp, flat, n_flat, corner_last, surf_last, c1, c2, s1, s2, s3, out, seq);
 }
-__global__ void __launch_bounds__(LP_NT) odom_loop_batch_kernel(const OdK* __restrict__ tab) {
+__global__ void __launch_bounds__(LP_NT, 2) odom_loop_batch_kernel(const OdK* __restrict__ tab) {
   const OdK& A = tab[blockIdx.y];
   if (!A.do_loop) return;
   odom_loop_body(A.la, A.sharp, A.n_sharp, A.flat, A.n_flat, A.corner_last, A.surf_last, A.c1, A.c2, A.s1, A.s2, A.s3, A.out, A.seq);
