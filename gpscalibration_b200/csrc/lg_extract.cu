@@ -16,7 +16,12 @@
 
 namespace {
 
-constexpr int SR_NT = 256, SR_ITEMS = 4, SR_TILE = SR_NT * SR_ITEMS;
+constexpr int SR_NT = 256;
+// Points per thread of the ring / scatter kernels: 1 for sweeps up to 64 k points (a 28.8 k-point sweep then spreads over 113
+// CTAs instead of 29: the per-point atanf / atan2f chains are the kernel's latency), 4 above (keeps the (ring, CTA) table
+// that one CTA scans short).  The kernels derive it from n and the CTA count, so both see the same tiling.
+static inline int sr_items_for(int n) { return n <= 65536 ? 1 : 4; }
+__device__ __forceinline__ int sr_items(int n, int nblocks) { return (n + nblocks * SR_NT - 1) / (nblocks * SR_NT); }
 constexpr int MAXR = 64;
 
 // cond bits written by sr_curv_kernel
@@ -106,9 +111,9 @@ __device__ __forceinline__ void sr_ring_kernel_body(SrParams prm, const float* _
   __syncthreads();
   const float startOri = s_ori[0];
   int jmin = 0x7fffffff;
-  const int base = blockIdx.x * SR_TILE;
-#pragma unroll
-  for (int c = 0; c < SR_ITEMS; c++) {
+  const int items = sr_items(n, nblocks);
+  const int base = blockIdx.x * items * SR_NT;
+  for (int c = 0; c < items; c++) {
     int i = base + c * SR_NT + tid;
     if (i >= n) break;
     const float* p = pt_at(xyz, stride_bytes, i);
@@ -189,8 +194,9 @@ __device__ __forceinline__ void sr_scatter_kernel_body(SrParams prm, const float
   __syncthreads();
   const float startOri = s_ori[0], endOri = s_ori[1];
   const int jstar = meta[SRM_JSTAR];
-  const int base = blockIdx.x * SR_TILE;
-  for (int c = 0; c < SR_ITEMS; c++) {
+  const int items = sr_items(n, nblocks);
+  const int base = blockIdx.x * items * SR_NT;
+  for (int c = 0; c < items; c++) {
     if (tid < MAXR) {
 #pragma unroll
       for (int k = 0; k < SR_NT / 32; k++) s_wcnt[k][tid] = 0;
@@ -1375,7 +1381,7 @@ __global__ void __launch_bounds__(256) sr_concat_batch_kernel(const SrK* __restr
 static int lg_extract_prepare(SrWs& ws, const SrParams& prm, int n, cudaStream_t st, int* nblocks_out) {
   const int R = prm.n_scans;
   if (R > MAXR || R < 1) return LOAM_EINVAL;
-  const int nblocks = std::max(1, lg_div_up(n, SR_TILE));
+  const int nblocks = std::max(1, lg_div_up(n, SR_NT * sr_items_for(n)));
   *nblocks_out = nblocks;
   LG_CHECK(ws.ring8.ensure((size_t)n + 16, st));
   LG_CHECK(ws.ori_raw.ensure((size_t)(n + 16) * 4, st));
