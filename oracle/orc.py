@@ -47,6 +47,11 @@ def lib():
         L.orc_sr_imu.argtypes = [vp, C.c_double, vp, vp, vp]
         L.orc_sr_extract_imu.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, vp]
         L.orc_sr_cloud.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.orc_lonode_create.restype = vp
+        L.orc_lonode_destroy.argtypes = [vp]
+        L.orc_lonode_control.argtypes = [vp, C.c_int]
+        L.orc_lonode_step.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_lonode_cloud.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_sr_ints.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_sr_curvature.argtypes = [vp, vp, C.c_int]
         L.orc_transform_to_start.argtypes = [vp, C.c_int, vp, vp]
@@ -193,6 +198,40 @@ class ScanRegistration:
         out = np.empty(n, np.float32)
         lib().orc_sr_curvature(self._h, out.ctypes.data, n)
         return out
+
+
+class LaserOdometry:
+    """The odometry node alone: one main-loop body (LO:502-1147) per step, /imu_trans as an input."""
+
+    def __init__(self):
+        self._h = lib().orc_lonode_create()
+
+    def __del__(self):
+        try:
+            lib().orc_lonode_destroy(self._h)
+        except Exception:
+            pass
+
+    def control(self, inited):
+        lib().orc_lonode_control(self._h, int(inited))
+
+    def step(self, feat, imu12=None):
+        """feat = [full, sharp, less_sharp, flat, less_flat]; returns (out18, [corner_last, surf_last, full_res] or None)."""
+        full, sharp, less_sharp, flat, less_flat = (_f32(x) for x in feat)
+        out = np.zeros(18, np.float32)
+        imu = _f32(imu12).ctypes.data if imu12 is not None else None
+        lib().orc_lonode_step(self._h, sharp.ctypes.data, sharp.shape[0], less_sharp.ctypes.data, less_sharp.shape[0], flat.ctypes.data,
+                          flat.shape[0], less_flat.ctypes.data, less_flat.shape[0], full.ctypes.data, full.shape[0], imu, out.ctypes.data)
+        clouds = None
+        if out[13] > 0:
+            clouds = []
+            for w in range(3):
+                n = lib().orc_lonode_cloud(self._h, w, None, 0)
+                c = np.empty((n, 4), np.float32)
+                if n:
+                    lib().orc_lonode_cloud(self._h, w, c.ctypes.data, n)
+                clouds.append(c)
+        return out, clouds
 
 
 def transform_to_end(pts4, T, imu12=None):

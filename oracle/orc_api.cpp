@@ -329,6 +329,43 @@ void* orc_pipeline_create(int n_scans, int ring_mode, float ang_min, float ang_s
   return p;
 }
 void orc_pipeline_destroy(void* h) { delete (Pipeline*)h; }
+
+// The odometry node alone (one main-loop body LO:502-1147 per call) with the twelve floats of /imu_trans as input: pins the
+// IMU formulas of laserOdometry (LO:201-225, 385-409, 566-568, 1053-1064) against the reference's own laserOdometry.cpp.
+// out18 = transformSum[6], transformation[6], {odometry published, clouds published, full-res published, iterations, 0, 0}.
+struct LOH {
+  LaserOdometry lo;
+  OdomOut oo;
+};
+void* orc_lonode_create() { return new LOH(); }
+void orc_lonode_destroy(void* h) { delete (LOH*)h; }
+void orc_lonode_control(void* h, int inited) { ((LOH*)h)->lo.control(inited != 0); }
+int orc_lonode_step(void* hv, const float* sharp, int ns, const float* less_sharp, int nls, const float* flat, int nf, const float* less_flat,
+                int nlf, const float* full, int nfull, const float* imu12, float* out18) {
+  LOH* h = (LOH*)hv;
+  Cloud a, b, c, d, e;
+  to_cloud(sharp, ns, a);
+  to_cloud(less_sharp, nls, b);
+  to_cloud(flat, nf, c);
+  to_cloud(less_flat, nlf, d);
+  to_cloud(full, nfull, e);
+  h->lo.process(a, b, c, d, e, imu_from(imu12), h->oo);
+  for (int i = 0; i < 6; i++) {
+    out18[i] = h->oo.transformSum[i];
+    out18[6 + i] = h->oo.transformation[i];
+  }
+  out18[12] = h->oo.odomPublished ? 1.f : 0.f;
+  out18[13] = h->oo.cloudsPublished ? 1.f : 0.f;
+  out18[14] = h->oo.fullResPublished ? 1.f : 0.f;
+  out18[15] = (float)h->oo.iterations;
+  out18[16] = out18[17] = 0.f;
+  return 0;
+}
+// which: 0 /laser_cloud_corner_last, 1 /laser_cloud_surf_last, 2 /velodyne_cloud_3 (valid when the flags of the step say so)
+int orc_lonode_cloud(void* hv, int which, float* buf, int cap) {
+  LOH* h = (LOH*)hv;
+  return from_cloud(which == 0 ? h->oo.cornerLast : (which == 1 ? h->oo.surfLast : h->oo.fullRes), buf, cap);
+}
 void orc_pipeline_set_ros_hop(void* h, int on) { ((Pipeline*)h)->ros_hop = on != 0; }
 void orc_odometry_ros_hop(const float* in6, float* out6) { odometry_ros_hop(in6, out6); }
 // IMControl{systemInited=false} (IN:281-284): odometry re-initialises on the next sweep, mapping when it sees zero odometry.

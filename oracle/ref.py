@@ -363,3 +363,34 @@ class SrWithImu:
         tr = np.zeros(12, np.float32)
         self.L.ref_sr_imu_trans(tr.ctypes.data)
         return [_cloud(self.L.ref_sr_cloud, w) for w in range(5)], tr
+
+
+class LoWithImu:
+    """A PRIVATE copy of the reference's laserOdometry.cpp (its state lives in file-scope globals) stepped with the twelve
+    floats of /imu_trans: the IMU formulas of LO:201-225, 385-409, 566-568, 1053-1064."""
+
+    def __init__(self):
+        import shutil
+        import tempfile
+        self._dir = tempfile.mkdtemp(prefix="reflo_")
+        so = os.path.join(self._dir, "libref_lo_imu.so")
+        shutil.copy(os.path.join(_DIR, "libref_lo.so"), so)
+        L = C.CDLL(so)
+        vp = C.c_void_p
+        L.ref_lo_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
+        L.ref_lo_cloud.argtypes = [C.c_int, vp, C.c_int]
+        L.ref_lo_start()
+        self.L = L
+
+    def step(self, feat, stamp, imu12):
+        full, sharp, less_sharp, flat, less_flat = (np.ascontiguousarray(x, np.float32) for x in feat)
+        imu = np.ascontiguousarray(imu12, np.float32)
+        out = np.zeros(18, np.float32)
+        self.L.ref_lo_step(sharp.ctypes.data, sharp.shape[0], less_sharp.ctypes.data, less_sharp.shape[0], flat.ctypes.data, flat.shape[0],
+                           less_flat.ctypes.data, less_flat.shape[0], full.ctypes.data, full.shape[0], imu.ctypes.data, float(stamp),
+                           out.ctypes.data)
+        clouds = [_cloud(self.L.ref_lo_cloud, w) for w in range(3)] if out[13] > 0 else None
+        return out, clouds
+
+    def close(self):
+        self.L.ref_lo_stop()
