@@ -81,6 +81,47 @@ def test_oracle_imu_branch_matches_reference(orc, seed):
 
 
 @pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_reproduces_reference_imu_golden(orc, seed):
+    """tests/golden/ref_imu_seq.npz was written by the reference's own scanRegistration.cpp (IMU branch) and laserOdometry.cpp
+    (tests/golden/make_golden_imu.py); it travels to boxes without /root/reference.  The oracle reproduces it exactly:
+    /imu_trans, sizes and hashes of the five clouds, the odometry node's poses, flags and published clouds."""
+    import hashlib
+    import os
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_imu_seq.npz"))
+    p = f"s{seed}_"
+    osr, olo = orc.ScanRegistration(), orc.LaserOdometry()
+    in_hash, k = hashlib.sha256(), 0
+    for ev in scenario(seed):
+        if ev[0] == "imu":
+            for v in ev[1:]:
+                in_hash.update(np.ascontiguousarray(v, np.float64).tobytes())
+            osr.imu(*ev[1:])
+            continue
+        _, stamp, xyz = ev
+        in_hash.update(np.ascontiguousarray(xyz, np.float32).tobytes())
+        oc, otr = osr.extract_imu(xyz, stamp)
+        feat = [oc[n] for n in ("full", "sharp", "less_sharp", "flat", "less_flat")]
+        assert np.array_equal(otr.view(np.uint32), g[p + "imu_trans"][k].view(np.uint32)), k
+        assert [f.shape[0] for f in feat] == g[p + "counts"][k].tolist(), k
+        assert [sha(f) for f in feat] == [str(h) for h in g[p + "cloud_hash"][k]], k
+        out, clouds = olo.step(feat, otr)
+        assert np.array_equal(out[:15].view(np.uint32), g[p + "lo_out"][k].view(np.uint32)), k
+        want_hash = [str(h) for h in g[p + "lo_cloud_hash"][k]]
+        if clouds is None:
+            assert want_hash == ["", "", ""], k
+        else:
+            # /velodyne_cloud_3 is only republished every second sweep: the reference's capture keeps the last one
+            n_cmp = 3 if out[14] > 0 else 2
+            assert [sha(c) for c in clouds[:n_cmp]] == want_hash[:n_cmp], k
+        k += 1
+    assert k == 10 and in_hash.hexdigest() == str(g[p + "in_hash"])  # the scenario is still the one the fixture was made from
+
+
+@pytest.mark.parametrize("seed", [0, 1])
 def test_oracle_odometry_with_imu_trans_matches_reference(orc, seed):
     """The odometry node fed with a NON-ZERO /imu_trans (LO:201-225 TransformToEnd's IMU rotations, LO:385-409 the handler,
     LO:566-568 the velocity prior, LO:1053-1064 the shift and PluginIMURotation): the oracle's restatement against the
