@@ -394,3 +394,67 @@ class LoWithImu:
 
     def close(self):
         self.L.ref_lo_stop()
+
+
+class PrivateNodes:
+    """PRIVATE copies of all three reference nodes (their state -- incl. scanRegistration's never re-initialised static
+    arrays -- lives in file-scope globals and would otherwise depend on what ran before in this process), wired like
+    `process()`: one sweep through scanRegistration -> laserOdometry -> laserMapping."""
+
+    def __init__(self):
+        import shutil
+        import tempfile
+        self._dir = tempfile.mkdtemp(prefix="refnodes_")
+        libs = []
+        for name in ("sr", "lo", "lm"):
+            so = os.path.join(self._dir, f"libref_{name}_private.so")
+            shutil.copy(os.path.join(_DIR, f"libref_{name}.so"), so)
+            libs.append(C.CDLL(so))
+        sr, lo, lm = libs
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        sr.ref_sr_process.argtypes = [vp, C.c_int, C.c_double]
+        sr.ref_sr_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lo.ref_lo_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
+        lo.ref_lo_odometry.argtypes = [vp]
+        lo.ref_lo_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lm.ref_lm_odometry_only.argtypes = [vp, C.c_double]
+        lm.ref_lm_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
+        lm.ref_lm_map_size.argtypes = [ip, ip]
+        lo.ref_lo_start()
+        lm.ref_lm_start()
+        self.sr, self.lo, self.lm = sr, lo, lm
+
+    def process(self, xyz, stamp):
+        r = SweepOut()
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        self.sr.ref_sr_process(xyz.ctypes.data, xyz.shape[0], float(stamp))
+        full, sharp, less_sharp, flat, less_flat = feat = [_cloud(self.sr.ref_sr_cloud, w) for w in range(5)]
+        r.features = feat
+        o = np.zeros(18, np.float32)
+        self.lo.ref_lo_step(sharp.ctypes.data, sharp.shape[0], less_sharp.ctypes.data, less_sharp.shape[0], flat.ctypes.data, flat.shape[0],
+                            less_flat.ctypes.data, less_flat.shape[0], full.ctypes.data, full.shape[0], None, float(stamp), o.ctypes.data)
+        pose7 = np.zeros(7, np.float64)
+        self.lo.ref_lo_odometry(pose7.ctypes.data)
+        r.odom, r.rel = o[:6].copy(), o[6:12].copy()
+        r.odom_published, r.clouds_published, r.fullres_published = bool(o[12] > 0), bool(o[13] > 0), bool(o[14] > 0)
+        r.mapping_ran, r.mapped, r.bef_mapped, r.tobe_mapped = False, None, None, None
+        if r.odom_published:
+            if not r.fullres_published:
+                self.lm.ref_lm_odometry_only(pose7.ctypes.data, float(stamp))
+            else:
+                c, s, f = [_cloud(self.lo.ref_lo_cloud, w) for w in range(3)]
+                m = np.zeros(24, np.float32)
+                self.lm.ref_lm_step(c.ctypes.data, c.shape[0], s.ctypes.data, s.shape[0], f.ctypes.data, f.shape[0], pose7.ctypes.data,
+                                    float(stamp), m.ctypes.data)
+                r.mapping_ran = True
+                r.mapped, r.bef_mapped, r.tobe_mapped = m[:6].copy(), m[6:12].copy(), m[12:18].copy()
+        return r
+
+    def map_size(self):
+        a, b = C.c_int(), C.c_int()
+        self.lm.ref_lm_map_size(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        self.lo.ref_lo_stop()
+        self.lm.ref_lm_stop()

@@ -1,0 +1,99 @@
+"""Pins the oracle's scanRegistration on the EDGE inputs the GPU parity tests use -- empty rings (true VLP-16 angles, sky-facing
+top rings, an occluded ring mid-sequence: the stale / overlapping scanStartInd / scanEndInd of SR:480-490 and the five
+never re-initialised entries of the static arrays, state carried from sweep to sweep), NaN / inf points and a ragged tail,
+dense rings with curvature ties -- against the reference's OWN scanRegistration.cpp (a private copy of
+oracle/_ref/libref_sr.so per sequence: the node keeps its state in file-scope globals), bit for bit on all five clouds.
+The GPU tests compare the CUDA path with the oracle on the same inputs; this closes the chain to the reference's code."""
+import numpy as np
+import pytest
+
+NAMES = ("full", "sharp", "less_sharp", "flat", "less_flat")
+
+
+def _pin(orc, sweeps):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    r = ref.SrWithImu()  # no IMU message is ever sent: imuPointerLast stays -1 and the plain path runs (SR:364)
+    o = orc.ScanRegistration()
+    sizes = []
+    for k, xyz in enumerate(sweeps):
+        feat, tr = r.process(xyz, 100.0 + 0.1 * k)
+        oc = o.extract(xyz)
+        assert not tr.any()
+        for i, nm in enumerate(NAMES):
+            a, b = feat[i], oc[nm]
+            assert a.shape == b.shape, (k, nm, a.shape, b.shape)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (k, nm)
+        sizes.append([f.shape[0] for f in feat])
+    return o, sizes
+
+
+def _elev(xyz):
+    return np.degrees(np.arctan2(xyz[:, 2], np.hypot(xyz[:, 0], xyz[:, 1])))
+
+
+def test_true_vlp16_angles_four_sweeps(orc):
+    from gpscalibration_b200 import SweepGenerator
+    g = SweepGenerator(sensor=1, scene=0, seed=0xC0FFEE)
+    o, sizes = _pin(orc, [g.sweep(k)[0].copy() for k in range(4)])
+    assert (o.ints("scan_start")[[6, 8, 10]] == 0).all() and (o.ints("scan_end")[[5, 7, 9]] == 0).all()
+    assert sizes[-1][4] > sizes[-1][0] // 4  # the virtual rings contribute the earlier rings again
+
+
+def test_nan_inf_and_ragged_tail(orc, sweeps16):
+    xyz = sweeps16[2].copy()
+    rng = np.random.default_rng(3)
+    bad = rng.choice(xyz.shape[0], 500, replace=False)
+    xyz[bad[:250], 0] = np.nan
+    xyz[bad[250:], 2] = np.inf
+    xyz[0] = np.nan
+    xyz[-1] = np.nan
+    _pin(orc, [xyz[:-777]])
+
+
+def test_top_rings_missing_then_full(orc, sweeps16):
+    cuts = [sweeps16[k][_elev(sweeps16[k]) < 4.0] for k in (3, 4)]
+    o, _ = _pin(orc, cuts[:1])
+    assert o.ints("scan_start")[15] == 0 and o.ints("scan_end")[12] == 0
+    _pin(orc, cuts + [sweeps16[5]])  # a fully populated sweep afterwards: the five stale entries keep their marks
+
+
+def test_occluded_rings_mid_sequence(orc, sweeps16):
+    xyz = sweeps16[1]
+    e = _elev(xyz)
+    _pin(orc, [sweeps16[0], xyz[np.abs(e + 2.0) > 0.5], xyz[e > -14.0], sweeps16[2]])
+
+
+def test_dense_rings_with_curvature_ties(orc):
+    from test_select_rounds import _dense_cylinder
+    _pin(orc, [_dense_cylinder()])
+
+
+def test_whole_pipeline_on_true_vlp16_angles(orc):
+    """Empty rings every sweep, through all three nodes: feature clouds, odometry and mapped poses, publish pattern and map
+    sizes of the oracle's pipeline equal to the reference's own three translation units (private copies), bit for bit."""
+    from gpscalibration_b200 import SweepGenerator
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = SweepGenerator(sensor=1, scene=0, seed=0xC0FFEE)
+    nodes = ref.PrivateNodes()
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    try:
+        ran = 0
+        for k in range(10):
+            x = g.sweep(k)[0].copy()
+            r = nodes.process(x, 300.0 + 0.1 * k)
+            o = pipe.process(x)
+            for i, nm in enumerate(NAMES):
+                assert np.array_equal(r.features[i].view(np.uint32), pipe.cloud(nm).view(np.uint32)), (k, nm)
+            assert r.odom_published == bool(o.odom_published) and r.mapping_ran == bool(o.mapping_ran), k
+            assert np.array_equal(r.odom, np.array(o.odom, np.float32)), k
+            if r.mapping_ran:
+                ran += 1
+                assert np.array_equal(r.mapped, np.array(o.mapped, np.float32)), k
+        assert ran >= 4 and list(nodes.map_size()) == list(pipe.map_size())
+    finally:
+        nodes.close()
