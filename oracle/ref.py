@@ -417,12 +417,17 @@ class PrivateNodes:
         lo.ref_lo_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
         lo.ref_lo_odometry.argtypes = [vp]
         lo.ref_lo_cloud.argtypes = [C.c_int, vp, C.c_int]
+        lo.ref_lo_control.argtypes = [C.c_int]
         lm.ref_lm_odometry_only.argtypes = [vp, C.c_double]
         lm.ref_lm_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
         lm.ref_lm_map_size.argtypes = [ip, ip]
         lo.ref_lo_start()
         lm.ref_lm_start()
         self.sr, self.lo, self.lm = sr, lo, lm
+
+    def control_reset(self):
+        """IMControl{systemInited=false} to laserOdometry (IN:281-284)."""
+        self.lo.ref_lo_control(0)
 
     def process(self, xyz, stamp):
         r = SweepOut()

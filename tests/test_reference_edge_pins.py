@@ -1,9 +1,11 @@
-"""Pins the oracle's scanRegistration on the EDGE inputs the GPU parity tests use -- empty rings (true VLP-16 angles, sky-facing
+"""Pins the oracle on the EDGE inputs and flows the GPU parity tests use -- for scanRegistration -- empty rings (true VLP-16 angles, sky-facing
 top rings, an occluded ring mid-sequence: the stale / overlapping scanStartInd / scanEndInd of SR:480-490 and the five
 never re-initialised entries of the static arrays, state carried from sweep to sweep), NaN / inf points and a ragged tail,
 dense rings with curvature ties -- against the reference's OWN scanRegistration.cpp (a private copy of
 oracle/_ref/libref_sr.so per sequence: the node keeps its state in file-scope globals), bit for bit on all five clouds.
-The GPU tests compare the CUDA path with the oracle on the same inputs; this closes the chain to the reference's code."""
+Further down: the whole pipeline on empty-ring sweeps, the cube grid rolling over hundreds of metres, and the reset protocol,
+against private copies of all three nodes.  The GPU tests compare the CUDA path with the oracle on the same inputs; this
+closes the chain to the reference's code."""
 import numpy as np
 import pytest
 
@@ -95,5 +97,67 @@ def test_whole_pipeline_on_true_vlp16_angles(orc):
                 ran += 1
                 assert np.array_equal(r.mapped, np.array(o.mapped, np.float32)), k
         assert ran >= 4 and list(nodes.map_size()) == list(pipe.map_size())
+    finally:
+        nodes.close()
+
+
+def test_mapping_cube_grid_rolls_like_the_reference_code(orc, sweeps16):
+    """laserMapping alone, driven along a path that travels hundreds of metres and back: the 21 x 11 x 21 cube grid re-centres in
+    every direction (LM:497-657), cubes are cleared, points land in cubes outside the voxel-gridded set.  The oracle's node
+    against the reference's own laserMapping.cpp (private copy) on the SAME parsed transformSum (read back from the
+    reference's handler, so the quaternion message hop is not part of this test): transformAftMapped / BefMapped /
+    TobeMapped and the map sizes, bit for bit.  The GPU test of the same name compares the CUDA path with the oracle."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    f = orc.ScanRegistration().extract(sweeps16[0])
+    T0 = np.zeros(6, np.float32)
+    corner = orc.transform_to_end(f["less_sharp"], T0)
+    surf = orc.transform_to_end(f["less_flat"], T0)
+    full = orc.transform_to_end(f["full"], T0)
+    nodes = ref.PrivateNodes()
+    lm = orc.LaserMapping()
+    path = [(0.0, 0.0, 0.0)]
+    for step in ((45.0, 0.0, 0.0),) * 10 + ((0.0, 0.0, 45.0),) * 9 + ((0.0, 40.0, 0.0),) * 5 + ((-45.0, -20.0, -45.0),) * 14:
+        path.append(tuple(a + b for a, b in zip(path[-1], step)))
+    try:
+        for k, (x, y, z) in enumerate(path[1:]):
+            Tsum = np.array([0.001 * k, 0.02 * k, -0.0005 * k, x, y, z], np.float32)
+            m = np.zeros(24, np.float32)
+            pose7 = ref.pose7_from_T(Tsum)
+            nodes.lm.ref_lm_step(corner.ctypes.data, corner.shape[0], surf.ctypes.data, surf.shape[0], full.ctypes.data, full.shape[0],
+                                 pose7.ctypes.data, 400.0 + 0.1 * k, m.ctypes.data)
+            ro = lm.step(m[18:24].copy(), corner, surf, full)  # the transformSum the reference's handler parsed
+            assert np.array_equal(m[:18].view(np.uint32), ro[:18].view(np.uint32)), (k, x, y, z)
+            assert list(nodes.map_size()) == [int(ro[23]), int(ro[24])], k
+    finally:
+        nodes.close()
+
+
+def test_reset_protocol_like_the_reference_code(orc, sweeps16):
+    """IMControl{systemInited=false} between two sweeps (IN:281-284): laserOdometry re-initialises on the next sweep, laserMapping
+    resets when it sees the zero pose (LM:316-319).  The oracle's pipeline against private copies of the reference's three
+    nodes across the reset: clouds, poses, publish pattern and map sizes, bit for bit."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    nodes = ref.PrivateNodes()
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    try:
+        for k in range(11):
+            if k == 5:
+                nodes.control_reset()
+                pipe.reset()
+            r = nodes.process(sweeps16[k], 500.0 + 0.1 * k)
+            o = pipe.process(sweeps16[k])
+            for i, nm in enumerate(NAMES):
+                assert np.array_equal(r.features[i].view(np.uint32), pipe.cloud(nm).view(np.uint32)), (k, nm)
+            assert r.odom_published == bool(o.odom_published) and r.mapping_ran == bool(o.mapping_ran), k
+            assert np.array_equal(r.odom, np.array(o.odom, np.float32)), k
+            if r.mapping_ran:
+                assert np.array_equal(r.mapped, np.array(o.mapped, np.float32)), k
+            assert list(nodes.map_size()) == list(pipe.map_size()), k
+        assert np.abs(r.odom[3:]).max() > 0.1  # and the odometry moved again after the reset
     finally:
         nodes.close()
