@@ -421,9 +421,14 @@ class PrivateNodes:
         lm.ref_lm_odometry_only.argtypes = [vp, C.c_double]
         lm.ref_lm_step.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_double, vp]
         lm.ref_lm_map_size.argtypes = [ip, ip]
+        lm.ref_lm_cloud.argtypes = [C.c_int, vp, C.c_int]
         lo.ref_lo_start()
         lm.ref_lm_start()
         self.sr, self.lo, self.lm = sr, lo, lm
+
+    def lm_cloud(self, which):
+        """The last published /laser_cloud_surround (0) or /velodyne_cloud_registered (1)."""
+        return _cloud(self.lm.ref_lm_cloud, which)
 
     def control_reset(self):
         """IMControl{systemInited=false} to laserOdometry (IN:281-284)."""

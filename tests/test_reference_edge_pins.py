@@ -161,3 +161,33 @@ def test_reset_protocol_like_the_reference_code(orc, sweeps16):
         assert np.abs(r.odom[3:]).max() > 0.1  # and the odometry moved again after the reset
     finally:
         nodes.close()
+
+
+def test_registered_and_surround_clouds_like_the_reference_code(orc, sweeps16):
+    """/velodyne_cloud_registered (LM:1103-1112, every mapping run) and /laser_cloud_surround (LM:1081-1101, the first run and
+    every fifth one after it): the oracle's clouds against what the reference's own laserMapping.cpp publishes, bit for bit.
+    The GPU tests compare the CUDA path's two clouds with the oracle's."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    nodes = ref.PrivateNodes()
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    try:
+        n_surround = 0
+        for k in range(14):
+            r = nodes.process(sweeps16[k], 600.0 + 0.1 * k)
+            o = pipe.process(sweeps16[k])
+            assert r.mapping_ran == bool(o.mapping_ran), k
+            if not r.mapping_ran:
+                continue
+            a, b = nodes.lm_cloud(1), pipe.cloud("registered")
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
+            s = pipe.cloud("surround")  # empty unless this run published it
+            if s.shape[0]:
+                n_surround += 1
+                c = nodes.lm_cloud(0)
+                assert c.shape == s.shape and np.array_equal(c.view(np.uint32), s.view(np.uint32)), k
+        assert n_surround == 2
+    finally:
+        nodes.close()
