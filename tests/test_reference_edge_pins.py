@@ -191,3 +191,32 @@ def test_registered_and_surround_clouds_like_the_reference_code(orc, sweeps16):
         assert n_surround == 2
     finally:
         nodes.close()
+
+
+@pytest.mark.parametrize("scene,seed", [(1, 0xC0FFEE + 7), (0, 12345)])
+def test_whole_pipeline_other_scenes_and_seeds(orc, scene, seed):
+    """The three nodes on sequences other than the golden one (the second synthetic scene; another seed): the oracle's pipeline
+    against private copies of the reference's own translation units, bit for bit over twelve sweeps."""
+    from gpscalibration_b200 import SweepGenerator
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = SweepGenerator(sensor=0, scene=scene, seed=seed)
+    nodes = ref.PrivateNodes()
+    pipe = orc.Pipeline()
+    pipe.set_ros_hop(True)
+    try:
+        for k in range(12):
+            x = g.sweep(k)[0].copy()
+            r = nodes.process(x, 700.0 + 0.1 * k)
+            o = pipe.process(x)
+            for i, nm in enumerate(NAMES):
+                assert np.array_equal(r.features[i].view(np.uint32), pipe.cloud(nm).view(np.uint32)), (k, nm)
+            assert r.odom_published == bool(o.odom_published) and r.mapping_ran == bool(o.mapping_ran), k
+            assert np.array_equal(r.odom, np.array(o.odom, np.float32)), k
+            assert np.array_equal(r.rel, np.array(o.rel, np.float32)), k
+            if r.mapping_ran:
+                assert np.array_equal(r.mapped, np.array(o.mapped, np.float32)), k
+        assert list(nodes.map_size()) == list(pipe.map_size())
+    finally:
+        nodes.close()
