@@ -154,6 +154,7 @@ int loam_launch_latency(loam_handle* h, int n, double* period_us, double* roundt
  * Results stay device-resident for loam_odometry_process; counts are returned; clouds via loam_get_cloud. */
 int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* Same, the sweep already resident in device memory of this handle's GPU. */
+int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* The IMU branch of scanRegistration (dormant in the shipped pipeline -- input_data replays only velodyne_points -- but
  * live code).  loam_imu_push replaces the body of imuHandler (SR:754-837 incl. AccumulateIMUShift SR:187-233): one
  * sensor_msgs/Imu message (orientation quaternion {x, y, z, w}, angular velocity, linear acceleration, header stamp).
@@ -165,7 +166,6 @@ int loam_extract(loam_handle* h, const float* xyz_host, int n, int stride_bytes,
 int loam_imu_push(loam_handle* h, double stamp, const double orientation_xyzw[4], const double angular_velocity[3],
                   const double linear_acceleration[3]);
 int loam_get_imu_trans(loam_handle* h, float out12[12]);
-int loam_extract_device(loam_handle* h, const float* xyz_dev, int n, int stride_bytes, double stamp, const float* imu_trans, loam_counts* out);
 /* Batched form of loam_extract (SURVEY 8b `*_batch`): one sweep of each of B independent sequences (B handles on the same
  * device, same n_scans).  Every extraction kernel is launched ONCE for the whole batch (grid.y = sequence) and the counts
  * come back with one synchronisation, so B sweeps cost eight launches instead of 8 B; results are those of B loam_extract
